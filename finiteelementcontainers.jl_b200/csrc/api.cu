@@ -1,0 +1,672 @@
+// api.cu -- the extern "C" entry points declared in include/fecb200.h.
+#include "common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <memory>
+
+namespace fec {
+thread_local std::string g_last_error;
+
+void launch_vector(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
+  switch (b.elem_type) {
+    case FECB200_QUAD4: case FECB200_TRI3: launch_vector_quad_tri(h, b, a); break;
+    case FECB200_HEX8: launch_vector_hex8(h, b, a); break;
+    case FECB200_TET4: case FECB200_TET10: launch_vector_tet(h, b, a); break;
+    default: throw Error("fecb200: unknown element type");
+  }
+}
+void launch_matrix(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
+  switch (b.elem_type) {
+    case FECB200_QUAD4: case FECB200_TRI3: launch_matrix_quad_tri(h, b, a); break;
+    case FECB200_HEX8: launch_matrix_hex8(h, b, a); break;
+    case FECB200_TET4: case FECB200_TET10: launch_matrix_tet(h, b, a); break;
+    default: throw Error("fecb200: unknown element type");
+  }
+}
+
+static int elem_nnpe(int t) {
+  switch (t) {
+    case FECB200_QUAD4: return 4; case FECB200_TRI3: return 3; case FECB200_HEX8: return 8;
+    case FECB200_TET4: return 4; case FECB200_TET10: return 10; default: return -1;
+  }
+}
+static int elem_nd(int t) { return (t == FECB200_QUAD4 || t == FECB200_TRI3) ? 2 : 3; }
+static int phys_nstate(int p) { return p == FECB200_PHYS_J2_PLASTICITY ? 7 : 0; }
+
+// copy `n` doubles from a host-or-device pointer into device staging
+static const double* stage_in(fecb200_handle* h, const double* src, double* staging, int64_t n) {
+  if (is_device_ptr(src)) return src;
+  FEC_CUDA(cudaMemcpyAsync(staging, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return staging;
+}
+static void copy_out(fecb200_handle* h, double* dst, const double* src_dev, int64_t n) {
+  if (dst == src_dev) return;
+  const bool dev = is_device_ptr(dst);
+  FEC_CUDA(cudaMemcpyAsync(dst, src_dev, n * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                           h->stream));
+  if (!dev) FEC_CUDA(cudaStreamSynchronize(h->stream));
+}
+static int64_t len_Uu(fecb200_handle* h) { return h->opts.condensed ? h->ndof : h->n_unknowns; }
+
+static void assemble_vector_impl(fecb200_handle* h, int mode, const double* Uu_dev, const double* Vu_dev,
+                                 double* out_field) {
+  FEC_CUDA(cudaMemsetAsync(out_field, 0, h->ndof * sizeof(double), h->stream));  // fill!(storage, 0)  Vector.jl:30
+  k_update_field(h, h->d_U.p, Uu_dev, true);
+  if (Vu_dev) k_update_field(h, h->d_V.p, Vu_dev, false);  // V's BC slots stay 0 (Parameters.jl:415-425)
+  h->last_ms = 0.f;
+  for (auto& b : h->blocks) {
+    VecLaunch a{h->d_U.p, Vu_dev ? h->d_V.p : nullptr, out_field, mode};
+    launch_vector(h, b, a);
+  }
+}
+
+static double* nz_for_kind(fecb200_handle* h, int kind, bool alloc) {
+  FEC_REQUIRE(!h->opts.matrix_free,
+              "assemble_matrix! called on a matrix-free SparseMatrixAssembler.  Re-create the assembler with "
+              "matrix_free=false to enable matrix assembly.");  // Matrix.jl:23-28
+  FEC_REQUIRE(h->matrix_ready, "matrix pattern not built");
+  if (kind == FECB200_STIFFNESS) return h->d_nz_stiff.p;
+  if (kind == FECB200_MASS) {
+    if (!h->d_nz_mass.p && alloc) { h->d_nz_mass.alloc(h->nnz); h->d_nz_mass.zero(h->stream); }
+    return h->d_nz_mass.p;
+  }
+  throw Error("fecb200: matrix kind must be FECB200_STIFFNESS or FECB200_MASS");
+}
+
+static void ensure_cg(fecb200_handle* h) {
+  const int64_t n = len_Uu(h);
+  if ((int64_t)h->d_cg_r.n < n) { h->d_cg_r.alloc(n); h->d_cg_p.alloc(n); h->d_cg_Ap.alloc(n); h->d_cg_x.alloc(n); }
+}
+
+// operator application for CG: y = K x (assembled) or the matrix-free action at the current U
+static void apply_operator(fecb200_handle* h, bool matrix_free, const double* x, double* y) {
+  if (!matrix_free) {
+    spmv(h, h->d_nz_stiff.p, x, y);
+  } else {
+    FEC_CUDA(cudaMemsetAsync(h->d_Av.p, 0, h->ndof * sizeof(double), h->stream));
+    k_update_field(h, h->d_V.p, x, false);
+    for (auto& b : h->blocks) {
+      VecLaunch a{h->d_U.p, h->d_V.p, h->d_Av.p, MODE_ACTION_STIFFNESS};
+      launch_vector(h, b, a);
+    }
+    k_hvp_accessor(h, x, y);
+  }
+}
+
+static void cg_impl(fecb200_handle* h, const double* b_dev, double* x_dev, double atol, double rtol, int64_t itmax,
+                    bool matrix_free, int64_t* iters_out, double* rnorm_out) {
+  // Krylov.jl cg with x0 = 0: r = b, p = r; stop when ||r|| <= atol + rtol ||r0||
+  const int64_t n = len_Uu(h);
+  ensure_cg(h);
+  double* r = h->d_cg_r.p; double* p = h->d_cg_p.p; double* Ap = h->d_cg_Ap.p;
+  FEC_CUDA(cudaMemsetAsync(x_dev, 0, n * sizeof(double), h->stream));
+  FEC_CUDA(cudaMemcpyAsync(r, b_dev, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  FEC_CUDA(cudaMemcpyAsync(p, b_dev, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  double gamma = dot(h, r, r, n);
+  const double rn0 = std::sqrt(gamma);
+  const double tol = atol + rtol * rn0;
+  int64_t it = 0;
+  while (rn0 > 0 && std::sqrt(gamma) > tol && it < itmax) {
+    apply_operator(h, matrix_free, p, Ap);
+    const double pAp = dot(h, p, Ap, n);
+    const double alpha = gamma / pAp;
+    axpy(h, alpha, p, x_dev, n);
+    axpy(h, -alpha, Ap, r, n);
+    const double gnew = dot(h, r, r, n);
+    xpay(h, r, gnew / gamma, p, n);  // p = r + beta p
+    gamma = gnew;
+    ++it;
+  }
+  if (iters_out) *iters_out = it;
+  if (rnorm_out) *rnorm_out = std::sqrt(gamma);
+}
+
+}  // namespace fec
+
+using namespace fec;
+
+#define FEC_API_BEGIN try {
+#define FEC_API_END                                     \
+  return 0;                                             \
+  }                                                     \
+  catch (const std::exception& e) {                     \
+    fec::g_last_error = e.what();                       \
+    return 1;                                           \
+  }                                                     \
+  catch (...) {                                         \
+    fec::g_last_error = "fecb200: unknown exception";   \
+    return 1;                                           \
+  }
+
+extern "C" {
+
+const char* fecb200_last_error(void) { return fec::g_last_error.c_str(); }
+int fecb200_version(void) { return 100; }
+
+int fecb200_create(const fecb200_mesh_desc* mesh, const fecb200_opts* opts, fecb200_handle** out) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(mesh && opts && out, "null argument");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    throw Error("fecb200: no CUDA device available -- libfecb200 has no CPU fallback");
+  }
+  FEC_REQUIRE(opts->device >= 0 && opts->device < ndev, "bad device ordinal");
+  FEC_REQUIRE(mesh->nf >= 1 && mesh->nf <= 3, "NF must be 1..3");
+  FEC_REQUIRE(mesh->ndim == 2 || mesh->ndim == 3, "ndim must be 2 or 3");
+  FEC_REQUIRE(mesh->nblocks >= 1 && mesh->nblocks <= 16, "1..16 element blocks (MAX_BLOCKS, FunctionSpaces.jl:63)");
+  FEC_REQUIRE(mesh->nnodes > 0 && mesh->nnodes * (int64_t)mesh->nf < (int64_t)INT32_MAX, "bad node count");
+  FEC_REQUIRE(opts->matrix_type == FECB200_CSC || opts->matrix_type == FECB200_CSR,
+              "Unsupported sparse matrix type. Only csc and csr are supported.");
+  FEC_CUDA(cudaSetDevice(opts->device));
+  std::unique_ptr<fecb200_handle> h(new fecb200_handle());
+  h->device = opts->device;
+  h->opts = *opts;
+  h->nd = mesh->ndim; h->nf = mesh->nf; h->nn = mesh->nnodes; h->ndof = h->nn * h->nf;
+  FEC_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  FEC_CUDA(cudaEventCreate(&h->ev0));
+  FEC_CUDA(cudaEventCreate(&h->ev1));
+  const int te = opts->tile_elems > 0 ? opts->tile_elems : 256;
+  FEC_REQUIRE(te == 256, "tile_elems: this build ships 256-element tiles");
+  h->blocks.resize(mesh->nblocks);
+  for (int bi = 0; bi < mesh->nblocks; ++bi) {
+    const fecb200_block_desc& d = mesh->blocks[bi];
+    BlockPlan& b = h->blocks[bi];
+    FEC_REQUIRE(elem_nnpe(d.elem_type) == d.nnpe, "nnpe does not match the element type");
+    FEC_REQUIRE(elem_nd(d.elem_type) == mesh->ndim, "element dimension does not match ndim");
+    FEC_REQUIRE(d.nelem > 0 && d.nelem < (int64_t)INT32_MAX / 16, "bad element count");
+    FEC_REQUIRE(d.nq >= 1 && d.nq <= kMaxNQ, "unsupported number of quadrature points");
+    FEC_REQUIRE(d.nprops >= 0 && d.nprops <= kMaxProps, "too many properties");
+    FEC_REQUIRE(d.nstate == phys_nstate(d.physics_id), "nstate does not match the physics");
+    b.elem_type = d.elem_type; b.nnpe = d.nnpe; b.nd = mesh->ndim; b.nq = d.nq; b.physics = d.physics_id;
+    b.nprops = d.nprops; b.nstate = d.nstate; b.ne = d.nelem; b.te = te;
+    b.N.assign(d.N, d.N + (size_t)d.nq * d.nnpe);
+    b.dN.assign(d.dN, d.dN + (size_t)d.nq * d.nnpe * mesh->ndim);
+    b.w.assign(d.w, d.w + d.nq);
+    if (d.nprops) b.props.assign(d.props, d.props + d.nprops);
+    b.conn0.resize((size_t)d.nelem * d.nnpe);
+    for (size_t i = 0; i < b.conn0.size(); ++i) {
+      const int64_t n = d.conn[i];
+      FEC_REQUIRE(n >= 1 && n <= mesh->nnodes, "connectivity entry out of range (expects 1-based node ids)");
+      b.conn0[i] = (int32_t)(n - 1);
+    }
+    build_block_tiles(h.get(), b, mesh->coords);
+    if (b.nstate) {
+      b.d_state_old.alloc((size_t)b.nstate * b.nq * b.ne); b.d_state_old.zero(h->stream);
+      b.d_state_new.alloc((size_t)b.nstate * b.nq * b.ne); b.d_state_new.zero(h->stream);
+    }
+  }
+  {
+    std::vector<double> X(mesh->coords, mesh->coords + (size_t)h->nn * h->nd);
+    h->d_X.upload(X, h->stream);
+  }
+  h->d_U.alloc(h->ndof); h->d_U.zero(h->stream);
+  h->d_V.alloc(h->ndof); h->d_V.zero(h->stream);
+  h->d_R.alloc(h->ndof); h->d_R.zero(h->stream);
+  h->d_Av.alloc(h->ndof); h->d_Av.zero(h->stream);
+  if (!opts->matrix_free) build_adjacency(h.get());
+  build_dof_structures(h.get());
+  FEC_CUDA(cudaStreamSynchronize(h->stream));
+  *out = h.release();
+  FEC_API_END
+}
+
+int fecb200_destroy(fecb200_handle* h) {
+  FEC_API_BEGIN
+  if (h) {
+    cudaSetDevice(h->device);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    cudaStream_t s = h->own_stream ? h->stream : nullptr;
+    cudaStreamSynchronize(h->stream);
+    delete h;
+    if (s) cudaStreamDestroy(s);
+  }
+  FEC_API_END
+}
+
+int fecb200_set_stream(fecb200_handle* h, void* cuda_stream) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h, "null handle");
+  FEC_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  if (cuda_stream) { h->stream = (cudaStream_t)cuda_stream; h->own_stream = false; }
+  else { FEC_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+  FEC_API_END
+}
+
+int fecb200_synchronize(fecb200_handle* h) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h, "null handle");
+  FEC_CUDA(cudaStreamSynchronize(h->stream));
+  FEC_API_END
+}
+
+int fecb200_update_dofs(fecb200_handle* h, const int64_t* dd, int64_t nd, const int64_t* pa, const int64_t* pb,
+                        int64_t np) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h, "null handle");
+  FEC_CUDA(cudaSetDevice(h->device));
+  h->dirichlet_dofs.assign(dd, dd + nd);
+  h->per_a.assign(pa, pa + np);
+  h->per_b.assign(pb, pb + np);
+  build_dof_structures(h);
+  FEC_CUDA(cudaStreamSynchronize(h->stream));
+  FEC_API_END
+}
+
+int fecb200_sizes(fecb200_handle* h, int64_t* n_total, int64_t* n_unknowns, int64_t* lu) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h, "null handle");
+  if (n_total) *n_total = h->ndof;
+  if (n_unknowns) *n_unknowns = h->n_unknowns;
+  if (lu) *lu = len_Uu(h);
+  FEC_API_END
+}
+
+int fecb200_dof_maps_copy(fecb200_handle* h, int64_t* unknown_dofs, int64_t* dof_to_unknown) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h, "null handle");
+  if (unknown_dofs) std::copy(h->unknown_dofs.begin(), h->unknown_dofs.end(), unknown_dofs);
+  if (dof_to_unknown) std::copy(h->dof_to_unknown.begin(), h->dof_to_unknown.end(), dof_to_unknown);
+  FEC_API_END
+}
+
+int fecb200_pattern_sizes(fecb200_handle* h, int64_t* n, int64_t* nnz) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h, "null handle");
+  FEC_REQUIRE(h->matrix_ready, "no matrix pattern (matrix_free assembler)");
+  if (n) *n = h->nmat;
+  if (nnz) *nnz = h->nnz;
+  FEC_API_END
+}
+
+int fecb200_pattern_copy(fecb200_handle* h, int64_t* ptr, int64_t* idx) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h, "null handle");
+  export_pattern(h, ptr, idx);
+  FEC_API_END
+}
+
+int fecb200_set_dirichlet_values(fecb200_handle* h, const int64_t* dofs, const double* vals, int64_t n) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h, "null handle");
+  FEC_CUDA(cudaSetDevice(h->device));
+  std::vector<int32_t> bd(n);
+  for (int64_t i = 0; i < n; ++i) {
+    FEC_REQUIRE(dofs[i] >= 1 && dofs[i] <= h->ndof, "dirichlet dof out of range");
+    bd[i] = (int32_t)(dofs[i] - 1);
+  }
+  std::vector<double> bv(vals, vals + n);
+  h->n_bc = n;
+  h->d_bc_dofs.upload(bd, h->stream);
+  h->d_bc_vals.upload(bv, h->stream);
+  FEC_API_END
+}
+
+int fecb200_set_periodic_values(fecb200_handle* h, const double* vals, int64_t n) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h, "null handle");
+  FEC_REQUIRE(n == h->n_per, "periodic value count does not match the resolved periodic pairs");
+  std::vector<double> pv(n, 0.0);
+  if (vals) pv.assign(vals, vals + n);
+  h->d_per_vals.upload(pv, h->stream);
+  FEC_API_END
+}
+
+int fecb200_set_time(fecb200_handle* h, double t, double dt) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h, "null handle");
+  h->t = t; h->dt = dt;
+  FEC_API_END
+}
+
+int fecb200_set_source_q(fecb200_handle* h, int32_t block, const double* fq) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && block >= 0 && block < (int)h->blocks.size(), "bad block index");
+  FEC_CUDA(cudaSetDevice(h->device));
+  BlockPlan& b = h->blocks[block];
+  const int64_t n = b.ne * b.nq;
+  if (!fq) { b.d_source.release(); return 0; }
+  DevBuf<double> tmp;
+  const double* src = fq;
+  if (!is_device_ptr(fq)) {
+    tmp.alloc(n);
+    FEC_CUDA(cudaMemcpyAsync(tmp.p, fq, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    src = tmp.p;
+  }
+  if ((int64_t)b.d_source.n != n) b.d_source.alloc(n);
+  k_permute_source_in(h, b, src, b.d_source.p);
+  FEC_CUDA(cudaStreamSynchronize(h->stream));
+  FEC_API_END
+}
+
+int fecb200_state_set(fecb200_handle* h, int32_t block, int32_t which, const double* state) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && block >= 0 && block < (int)h->blocks.size(), "bad block index");
+  FEC_CUDA(cudaSetDevice(h->device));
+  BlockPlan& b = h->blocks[block];
+  const int64_t n = b.ne * b.nq * b.nstate;
+  if (!n) return 0;
+  DevBuf<double> tmp;
+  const double* src = state;
+  if (!is_device_ptr(state)) {
+    tmp.alloc(n);
+    FEC_CUDA(cudaMemcpyAsync(tmp.p, state, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    src = tmp.p;
+  }
+  k_permute_state_in(h, b, src, which ? b.d_state_new.p : b.d_state_old.p);
+  FEC_CUDA(cudaStreamSynchronize(h->stream));
+  FEC_API_END
+}
+
+int fecb200_state_get(fecb200_handle* h, int32_t block, int32_t which, double* state) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && block >= 0 && block < (int)h->blocks.size(), "bad block index");
+  FEC_CUDA(cudaSetDevice(h->device));
+  BlockPlan& b = h->blocks[block];
+  const int64_t n = b.ne * b.nq * b.nstate;
+  if (!n) return 0;
+  const double* src = which ? b.d_state_new.p : b.d_state_old.p;
+  if (is_device_ptr(state)) {
+    k_permute_state_out(h, b, src, state);
+    FEC_CUDA(cudaStreamSynchronize(h->stream));
+  } else {
+    DevBuf<double> tmp;
+    tmp.alloc(n);
+    k_permute_state_out(h, b, src, tmp.p);
+    FEC_CUDA(cudaMemcpyAsync(state, tmp.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    FEC_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  FEC_API_END
+}
+
+int fecb200_state_swap(fecb200_handle* h) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h, "null handle");
+  for (auto& b : h->blocks) {
+    const size_t n = b.d_state_old.n;
+    if (n) FEC_CUDA(cudaMemcpyAsync(b.d_state_old.p, b.d_state_new.p, n * sizeof(double), cudaMemcpyDeviceToDevice,
+                                    h->stream));
+  }
+  FEC_API_END
+}
+
+int fecb200_assemble_vector(fecb200_handle* h, int32_t kind, const double* Uu) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && Uu, "null argument");
+  FEC_REQUIRE(kind == FECB200_RESIDUAL, "assemble_vector: kind must be FECB200_RESIDUAL");
+  FEC_CUDA(cudaSetDevice(h->device));
+  const double* u = stage_in(h, Uu, h->d_Uu.p, len_Uu(h));
+  assemble_vector_impl(h, MODE_RESIDUAL, u, nullptr, h->d_R.p);
+  FEC_API_END
+}
+
+int fecb200_residual(fecb200_handle* h, double* out) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && out, "null argument");
+  FEC_CUDA(cudaSetDevice(h->device));
+  const bool dev = is_device_ptr(out);
+  double* target = dev ? out : h->d_out.p;
+  k_residual_accessor(h, target);
+  if (!dev) copy_out(h, out, target, len_Uu(h));
+  FEC_API_END
+}
+
+int fecb200_assemble_matrix(fecb200_handle* h, int32_t kind, const double* Uu) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && Uu, "null argument");
+  FEC_CUDA(cudaSetDevice(h->device));
+  double* nz = nz_for_kind(h, kind, true);
+  const double* u = stage_in(h, Uu, h->d_Uu.p, len_Uu(h));
+  FEC_CUDA(cudaMemsetAsync(nz, 0, h->nnz * sizeof(double), h->stream));  // fill!(storage, 0)  Matrix.jl:39
+  k_update_field(h, h->d_U.p, u, true);
+  h->last_ms = 0.f;
+  for (auto& b : h->blocks) {
+    MatLaunch a{h->d_U.p, nz, kind};
+    launch_matrix(h, b, a);
+  }
+  (kind == FECB200_STIFFNESS ? h->stiff_adjusted : h->mass_adjusted) = false;
+  FEC_API_END
+}
+
+static double* adjusted_values(fecb200_handle* h, int kind) {
+  double* nz = nz_for_kind(h, kind, false);
+  FEC_REQUIRE(nz, "matrix of this kind has not been assembled");
+  bool& adj = (kind == FECB200_STIFFNESS) ? h->stiff_adjusted : h->mass_adjusted;
+  if (h->opts.condensed && !adj) { k_adjust_matrix(h, nz); adj = true; }
+  return nz;
+}
+
+int fecb200_matrix_values(fecb200_handle* h, int32_t kind, double* out) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && out, "null argument");
+  FEC_CUDA(cudaSetDevice(h->device));
+  double* nz = adjusted_values(h, kind);
+  copy_out(h, out, nz, h->nnz);
+  FEC_API_END
+}
+
+int fecb200_matrix_values_device(fecb200_handle* h, int32_t kind, double** nz_dev) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && nz_dev, "null argument");
+  FEC_CUDA(cudaSetDevice(h->device));
+  *nz_dev = adjusted_values(h, kind);
+  FEC_API_END
+}
+
+int fecb200_assemble_action(fecb200_handle* h, int32_t kind, const double* Uu, const double* Vu) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && Uu && Vu, "null argument");
+  FEC_REQUIRE(kind == FECB200_STIFFNESS || kind == FECB200_MASS, "action kind must be STIFFNESS or MASS");
+  FEC_CUDA(cudaSetDevice(h->device));
+  const double* u = stage_in(h, Uu, h->d_Uu.p, len_Uu(h));
+  const double* v = stage_in(h, Vu, h->d_Vu.p, len_Uu(h));
+  assemble_vector_impl(h, kind == FECB200_STIFFNESS ? MODE_ACTION_STIFFNESS : MODE_ACTION_MASS, u, v, h->d_Av.p);
+  FEC_API_END
+}
+
+int fecb200_assemble_action_full(fecb200_handle* h, int32_t kind, const double* U_full, const double* v_full) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && U_full && v_full, "null argument");
+  FEC_REQUIRE(kind == FECB200_STIFFNESS || kind == FECB200_MASS, "action kind must be STIFFNESS or MASS");
+  FEC_CUDA(cudaSetDevice(h->device));
+  // _update_for_assembly_full! (Parameters.jl:432-442): plain copies, BC slots are NOT overwritten
+  const auto kindU = is_device_ptr(U_full) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  const auto kindV = is_device_ptr(v_full) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  FEC_CUDA(cudaMemcpyAsync(h->d_U.p, U_full, h->ndof * sizeof(double), kindU, h->stream));
+  FEC_CUDA(cudaMemcpyAsync(h->d_V.p, v_full, h->ndof * sizeof(double), kindV, h->stream));
+  FEC_CUDA(cudaMemsetAsync(h->d_Av.p, 0, h->ndof * sizeof(double), h->stream));
+  h->last_ms = 0.f;
+  for (auto& b : h->blocks) {
+    VecLaunch a{h->d_U.p, h->d_V.p, h->d_Av.p, kind == FECB200_STIFFNESS ? MODE_ACTION_STIFFNESS : MODE_ACTION_MASS};
+    launch_vector(h, b, a);
+  }
+  k_zero_bc_slots(h, h->d_V.p);  // restore the "BC slots of V are zero" invariant (MatrixAction.jl:137-148)
+  FEC_API_END
+}
+
+int fecb200_hvp(fecb200_handle* h, const double* v, double* out) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && out, "null argument");
+  FEC_CUDA(cudaSetDevice(h->device));
+  const double* vd = nullptr;
+  if (h->opts.condensed) {
+    FEC_REQUIRE(v, "hvp needs v in condensed mode");
+    vd = stage_in(h, v, h->d_Vu.p, h->ndof);
+  }
+  const bool dev = is_device_ptr(out);
+  double* target = dev ? out : h->d_out.p;
+  k_hvp_accessor(h, vd, target);
+  if (!dev) copy_out(h, out, target, len_Uu(h));
+  FEC_API_END
+}
+
+int fecb200_field_copy(fecb200_handle* h, int32_t which, double* out) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && out, "null argument");
+  FEC_CUDA(cudaSetDevice(h->device));
+  const double* src = nullptr;
+  switch (which) {
+    case FECB200_FIELD_U: src = h->d_U.p; break;
+    case FECB200_FIELD_RESIDUAL: src = h->d_R.p; break;
+    case FECB200_FIELD_ACTION: src = h->d_Av.p; break;
+    case FECB200_FIELD_V: src = h->d_V.p; break;
+    default: throw Error("fecb200: bad field selector");
+  }
+  copy_out(h, out, src, h->ndof);
+  if (is_device_ptr(out)) FEC_CUDA(cudaStreamSynchronize(h->stream));
+  FEC_API_END
+}
+
+int fecb200_cg_solve(fecb200_handle* h, const double* b, double* x, double atol, double rtol, int64_t itmax,
+                     int32_t matrix_free, int64_t* iters_out, double* rnorm_out) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && b && x, "null argument");
+  FEC_CUDA(cudaSetDevice(h->device));
+  const int64_t n = len_Uu(h);
+  if (!matrix_free) FEC_REQUIRE(h->matrix_ready && !h->opts.matrix_free, "no assembled matrix for CG");
+  ensure_cg(h);
+  const double* bd = stage_in(h, b, h->d_Vu.p, n);
+  const bool dev = is_device_ptr(x);
+  double* xd = dev ? x : h->d_cg_x.p;
+  if (atol < 0) atol = std::sqrt(2.220446049250313e-16);
+  if (rtol < 0) rtol = std::sqrt(2.220446049250313e-16);
+  if (itmax <= 0) itmax = 2 * n;
+  if (!matrix_free) adjusted_values(h, FECB200_STIFFNESS);
+  cg_impl(h, bd, xd, atol, rtol, itmax, matrix_free != 0, iters_out, rnorm_out);
+  if (!dev) copy_out(h, x, xd, n);
+  FEC_API_END
+}
+
+int fecb200_newton_solve(fecb200_handle* h, double* Uu, int32_t max_iters, double tol, int32_t matrix_free,
+                         int32_t* newton_iters_out, int64_t* cg_iters_out, double* rnorm_out) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && Uu, "null argument");
+  FEC_CUDA(cudaSetDevice(h->device));
+  const int64_t n = len_Uu(h);
+  ensure_cg(h);
+  const bool dev = is_device_ptr(Uu);
+  double* u = h->d_Uu.p;
+  if (dev) FEC_CUDA(cudaMemcpyAsync(u, Uu, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  else FEC_CUDA(cudaMemcpyAsync(u, Uu, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (max_iters <= 0) max_iters = 10;   // NewtonSolverSettings() (Solvers.jl:174-176)
+  if (tol <= 0) tol = 1e-12;
+  const double eps = std::sqrt(2.220446049250313e-16);
+  double R0 = 0.0, nR = 0.0;
+  int64_t cg_total = 0;
+  int it = 0;
+  double* Rb = h->d_out.p;   // residual(asm)
+  double* dU = h->d_cg_x.p;
+  for (it = 1; it <= max_iters; ++it) {
+    // solve!(IterativeLinearSolver) (Solvers.jl:128-153)
+    assemble_vector_impl(h, MODE_RESIDUAL, u, nullptr, h->d_R.p);
+    k_residual_accessor(h, Rb);
+    if (!matrix_free) {
+      double* nz = nz_for_kind(h, FECB200_STIFFNESS, true);
+      FEC_CUDA(cudaMemsetAsync(nz, 0, h->nnz * sizeof(double), h->stream));
+      for (auto& b : h->blocks) { MatLaunch a{h->d_U.p, nz, FECB200_STIFFNESS}; launch_matrix(h, b, a); }
+      h->stiff_adjusted = false;
+      adjusted_values(h, FECB200_STIFFNESS);
+    }
+    int64_t cgit = 0;
+    cg_impl(h, Rb, dU, eps, eps, 2 * n, matrix_free != 0, &cgit, nullptr);
+    cg_total += cgit;
+    axpy(h, -1.0, dU, u, n);  // Uu += -solution
+    const double ndU = std::sqrt(dot(h, dU, dU, n));
+    nR = std::sqrt(dot(h, Rb, Rb, n));
+    if (it == 1) R0 = nR;
+    const double rel = R0 > 0.0 ? nR / R0 : nR;
+    if (ndU < tol || nR < tol || rel < tol) break;
+  }
+  if (it > max_iters) it = max_iters;
+  copy_out(h, Uu, u, n);
+  FEC_CUDA(cudaStreamSynchronize(h->stream));
+  if (newton_iters_out) *newton_iters_out = it;
+  if (cg_iters_out) *cg_iters_out = cg_total;
+  if (rnorm_out) *rnorm_out = nR;
+  FEC_API_END
+}
+
+int fecb200_halo_setup(fecb200_handle* h, int32_t n_neighbors, const int32_t* ranks, const int64_t* send_ptr,
+                       const int64_t* send_nodes, const int64_t* recv_ptr, const int64_t* recv_nodes) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h, "null handle");
+  FEC_CUDA(cudaSetDevice(h->device));
+  h->n_neighbors = n_neighbors;
+  h->neighbor_ranks.assign(ranks, ranks + n_neighbors);
+  h->send_ptr.assign(send_ptr, send_ptr + n_neighbors + 1);
+  h->recv_ptr.assign(recv_ptr, recv_ptr + n_neighbors + 1);
+  std::vector<int32_t> sn(h->send_ptr.back()), rn(h->recv_ptr.back());
+  for (size_t i = 0; i < sn.size(); ++i) {
+    FEC_REQUIRE(send_nodes[i] >= 1 && send_nodes[i] <= h->nn, "halo send node out of range");
+    sn[i] = (int32_t)(send_nodes[i] - 1);
+  }
+  for (size_t i = 0; i < rn.size(); ++i) {
+    FEC_REQUIRE(recv_nodes[i] >= 1 && recv_nodes[i] <= h->nn, "halo recv node out of range");
+    rn[i] = (int32_t)(recv_nodes[i] - 1);
+  }
+  h->d_send_nodes.upload(sn, h->stream);
+  h->d_recv_nodes.upload(rn, h->stream);
+  h->d_sendbuf.alloc(sn.size() * h->nf);
+  FEC_API_END
+}
+
+static double* field_ptr(fecb200_handle* h, int which) {
+  switch (which) {
+    case FECB200_FIELD_U: return h->d_U.p;
+    case FECB200_FIELD_RESIDUAL: return h->d_R.p;
+    case FECB200_FIELD_ACTION: return h->d_Av.p;
+    case FECB200_FIELD_V: return h->d_V.p;
+    default: throw Error("fecb200: bad field selector");
+  }
+}
+
+int fecb200_halo_pack(fecb200_handle* h, int32_t which, double** sendbuf_dev, int64_t* n_doubles) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && sendbuf_dev, "null argument");
+  FEC_CUDA(cudaSetDevice(h->device));
+  halo_pack(h, field_ptr(h, which), h->d_sendbuf.p);
+  *sendbuf_dev = h->d_sendbuf.p;
+  if (n_doubles) *n_doubles = (int64_t)h->d_sendbuf.n;
+  FEC_API_END
+}
+
+int fecb200_halo_unpack_add(fecb200_handle* h, int32_t which, const double* recvbuf_dev) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && recvbuf_dev, "null argument");
+  FEC_CUDA(cudaSetDevice(h->device));
+  halo_unpack_add(h, field_ptr(h, which), recvbuf_dev);
+  FEC_API_END
+}
+
+int fecb200_halo_recv_size(fecb200_handle* h, int64_t* n_doubles) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && n_doubles, "null argument");
+  *n_doubles = (int64_t)h->d_recv_nodes.n * h->nf;
+  FEC_API_END
+}
+
+int fecb200_launch_count(fecb200_handle* h, int64_t* n) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && n, "null argument");
+  *n = h->launches;
+  FEC_API_END
+}
+
+int fecb200_enable_timing(fecb200_handle* h, int32_t on) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h, "null handle");
+  h->timing = on != 0;
+  FEC_API_END
+}
+
+int fecb200_last_kernel_ms(fecb200_handle* h, float* ms) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && ms, "null argument");
+  *ms = h->last_ms;
+  FEC_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,189 @@
+// common.cuh -- internal declarations of libfecb200 (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include "../../include/fecb200.h"
+
+namespace fec {
+
+extern thread_local std::string g_last_error;
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define FEC_CUDA(call)                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = (call);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      char _buf[512];                                                                      \
+      snprintf(_buf, sizeof _buf, "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e),      \
+               __FILE__, __LINE__, cudaGetErrorString(_e));                                \
+      throw fec::Error(_buf);                                                              \
+    }                                                                                      \
+  } while (0)
+
+#define FEC_REQUIRE(cond, msg)                                                             \
+  do {                                                                                     \
+    if (!(cond)) throw fec::Error(std::string("fecb200: ") + (msg));                       \
+  } while (0)
+
+template <class T>
+struct DevBuf {  // owning device array
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) FEC_CUDA(cudaMalloc(&p, count * sizeof(T)));
+  }
+  void upload(const std::vector<T>& v, cudaStream_t s) {
+    alloc(v.size());
+    if (!v.empty()) {
+      FEC_CUDA(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+      FEC_CUDA(cudaStreamSynchronize(s));
+    }
+  }
+  void zero(cudaStream_t s) { if (n) FEC_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+};
+
+constexpr int kMaxProps = 8;
+constexpr int kMaxNQ = 27;  // runtime-NQ kernels (e.g. 3-point GLL on hex8)
+
+// One element block: FunctionSpace block + ReferenceFE tables + physics (host side of the plan)
+struct BlockPlan {
+  int elem_type = 0, nnpe = 0, nd = 0, nq = 0, physics = 0, nprops = 0, nstate = 0;
+  int64_t ne = 0;
+  std::vector<double> N, dN, w, props;
+  std::vector<int32_t> conn0;  // [ne*nnpe] 0-based node ids, caller's element order
+  // tiling (vector kernels): elements permuted into locality-ordered tiles of `te` elements
+  int te = 0, ntiles = 0, max_tile_nodes = 0;
+  std::vector<int32_t> perm;   // tile order -> original element index
+  DevBuf<int32_t> d_perm;
+  DevBuf<int32_t> d_tile_node_ptr, d_tile_nodes, d_inc_ptr;
+  DevBuf<uint16_t> d_lconn, d_inc;
+  DevBuf<int32_t> d_conn_perm;  // [ne*nnpe] global node ids in tile order (matrix kernels)
+  DevBuf<uint8_t> d_epos;       // [ne*nnpe*nnpe] position of node a in the adjacency row of node b
+  DevBuf<double> d_state_old, d_state_new;  // [(s*nq+q)*ne + e_tile_order]
+  DevBuf<double> d_source;                  // [q*ne + e_tile_order]
+};
+
+}  // namespace fec
+
+struct fecb200_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  fecb200_opts opts{};
+  int nd = 0, nf = 0;
+  int64_t nn = 0, ndof = 0;
+  std::vector<fec::BlockPlan> blocks;
+  double t = 0.0, dt = 0.0;
+
+  // full-length nodal fields (H1Field data: [(n)*NF + d])
+  fec::DevBuf<double> d_X, d_U, d_V, d_R, d_Av;
+  // unknown-length / staging vectors
+  fec::DevBuf<double> d_Uu, d_Vu, d_out;
+
+  // DofManager (host copies are 1-based Int64 like the reference)
+  std::vector<int64_t> dirichlet_dofs, unknown_dofs, dof_to_unknown, per_a, per_b, b2a_unknown;
+  int64_t n_unknowns = 0;
+  fec::DevBuf<int32_t> d_unknown_dofs;  // 0-based dof ids
+  fec::DevBuf<int32_t> d_d2u;           // dof -> index into Uu (or -1)
+  fec::DevBuf<double> d_constraint;     // 1.0 at Dirichlet dofs
+  // Dirichlet / periodic values
+  int64_t n_bc = 0, n_per = 0;
+  fec::DevBuf<int32_t> d_bc_dofs, d_per_a, d_per_b;
+  fec::DevBuf<double> d_bc_vals, d_per_vals;
+
+  // node adjacency and the (block-compressed) CSR structure
+  std::vector<int32_t> adjptr, adj;  // host
+  fec::DevBuf<int32_t> d_adjptr, d_adj;
+  bool matrix_ready = false;
+  int64_t nmat = 0, nnz = 0;
+  std::vector<int64_t> rowstart_h;   // per dof, -1 if the row is eliminated
+  std::vector<uint8_t> freemask_h;   // per node
+  fec::DevBuf<uint16_t> d_coloff;    // per adjacency entry: kept dofs before this neighbour in the row
+  fec::DevBuf<uint8_t> d_freemask;
+  fec::DevBuf<int64_t> d_rowstart, d_diagslot;
+  fec::DevBuf<double> d_nz_stiff, d_nz_mass, d_scratch;
+  bool stiff_adjusted = false, mass_adjusted = false;
+
+  // halo exchange
+  int n_neighbors = 0;
+  std::vector<int32_t> neighbor_ranks;
+  std::vector<int64_t> send_ptr, recv_ptr;
+  fec::DevBuf<int32_t> d_send_nodes, d_recv_nodes;
+  fec::DevBuf<double> d_sendbuf;
+
+  // instrumentation
+  int64_t launches = 0;
+  bool timing = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms = 0.f;
+
+  // CG workspace
+  fec::DevBuf<double> d_cg_r, d_cg_p, d_cg_Ap, d_cg_x, d_red;
+};
+
+namespace fec {
+
+// plan.cu
+void build_block_tiles(fecb200_handle* h, BlockPlan& b, const double* coords);
+void build_adjacency(fecb200_handle* h);
+void build_dof_structures(fecb200_handle* h);
+void export_pattern(fecb200_handle* h, int64_t* ptr, int64_t* idx);
+
+// dispatch (one translation unit per element family)
+enum { MODE_RESIDUAL = 0, MODE_ACTION_STIFFNESS = 1, MODE_ACTION_MASS = 2 };
+struct VecLaunch { const double* U; const double* V; double* out; int mode; };
+struct MatLaunch { const double* U; double* nz; int kind; };
+void launch_vector(fecb200_handle* h, BlockPlan& b, const VecLaunch& a);
+void launch_matrix(fecb200_handle* h, BlockPlan& b, const MatLaunch& a);
+void launch_vector_quad_tri(fecb200_handle* h, BlockPlan& b, const VecLaunch& a);
+void launch_matrix_quad_tri(fecb200_handle* h, BlockPlan& b, const MatLaunch& a);
+void launch_vector_hex8(fecb200_handle* h, BlockPlan& b, const VecLaunch& a);
+void launch_matrix_hex8(fecb200_handle* h, BlockPlan& b, const MatLaunch& a);
+void launch_vector_tet(fecb200_handle* h, BlockPlan& b, const VecLaunch& a);
+void launch_matrix_tet(fecb200_handle* h, BlockPlan& b, const MatLaunch& a);
+
+// aux.cu
+void k_update_field(fecb200_handle* h, double* field, const double* Uu, bool with_bcs);
+void k_extract_unknowns(fecb200_handle* h, const double* field, double* out);
+void k_residual_accessor(fecb200_handle* h, double* out);
+void k_hvp_accessor(fecb200_handle* h, const double* v, double* out);
+void k_adjust_matrix(fecb200_handle* h, double* nz);
+void k_permute_state_in(fecb200_handle* h, BlockPlan& b, const double* src_dev, double* dst);
+void k_permute_state_out(fecb200_handle* h, BlockPlan& b, const double* src, double* dst_dev);
+void k_permute_source_in(fecb200_handle* h, BlockPlan& b, const double* src_dev, double* dst);
+void k_zero_bc_slots(fecb200_handle* h, double* field);
+void spmv(fecb200_handle* h, const double* nz, const double* x, double* y);
+double dot(fecb200_handle* h, const double* a, const double* b, int64_t n);
+void axpy(fecb200_handle* h, double alpha, const double* x, double* y, int64_t n);
+void xpay(fecb200_handle* h, const double* x, double beta, double* y, int64_t n);  // y = x + beta*y
+void halo_pack(fecb200_handle* h, const double* field, double* buf);
+void halo_unpack_add(fecb200_handle* h, double* field, const double* buf);
+
+inline bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a{};
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace fec

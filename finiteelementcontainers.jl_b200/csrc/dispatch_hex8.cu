@@ -1,0 +1,48 @@
+// dispatch_hex8.cu -- HEX8 instantiations of the element kernels (3-D, 8 nodes).
+// Hot configurations (BASELINE.json configs 2, 3, 5): Poisson NF=1 and neo-Hookean NF=3 with 8-point rules.
+#include "kernels.cuh"
+
+namespace fec {
+
+template <class Phys, int NF, int MINB>
+static void vec8(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
+  FEC_REQUIRE(b.nq == 8, "HEX8: this physics is compiled for 8-point quadrature rules only");
+  run_vec_modes<3, 8, NF, 8, Phys, kTE, MINB>(h, b, a);
+}
+template <class Phys, int NF, int EPB>
+static void mat8(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
+  FEC_REQUIRE(b.nq == 8, "HEX8: this physics is compiled for 8-point quadrature rules only");
+  run_mat<3, 8, NF, 8, Phys, EPB>(h, b, a);
+}
+
+void launch_vector_hex8(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
+  switch (b.physics) {
+    case FECB200_PHYS_POISSON:
+      FEC_REQUIRE(h->nf == 1, "Poisson needs NF = 1");
+      if (b.nq == 8) run_vec_modes<3, 8, 1, 8, PhysPoisson<3>, kTE, 2>(h, b, a);
+      else run_vec_modes<3, 8, 1, 0, PhysPoisson<3>, kTE, 2>(h, b, a);
+      break;
+    case FECB200_PHYS_LINEAR_ELASTIC: FEC_REQUIRE(h->nf == 3, "mechanics needs NF = ND"); vec8<PhysLinearElastic<3>, 3, 2>(h, b, a); break;
+    case FECB200_PHYS_NEOHOOKEAN: FEC_REQUIRE(h->nf == 3, "mechanics needs NF = ND"); vec8<PhysNeoHookean<3>, 3, 2>(h, b, a); break;
+    case FECB200_PHYS_NEOHOOKEAN_AS_WRITTEN: FEC_REQUIRE(h->nf == 3, "mechanics needs NF = ND"); vec8<PhysNeoHookeanAsWritten<3>, 3, 2>(h, b, a); break;
+    case FECB200_PHYS_J2_PLASTICITY: FEC_REQUIRE(h->nf == 3, "mechanics needs NF = ND"); vec8<PhysJ2<3>, 3, 2>(h, b, a); break;
+    default: throw Error("fecb200: unsupported physics for HEX8");
+  }
+}
+
+void launch_matrix_hex8(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
+  switch (b.physics) {
+    case FECB200_PHYS_POISSON:
+      FEC_REQUIRE(h->nf == 1, "Poisson needs NF = 1");
+      if (b.nq == 8) run_mat<3, 8, 1, 8, PhysPoisson<3>, 32>(h, b, a);
+      else run_mat<3, 8, 1, 0, PhysPoisson<3>, 32>(h, b, a);
+      break;
+    case FECB200_PHYS_LINEAR_ELASTIC: mat8<PhysLinearElastic<3>, 3, 16>(h, b, a); break;
+    case FECB200_PHYS_NEOHOOKEAN: mat8<PhysNeoHookean<3>, 3, 16>(h, b, a); break;
+    case FECB200_PHYS_NEOHOOKEAN_AS_WRITTEN: mat8<PhysNeoHookeanAsWritten<3>, 3, 16>(h, b, a); break;
+    case FECB200_PHYS_J2_PLASTICITY: mat8<PhysJ2<3>, 3, 16>(h, b, a); break;
+    default: throw Error("fecb200: unsupported physics for HEX8");
+  }
+}
+
+}  // namespace fec

@@ -1,0 +1,589 @@
+// kernels.cuh -- element kernels of the assembly hot path (sm_100a, FP64).
+//
+// Replaces the reference's one-thread-per-element KernelAbstractions loops
+//   _assemble_block!                      src/assemblers/Assemblers.jl:402-464
+//   _assemble_block_matrix_free_action!   src/assemblers/MatrixAction.jl:49-77
+//   _assemble_block_matrix_action!        src/assemblers/MatrixAction.jl:208-270
+// with two hand-written kernel families:
+//
+//  k_vec  (residual / matrix-free action): one CTA per locality tile of TE elements.
+//     1. the tile's unique nodes are gathered ONCE into shared memory (X, U, V) -- each node is
+//        read once per tile instead of once per incident element,
+//     2. one thread per element runs the quadrature loop in registers; reference tables
+//        (N, dN/dxi, w) live in the kernel-parameter constant bank and feed DFMA as uniform operands,
+//     3. element vectors are staged in shared memory and reduced per NODE in a fixed order by the
+//        tile's node-owner threads (deterministic segmented reduction, no shared-memory atomics:
+//        FP64 shared atomics are CAS loops on sm_100a),
+//     4. one red.global.add.f64 per (node, dof) per tile -- only tile-boundary nodes ever see
+//        more than one.
+//
+//  k_mat  (stiffness / mass): NNPE threads per element.  Thread q computes the geometry and the
+//     material tangent of quadrature point q once and publishes it in shared memory; thread b then
+//     owns block-column b of K_el in registers and writes it straight into the CSR/CSC values
+//     through the precomputed element -> CSR slot map (node-pair position bytes + per-row offsets).
+//     No COO is ever materialised (the reference writes 576 doubles/element of COO and runs
+//     SparseArrays.sparse! every Newton iteration, SparsityPatterns.jl:301-308).
+#pragma once
+#include "common.cuh"
+#include "physics.cuh"
+#include <memory>
+
+namespace fec {
+
+template <int ND, int NNPE, int NQT>
+struct Tables {
+  static constexpr int NQ = (NQT > 0) ? NQT : kMaxNQ;
+  double N[NQ][NNPE];
+  double dN[NQ][NNPE][ND];
+  double w[NQ];
+};
+
+template <int ND, int NNPE, int NQT>
+struct VecParams {
+  const double* X;
+  const double* U;
+  const double* V;
+  double* out;
+  const int32_t* tile_node_ptr;
+  const int32_t* tile_nodes;
+  const uint16_t* lconn;
+  const int32_t* inc_ptr;
+  const uint16_t* inc;
+  const double* state_old;
+  double* state_new;
+  const double* source;
+  int32_t ne, nq;
+  double props[kMaxProps];
+  Tables<ND, NNPE, NQT> tab;
+};
+
+template <int ND>
+FEC_DEV double invert(const double (&J)[ND][ND], double (&Ji)[ND][ND]) {
+  if constexpr (ND == 2) {
+    const double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    const double id = 1.0 / det;
+    Ji[0][0] = J[1][1] * id; Ji[0][1] = -J[0][1] * id;
+    Ji[1][0] = -J[1][0] * id; Ji[1][1] = J[0][0] * id;
+    return det;
+  } else {
+    const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+    const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+    const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+    const double id = 1.0 / det;
+    Ji[0][0] = c00 * id; Ji[1][0] = c01 * id; Ji[2][0] = c02 * id;
+    Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+    Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+    Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+    Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+    Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+    Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+    return det;
+  }
+}
+
+// One quadrature point of the vector kernels.  MappedH1OrL2Interpolants (src/Physics.jl:86-92):
+//   J[i][j] = sum_a x[a][i] dN[a][j],  dN_X = dN J^-1,  JxW = det J * w.
+// dN_X is never formed: grad u = (sum_a u_a (x) dN_a) J^-1 and the scatter uses P J^-T, which is the
+// same arithmetic with 2*NNPE*ND*ND fewer FMAs per point.
+template <int ND, int NNPE, int NF, class Phys, int MODE, class Tab>
+FEC_DEV void vec_qp(const Tab& tab, const int q, const double (&x)[NNPE][ND], const double (&u)[NNPE][NF],
+                    const double (&v)[NNPE][NF], const double* props, const double fq, const double* so, double* sn,
+                    double (&r)[NNPE][NF]) {
+  double J[ND][ND];
+#pragma unroll
+  for (int i = 0; i < ND; ++i)
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < NNPE; ++a) s = fma(x[a][i], tab.dN[q][a][j], s);
+      J[i][j] = s;
+    }
+  double Ji[ND][ND];
+  const double JxW = invert<ND>(J, Ji) * tab.w[q];
+
+  if constexpr (MODE == MODE_ACTION_MASS) {
+    // mass_action: JxW rho N (N . v)   (TestPoissonCommon.jl:66-72, Formulations.jl:264-288)
+    const double rho = Phys::density(props) * JxW;
+#pragma unroll
+    for (int d = 0; d < NF; ++d) {
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < NNPE; ++a) s = fma(tab.N[q][a], v[a][d], s);
+      s *= rho;
+#pragma unroll
+      for (int a = 0; a < NNPE; ++a) r[a][d] = fma(tab.N[q][a], s, r[a][d]);
+    }
+    return;
+  } else {
+    // grad u in reference coordinates, then push to physical
+    double gx[NF][ND], gu[NF][ND];
+#pragma unroll
+    for (int d = 0; d < NF; ++d)
+#pragma unroll
+      for (int j = 0; j < ND; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < NNPE; ++a) s = fma(u[a][d], tab.dN[q][a][j], s);
+        gx[d][j] = s;
+      }
+#pragma unroll
+    for (int d = 0; d < NF; ++d)
+#pragma unroll
+      for (int k = 0; k < ND; ++k) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < ND; ++j) s = fma(gx[d][j], Ji[j][k], s);
+        gu[d][k] = s;
+      }
+    double P[NF][ND], b[NF];
+    if constexpr (MODE == MODE_RESIDUAL) {
+      Phys::flux(gu, fq, props, so, sn, P, b);
+    } else {
+      double gvx[NF][ND], gv[NF][ND];
+#pragma unroll
+      for (int d = 0; d < NF; ++d)
+#pragma unroll
+        for (int j = 0; j < ND; ++j) {
+          double s = 0.0;
+#pragma unroll
+          for (int a = 0; a < NNPE; ++a) s = fma(v[a][d], tab.dN[q][a][j], s);
+          gvx[d][j] = s;
+        }
+#pragma unroll
+      for (int d = 0; d < NF; ++d)
+#pragma unroll
+        for (int k = 0; k < ND; ++k) {
+          double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < ND; ++j) s = fma(gvx[d][j], Ji[j][k], s);
+          gv[d][k] = s;
+        }
+      Phys::dflux(gu, gv, props, so, P);
+#pragma unroll
+      for (int d = 0; d < NF; ++d) b[d] = 0.0;
+    }
+    // Pxi[d][j] = JxW sum_k P[d][k] Ji[j][k]
+    double Px[NF][ND];
+#pragma unroll
+    for (int d = 0; d < NF; ++d)
+#pragma unroll
+      for (int j = 0; j < ND; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < ND; ++k) s = fma(P[d][k], Ji[j][k], s);
+        Px[d][j] = s * JxW;
+      }
+#pragma unroll
+    for (int a = 0; a < NNPE; ++a)
+#pragma unroll
+      for (int d = 0; d < NF; ++d) {
+        double s = r[a][d];
+#pragma unroll
+        for (int j = 0; j < ND; ++j) s = fma(tab.dN[q][a][j], Px[d][j], s);
+        if constexpr (MODE == MODE_RESIDUAL && Phys::kHasSource) s = fma(tab.N[q][a] * JxW, b[d], s);
+        r[a][d] = s;
+      }
+  }
+}
+
+template <int ND, int NNPE, int NF, int NQT, class Phys, int MODE, int TE, int MINB>
+__global__ void __launch_bounds__(TE, MINB) k_vec(const __grid_constant__ VecParams<ND, NNPE, NQT> p) {
+  extern __shared__ double smem[];
+  constexpr bool kNeedV = (MODE != MODE_RESIDUAL);
+  constexpr int NS = Phys::NS;
+  const int tile = blockIdx.x, tid = threadIdx.x;
+  const int nb = p.tile_node_ptr[tile];
+  const int nn = p.tile_node_ptr[tile + 1] - nb;
+
+  // ---- 1. gather the tile's nodes once
+  double* sX = smem;
+  double* sU = sX + nn * ND;
+  double* sV = sU + nn * NF;
+  for (int i = tid; i < nn; i += TE) {
+    const int n = p.tile_nodes[nb + i];
+#pragma unroll
+    for (int j = 0; j < ND; ++j) sX[i * ND + j] = p.X[(size_t)n * ND + j];
+#pragma unroll
+    for (int d = 0; d < NF; ++d) sU[i * NF + d] = p.U[(size_t)n * NF + d];
+    if constexpr (kNeedV) {
+#pragma unroll
+      for (int d = 0; d < NF; ++d) sV[i * NF + d] = p.V[(size_t)n * NF + d];
+    }
+  }
+  __syncthreads();
+
+  // ---- 2. element-level fields into registers (_element_level_fields_flat, Assemblers.jl:161-188)
+  const int e = tile * TE + tid;
+  const bool active = e < p.ne;
+  double x[NNPE][ND], u[NNPE][NF], v[NNPE][NF];
+  if (active) {
+#pragma unroll
+    for (int a = 0; a < NNPE; ++a) {
+      const int l = p.lconn[((size_t)tile * NNPE + a) * TE + tid];
+#pragma unroll
+      for (int j = 0; j < ND; ++j) x[a][j] = sX[l * ND + j];
+#pragma unroll
+      for (int d = 0; d < NF; ++d) u[a][d] = sU[l * NF + d];
+#pragma unroll
+      for (int d = 0; d < NF; ++d) v[a][d] = kNeedV ? sV[l * NF + d] : 0.0;
+    }
+  }
+  __syncthreads();  // node data consumed; shared memory is re-used as the element-vector stage
+
+  // ---- 3. quadrature loop in registers
+  double r[NNPE][NF];
+#pragma unroll
+  for (int a = 0; a < NNPE; ++a)
+#pragma unroll
+    for (int d = 0; d < NF; ++d) r[a][d] = 0.0;
+  if (active) {
+    auto body = [&](const int q) {
+      double so[NS > 0 ? NS : 1], sn[NS > 0 ? NS : 1];
+      if constexpr (NS > 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) so[s] = p.state_old[((size_t)s * p.nq + q) * p.ne + e];
+      }
+      double fq = 0.0;
+      if constexpr (Phys::kHasSource && MODE == MODE_RESIDUAL) {
+        if (p.source) fq = p.source[(size_t)q * p.ne + e];
+      }
+      vec_qp<ND, NNPE, NF, Phys, MODE>(p.tab, q, x, u, v, p.props, fq, so,
+                                       (NS > 0 && MODE == MODE_RESIDUAL) ? sn : nullptr, r);
+      if constexpr (NS > 0 && MODE == MODE_RESIDUAL) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) p.state_new[((size_t)s * p.nq + q) * p.ne + e] = sn[s];
+      }
+    };
+    if constexpr (NQT > 0) {
+#pragma unroll
+      for (int q = 0; q < NQT; ++q) body(q);
+    } else {
+      for (int q = 0; q < p.nq; ++q) body(q);
+    }
+  }
+
+  // ---- 4. stage element vectors, reduce per node in fixed order, one red per (node, dof)
+  double* sR = smem;
+#pragma unroll
+  for (int a = 0; a < NNPE; ++a)
+#pragma unroll
+    for (int d = 0; d < NF; ++d) sR[(a * NF + d) * TE + tid] = r[a][d];
+  __syncthreads();
+  for (int i = tid; i < nn; i += TE) {
+    double acc[NF];
+#pragma unroll
+    for (int d = 0; d < NF; ++d) acc[d] = 0.0;
+    const int k0 = p.inc_ptr[nb + i], k1 = p.inc_ptr[nb + i + 1];
+    for (int k = k0; k < k1; ++k) {
+      const int s = p.inc[k];  // = a*NF*TE + t
+#pragma unroll
+      for (int d = 0; d < NF; ++d) acc[d] += sR[s + d * TE];
+    }
+    const int n = p.tile_nodes[nb + i];
+#pragma unroll
+    for (int d = 0; d < NF; ++d) atomicAdd(&p.out[(size_t)n * NF + d], acc[d]);  // RED.E.ADD.F64
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Matrix kernel
+// ------------------------------------------------------------------------------------------------
+template <int ND, int NNPE, int NQT>
+struct MatParams {
+  const double* X;
+  const double* U;
+  double* nz;
+  const int32_t* conn;      // [ne*NNPE] tile-ordered global node ids
+  const uint8_t* epos;      // [ne*NNPE*NNPE]  epos[(e*NNPE + b)*NNPE + a] = position of node a in adj row of node b
+  const int32_t* adjptr;
+  const uint16_t* coloff;
+  const uint8_t* freemask;
+  const int64_t* rowstart;
+  const double* state_old;
+  int32_t ne, nq;
+  double props[kMaxProps];
+  Tables<ND, NNPE, NQT> tab;
+};
+
+// KIND: FECB200_STIFFNESS / FECB200_MASS.  TRANS selects which triangle convention is produced:
+// the reference labels COO slot (i,j) with (row=dof_conn[i], col=dof_conn[j]) but stores K_el.data
+// column-major, i.e. global K[dof_i, dof_j] += K_el[j, i]  (Assemblers.jl:109-124 vs
+// SparsityPatterns.jl:76-83).  Thread b owns block-column b of K_el and therefore block-ROW
+// conn[b] of the global matrix: contiguous CSR rows.  For CSC output the same addressing is used on the
+// transposed element matrix (TRANS = true).
+template <int ND, int NNPE, int NF, int NQT, class Phys, int KIND, int EPB, bool TRANS>
+__global__ void __launch_bounds__(EPB * NNPE) k_mat(const __grid_constant__ MatParams<ND, NNPE, NQT> p) {
+  extern __shared__ double smem[];
+  constexpr int NDF = NF * ND;
+  constexpr int NS = Phys::NS;
+  constexpr int SLOT = (KIND == FECB200_MASS) ? (NNPE + 1) : (NNPE * ND + NDF * NDF);
+  const int tid = threadIdx.x;
+  const int el = tid / NNPE, r = tid % NNPE;
+  const int e = blockIdx.x * EPB + el;
+  const bool active = e < p.ne;
+  double* myslots = smem + (size_t)el * NNPE * SLOT;
+
+  int conn[NNPE];
+  double x[NNPE][ND], u[NNPE][NF];
+  if (active) {
+#pragma unroll
+    for (int a = 0; a < NNPE; ++a) {
+      const int n = p.conn[(size_t)e * NNPE + a];
+      conn[a] = n;
+#pragma unroll
+      for (int j = 0; j < ND; ++j) x[a][j] = p.X[(size_t)n * ND + j];
+#pragma unroll
+      for (int d = 0; d < NF; ++d) u[a][d] = p.U[(size_t)n * NF + d];
+    }
+  }
+
+  double acc[NNPE][NF][NF];  // K_el[(a,d1),(b=r,d2)]  (or its transpose for TRANS)
+#pragma unroll
+  for (int a = 0; a < NNPE; ++a)
+#pragma unroll
+    for (int i = 0; i < NF; ++i)
+#pragma unroll
+      for (int j = 0; j < NF; ++j) acc[a][i][j] = 0.0;
+
+  const int nq = (NQT > 0) ? NQT : p.nq;
+  for (int q0 = 0; q0 < nq; q0 += NNPE) {
+    const int q = q0 + r;
+    if (active && q < nq) {
+      // geometry of quadrature point q (thread r of the element)
+      double J[ND][ND];
+#pragma unroll
+      for (int i = 0; i < ND; ++i)
+#pragma unroll
+        for (int j = 0; j < ND; ++j) {
+          double s = 0.0;
+#pragma unroll
+          for (int a = 0; a < NNPE; ++a) s = fma(x[a][i], p.tab.dN[q][a][j], s);
+          J[i][j] = s;
+        }
+      double Ji[ND][ND];
+      const double JxW = invert<ND>(J, Ji) * p.tab.w[q];
+      double* slot = myslots + (size_t)r * SLOT;
+      if constexpr (KIND == FECB200_MASS) {
+#pragma unroll
+        for (int a = 0; a < NNPE; ++a) slot[a] = p.tab.N[q][a];
+        slot[NNPE] = JxW * Phys::density(p.props);
+      } else {
+        double gu[NF][ND];
+#pragma unroll
+        for (int d = 0; d < NF; ++d)
+#pragma unroll
+          for (int k = 0; k < ND; ++k) gu[d][k] = 0.0;
+#pragma unroll
+        for (int a = 0; a < NNPE; ++a) {
+          double g[ND];
+#pragma unroll
+          for (int k = 0; k < ND; ++k) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < ND; ++j) s = fma(p.tab.dN[q][a][j], Ji[j][k], s);
+            g[k] = s;
+            slot[a * ND + k] = s;
+          }
+#pragma unroll
+          for (int d = 0; d < NF; ++d)
+#pragma unroll
+            for (int k = 0; k < ND; ++k) gu[d][k] = fma(u[a][d], g[k], gu[d][k]);
+        }
+        double so[NS > 0 ? NS : 1];
+        if constexpr (NS > 0) {
+#pragma unroll
+          for (int s = 0; s < NS; ++s) so[s] = p.state_old[((size_t)s * p.nq + q) * p.ne + e];
+        }
+        double A[NDF][NDF];
+        Phys::tangent(gu, p.props, so, A);
+#pragma unroll
+        for (int i = 0; i < NDF; ++i)
+#pragma unroll
+          for (int j = 0; j < NDF; ++j) slot[NNPE * ND + i * NDF + j] = A[i][j] * JxW;
+      }
+    }
+    __syncthreads();
+    if (active) {
+      const int nc = (nq - q0) < NNPE ? (nq - q0) : NNPE;
+      for (int c = 0; c < nc; ++c) {
+        const double* slot = myslots + (size_t)c * SLOT;
+        if constexpr (KIND == FECB200_MASS) {
+          const double f = slot[NNPE] * slot[r];
+#pragma unroll
+          for (int a = 0; a < NNPE; ++a) {
+            const double m = f * slot[a];
+#pragma unroll
+            for (int d = 0; d < NF; ++d) acc[a][d][d] += m;
+          }
+        } else {
+          double gb[ND];
+#pragma unroll
+          for (int k = 0; k < ND; ++k) gb[k] = slot[r * ND + k];
+          const double* A = slot + NNPE * ND;
+          // s[(d1,j1)][d2] = sum_j2 A[(d1,j1)][(d2,j2)] gb[j2]      (TRANS: A[(d2,j2)][(d1,j1)])
+          double s[NDF][NF];
+#pragma unroll
+          for (int i = 0; i < NDF; ++i)
+#pragma unroll
+            for (int d2 = 0; d2 < NF; ++d2) {
+              double t = 0.0;
+#pragma unroll
+              for (int j2 = 0; j2 < ND; ++j2)
+                t = fma(TRANS ? A[(d2 * ND + j2) * NDF + i] : A[i * NDF + d2 * ND + j2], gb[j2], t);
+              s[i][d2] = t;
+            }
+#pragma unroll
+          for (int a = 0; a < NNPE; ++a) {
+            double ga[ND];
+#pragma unroll
+            for (int k = 0; k < ND; ++k) ga[k] = slot[a * ND + k];
+#pragma unroll
+            for (int d1 = 0; d1 < NF; ++d1)
+#pragma unroll
+              for (int d2 = 0; d2 < NF; ++d2) {
+                double t = acc[a][d1][d2];
+#pragma unroll
+                for (int j1 = 0; j1 < ND; ++j1) t = fma(ga[j1], s[d1 * ND + j1][d2], t);
+                acc[a][d1][d2] = t;
+              }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- scatter block-row conn[r]: slot = rowstart[row dof] + coloff[adj entry] + rank of d1 among kept dofs
+  if (active) {
+    const int nb = conn[r];
+    const int abase = p.adjptr[nb];
+    const uint8_t* ep = p.epos + ((size_t)e * NNPE + r) * NNPE;
+    int64_t rs[NF];
+#pragma unroll
+    for (int d2 = 0; d2 < NF; ++d2) rs[d2] = p.rowstart[(size_t)nb * NF + d2];
+#pragma unroll
+    for (int a = 0; a < NNPE; ++a) {
+      const int off = p.coloff[abase + ep[a]];
+      const unsigned mask = p.freemask[conn[a]];
+#pragma unroll
+      for (int d2 = 0; d2 < NF; ++d2) {
+        if (rs[d2] < 0) continue;
+#pragma unroll
+        for (int d1 = 0; d1 < NF; ++d1) {
+          if (mask & (1u << d1)) {
+            const int rank = __popc(mask & ((1u << d1) - 1u));
+            atomicAdd(&p.nz[rs[d2] + off + rank], acc[a][d1][d2]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launch helpers
+// ------------------------------------------------------------------------------------------------
+template <int ND, int NNPE, int NQT>
+void fill_tables(const BlockPlan& b, Tables<ND, NNPE, NQT>& t) {
+  constexpr int NQ = Tables<ND, NNPE, NQT>::NQ;
+  FEC_REQUIRE(b.nq <= NQ, "too many quadrature points for this kernel instantiation");
+  memset(&t, 0, sizeof(t));
+  for (int q = 0; q < b.nq; ++q) {
+    for (int a = 0; a < NNPE; ++a) {
+      t.N[q][a] = b.N[(size_t)q * NNPE + a];
+      for (int j = 0; j < ND; ++j) t.dN[q][a][j] = b.dN[((size_t)q * NNPE + a) * ND + j];
+    }
+    t.w[q] = b.w[q];
+  }
+}
+
+inline void timing_begin(fecb200_handle* h) {
+  if (h->timing) FEC_CUDA(cudaEventRecord(h->ev0, h->stream));
+}
+inline void timing_end(fecb200_handle* h) {
+  if (h->timing) {
+    FEC_CUDA(cudaEventRecord(h->ev1, h->stream));
+    FEC_CUDA(cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    FEC_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms += ms;
+  }
+}
+
+template <int ND, int NNPE, int NF, int NQT, class Phys, int MODE, int TE, int MINB>
+void run_vec(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
+  FEC_REQUIRE(b.te == TE, "tile size does not match the compiled kernel");
+  auto pp = std::make_unique<VecParams<ND, NNPE, NQT>>();  // large: keep off the stack
+  auto& p = *pp;
+  p.X = h->d_X.p; p.U = a.U; p.V = a.V; p.out = a.out;
+  p.tile_node_ptr = b.d_tile_node_ptr.p; p.tile_nodes = b.d_tile_nodes.p; p.lconn = b.d_lconn.p;
+  p.inc_ptr = b.d_inc_ptr.p; p.inc = b.d_inc.p;
+  p.state_old = b.d_state_old.p; p.state_new = b.d_state_new.p; p.source = b.d_source.p;
+  p.ne = (int32_t)b.ne; p.nq = b.nq;
+  for (int i = 0; i < kMaxProps; ++i) p.props[i] = i < (int)b.props.size() ? b.props[i] : 0.0;
+  fill_tables<ND, NNPE, NQT>(b, p.tab);
+  const int nfields = (MODE == MODE_RESIDUAL) ? 1 : 2;
+  size_t sm_nodes = (size_t)b.max_tile_nodes * (ND + nfields * NF) * sizeof(double);
+  size_t sm_stage = (size_t)NNPE * NF * TE * sizeof(double);
+  size_t smem = sm_nodes > sm_stage ? sm_nodes : sm_stage;
+  auto kern = k_vec<ND, NNPE, NF, NQT, Phys, MODE, TE, MINB>;
+  FEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  timing_begin(h);
+  kern<<<b.ntiles, TE, smem, h->stream>>>(p);
+  FEC_CUDA(cudaGetLastError());
+  timing_end(h);
+  h->launches++;
+}
+
+template <int ND, int NNPE, int NF, int NQT, class Phys, int KIND, int EPB, bool TRANS>
+void run_mat_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
+  auto pp = std::make_unique<MatParams<ND, NNPE, NQT>>();
+  auto& p = *pp;
+  p.X = h->d_X.p; p.U = a.U; p.nz = a.nz;
+  p.conn = b.d_conn_perm.p; p.epos = b.d_epos.p;
+  p.adjptr = h->d_adjptr.p; p.coloff = h->d_coloff.p; p.freemask = h->d_freemask.p; p.rowstart = h->d_rowstart.p;
+  p.state_old = b.d_state_old.p;
+  p.ne = (int32_t)b.ne; p.nq = b.nq;
+  for (int i = 0; i < kMaxProps; ++i) p.props[i] = i < (int)b.props.size() ? b.props[i] : 0.0;
+  fill_tables<ND, NNPE, NQT>(b, p.tab);
+  constexpr int NDF = NF * ND;
+  constexpr int SLOT = (KIND == FECB200_MASS) ? (NNPE + 1) : (NNPE * ND + NDF * NDF);
+  size_t smem = (size_t)EPB * NNPE * SLOT * sizeof(double);
+  auto kern = k_mat<ND, NNPE, NF, NQT, Phys, KIND, EPB, TRANS>;
+  FEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)((b.ne + EPB - 1) / EPB);
+  timing_begin(h);
+  kern<<<grid, EPB * NNPE, smem, h->stream>>>(p);
+  FEC_CUDA(cudaGetLastError());
+  timing_end(h);
+  h->launches++;
+}
+
+template <int ND, int NNPE, int NF, int NQT, class Phys, int EPB>
+void run_mat(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
+  const bool trans = (h->opts.matrix_type == FECB200_CSC);
+  if (a.kind == FECB200_MASS) {
+    // the mass matrix is symmetric: one instantiation serves CSR and CSC
+    run_mat_t<ND, NNPE, NF, NQT, Phys, FECB200_MASS, EPB, false>(h, b, a);
+  } else if (trans) {
+    run_mat_t<ND, NNPE, NF, NQT, Phys, FECB200_STIFFNESS, EPB, true>(h, b, a);
+  } else {
+    run_mat_t<ND, NNPE, NF, NQT, Phys, FECB200_STIFFNESS, EPB, false>(h, b, a);
+  }
+}
+
+template <int ND, int NNPE, int NF, int NQT, class Phys, int TE, int MINB>
+void run_vec_modes(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
+  switch (a.mode) {
+    case MODE_RESIDUAL: run_vec<ND, NNPE, NF, NQT, Phys, MODE_RESIDUAL, TE, MINB>(h, b, a); break;
+    case MODE_ACTION_STIFFNESS: run_vec<ND, NNPE, NF, NQT, Phys, MODE_ACTION_STIFFNESS, TE, MINB>(h, b, a); break;
+    case MODE_ACTION_MASS: run_vec<ND, NNPE, NF, NQT, Phys, MODE_ACTION_MASS, TE, MINB>(h, b, a); break;
+    default: throw Error("fecb200: bad vector mode");
+  }
+}
+
+constexpr int kTE = 256;  // elements per tile / threads per CTA of the vector kernels
+
+}  // namespace fec

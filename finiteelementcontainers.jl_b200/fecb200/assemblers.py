@@ -1,0 +1,338 @@
+"""SparseMatrixAssembler and the assemble_* entry points (src/assemblers/*.jl) on libfecb200.
+
+Python cannot spell `assemble_vector!`; the trailing `!` is dropped.  Everything else keeps the
+reference's names, argument order and error behaviour:
+
+    asm = SparseMatrixAssembler(u; sparse_matrix_type=:csr, use_condensed=false, matrix_free=false)
+    p   = create_parameters(mesh, asm, physics, props; dirichlet_bcs=dbcs)
+    assemble_vector!(asm, residual, Uu, p);            R  = residual(asm)
+    assemble_stiffness!(asm, stiffness, Uu, p);        K  = stiffness(asm)
+    assemble_matrix_action!(asm, stiffness, Uu, Vu, p) Kv = hvp(asm, Vu)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+from ._lib import FECError, check, lib
+from .bcs import DirichletBCs, TimeStepper
+from .fields import H1Field
+from .function_spaces import AbstractFunction, DofManager
+from .physics import AbstractPhysics, Poisson, kind_of
+
+
+class SparseMatrixAssembler:
+    """SparseMatrixAssembler(dof_or_var; sparse_matrix_type, use_condensed, use_inplace_methods,
+    use_sparse_vector, matrix_free)  (src/assemblers/SparseMatrixAssembler.jl:64-133)."""
+
+    def __init__(self, dof_or_var, *, sparse_matrix_type="csc", use_condensed=False, use_inplace_methods=False,
+                 use_sparse_vector=False, matrix_free=False, device=0):
+        if isinstance(dof_or_var, AbstractFunction):
+            dof_or_var = DofManager(dof_or_var, use_condensed=use_condensed)
+        self.dof = dof_or_var
+        if sparse_matrix_type not in ("csc", "csr"):
+            raise ValueError(f"Unsupported sparse matrix type {sparse_matrix_type}. Only :csc, and :csr are supported.")
+        if use_sparse_vector:
+            raise NotImplementedError("use_sparse_vector=true is not on the B200 path (SURVEY B6)")
+        self.sparse_matrix_type = sparse_matrix_type
+        self.use_inplace_methods = bool(use_inplace_methods)
+        self.matrix_free = bool(matrix_free)
+        self.device = device
+        self._h = None
+        self._pattern = None
+        self._keep = []
+
+    # -- handle lifecycle ----------------------------------------------------------------------
+    def _require(self):
+        if self._h is None:
+            raise FECError("assembler has no device handle yet: call create_parameters(mesh, asm, physics, props; ...)")
+        return self._h
+
+    def _create_handle(self, fspace, physics_list, props_list):
+        if self._h is not None:
+            check(lib.fecb200_destroy(self._h))
+            self._h = None
+        nb = fspace.num_blocks()
+        blocks = (_lib.BlockDesc * nb)()
+        keep = []
+        for b in range(nb):
+            rf = fspace.ref_fes[b]
+            ph = physics_list[b]
+            conn, cp = _lib.i64(fspace.elem_conns.block(b).reshape(-1, order="F"))
+            N, Np = _lib.f64(rf.N)
+            dN, dNp = _lib.f64(rf.dN)
+            w, wp = _lib.f64(rf.w)
+            pr, prp = _lib.f64(props_list[b])
+            keep += [conn, N, dN, w, pr]
+            d = blocks[b]
+            d.elem_type, d.nnpe, d.nelem, d.conn = rf.elem_id, rf.num_cell_dofs, fspace.elem_conns.nelems[b], cp
+            d.nq, d.N, d.dN, d.w = rf.num_quadrature_points, Np, dNp, wp
+            d.physics_id, d.nprops, d.props, d.nstate = ph.physics_id, len(pr), prp, ph.NS
+        X, Xp = _lib.f64(fspace.coords.data_flat)
+        mesh = _lib.MeshDesc(fspace.num_nodes(), fspace.num_dimensions(), self.dof.nf, nb, blocks, Xp)
+        opts = _lib.Opts(_lib.CSR if self.sparse_matrix_type == "csr" else _lib.CSC, int(self.dof.condensed),
+                         int(self.matrix_free), self.device, 0)
+        h = _lib.Handle()
+        check(lib.fecb200_create(C.byref(mesh), C.byref(opts), C.byref(h)))
+        self._h = h
+        self._pattern = None
+
+    def close(self):
+        if self._h is not None:
+            lib.fecb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- sizes / maps ----------------------------------------------------------------------------
+    def sizes(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib.fecb200_sizes(self._require(), C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def _refresh_dof_maps(self):
+        ntot, nunk, _ = self.sizes()
+        ud = np.empty(nunk, dtype=np.int64)
+        d2u = np.empty(ntot, dtype=np.int64)
+        check(lib.fecb200_dof_maps_copy(self._h, ud.ctypes.data_as(_lib.c_i64p), d2u.ctypes.data_as(_lib.c_i64p)))
+        self.dof.unknown_dofs, self.dof.dof_to_unknown = ud, d2u
+
+    def pattern(self):
+        """(n, ptr, idx): rowptr/colval (csr) or colptr/rowval (csc), Int64 1-based."""
+        if self._pattern is None:
+            n, nnz = C.c_int64(), C.c_int64()
+            check(lib.fecb200_pattern_sizes(self._require(), C.byref(n), C.byref(nnz)))
+            ptr = np.empty(n.value + 1, dtype=np.int64)
+            idx = np.empty(nnz.value, dtype=np.int64)
+            check(lib.fecb200_pattern_copy(self._h, ptr.ctypes.data_as(_lib.c_i64p), idx.ctypes.data_as(_lib.c_i64p)))
+            self._pattern = (n.value, ptr, idx)
+        return self._pattern
+
+    def launch_count(self):
+        n = C.c_int64()
+        check(lib.fecb200_launch_count(self._require(), C.byref(n)))
+        return n.value
+
+
+class Parameters:
+    """The slice of Parameters (src/Parameters.jl:37-73) the hot path touches; device-resident
+    fields live inside the handle (`p |> cuda`)."""
+
+    def __init__(self, mesh, asm, physics, props, dirichlet_bcs, times):
+        self.mesh, self.asm = mesh, asm
+        self.physics, self.properties = physics, props
+        self.dirichlet_bcs = dirichlet_bcs
+        self.times = times
+        self.coords = mesh.nodal_coords
+
+    @property
+    def field(self):
+        """p.field (full-length H1Field), copied back from the device"""
+        out = np.empty(len(self.asm.dof))
+        check(lib.fecb200_field_copy(self.asm._require(), _lib.FIELD_U, _lib.ptr(out)))
+        return H1Field(out.reshape(self.asm.dof.nf, -1, order="F"))
+
+    def state(self, block=0, which="new"):
+        b = self.asm.dof.var.fspace
+        ph = self.physics[block]
+        nq, ne = b.ref_fes[block].num_quadrature_points, b.elem_conns.nelems[block]
+        out = np.zeros(ph.NS * nq * ne)
+        check(lib.fecb200_state_get(self.asm._require(), block, 1 if which == "new" else 0, _lib.ptr(out)))
+        return out.reshape(ph.NS, nq, ne, order="F")
+
+    def set_state(self, state, block=0, which="old"):
+        s = np.ascontiguousarray(np.asarray(state, dtype=float).reshape(-1, order="F"))
+        check(lib.fecb200_state_set(self.asm._require(), block, 1 if which == "new" else 0, _lib.ptr(s)))
+
+
+def _per_block(x, nb, kind):
+    if isinstance(x, dict):
+        return list(x.values())
+    if isinstance(x, (list, tuple)) and len(x) == nb and (kind is None or all(isinstance(v, kind) for v in x)):
+        return list(x)
+    return [x] * nb
+
+
+def create_parameters(mesh, asm, physics, props=None, *, dirichlet_bcs=(), times=None):
+    """create_parameters(mesh, asm, physics, props; dirichlet_bcs, times)  (src/Parameters.jl:288-302):
+    builds the device handle (the `|> cuda` step), the BC containers, and calls update_dofs!."""
+    fspace = asm.dof.var.fspace
+    nb = fspace.num_blocks()
+    physics_list = _per_block(physics, nb, AbstractPhysics)
+    if props is None:
+        props_list = [ph.create_properties() for ph in physics_list]
+    elif isinstance(props, dict):
+        props_list = list(props.values())
+    elif (nb > 1 and isinstance(props, (list, tuple)) and len(props) == nb
+          and all(isinstance(v, (np.ndarray, list, tuple)) for v in props)):
+        props_list = list(props)           # one property vector per block
+    else:
+        props_list = [props] * nb          # one SVector{NP} shared by every block
+    props_list = [np.atleast_1d(np.asarray(p, dtype=float)).reshape(-1) for p in props_list]
+    for ph in physics_list:
+        if ph.NF != asm.dof.nf:
+            raise FECError(f"physics has NF={ph.NF} but the function has {asm.dof.nf} fields")
+    asm._create_handle(fspace, physics_list, props_list)
+    times = times if times is not None else TimeStepper(0.0, 0.0, 1)
+    dbcs = DirichletBCs(mesh, asm.dof, list(dirichlet_bcs))
+    p = Parameters(mesh, asm, physics_list, props_list, dbcs, times)
+    update_dofs(asm, dbcs)
+    update_bc_values(p)
+    _upload_sources(p)
+    return p
+
+
+def _upload_sources(p):
+    """evaluate Poisson.func at the quadrature points X_q = sum_a N[q,a] x_a and upload f_q[NQ,NE]"""
+    fspace = p.asm.dof.var.fspace
+    X = np.asarray(fspace.coords)
+    for b, ph in enumerate(p.physics):
+        if isinstance(ph, Poisson) and ph.func is not None:
+            rf = fspace.ref_fes[b]
+            conn = fspace.elem_conns.block(b)                      # (NNPE, NE) 1-based
+            xe = X[:, conn - 1]                                    # (ND, NNPE, NE)
+            Xq = np.einsum("qa,dae->eqd", rf.N, xe)                # (NE, NQ, ND)
+            f = np.asarray(ph.func(Xq.reshape(-1, Xq.shape[2]), p.times.time_current), dtype=float)
+            fq = np.ascontiguousarray(np.broadcast_to(f, (Xq.shape[0] * Xq.shape[1],)))
+            check(lib.fecb200_set_source_q(p.asm._require(), b, _lib.ptr(fq)))
+
+
+def update_dofs(asm, dbcs, periodic=((), ())):
+    """update_dofs!(asm, dbcs, pbcs)  (SparseMatrixAssembler.jl:228-274)"""
+    dd = dbcs.dirichlet_dofs() if isinstance(dbcs, DirichletBCs) else np.asarray(dbcs, dtype=np.int64)
+    dd, ddp = _lib.i64(dd)
+    pa, pap = _lib.i64(periodic[0])
+    pb, pbp = _lib.i64(periodic[1])
+    check(lib.fecb200_update_dofs(asm._require(), ddp, len(dd), pap, pbp, len(pa)))
+    asm.dof.dirichlet_dofs = dd
+    asm._refresh_dof_maps()
+    asm._pattern = None
+
+
+def update_bc_values(p):
+    """update_bc_values!(p, asm) (Parameters.jl:358): evaluate BC closures, push dofs/vals."""
+    bcs = p.dirichlet_bcs
+    bcs.update_bc_values(p.coords, p.times.time_current)
+    d, dp = _lib.i64(bcs.dofs)
+    v, vp = _lib.f64(bcs.vals)
+    check(lib.fecb200_set_dirichlet_values(p.asm._require(), dp, vp, len(d)))
+
+
+def update_time(p):
+    """update_time!(p) (Parameters.jl:447)"""
+    p.times.time_current += p.times.dt
+    check(lib.fecb200_set_time(p.asm._require(), p.times.time_current, p.times.dt))
+
+
+def create_field(asm):
+    return H1Field.zeros(asm.dof.nf, asm.dof.nn)
+
+
+def create_unknowns(asm):
+    """create_unknowns(asm) (DofManagers.jl:168-175)"""
+    return np.zeros(asm.sizes()[2])
+
+
+# ---- assembly entry points --------------------------------------------------------------------
+
+def assemble_vector(asm, func, Uu, p):
+    """assemble_vector!(asm, residual, Uu, p)  (src/assemblers/Vector.jl:4-74)"""
+    kind = kind_of(func, (_lib.RESIDUAL,))
+    check(lib.fecb200_assemble_vector(asm._require(), kind, _lib.ptr(Uu)))
+
+
+def _check_matrix_assembly_supported(asm, fname):
+    if asm.matrix_free:
+        raise FECError(f"{fname} called on a matrix-free SparseMatrixAssembler.  Re-create the assembler with "
+                       "matrix_free=false to enable matrix assembly.")
+
+
+def assemble_stiffness(asm, func, Uu, p):
+    """assemble_stiffness!(asm, stiffness, Uu, p)  (src/assemblers/Matrix.jl:12-21)"""
+    _check_matrix_assembly_supported(asm, "assemble_stiffness!")
+    kind_of(func, (_lib.STIFFNESS,))
+    check(lib.fecb200_assemble_matrix(asm._require(), _lib.STIFFNESS, _lib.ptr(Uu)))
+
+
+def assemble_mass(asm, func, Uu, p):
+    """assemble_mass!(asm, mass, Uu, p)  (src/assemblers/Matrix.jl:1-10)"""
+    _check_matrix_assembly_supported(asm, "assemble_mass!")
+    kind_of(func, (_lib.MASS,))
+    check(lib.fecb200_assemble_matrix(asm._require(), _lib.MASS, _lib.ptr(Uu)))
+
+
+def assemble_matrix_action(asm, func, Uu, Vu, p):
+    """assemble_matrix_action!(asm, stiffness | mass, Uu, Vu, p)  (MatrixAction.jl:154-238).
+    Evaluated matrix-free on the device: identical to K_el * v_el up to rounding."""
+    kind = kind_of(func, (_lib.STIFFNESS, _lib.MASS))
+    check(lib.fecb200_assemble_action(asm._require(), kind, _lib.ptr(Uu), _lib.ptr(Vu)))
+
+
+def assemble_matrix_free_action(asm, func_action, Uu, Vu, p):
+    """assemble_matrix_free_action!(asm, stiffness_action, Uu, Vu, p)  (MatrixAction.jl:9-77)"""
+    kind = kind_of(func_action, (_lib.STIFFNESS, _lib.MASS))
+    check(lib.fecb200_assemble_action(asm._require(), kind, _lib.ptr(Uu), _lib.ptr(Vu)))
+
+
+def assemble_matrix_free_action_full(asm, func_action, U_full, v_full, p):
+    """assemble_matrix_free_action_full!(asm, f, U_full, v_full, p)  (MatrixAction.jl:99-149)"""
+    kind = kind_of(func_action, (_lib.STIFFNESS, _lib.MASS))
+    n = len(asm.dof)
+    if np.size(U_full) != n or np.size(v_full) != n:
+        raise AssertionError("U_full and v_full must have the full DOF length")
+    check(lib.fecb200_assemble_action_full(asm._require(), kind, _lib.ptr(U_full), _lib.ptr(v_full)))
+
+
+# ---- accessors ---------------------------------------------------------------------------------
+
+def _residual_accessor(asm, out=None):
+    """residual(asm)  (src/assemblers/Assemblers.jl:347-371)"""
+    out = np.empty(asm.sizes()[2]) if out is None else out
+    check(lib.fecb200_residual(asm._require(), _lib.ptr(out)))
+    return out
+
+
+def hvp(asm, v, out=None):
+    """hvp(asm, v)  (src/assemblers/Assemblers.jl:310-324)"""
+    out = np.empty(asm.sizes()[2]) if out is None else out
+    check(lib.fecb200_hvp(asm._require(), _lib.ptr(v), _lib.ptr(out)))
+    return out
+
+
+def _sparse(asm, kind):
+    n, ptr, idx = asm.pattern()
+    nz = np.empty(len(idx))
+    check(lib.fecb200_matrix_values(asm._require(), kind, _lib.ptr(nz)))
+    cls = sp.csr_matrix if asm.sparse_matrix_type == "csr" else sp.csc_matrix
+    return cls((nz, idx - 1, ptr - 1), shape=(n, n))
+
+
+def _stiffness_accessor(asm):
+    """stiffness(asm)  (Assemblers.jl:376-388): scipy csr/csc matrix with the reference's pattern"""
+    if asm.matrix_free:
+        n = asm.sizes()[2]
+        return sp.csc_matrix((n, n))
+    return _sparse(asm, _lib.STIFFNESS)
+
+
+def _mass_accessor(asm):
+    """mass(asm)  (Assemblers.jl:329-341)"""
+    if asm.matrix_free:
+        n = asm.sizes()[2]
+        return sp.csc_matrix((n, n))
+    return _sparse(asm, _lib.MASS)
+
+
+def full_field(asm, which="residual"):
+    """full-length storage of the assembler (residual_storage / stiffness_action_storage)"""
+    out = np.empty(len(asm.dof))
+    sel = {"u": _lib.FIELD_U, "residual": _lib.FIELD_RESIDUAL, "action": _lib.FIELD_ACTION, "v": _lib.FIELD_V}[which]
+    check(lib.fecb200_field_copy(asm._require(), sel, _lib.ptr(out)))
+    return out

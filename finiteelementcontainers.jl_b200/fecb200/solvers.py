@@ -1,0 +1,71 @@
+"""Callers of the hot path (src/Solvers.jl, src/integrators/QuasiStaticIntegrator.jl), run
+device-resident inside libfecb200."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+from .assemblers import update_bc_values, update_time
+
+
+class IterativeLinearSolver:
+    """IterativeLinearSolver(asm, :cg) (src/Solvers.jl:92-153).  Krylov.jl CG defaults."""
+
+    def __init__(self, assembler, solver_sym="cg", matrix_free=None):
+        if str(solver_sym).lower() not in ("cg", "cgsolver"):
+            raise ValueError("only CG is implemented on the device")
+        self.assembler = assembler
+        self.matrix_free = assembler.matrix_free if matrix_free is None else bool(matrix_free)
+        self.cg_iterations = 0
+
+    def solve(self, b, x=None, atol=-1.0, rtol=-1.0, itmax=0):
+        asm = self.assembler
+        x = np.empty(asm.sizes()[2]) if x is None else x
+        its, rn = C.c_int64(), C.c_double()
+        check(lib.fecb200_cg_solve(asm._require(), _lib.ptr(b), _lib.ptr(x), atol, rtol, itmax,
+                                   int(self.matrix_free), C.byref(its), C.byref(rn)))
+        self.cg_iterations = its.value
+        return x, its.value, rn.value
+
+
+class NewtonSolver:
+    """NewtonSolver(linear_solver) (src/Solvers.jl:178-220): <= 10 iterations, tolerances 1e-12."""
+
+    def __init__(self, linear_solver, max_iters=10, tol=1e-12):
+        self.linear_solver = linear_solver
+        self.max_iters, self.tol = max_iters, tol
+        self.iterations = 0
+        self.cg_iterations = 0
+        self.residual_norm = 0.0
+
+    def solve(self, Uu, p):
+        asm = self.linear_solver.assembler
+        nit, cgit, rn = C.c_int32(), C.c_int64(), C.c_double()
+        check(lib.fecb200_newton_solve(asm._require(), _lib.ptr(Uu), self.max_iters, self.tol,
+                                       int(self.linear_solver.matrix_free), C.byref(nit), C.byref(cgit), C.byref(rn)))
+        self.iterations, self.cg_iterations, self.residual_norm = nit.value, cgit.value, rn.value
+        return Uu
+
+
+class QuasiStaticIntegrator:
+    """QuasiStaticIntegrator(solver) + evolve! (src/integrators/QuasiStaticIntegrator.jl:16-34)"""
+
+    def __init__(self, solver):
+        self.solver = solver
+        self.solution = None
+        self.failed = False
+
+    def evolve(self, p):
+        asm = self.solver.linear_solver.assembler
+        if self.solution is None:
+            self.solution = np.zeros(asm.sizes()[2])
+        update_time(p)
+        update_bc_values(p)
+        self.solver.solve(self.solution, p)
+        # _update_for_assembly!(p, dof, solution): the handle's field already holds the last iterate's
+        # BC-enforced field; state_old <- state_new at the end of the load step
+        check(lib.fecb200_state_swap(asm._require()))
+        return self.solution

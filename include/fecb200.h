@@ -1,0 +1,209 @@
+/*
+ * fecb200.h -- C ABI of libfecb200.so: the B200-native FE assembly hot path of
+ * FiniteElementContainers.jl (element-wise residual / stiffness / matrix-action assembly
+ * over H1 spaces), hand-written CUDA for sm_100a, FP64.
+ *
+ * This is the drop-in boundary.  The reference has no FFI layer: its
+ * seam is Julia multiple dispatch on the assembler type (ext/CUDAExt.jl:8-31 is the only
+ * backend hook).  A Julia `B200Assembler <: AbstractAssembler` therefore binds the entry
+ * points below with `ccall` (see INTEGRATION.md and finiteelementcontainers.jl_b200/julia/).
+ * Every function cites the reference interface it replaces (path:line under the
+ * reference tree).
+ *
+ * Conventions
+ *   - all functions return 0 on success, non-zero on error; fecb200_last_error() gives text.
+ *     No exceptions cross the boundary (the reference throws Julia exceptions; the shim
+ *     converts a non-zero status into `error(...)`).
+ *   - every index array crossing the boundary is Int64 and 1-based, as in the reference
+ *     (Connectivity: src/Fields.jl:129-160; patterns: src/assemblers/SparsityPatterns.jl:30-51).
+ *   - dof id of (field d, node n) = NF*(n-1) + d  (src/DofManagers.jl:41-58).
+ *   - pointers marked [host|device] may be host or device memory (detected with
+ *     cudaPointerGetAttributes); device pointers (e.g. a CuArray) are used in place.
+ *   - the handle owns all device memory it allocates; the caller owns every buffer it passes.
+ *   - one handle <-> one CUDA device + one stream; calls on one handle are not re-entrant.
+ *   - there is NO CPU fallback: creation fails if no CUDA device is present.
+ */
+#ifndef FECB200_H
+#define FECB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fecb200_handle fecb200_handle;
+
+/* element topologies (Exodus node ordering; src/FunctionSpaces.jl:1-29 names) */
+enum { FECB200_QUAD4 = 1, FECB200_TRI3 = 2, FECB200_HEX8 = 3, FECB200_TET4 = 4, FECB200_TET10 = 5 };
+
+/* CUDA-side physics (replaces the Julia closures of src/Physics.jl:1-18, which cannot cross a C ABI) */
+enum {
+  FECB200_PHYS_POISSON = 1,            /* test/poisson/TestPoissonCommon.jl:4-139   NF=1          */
+  FECB200_PHYS_LINEAR_ELASTIC = 2,     /* test/mechanics/TestMechanicsCommon.jl:3-236  props (rho,K,G) */
+  FECB200_PHYS_NEOHOOKEAN = 3,         /* TestMechanicsLargeDeformation.jl:17-27, stress-free U(J)  */
+  FECB200_PHYS_NEOHOOKEAN_AS_WRITTEN = 4, /* the script's U(J) verbatim               */
+  FECB200_PHYS_J2_PLASTICITY = 5       /* NS=7 state, props (rho,K,G,sigma_y,H); hooks only in the reference */
+};
+
+/* which element-level function is assembled: the `f` argument of assemble_vector! etc.
+ * (mapped by identity on the Julia side: residual / stiffness / mass / stiffness_action) */
+enum { FECB200_RESIDUAL = 1, FECB200_STIFFNESS = 2, FECB200_MASS = 3 };
+
+/* sparse_matrix_type of SparseMatrixAssembler (src/assemblers/SparseMatrixAssembler.jl:64-76) */
+enum { FECB200_CSC = 1, FECB200_CSR = 2 };
+
+/* field selectors for fecb200_field_copy */
+enum { FECB200_FIELD_U = 1, FECB200_FIELD_RESIDUAL = 2, FECB200_FIELD_ACTION = 3, FECB200_FIELD_V = 4 };
+
+/* One element block: FunctionSpace block + its ReferenceFE tables + Physics + props
+ * (src/FunctionSpaces.jl:158-237, src/assemblers/Assemblers.jl:129-131).  The reference
+ * element tables are NOT hard-coded in the library: ReferenceFiniteElements.jl is not
+ * vendored by the reference, so the host passes `ref_fe.cell_interps[q]` as arrays. */
+typedef struct {
+  int32_t elem_type;      /* FECB200_HEX8 ...                                            */
+  int32_t nnpe;           /* nodes per element                                            */
+  int64_t nelem;
+  const int64_t* conn;    /* [nnpe*nelem], 1-based node ids, element-major (Connectivity.data) */
+  int32_t nq;             /* quadrature points                                            */
+  const double* N;        /* [nq*nnpe]        N[q*nnpe + a]                                */
+  const double* dN;       /* [nq*nnpe*ndim]   dN[(q*nnpe + a)*ndim + j] = dN_a/dxi_j       */
+  const double* w;        /* [nq]                                                         */
+  int32_t physics_id;     /* FECB200_PHYS_*                                               */
+  int32_t nprops;
+  const double* props;    /* [nprops]  SVector{NP} props of the block (Assemblers.jl:193-202) */
+  int32_t nstate;         /* NS of AbstractPhysics{NF,NP,NS}; state arrays are [NS,NQ,NE] */
+} fecb200_block_desc;
+
+typedef struct {
+  int64_t nnodes;
+  int32_t ndim;
+  int32_t nf;             /* dofs per node (NF)                                           */
+  int32_t nblocks;
+  const fecb200_block_desc* blocks;
+  const double* coords;   /* [ndim*nnodes]  H1Field data: coords[(n-1)*ndim + j]  (src/Fields.jl:36-40) */
+} fecb200_mesh_desc;
+
+typedef struct {
+  int32_t matrix_type;    /* FECB200_CSC | FECB200_CSR                                    */
+  int32_t condensed;      /* DofManager{Condensed}  (src/DofManagers.jl:21-58)            */
+  int32_t matrix_free;    /* SparseMatrixAssembler(...; matrix_free=true) (:82-88)        */
+  int32_t device;         /* CUDA device ordinal                                          */
+  int32_t tile_elems;     /* elements per CTA tile for the vector kernels; 0 = default    */
+  int32_t reserved[3];
+} fecb200_opts;
+
+const char* fecb200_last_error(void);
+int fecb200_version(void);
+
+/* SparseMatrixAssembler(dof; ...) + Parameters device upload: builds DOF maps, element tiles,
+ * node adjacency / CSR pattern and the element->CSR slot maps on the device.
+ * replaces: SparseMatrixAssembler ctor (SparseMatrixAssembler.jl:64-124), SparseMatrixPattern
+ * (SparsityPatterns.jl:53-117), `asm |> cuda` / `p |> cuda` (ext/CUDAExt.jl:8-14). */
+int fecb200_create(const fecb200_mesh_desc* mesh, const fecb200_opts* opts, fecb200_handle** out);
+int fecb200_destroy(fecb200_handle* h);
+
+/* use an existing CUDA stream (cudaStream_t) for all work of this handle; NULL = own stream */
+int fecb200_set_stream(fecb200_handle* h, void* cuda_stream);
+int fecb200_synchronize(fecb200_handle* h);
+
+/* update_dofs!(asm, dbcs, pbcs)  (SparseMatrixAssembler.jl:228-274, DofManagers.jl:227-298,
+ * SparsityPatterns.jl:160-231).  dirichlet_dofs need not be sorted/unique. */
+int fecb200_update_dofs(fecb200_handle* h, const int64_t* dirichlet_dofs, int64_t n_dirichlet,
+                        const int64_t* periodic_side_a, const int64_t* periodic_side_b, int64_t n_periodic);
+
+/* sizes: n_total = NF*NN, n_unknowns = length(dof.unknown_dofs); length(Uu) = n_unknowns
+ * (non-condensed) or n_total (condensed)  (DofManagers.jl:168-175) */
+int fecb200_sizes(fecb200_handle* h, int64_t* n_total_dofs, int64_t* n_unknowns, int64_t* len_Uu);
+/* DofManager arrays, 1-based Int64: unknown_dofs[n_unknowns], dof_to_unknown[n_total] (-1 Dirichlet,
+ * -2 periodic side b).  "DOF numbering bit-exact" is checked on these. Either may be NULL. */
+int fecb200_dof_maps_copy(fecb200_handle* h, int64_t* unknown_dofs, int64_t* dof_to_unknown);
+
+/* sparsity pattern of stiffness(asm)/mass(asm): n x n with nnz stored entries, explicit zeros kept.
+ * ptr[n+1], idx[nnz] Int64 1-based: (rowptr, colval) for CSR, (colptr, rowval) for CSC, exactly what
+ * SparseArrays.sparse! / SparseMatrixCSR(csc) produce (SparsityPatterns.jl:301-329). [host] */
+int fecb200_pattern_sizes(fecb200_handle* h, int64_t* n, int64_t* nnz);
+int fecb200_pattern_copy(fecb200_handle* h, int64_t* ptr, int64_t* idx);
+
+/* Dirichlet values: U[dofs[i]] = vals[i] before every assemble (update_field_dirichlet_bcs!,
+ * src/bcs/DirichletBCs.jl:411-418; values come from update_bc_values!, Parameters.jl:358). */
+int fecb200_set_dirichlet_values(fecb200_handle* h, const int64_t* dofs, const double* vals, int64_t n);
+/* periodic offsets: U[b] = U[a] + val (src/bcs/PeriodicBCs.jl:253-262); NULL = zeros */
+int fecb200_set_periodic_values(fecb200_handle* h, const double* vals, int64_t n);
+int fecb200_set_time(fecb200_handle* h, double t, double dt);
+/* Poisson source f(X_q, t) pre-evaluated at quadrature points on the host (the closure
+ * physics.func of TestPoissonCommon.jl:4-6 cannot cross the ABI; same pattern as
+ * src/bcs/Sources.jl:55-66).  fq[q + nq*e], element order of the block's conn. [host|device] */
+int fecb200_set_source_q(fecb200_handle* h, int32_t block, const double* fq);
+
+/* state variables [NS,NQ,NE] per block (Parameters.jl:1-23, Assemblers.jl:248-251).
+ * which = 0 state_old, 1 state_new. */
+int fecb200_state_set(fecb200_handle* h, int32_t block, int32_t which, const double* state);
+int fecb200_state_get(fecb200_handle* h, int32_t block, int32_t which, double* state);
+int fecb200_state_swap(fecb200_handle* h); /* state_old <- state_new at the end of a load step */
+
+/* assemble_vector!(asm, residual, Uu, p)  (src/assemblers/Vector.jl:4-74): zero storage,
+ * _update_for_assembly! (Parameters.jl:404-413), element kernel, nodal scatter.
+ * Uu [host|device], length len_Uu. */
+int fecb200_assemble_vector(fecb200_handle* h, int32_t kind, const double* Uu);
+/* residual(asm) (src/assemblers/Assemblers.jl:347-371): condensed -> R*(1-c); else periodic
+ * fold + gather of unknowns.  out [host|device], length len_Uu. */
+int fecb200_residual(fecb200_handle* h, double* out);
+
+/* assemble_stiffness!/assemble_mass! (src/assemblers/Matrix.jl:1-75) fused with the sparse!
+ * realisation: values are accumulated straight into the CSR/CSC nzval (no COO is materialised). */
+int fecb200_assemble_matrix(fecb200_handle* h, int32_t kind, const double* Uu);
+/* stiffness(asm)/mass(asm) (Assemblers.jl:329-388): applies the condensed-mode constraint
+ * adjustment (assemblers/Utils.jl:53-148: row/col scaling by (1-c), penalty 1e6*tr(K)/n on
+ * constrained diagonals) and copies nzval [nnz] out. [host|device] */
+int fecb200_matrix_values(fecb200_handle* h, int32_t kind, double* nzval_out);
+/* device pointer to the handle's nzval storage (valid until destroy / update_dofs) */
+int fecb200_matrix_values_device(fecb200_handle* h, int32_t kind, double** nzval_dev);
+
+/* assemble_matrix_action!(asm, f, Uu, Vu, p) and assemble_matrix_free_action! (MatrixAction.jl:9-77,
+ * 154-238): always evaluated matrix-free.  kind = FECB200_STIFFNESS or FECB200_MASS. */
+int fecb200_assemble_action(fecb200_handle* h, int32_t kind, const double* Uu, const double* Vu);
+/* assemble_matrix_free_action_full! (MatrixAction.jl:99-149): caller passes full-length U, v */
+int fecb200_assemble_action_full(fecb200_handle* h, int32_t kind, const double* U_full, const double* v_full);
+/* hvp(asm, v) (Assemblers.jl:310-324): condensed -> (1-c)Av + c v ; else gather unknowns */
+int fecb200_hvp(fecb200_handle* h, const double* v, double* out);
+
+/* copy of a full-length nodal field (p.field, residual_storage, stiffness_action_storage) */
+int fecb200_field_copy(fecb200_handle* h, int32_t which, double* out);
+
+/* ---- callers of the path: device-resident Krylov / Newton ---------------
+ * krylov_solve!(ws, stiffness(asm), residual(asm)) with CG (src/Solvers.jl:128-153); Krylov.jl
+ * defaults atol = rtol = sqrt(eps), itmax = 2n.  Solves K x = b on the device using the handle's
+ * assembled matrix (matrix_free = 0) or the matrix-free operator at the current U (matrix_free = 1). */
+int fecb200_cg_solve(fecb200_handle* h, const double* b, double* x, double atol, double rtol,
+                     int64_t itmax, int32_t matrix_free, int64_t* iters_out, double* rnorm_out);
+/* solve!(NewtonSolver, Uu, p) (src/Solvers.jl:193-220): <= max_iters, |dU|,|R|,|R|/|R0| < tol.
+ * Uu is updated in place [host|device]. */
+int fecb200_newton_solve(fecb200_handle* h, double* Uu, int32_t max_iters, double tol,
+                         int32_t matrix_free, int32_t* newton_iters_out, int64_t* cg_iters_out,
+                         double* rnorm_out);
+
+/* ---- multi-GPU (ext/PartitionedArraysExt.jl:223-233, 449-481): one handle per rank over the
+ * rank-local mesh (owned nodes first, then ghosts).  The halo lists say which local nodes are
+ * sent to / received from each neighbour rank.  Buffers are packed/unpacked on the device; the
+ * exchange itself is driven by the host (NCCL send/recv or peer memory). ---------------------- */
+int fecb200_halo_setup(fecb200_handle* h, int32_t n_neighbors, const int32_t* neighbor_ranks,
+                       const int64_t* send_ptr, const int64_t* send_nodes,  /* ghosts I hold -> owner   */
+                       const int64_t* recv_ptr, const int64_t* recv_nodes); /* my owned, ghosted by nbr */
+/* pack field values (NF per node) of the ghost nodes into a contiguous device buffer */
+int fecb200_halo_pack(fecb200_handle* h, int32_t which_field, double** sendbuf_dev, int64_t* n_doubles);
+/* owner side: add received ghost contributions into the owned entries */
+int fecb200_halo_unpack_add(fecb200_handle* h, int32_t which_field, const double* recvbuf_dev);
+int fecb200_halo_recv_size(fecb200_handle* h, int64_t* n_doubles);
+
+/* ---- instrumentation: kernels launched by this handle since creation (bench `gpu_launches`) */
+int fecb200_launch_count(fecb200_handle* h, int64_t* n);
+/* last kernel timing (ms) measured with CUDA events on the handle's stream around the dominant
+ * element kernel of the last assemble_* call; enabled by fecb200_enable_timing(h, 1) */
+int fecb200_enable_timing(fecb200_handle* h, int32_t on);
+int fecb200_last_kernel_ms(fecb200_handle* h, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FECB200_H */

@@ -1,0 +1,334 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the fecb200 host mirror) against the
+oracle on the same seeded inputs.  Integer outputs (DOF maps, rowptr/colval) must be bit-exact;
+FP64 values within 1e-12 relative (north_star; reassociation from atomic ordering and FMA).
+Modelled on the reference's test/TestAssemblers.jl:78-430."""
+import os
+
+import numpy as np
+import pytest
+
+import fec_oracle as O
+from util_parity import GOLDEN, RTOL, build_pair, perturb, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def F():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import fecb200
+    return fecb200
+
+
+def _boundary_nodes(mesh, names):
+    return np.unique(np.concatenate([mesh.nodeset_nodes[n] for n in names]))
+
+
+def _check_pattern_and_values(F, asm, oasm, K):
+    n, ptr, idx = asm.pattern()
+    optr, oidx, onz = oasm.stiffness()
+    assert n == oasm.n
+    assert np.array_equal(ptr, optr), "rowptr/colptr not bit-exact"
+    assert np.array_equal(idx, oidx), "colval/rowval not bit-exact"
+    assert rel_err(K.data, onz) < RTOL, rel_err(K.data, onz)
+
+
+def _check_dof_maps(asm, oasm):
+    assert np.array_equal(asm.dof.unknown_dofs, oasm.dof["unknown_dofs"])
+    assert np.array_equal(asm.dof.dof_to_unknown, oasm.dof["dof_to_unknown"])
+
+
+SRC3 = lambda X: 3 * np.pi ** 2 * np.sin(np.pi * X[:, 0]) * np.sin(np.pi * X[:, 1]) * np.sin(np.pi * X[:, 2])
+SRC2 = lambda X: 2 * np.pi ** 2 * np.sin(np.pi * X[:, 0]) * np.sin(np.pi * X[:, 1])
+
+
+@pytest.mark.parametrize("matrix_type", ["csr", "csc"])
+@pytest.mark.parametrize("condensed", [False, True])
+def test_poisson_hex8(F, condensed, matrix_type):
+    """BASELINE config 2 at oracle size: residual, CSR/CSC stiffness, matrix action, mass."""
+    n = 9
+    mesh = perturb(F.StructuredMesh("hex", (0, 0, 0), (1, 1, 1), (n + 1,) * 3), 0.15 / n)
+    bc = _boundary_nodes(mesh, ["bottom", "top", "left", "right", "back", "front"])
+    asm, p, oasm = build_pair(F, mesh, "poisson", None, condensed=condensed, matrix_type=matrix_type,
+                              bc_nodes_1based=bc, func=SRC3)
+    _check_dof_maps(asm, oasm)
+    rng = np.random.default_rng(42)
+    Uu = rng.uniform(-1, 1, asm.sizes()[2])
+    Vu = np.random.default_rng(7).uniform(0, 1, asm.sizes()[2])
+    F.assemble_vector(asm, F.residual, Uu, p)
+    R = F.residual(asm)
+    oasm.assemble_vector(Uu)
+    assert rel_err(R, oasm.residual()) < RTOL
+    F.assemble_stiffness(asm, F.stiffness, Uu, p)
+    K = F.stiffness(asm)
+    oasm.assemble_stiffness(Uu)
+    _check_pattern_and_values(F, asm, oasm, K)
+    F.assemble_matrix_action(asm, F.stiffness, Uu, Vu, p)
+    Kv = F.hvp(asm, Vu)
+    oasm.assemble_matrix_action(Uu, Vu)
+    assert rel_err(Kv, oasm.hvp(Vu)) < RTOL
+    # matrix-free entry point gives the same numbers (TestAssemblers.jl:279-311)
+    F.assemble_matrix_free_action(asm, F.stiffness_action, Uu, Vu, p)
+    assert rel_err(F.hvp(asm, Vu), Kv) < 1e-14
+    # mass matrix and its action (TestAssemblers.jl:160-178)
+    F.assemble_mass(asm, F.mass, Uu, p)
+    M = F.mass(asm)
+    oasm.assemble_stiffness(Uu, kind="mass")
+    _, _, onz = oasm.stiffness()
+    assert rel_err(M.data, onz) < RTOL
+    F.assemble_matrix_action(asm, F.mass, Uu, Vu, p)
+    Mv = F.hvp(asm, Vu)
+    oasm.assemble_matrix_action(Uu, Vu, kind="mass")
+    assert rel_err(Mv, oasm.hvp(Vu)) < RTOL
+    asm.close()
+
+
+@pytest.mark.parametrize("phys", ["neo", "neo_as_written", "linear"])
+@pytest.mark.parametrize("condensed", [False, True])
+def test_mechanics_hex8(F, phys, condensed):
+    """BASELINE config 3 at oracle size: neo-Hookean residual + tangent + action."""
+    n = 6
+    mesh = perturb(F.StructuredMesh("hex", (0, 0, 0), (1, 1, 1), (n + 1,) * 3), 0.15 / n)
+    props = np.array([1e3, 10e6, 1e6])
+    asm, p, oasm = build_pair(F, mesh, phys, props, condensed=condensed, matrix_type="csr",
+                              bc_nodes_1based=mesh.nodeset_nodes["bottom"])
+    _check_dof_maps(asm, oasm)
+    X = np.asarray(mesh.nodal_coords)
+    rng = np.random.default_rng(42)
+    Ufull = 0.02 * np.stack([np.sin(2 * np.pi * X[1]), np.sin(2 * np.pi * X[2]), np.sin(2 * np.pi * X[0])])
+    Ufull += rng.uniform(-1e-3, 1e-3, Ufull.shape) / n
+    Uflat = Ufull.reshape(-1, order="F")
+    Uu = Uflat.copy() if condensed else Uflat[asm.dof.unknown_dofs - 1]
+    Vu = np.random.default_rng(7).uniform(0, 1, len(Uu))
+    F.assemble_vector(asm, F.residual, Uu, p)
+    R = F.residual(asm)
+    oasm.assemble_vector(Uu)
+    assert rel_err(R, oasm.residual()) < RTOL
+    F.assemble_stiffness(asm, F.stiffness, Uu, p)
+    K = F.stiffness(asm)
+    oasm.assemble_stiffness(Uu)
+    _check_pattern_and_values(F, asm, oasm, K)
+    F.assemble_matrix_action(asm, F.stiffness, Uu, Vu, p)
+    Kv = F.hvp(asm, Vu)
+    oasm.assemble_matrix_action(Uu, Vu)
+    assert rel_err(Kv, oasm.hvp(Vu)) < RTOL
+    if not condensed:
+        assert rel_err(K @ Vu, Kv) < 1e-11
+    asm.close()
+
+
+@pytest.mark.parametrize("phys", ["poisson", "linear"])
+@pytest.mark.parametrize("matrix_type", ["csr", "csc"])
+@pytest.mark.parametrize("condensed", [False, True])
+def test_multi_block_quad4_tri3(F, phys, matrix_type, condensed):
+    """The reference's TestAssemblers fixture (test/TestAssemblers.jl:39-76): 280 QUAD4 + 170 TRI3."""
+    mesh = F.UnstructuredMesh(os.path.join(GOLDEN, "multi_block_quad4_tri3.npz"))
+    props = None if phys == "poisson" else np.array([1e3, 10e9, 1e9])
+    asm, p, oasm = build_pair(F, mesh, phys, props, condensed=condensed, matrix_type=matrix_type,
+                              bc_nodes_1based=mesh.sideset_nodes["boundary"], func=SRC2 if phys == "poisson" else None)
+    _check_dof_maps(asm, oasm)
+    rng = np.random.default_rng(3)
+    scale = 1.0 if phys == "poisson" else 1e-3
+    Uu = scale * rng.uniform(-1, 1, asm.sizes()[2])
+    Vu = rng.uniform(0, 1, asm.sizes()[2])
+    F.assemble_vector(asm, F.residual, Uu, p)
+    oasm.assemble_vector(Uu)
+    assert rel_err(F.residual(asm), oasm.residual()) < RTOL
+    F.assemble_stiffness(asm, F.stiffness, Uu, p)
+    oasm.assemble_stiffness(Uu)
+    _check_pattern_and_values(F, asm, oasm, F.stiffness(asm))
+    F.assemble_matrix_action(asm, F.stiffness, Uu, Vu, p)
+    oasm.assemble_matrix_action(Uu, Vu)
+    assert rel_err(F.hvp(asm, Vu), oasm.hvp(Vu)) < RTOL
+    F.assemble_mass(asm, F.mass, Uu, p)
+    oasm.assemble_stiffness(Uu, kind="mass")
+    assert rel_err(F.mass(asm).data, oasm.stiffness()[2]) < RTOL
+    asm.close()
+
+
+def test_poisson_gold_solve(F):
+    """BASELINE config 1: test/poisson/poisson.g (16384 QUAD4) Newton + CG on the device against
+    test/poisson/poisson.gold (TestPoisson.jl:54-103; exodiff default tolerance)."""
+    mesh = F.UnstructuredMesh(os.path.join(GOLDEN, "poisson_g.npz"))
+    gold = np.load(os.path.join(GOLDEN, "poisson_g.npz"))["gold_u"]
+    for condensed in (False, True):
+        V = F.FunctionSpace(mesh, F.H1Field, F.Lagrange)
+        u = F.ScalarFunction(V, "u")
+        asm = F.SparseMatrixAssembler(u, sparse_matrix_type="csr", use_condensed=condensed)
+        dbcs = [F.DirichletBC("u", lambda X, t: np.zeros(X.shape[0]), sideset_name=f"sset_{i}") for i in (1, 2, 3, 4)]
+        p = F.create_parameters(mesh, asm, F.Poisson(lambda X, t: SRC2(X)), None, dirichlet_bcs=dbcs)
+        solver = F.NewtonSolver(F.IterativeLinearSolver(asm, "cg"))
+        integ = F.QuasiStaticIntegrator(solver)
+        integ.evolve(p)
+        Ufield = p.field.data_flat
+        err = np.abs(Ufield - gold).max()
+        assert err < 1e-6, err
+        assert solver.iterations <= 10
+        asm.close()
+
+
+def test_newton_iteration_count_matches_oracle(F):
+    """north_star: 'Newton solves converge in the same number of iterations' (neo-Hookean, small)."""
+    n = 4
+    mesh = F.StructuredMesh("hex", (0, 0, 0), (1, 1, 1), (n + 1,) * 3)
+    props = np.array([1e3, 10e6, 1e6])
+    V = F.FunctionSpace(mesh, F.H1Field, F.Lagrange)
+    u = F.VectorFunction(V, "displ")
+    asm = F.SparseMatrixAssembler(u, sparse_matrix_type="csr", use_condensed=False)
+    zero = lambda X, t: np.zeros(X.shape[0])
+    pull = lambda X, t: np.full(X.shape[0], 0.1 * t)
+    dbcs = [F.DirichletBC(c, zero, nodeset_name="bottom") for c in u.names()] + \
+           [F.DirichletBC("displ_x", zero, nodeset_name="top"), F.DirichletBC("displ_z", zero, nodeset_name="top"),
+            F.DirichletBC("displ_y", pull, nodeset_name="top")]
+    p = F.create_parameters(mesh, asm, F.NeoHookean(F.ThreeDimensional()), props, dirichlet_bcs=dbcs,
+                            times=F.TimeStepper(0.0, 1.0, 10))
+    solver = F.NewtonSolver(F.IterativeLinearSolver(asm, "cg"))
+    integ = F.QuasiStaticIntegrator(solver)
+    # oracle twin
+    blk = O.Block(mesh.element_conns["block_1"], O.ref_fe_tables("HEX8", "gauss2"), O.NeoHookean(3), props=props)
+    oasm = O.OracleAssembler(np.asarray(mesh.nodal_coords), [blk], 3, condensed=False, matrix_type="csr")
+    oasm.update_dofs(p.dirichlet_bcs.dirichlet_dofs())
+    oUu = oasm.create_unknowns()
+    for step in range(2):
+        integ.evolve(p)
+        bcs = p.dirichlet_bcs
+        order = np.argsort(bcs.dofs, kind="stable")
+        d_sorted, first = np.unique(bcs.dofs[order], return_index=True)
+        # later BCs overwrite earlier ones on shared dofs, as the sequential loop in the reference does
+        vals = np.zeros(len(d_sorted))
+        for dof_id, val in zip(bcs.dofs, bcs.vals):
+            vals[np.searchsorted(d_sorted, dof_id)] = val
+        oasm.bc_vals[:] = vals
+        oUu, nits, cgits, hist = O.newton_solve(oasm, oUu)
+        assert solver.iterations == nits, (solver.iterations, nits)
+        assert rel_err(integ.solution, oUu) < 1e-8
+
+
+def test_j2_tet10_state(F):
+    """BASELINE config 4 at oracle size: stateful J2 on tet10: residual + state update + action."""
+    mesh = perturb(F.KuhnTet10Mesh(3), 0.02)
+    props = np.array([1e3, 10e9, 1e9, 2e8, 1e8])
+    asm, p, oasm = build_pair(F, mesh, "j2", props, condensed=False, matrix_type="csr",
+                              bc_nodes_1based=mesh.nodeset_nodes["bottom"], matrix_free=True)
+    X = np.asarray(mesh.nodal_coords)
+    U = 0.15 * np.stack([X[1] ** 2, 0.5 * X[1] * X[0], -0.3 * X[1]])  # yields a good fraction of points
+    Uu = U.reshape(-1, order="F")[asm.dof.unknown_dofs - 1]
+    rng = np.random.default_rng(5)
+    nq, ne = 4, mesh.element_conns["block_1"].shape[1]
+    so = np.zeros((7, nq, ne))
+    so[:2] = 1e-4 * rng.standard_normal((2, nq, ne)); so[2] = -so[0] - so[1]
+    so[3:6] = 1e-4 * rng.standard_normal((3, nq, ne)); so[6] = 1e-4 * rng.random((nq, ne))
+    p.set_state(so, which="old")
+    oasm.blocks[0].state_old[:] = so
+    F.assemble_vector(asm, F.residual, Uu, p)
+    R = F.residual(asm)
+    oasm.assemble_vector(Uu)
+    assert rel_err(R, oasm.residual()) < RTOL
+    sn = p.state(which="new")
+    osn = oasm.blocks[0].state_new
+    assert rel_err(sn, osn) < RTOL
+    frac = np.mean(osn[6] > so[6])
+    assert 0.05 < frac < 0.999, frac  # some, not all, quadrature points yield
+    Vu = rng.random(len(Uu))
+    F.assemble_matrix_free_action(asm, F.stiffness_action, Uu, Vu, p)
+    Kv = F.hvp(asm, Vu)
+    oasm.assemble_matrix_action(Uu, Vu)
+    assert rel_err(Kv, oasm.hvp(Vu)) < 1e-11
+    with pytest.raises(F.FECError, match="matrix-free"):
+        F.assemble_stiffness(asm, F.stiffness, Uu, p)
+    asm.close()
+
+
+def test_full_dof_action_and_invariant(F):
+    """assemble_matrix_free_action_full! (TestAssemblers.jl:341-430): (K_full v_full) and the
+    'BC slots of V are zero afterwards' invariant (MatrixAction.jl:137-148)."""
+    n = 5
+    mesh = F.StructuredMesh("hex", (0, 0, 0), (1, 1, 1), (n + 1,) * 3)
+    bc = _boundary_nodes(mesh, ["left"])
+    asm, p, oasm = build_pair(F, mesh, "poisson", None, condensed=False, matrix_type="csr", bc_nodes_1based=bc)
+    rng = np.random.default_rng(11)
+    ndof = len(asm.dof)
+    U_full, v_full = rng.standard_normal(ndof), rng.standard_normal(ndof)
+    F.assemble_matrix_free_action_full(asm, F.stiffness_action, U_full, v_full, p)
+    out = F.full_field(asm, "action")
+    Xo = np.asarray(mesh.nodal_coords)
+    ref = O.assemble_matrix_action(oasm.blocks, Xo, U_full.reshape(1, -1), v_full.reshape(1, -1), 1)
+    assert rel_err(out, ref) < RTOL
+    V_after = F.full_field(asm, "v")
+    assert np.all(V_after[p.dirichlet_bcs.dirichlet_dofs() - 1] == 0.0)
+    asm.close()
+
+
+def test_periodic_vector_path(F):
+    """periodic side-b dofs: field update U[b] = U[a] and residual fold-in (Assemblers.jl:357-368)."""
+    n = 4
+    mesh = F.StructuredMesh("quad", (0, 0), (1, 1), (n + 1, n + 1))
+    V = F.FunctionSpace(mesh, F.H1Field, F.Lagrange)
+    u = F.ScalarFunction(V, "u")
+    asm = F.SparseMatrixAssembler(u, sparse_matrix_type="csr", matrix_free=True)
+    p = F.create_parameters(mesh, asm, F.Poisson(lambda X, t: SRC2(X)), None,
+                            dirichlet_bcs=[F.DirichletBC("u", lambda X, t: np.zeros(X.shape[0]), nodeset_name="bottom")])
+    left, right = mesh.nodeset_nodes["left"][1:], mesh.nodeset_nodes["right"][1:]
+    F.update_dofs(asm, p.dirichlet_bcs, periodic=(left, right))
+    blk = O.Block(mesh.element_conns["block_1"], O.ref_fe_tables("QUAD4", "gauss2"), O.Poisson(SRC2))
+    oasm = O.OracleAssembler(np.asarray(mesh.nodal_coords), [blk], 1, condensed=False)
+    oasm.update_dofs(p.dirichlet_bcs.dirichlet_dofs(), left, right)
+    assert np.array_equal(asm.dof.unknown_dofs, oasm.dof["unknown_dofs"])
+    assert np.array_equal(asm.dof.dof_to_unknown, oasm.dof["dof_to_unknown"])
+    Uu = np.random.default_rng(2).standard_normal(asm.sizes()[2])
+    F.assemble_vector(asm, F.residual, Uu, p)
+    oasm.assemble_vector(Uu)
+    assert rel_err(F.residual(asm), oasm.residual()) < RTOL
+    asm.close()
+
+
+def test_device_pointers_zero_copy(F):
+    """Uu / outputs may be device buffers (a CuArray on the Julia side): used in place."""
+    import torch
+    n = 6
+    mesh = F.StructuredMesh("hex", (0, 0, 0), (1, 1, 1), (n + 1,) * 3)
+    asm, p, oasm = build_pair(F, mesh, "poisson", None, condensed=False, matrix_type="csr",
+                              bc_nodes_1based=mesh.nodeset_nodes["left"], func=SRC3)
+    Uu = np.random.default_rng(0).standard_normal(asm.sizes()[2])
+    dUu = torch.from_numpy(Uu).cuda()
+    dR = torch.empty_like(dUu)
+    F.assemble_vector(asm, F.residual, dUu, p)
+    F.residual(asm, dR)
+    torch.cuda.synchronize()
+    oasm.assemble_vector(Uu)
+    assert rel_err(dR.cpu().numpy(), oasm.residual()) < RTOL
+    asm.close()
+
+
+def test_large_roundtrip_properties(F):
+    """Size-independent properties at a size the oracle cannot assemble quickly (64^3 Poisson):
+    K*1 = 0 away from constraints (constants are in the kernel of the Laplacian), action linearity,
+    K v (assembled, device SpMV through CG machinery) == matrix-free action, symmetry v.Kw = w.Kv."""
+    n = 48
+    mesh = F.StructuredMesh("hex", (0, 0, 0), (1, 1, 1), (n + 1,) * 3)
+    V = F.FunctionSpace(mesh, F.H1Field, F.Lagrange)
+    u = F.ScalarFunction(V, "u")
+    asm = F.SparseMatrixAssembler(u, sparse_matrix_type="csr", use_condensed=False)
+    p = F.create_parameters(mesh, asm, F.Poisson(None), None, dirichlet_bcs=[])
+    N = asm.sizes()[2]
+    rng = np.random.default_rng(9)
+    Uu = rng.standard_normal(N)
+    one = np.ones(N)
+    F.assemble_matrix_action(asm, F.stiffness, Uu, one, p)
+    assert np.abs(F.hvp(asm, one)).max() < 1e-12
+    v, w = rng.standard_normal(N), rng.standard_normal(N)
+    F.assemble_matrix_action(asm, F.stiffness, Uu, v, p); Kv = F.hvp(asm, v).copy()
+    F.assemble_matrix_action(asm, F.stiffness, Uu, w, p); Kw = F.hvp(asm, w).copy()
+    F.assemble_matrix_action(asm, F.stiffness, Uu, 2 * v - 3 * w, p)
+    assert rel_err(F.hvp(asm, None), 2 * Kv - 3 * Kw) < 1e-12
+    assert abs(v @ Kw - w @ Kv) < 1e-10 * abs(v @ Kw)
+    F.assemble_stiffness(asm, F.stiffness, Uu, p)
+    K = F.stiffness(asm)
+    assert rel_err(K @ v, Kv) < 1e-12
+    assert abs(K - K.T).max() < 1e-13
+    # residual of the homogeneous problem equals K u
+    F.assemble_vector(asm, F.residual, Uu, p)
+    assert rel_err(F.residual(asm), K @ Uu) < 1e-12
+    asm.close()

@@ -1,0 +1,145 @@
+"""CPU-only tests: host-side mirror logic, and that libfecb200.so loads and exports every symbol
+include/fecb200.h declares (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import fec_oracle as O
+import fecb200 as F
+from fecb200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def test_header_symbols_exported():
+    hdr = open(os.path.join(ROOT, "include", "fecb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(fecb200_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in fecb200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.fecb200_version() == 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = F.StructuredMesh("hex", (0, 0, 0), (1, 1, 1), (3, 3, 3))
+    V = F.FunctionSpace(m, F.H1Field, F.Lagrange)
+    asm = F.SparseMatrixAssembler(F.ScalarFunction(V, "u"))
+    with pytest.raises(F.FECError, match="no CPU fallback"):
+        F.create_parameters(m, asm, F.Poisson(None))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "finiteelementcontainers.jl_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".jl")):
+                src = open(os.path.join(dp, f)).read()
+                assert "fec_oracle" not in src and "oracle/" not in src, f"{f} references the oracle"
+
+
+@pytest.mark.parametrize("el,counts", [("hex", (4, 3, 5)), ("quad", (4, 6)), ("tri", (3, 5))])
+def test_structured_mesh_matches_oracle(el, counts):
+    nd = len(counts)
+    m = F.StructuredMesh(el, (0.0,) * nd, (1.0,) * nd, counts)
+    o = O.structured_mesh(el, (0.0,) * nd, (1.0,) * nd, counts)
+    if el != "hex" or len(set(counts)) == 1:
+        assert np.array_equal(np.asarray(m.nodal_coords), o["coords"])
+    assert np.array_equal(m.element_conns["block_1"], o["conn"])
+    for k, v in o["nodesets"].items():
+        assert np.array_equal(m.nodeset_nodes[k], v), k
+
+
+def test_structured_mesh_known_answers():
+    # test/TestMesh.jl:96-128
+    m = F.StructuredMesh("quad", (0., 0.), (1., 1.), (3, 3))
+    assert np.array_equal(m.element_conns["block_1"], [[1, 4, 2, 5], [2, 5, 3, 6], [5, 8, 6, 9], [4, 7, 5, 8]])
+    m = F.StructuredMesh("tri", (0., 0.), (1., 1.), (3, 3))
+    assert np.array_equal(m.element_conns["block_1"],
+                          [[1, 1, 4, 4, 2, 2, 5, 5], [2, 5, 5, 8, 3, 6, 6, 9], [5, 4, 8, 7, 6, 5, 9, 8]])
+    with pytest.raises(ValueError):
+        F.StructuredMesh("bad element", (0., 0.), (1., 1.), (3, 3))
+    with pytest.raises(IndexError):
+        F.StructuredMesh("tri3", (0., 0.), (0., 1.), (3, 3))
+    with pytest.raises(AssertionError):
+        F.StructuredMesh("tet", (0., 0., 0.), (1., 1., 1.), (3, 3, 3))
+
+
+def test_hex_coords_cube():
+    m = F.StructuredMesh("hex", (0, 0, 0), (1, 1, 1), (3, 3, 3))
+    o = O.structured_mesh("hex", (0, 0, 0), (1, 1, 1), (3, 3, 3))
+    assert np.array_equal(np.asarray(m.nodal_coords), o["coords"])
+
+
+def test_tet10_mesh_matches_oracle():
+    m = F.KuhnTet10Mesh(2)
+    o = O.kuhn_tet10_mesh(2)
+    assert np.array_equal(np.asarray(m.nodal_coords), o["coords"])
+    assert np.array_equal(m.element_conns["block_1"], o["conn"])
+
+
+@pytest.mark.parametrize("el,rule,qt,qd", [("HEX8", "gauss2", "GaussLegendre", 2), ("HEX8", "gll2", "GaussLobattoLegendre", 2),
+                                            ("HEX8", "gll3", "GaussLobattoLegendre", 3), ("QUAD4", "gauss2", "GaussLegendre", 2),
+                                            ("TRI3", "tri3", "GaussLegendre", 2), ("TETRA4", "tet4", "GaussLegendre", 2),
+                                            ("TETRA10", "tet4", "GaussLegendre", 2), ("TETRA10", "tet1", "GaussLegendre", 1)])
+def test_reference_tables_match_oracle(el, rule, qt, qd):
+    rf = F.ReferenceFE(el, qt, qd)
+    N, dN, w = O.ref_fe_tables(el, rule)
+    assert np.allclose(rf.N, N, atol=1e-15) and np.allclose(rf.dN, dN, atol=1e-15) and np.allclose(rf.w, w, atol=1e-15)
+
+
+def test_h1field_layout():
+    # src/Fields.jl:36-40: data[(n-1)*NF + d]
+    f = F.H1Field(np.arange(6.0).reshape(2, 3))
+    assert f[1, 2] == 5.0
+    assert list(f.data_flat) == [0, 3, 1, 4, 2, 5]
+    z = F.H1Field.zeros(3, 4)
+    z.data_flat[3 * 2 + 1] = 7.0
+    assert z[1, 2] == 7.0
+
+
+def test_connectivity_offsets():
+    # test/TestFields.jl:1-37
+    a = np.arange(1, 13).reshape(4, 3, order="F")
+    b = np.arange(1, 7).reshape(3, 2, order="F")
+    c = F.Connectivity([a, b])
+    assert c.offsets == [1, 13] and c.nepes == [4, 3] and c.nelems == [3, 2]
+    assert np.array_equal(c.block(1), b) and np.array_equal(c.block(0), a)
+
+
+def test_unstructured_fixture_and_bcs():
+    m = F.UnstructuredMesh(os.path.join(GOLDEN, "multi_block_quad4_tri3.npz"))
+    assert m.num_nodes() == 406 and [m.element_conns[b].shape for b in m.element_block_names] == [(4, 280), (3, 170)]
+    assert set(m.element_types.values()) == {"QUAD4", "TRI3"}
+    V = F.FunctionSpace(m, F.H1Field, F.Lagrange)
+    u = F.VectorFunction(V, "displ")
+    assert u.names() == ["displ_x", "displ_y"]
+    dof = F.DofManager(u)
+    bcs = F.DirichletBCs(m, dof, [F.DirichletBC("displ_x", lambda X, t: 0.0, sideset_name="boundary"),
+                                  F.DirichletBC("displ_y", lambda X, t: 0.1 * t, sideset_name="boundary")])
+    dd = bcs.dirichlet_dofs()
+    assert len(dd) == 160 and np.all(np.diff(dd) > 0)
+    bcs.update_bc_values(m.nodal_coords, 2.0)
+    assert np.allclose(bcs.vals[:80], 0.0) and np.allclose(bcs.vals[80:], 0.2)
+    with pytest.raises(ValueError):
+        F.DirichletBC("u", lambda X, t: 0.0)
+    with pytest.raises(ValueError):
+        F.DirichletBC("u", lambda X, t: 0.0, nodeset_name="a", sideset_name="b")
+
+
+def test_element_function_tokens():
+    from fecb200.physics import kind_of
+    assert kind_of(F.residual, (_lib.RESIDUAL,)) == _lib.RESIDUAL
+    with pytest.raises(TypeError, match="no CPU fallback"):
+        kind_of(lambda *a: 0, (_lib.RESIDUAL,))
+    with pytest.raises(ValueError):
+        kind_of(F.stiffness, (_lib.RESIDUAL,))

@@ -1,0 +1,75 @@
+"""Shared helpers for the parity tests: build the SAME problem in the product (fecb200, CUDA)
+and in the oracle (oracle/fec_oracle.py, numpy)."""
+import os
+
+import numpy as np
+
+import fec_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL = 1e-12  # north_star: values within 1e-12 relative (FP64, atomic-order reassociation)
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    scale = max(np.abs(b).max(), 1e-300) if b.size else 1.0
+    return (np.abs(a - b).max() / scale) if b.size else 0.0
+
+
+_ORACLE_PHYS = {
+    "poisson": lambda f, nd: O.Poisson(f if f is not None else (lambda X: np.zeros(X.shape[0]))),
+    "linear": lambda f, nd: O.LinearElastic(nd),
+    "neo": lambda f, nd: O.NeoHookean(nd, "standard"),
+    "neo_as_written": lambda f, nd: O.NeoHookean(nd, "as_written"),
+    "j2": lambda f, nd: O.J2Plasticity(nd),
+}
+_RULES = {"QUAD4": "gauss2", "HEX8": "gauss2", "TRI3": "tri3", "TETRA4": "tet4", "TETRA10": "tet4"}
+
+
+def product_physics(F, name, nd, func=None):
+    form = F.ThreeDimensional() if nd == 3 else F.PlaneStrain()
+    return {
+        "poisson": lambda: F.Poisson((lambda X, t: func(X)) if func is not None else None),
+        "linear": lambda: F.Mechanics(form),
+        "neo": lambda: F.NeoHookean(form),
+        "neo_as_written": lambda: F.NeoHookean(form, variant="as_written"),
+        "j2": lambda: F.J2Plasticity(form),
+    }[name]()
+
+
+def build_pair(F, mesh, phys_name, props, *, condensed, matrix_type, bc_nodes_1based, bc_components=None,
+               func=None, matrix_free=False, bc_value=0.0):
+    """Returns (asm, p, oasm): product assembler + parameters, oracle assembler.
+    `mesh` is a fecb200 mesh; the oracle gets the very same arrays."""
+    nd = mesh.num_dimensions()
+    nf = 1 if phys_name == "poisson" else nd
+    V = F.FunctionSpace(mesh, F.H1Field, F.Lagrange, q_type="GaussLegendre", q_degree=2)
+    u = F.ScalarFunction(V, "u") if nf == 1 else F.VectorFunction(V, "displ")
+    asm = F.SparseMatrixAssembler(u, sparse_matrix_type=matrix_type, use_condensed=condensed, matrix_free=matrix_free)
+    comps = list(range(nf)) if bc_components is None else bc_components
+    names = u.names()
+    mesh.nodeset_nodes["__parity_bc__"] = np.asarray(bc_nodes_1based, dtype=np.int64)
+    dbcs = [F.DirichletBC(names[c], (lambda X, t, v=bc_value: np.full(X.shape[0], v)), nodeset_name="__parity_bc__")
+            for c in comps]
+    ph = product_physics(F, phys_name, nd, func)
+    p = F.create_parameters(mesh, asm, ph, props, dirichlet_bcs=dbcs)
+    # ---- oracle twin
+    blocks = []
+    for b in mesh.element_block_names:
+        t = mesh.element_types[b]
+        blocks.append(O.Block(mesh.element_conns[b], O.ref_fe_tables(t, _RULES[t]),
+                              _ORACLE_PHYS[phys_name](func, nd), props=props if props is not None else ()))
+    oasm = O.OracleAssembler(np.asarray(mesh.nodal_coords), blocks, nf, condensed=condensed, matrix_type=matrix_type)
+    dd = np.unique(np.concatenate([nf * (np.asarray(bc_nodes_1based) - 1) + c + 1 for c in comps])) \
+        if len(bc_nodes_1based) else np.zeros(0, dtype=np.int64)
+    oasm.update_dofs(dd)
+    oasm.bc_vals[:] = bc_value
+    return asm, p, oasm
+
+
+def perturb(mesh, amp, seed=1234):
+    """displace nodes by U(-amp, amp) (SURVEY 8d 'perturbed' variant: non-constant Jacobians)"""
+    rng = np.random.default_rng(seed)
+    X = np.asarray(mesh.nodal_coords)
+    X += rng.uniform(-amp, amp, X.shape)
+    return mesh
