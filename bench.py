@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the FE assembly hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+    python bench.py --impl reference --steps K --warmup W    (CPU port of the reference path)
+
+Workload (BASELINE.json config 3 / 5): neo-Hookean hex8, 3 dof/node, structured 192^3 elements PER GPU
+(weak scaling: 1 GPU 192^3, 2 GPUs 384x192x192, 4 GPUs 384x384x192, 8 GPUs 384^3), Float64.  One
+"step" = what one Newton iteration asks of the path: assemble_vector!(residual) + residual(asm), then
+assemble_stiffness!(stiffness) into the CSR values.  value = elements assembled per second over the
+whole job (all ranks), inputs resident in HBM.  `e2e` is the same step driven through the C ABI with
+pinned HOST buffers (H2D of Uu, D2H of the residual inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "finiteelementcontainers.jl_b200"))
+
+# algorithmic (compulsory) DRAM bytes per element, SURVEY.md 8(d) / DESIGN.md section 5
+BYTES_RESIDUAL = 136.0     # conn 64 + X 24 + U 24 + R 24
+BYTES_TANGENT = 2066.0     # conn 64 + X 24 + U 24 + CSR values 1954 (nnz/NE * 8)
+BYTES_ACTION = 160.0
+# FP64 flops per element counted from the kernels' instruction mix
+FLOPS_RESIDUAL = 7.0e3
+FLOPS_TANGENT = 45.4e3
+NEO_PROPS = np.array([1e3, 10.0e6, 1.0e6])
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", d
+    return 6650.0, "fallback (B200_PROFILING.md)", {}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self._halt = index, [], set(), threading.Event()
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=5)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def grid_for(world):
+    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
+
+
+def build_problem(F, n, rank, world, matrix_free=False):
+    """Rank-local neo-Hookean problem.  N = 1: StructuredMesh('hex', (0,0,0), (1,1,1), (n+1,)*3) with the
+    BCs of BASELINE config 3.  N > 1: this rank's brick of the global grid (see fecb200.partition)."""
+    if world == 1:
+        mesh = F.StructuredMesh("hex", (0., 0., 0.), (1., 1., 1.), (n + 1, n + 1, n + 1))
+        part = None
+    else:
+        from fecb200.partition import structured_brick_partition
+        mesh, part = structured_brick_partition(F, n, grid_for(world), rank)
+    V = F.FunctionSpace(mesh, F.H1Field, F.Lagrange, q_type="GaussLegendre", q_degree=2)
+    u = F.VectorFunction(V, "displ")
+    asm = F.SparseMatrixAssembler(u, sparse_matrix_type="csr", use_condensed=False, matrix_free=matrix_free,
+                                  device=int(os.environ.get("LOCAL_RANK", 0)))
+    zero = lambda X, t: np.zeros(X.shape[0])
+    pull = lambda X, t: np.full(X.shape[0], 0.1 * t)
+    dbcs = [F.DirichletBC(c, zero, nodeset_name="bottom") for c in u.names()]
+    dbcs += [F.DirichletBC("displ_x", zero, nodeset_name="top"), F.DirichletBC("displ_z", zero, nodeset_name="top"),
+             F.DirichletBC("displ_y", pull, nodeset_name="top")]
+    p = F.create_parameters(mesh, asm, F.NeoHookean(F.ThreeDimensional()), NEO_PROPS, dirichlet_bcs=dbcs,
+                            times=F.TimeStepper(0.0, 1.0, 10))
+    if part is not None:
+        part.attach(asm)
+    # raw-throughput state: u = 0.02 (sin 2 pi y, sin 2 pi z, sin 2 pi x) + U(-1e-3,1e-3) h
+    X = np.asarray(mesh.nodal_coords)
+    rng = np.random.default_rng(42 + rank)
+    U = 0.02 * np.stack([np.sin(2 * np.pi * X[1]), np.sin(2 * np.pi * X[2]), np.sin(2 * np.pi * X[0])])
+    U += rng.uniform(-1e-3, 1e-3, U.shape) / n
+    Uu = np.ascontiguousarray(U.reshape(-1, order="F")[asm.dof.unknown_dofs - 1])
+    return mesh, asm, p, Uu, part
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import fecb200 as F
+    from fecb200 import _lib
+    from fecb200._lib import check, lib
+
+    n = args.n
+    t0 = time.time()
+    mesh, asm, p, Uu_h, part = build_problem(F, n, rank, world)
+    setup_s = time.time() - t0
+    ne_local = mesh.element_conns["block_1"].shape[1] if part is None else part.n_owned_elements
+    h = asm._require()
+    stream = torch.cuda.Stream()
+    check(lib.fecb200_set_stream(h, stream.cuda_stream))
+    N = len(Uu_h)
+    with torch.cuda.stream(stream):
+        dUu = torch.from_numpy(Uu_h).cuda()
+        dR = torch.empty_like(dUu)
+    hUu = torch.from_numpy(Uu_h).pin_memory()
+    hR = torch.empty(N, dtype=torch.float64).pin_memory()
+    stream.synchronize()
+
+    def halo():
+        if part is not None:
+            part.halo_sum_residual(asm, stream)
+
+    def step_device():
+        F.assemble_vector(asm, F.residual, dUu, p)
+        halo()
+        F.residual(asm, dR)
+        F.assemble_stiffness(asm, F.stiffness, dUu, p)
+
+    def step_e2e():
+        F.assemble_vector(asm, F.residual, hUu, p)      # H2D of Uu inside
+        halo()
+        F.residual(asm, hR)                             # D2H of the residual inside (synchronous)
+        F.assemble_stiffness(asm, F.stiffness, hUu, p)  # H2D of Uu inside
+
+    def barrier():
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = asm.launch_count()
+    ms = timed(step_device, args.steps)
+    launches = asm.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    ne_total = ne_local * world if part is None else part.n_global_elements
+    value = ne_total * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the C ABI with pinned host buffers
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = ne_total * args.steps / (ms_e2e * 1e-3)
+
+    out = None
+    if rank == 0:
+        hbm, peak_src, peaks = load_peaks()
+        # ---- per-operation device timings (CUDA events on the launching stream) + roofline of the dominant kernel
+        def op_ms(fn, reps=5):
+            for _ in range(2):
+                fn()
+            return timed(fn, reps) / reps if world == 1 else None
+
+        roof, ops = {}, {}
+        if world == 1:
+            Vu = torch.rand(N, dtype=torch.float64, device="cuda")
+            t_res = op_ms(lambda: F.assemble_vector(asm, F.residual, dUu, p))
+            t_tan = op_ms(lambda: F.assemble_stiffness(asm, F.stiffness, dUu, p))
+            t_act = op_ms(lambda: F.assemble_matrix_free_action(asm, F.stiffness_action, dUu, Vu, p))
+            # dominant kernel alone: events recorded by the library around the element kernel launch
+            check(lib.fecb200_enable_timing(h, 1))
+            kms = []
+            import ctypes as C
+            for _ in range(5):
+                F.assemble_stiffness(asm, F.stiffness, dUu, p)
+                f = C.c_float()
+                check(lib.fecb200_last_kernel_ms(h, C.byref(f)))
+                kms.append(f.value)
+            kres = []
+            for _ in range(5):
+                F.assemble_vector(asm, F.residual, dUu, p)
+                f = C.c_float()
+                check(lib.fecb200_last_kernel_ms(h, C.byref(f)))
+                kres.append(f.value)
+            check(lib.fecb200_enable_timing(h, 0))
+            k_tan, k_res = float(np.mean(kms[1:])), float(np.mean(kres[1:]))
+            ach = BYTES_TANGENT * ne_local / (k_tan * 1e-3) / 1e9
+            # FP64 roof measured here with cuBLAS DGEMM (MEASURED_PEAKS.json has no FP64 entry)
+            a = torch.randn(6144, 6144, dtype=torch.float64, device="cuda")
+            torch.mm(a, a)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.mm(a, a); torch.mm(a, a); e1.record(); torch.cuda.synchronize()
+            fp64_peak = 2 * 2 * 6144 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+            del a
+            roof = {"bound": "hbm", "kernel": "k_mat<hex8,NF=3,neo-Hookean> (tangent -> CSR)", "achieved": round(ach, 1),
+                    "peak": hbm, "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / hbm, 4), "traffic": None,
+                    "algorithmic_bytes_per_element": BYTES_TANGENT, "kernel_ms": round(k_tan, 4),
+                    "fp64": {"flops_per_element": FLOPS_TANGENT,
+                             "achieved_tflops": round(FLOPS_TANGENT * ne_local / (k_tan * 1e-3) / 1e12, 2),
+                             "peak_tflops_dgemm_measured": round(fp64_peak, 1),
+                             "frac": round(FLOPS_TANGENT * ne_local / (k_tan * 1e-3) / 1e12 / fp64_peak, 4)},
+                    "residual_kernel": {"kernel_ms": round(k_res, 4),
+                                        "achieved_GBs": round(BYTES_RESIDUAL * ne_local / (k_res * 1e-3) / 1e9, 1),
+                                        "frac_hbm": round(BYTES_RESIDUAL * ne_local / (k_res * 1e-3) / 1e9 / hbm, 4),
+                                        "achieved_tflops": round(FLOPS_RESIDUAL * ne_local / (k_res * 1e-3) / 1e12, 2),
+                                        "frac_fp64": round(FLOPS_RESIDUAL * ne_local / (k_res * 1e-3) / 1e12 / fp64_peak, 4)}}
+            ops = {"residual_elements_per_s": round(ne_local / (t_res * 1e-3), 1),
+                   "tangent_elements_per_s": round(ne_local / (t_tan * 1e-3), 1),
+                   "action_elements_per_s": round(ne_local / (t_act * 1e-3), 1),
+                   "residual_ms": round(t_res, 4), "tangent_ms": round(t_tan, 4), "action_ms": round(t_act, 4)}
+        cpu = cpu_baseline(args.cpu_n) if (world == 1 and not args.no_cpu) else None
+        out = {
+            "metric": "assembled elements/s (residual + Jacobian), neo-Hookean hex8 FP64",
+            "value": round(value, 1), "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"neohookean_hex8_{n}^3_per_gpu residual+tangent(CSR) per Newton iteration",
+                       "elements_per_gpu": int(ne_local), "elements_total": int(ne_total), "dofs_per_gpu": int(len(asm.dof)),
+                       "csr_nnz_per_gpu": int(asm.pattern()[2].shape[0]) if args.report_nnz else None,
+                       "parallelism": f"domain decomposition x{world}" if world > 1 else "single GPU",
+                       "l2": "inputs and outputs larger than L2 (CSR values 13.8 GB at 192^3); no flush needed",
+                       "setup_s": round(setup_s, 1)},
+            "e2e": {"value": round(e2e_value, 1), "unit": "elements/s", "ms_per_step": round(ms_e2e / args.steps, 4),
+                    "h2d_bytes_per_step": int(2 * N * 8), "d2h_bytes_per_step": int(N * 8)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if roof:
+            out["roofline"] = roof
+        if ops:
+            out["ops"] = ops
+        if cpu:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    asm.close()
+    return out
+
+
+def _cpu_problem(n):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fec_oracle as O
+    import fec_oracle_clib as OC
+    m = O.structured_mesh("hex", (0., 0., 0.), (1., 1., 1.), (n + 1,) * 3)
+    X = m["coords"]
+    U = 0.02 * np.stack([np.sin(2 * np.pi * X[1]), np.sin(2 * np.pi * X[2]), np.sin(2 * np.pi * X[0])])
+    cp = OC.CProblem(m["conn"], X, O.ref_fe_tables("HEX8", "gauss2"), "neo", 3, NEO_PROPS)
+    return OC, cp, U.reshape(-1, order="F"), m
+
+
+def cpu_step_factory(n):
+    """One reference-style CPU step: assemble_vector! + assemble_stiffness! (COO) + stiffness(asm) (sparse!)."""
+    OC, cp, Uf, m = _cpu_problem(n)
+    nthreads = OC.max_threads()
+    Is, Js = cp.pattern()
+    ndof = 3 * m["coords"].shape[1]
+    ws = OC.SparseWorkspace(len(Is), ndof)
+    slots = np.arange(1, len(Is) + 1, dtype=np.int64)
+    coo = np.empty(len(Is))
+
+    def step():
+        cp.assemble_vector(Uf, nthreads=nthreads)
+        cp.assemble_matrix_coo(Uf, 2, nthreads=nthreads, out=coo)
+        ws.sparse_csc(Is, Js, slots, coo)
+
+    return step, cp.ne, nthreads
+
+
+def cpu_baseline(n):
+    step, ne, nthreads = cpu_step_factory(n)
+    step()
+    t0 = time.perf_counter()
+    reps = 0
+    while reps < 2 or (time.perf_counter() - t0 < 8.0 and reps < 20):
+        step()
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": round(ne / dt, 1), "unit": "elements/s", "cores": nthreads, "kind": "port",
+            "sample": f"neo-Hookean hex8 {n}^3 ({ne} elements): residual + COO tangent + sparse!, {reps} reps, "
+                      "C/OpenMP port of the reference CPU path (Julia is not installable here)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is Julia and
+    cannot be installed in this image (no julia, no network), so this times the C/OpenMP port of the
+    same algorithm (oracle/fec_oracle_c.c) with all host threads, on a bounded sample per step."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    n = args.cpu_n
+    step, ne, nthreads = cpu_step_factory(n)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = ne * args.steps / dt
+    sample = f"neo-Hookean hex8 {n}^3 ({ne} elements) per step: residual + COO tangent + sparse!"
+    print(json.dumps({
+        "impl": "reference", "metric": "assembled elements/s (residual + Jacobian), neo-Hookean hex8 FP64",
+        "value": round(v, 1), "unit": "elements/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"neohookean_hex8_{args.n}^3_per_gpu residual+tangent(CSR) per Newton iteration",
+                   "cpu_sample": sample},
+        "cpu_baseline": {"value": round(v, 1), "unit": "elements/s", "cores": nthreads, "kind": "port", "sample": sample},
+        "e2e": {"value": round(v, 1), "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=int(os.environ.get("FECB200_BENCH_N", 192)), help="elements per axis per GPU")
+    ap.add_argument("--cpu-n", type=int, default=48, help="elements per axis of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--report-nnz", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
