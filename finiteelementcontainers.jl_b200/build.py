@@ -21,9 +21,15 @@ LIB = os.path.join(LIBDIR, "libfecb200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp,-O3", "--expt-relaxed-constexpr"]
+# sweeps: FECB200_DEFINES="-DFEC_TE=128 -DFEC_MINB3=3" FECB200_VARIANT=te128_b3 python build.py
+DEFINES = os.environ.get("FECB200_DEFINES", "").split()
+VARIANT = os.environ.get("FECB200_VARIANT", "")
+if VARIANT:
+    OBJ = os.path.join(HERE, "build", VARIANT)
+    LIB = os.path.join(LIBDIR, f"libfecb200_{VARIANT}.so")
 
 SOURCES = ["api.cu", "aux.cu", "plan.cu", "dispatch_hex8.cu", "dispatch_quad_tri.cu", "dispatch_tet.cu"]
-HEADERS = ["common.cuh", "kernels.cuh", "physics.cuh", os.path.join("..", "..", "include", "fecb200.h")]
+HEADERS = ["common.cuh", "kernels.cuh", "kernel_mat2.cuh", "physics.cuh", os.path.join("..", "..", "include", "fecb200.h")]
 
 
 def _newer(target, deps):
@@ -35,7 +41,7 @@ def _newer(target, deps):
 
 def _compile(src):
     obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-    cmd = [NVCC, *ARCH, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [NVCC, *ARCH, *FLAGS, *DEFINES, "-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     return src, r.returncode, r.stdout + r.stderr
 

@@ -167,8 +167,8 @@ int fecb200_create(const fecb200_mesh_desc* mesh, const fecb200_opts* opts, fecb
   FEC_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   FEC_CUDA(cudaEventCreate(&h->ev0));
   FEC_CUDA(cudaEventCreate(&h->ev1));
-  const int te = opts->tile_elems > 0 ? opts->tile_elems : 256;
-  FEC_REQUIRE(te == 256, "tile_elems: this build ships 256-element tiles");
+  const int te = opts->tile_elems > 0 ? opts->tile_elems : kTE;
+  FEC_REQUIRE(te == kTE, "tile_elems does not match the tile size this build was compiled for");
   h->blocks.resize(mesh->nblocks);
   for (int bi = 0; bi < mesh->nblocks; ++bi) {
     const fecb200_block_desc& d = mesh->blocks[bi];

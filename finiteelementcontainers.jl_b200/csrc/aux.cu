@@ -105,6 +105,51 @@ void k_zero_bc_slots(fecb200_handle* h, double* field) {
   h->launches++;
 }
 
+// ---- per-element scatter records for k_mat2 (layout: Mat2Layout in kernel_mat2.cuh); one thread per element
+__global__ void k_build_emeta(const int32_t* conn, const uint8_t* epos, const int32_t* adjptr, const uint16_t* coloff,
+                              const uint8_t* freemask, const int64_t* rowstart, unsigned char* emeta, int nnpe, int nf,
+                              int rec, int64_t ne) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  const int32_t* c = conn + e * nnpe;
+  unsigned char* r = emeta + e * rec;
+  uint32_t* rs = reinterpret_cast<uint32_t*>(r);
+  uint16_t* ec = reinterpret_cast<uint16_t*>(r + nnpe * nf * 4);
+  uint8_t* mk = r + nnpe * nf * 4 + nnpe * nnpe * 2;
+  uint8_t* rk = mk + nnpe;
+  int rank[16];
+  for (int a = 0; a < nnpe; ++a) {
+    int k = 0;
+    for (int a2 = 0; a2 < nnpe; ++a2) k += (c[a2] < c[a]) || (c[a2] == c[a] && a2 < a);
+    rank[a] = k;
+    rk[a] = (uint8_t)k;
+    mk[k] = freemask[c[a]];
+  }
+  for (int b = 0; b < nnpe; ++b) {
+    for (int d = 0; d < nf; ++d) {
+      const int64_t v = rowstart[(int64_t)c[b] * nf + d];
+      rs[b * nf + d] = v < 0 ? 0xFFFFFFFFu : (uint32_t)v;
+    }
+    const int base = adjptr[c[b]];
+    for (int a = 0; a < nnpe; ++a) ec[b * nnpe + rank[a]] = coloff[base + epos[(e * nnpe + b) * nnpe + a]];
+  }
+}
+
+void build_ecol(fecb200_handle* h) {
+  if (!h->matrix_ready || h->nnz >= (int64_t)0xFFFFFFFFll) return;
+  for (auto& b : h->blocks) {
+    if (b.nnpe > 16) continue;
+    const size_t rec = (((size_t)b.nnpe * h->nf * 4 + (size_t)b.nnpe * b.nnpe * 2 + 2 * b.nnpe + 15) / 16) * 16;
+    if (b.d_emeta.n != rec * b.ne) b.d_emeta.alloc(rec * b.ne);
+    b.emeta_rec = rec;
+    k_build_emeta<<<grid_for(b.ne), 256, 0, h->stream>>>(b.d_conn_perm.p, b.d_epos.p, h->d_adjptr.p, h->d_coloff.p,
+                                                         h->d_freemask.p, h->d_rowstart.p, b.d_emeta.p, b.nnpe, h->nf,
+                                                         (int)rec, b.ne);
+    h->launches++;
+  }
+  FEC_CUDA(cudaGetLastError());
+}
+
 // ---- reductions ---------------------------------------------------------------------------
 __global__ void k_dot(const double* a, const double* b, int64_t n, double* out) {
   __shared__ double sh[32];

@@ -62,6 +62,19 @@ struct DevBuf {  // owning device array
   void zero(cudaStream_t s) { if (n) FEC_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
 };
 
+// tuning knobs of the vector kernels (overridable at build time for sweeps)
+#ifndef FEC_TE
+#define FEC_TE 128
+#endif
+#ifndef FEC_MINB3
+#define FEC_MINB3 2
+#endif
+#ifndef FEC_MINB1
+#define FEC_MINB1 2
+#endif
+constexpr int kTE = FEC_TE;        // elements per tile = threads per CTA of the vector kernels
+constexpr int kMinB3 = FEC_MINB3;  // __launch_bounds__ min CTAs/SM for NF = 3 vector kernels
+constexpr int kMinB1 = FEC_MINB1;  // ... for NF <= 2
 constexpr int kMaxProps = 8;
 constexpr int kMaxNQ = 27;  // runtime-NQ kernels (e.g. 3-point GLL on hex8)
 
@@ -79,6 +92,8 @@ struct BlockPlan {
   DevBuf<uint16_t> d_lconn, d_inc;
   DevBuf<int32_t> d_conn_perm;  // [ne*nnpe] global node ids in tile order (matrix kernels)
   DevBuf<uint8_t> d_epos;       // [ne*nnpe*nnpe] position of node a in the adjacency row of node b
+  DevBuf<unsigned char> d_emeta;  // [ne * emeta_rec] per-element scatter records of k_mat2 (kernel_mat2.cuh)
+  size_t emeta_rec = 0;
   DevBuf<double> d_state_old, d_state_new;  // [(s*nq+q)*ne + e_tile_order]
   DevBuf<double> d_source;                  // [q*ne + e_tile_order]
 };
@@ -172,6 +187,7 @@ void k_permute_state_in(fecb200_handle* h, BlockPlan& b, const double* src_dev, 
 void k_permute_state_out(fecb200_handle* h, BlockPlan& b, const double* src, double* dst_dev);
 void k_permute_source_in(fecb200_handle* h, BlockPlan& b, const double* src_dev, double* dst);
 void k_zero_bc_slots(fecb200_handle* h, double* field);
+void build_ecol(fecb200_handle* h);
 void spmv(fecb200_handle* h, const double* nz, const double* x, double* y);
 double dot(fecb200_handle* h, const double* a, const double* b, int64_t n);
 void axpy(fecb200_handle* h, double alpha, const double* x, double* y, int64_t n);

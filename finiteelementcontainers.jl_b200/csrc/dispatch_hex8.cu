@@ -1,6 +1,11 @@
 // dispatch_hex8.cu -- HEX8 instantiations of the element kernels (3-D, 8 nodes).
 // Hot configurations (BASELINE.json configs 2, 3, 5): Poisson NF=1 and neo-Hookean NF=3 with 8-point rules.
-#include "kernels.cuh"
+#include "kernel_mat2.cuh"
+
+#ifndef FEC_MAT2_WARPS
+#define FEC_MAT2_WARPS 4
+#endif
+#include <cstdlib>
 
 namespace fec {
 
@@ -12,20 +17,22 @@ static void vec8(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
 template <class Phys, int NF, int EPB>
 static void mat8(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   FEC_REQUIRE(b.nq == 8, "HEX8: this physics is compiled for 8-point quadrature rules only");
-  run_mat<3, 8, NF, 8, Phys, EPB>(h, b, a);
+  // symmetric tangents (all shipped mechanics physics): pair-owner kernel with staged, coalesced REDs
+  if (a.kind == FECB200_STIFFNESS && !getenv("FECB200_KMAT1")) run_mat2<3, 8, NF, 8, Phys, FEC_MAT2_WARPS>(h, b, a);
+  else run_mat<3, 8, NF, 8, Phys, EPB>(h, b, a);
 }
 
 void launch_vector_hex8(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
   switch (b.physics) {
     case FECB200_PHYS_POISSON:
       FEC_REQUIRE(h->nf == 1, "Poisson needs NF = 1");
-      if (b.nq == 8) run_vec_modes<3, 8, 1, 8, PhysPoisson<3>, kTE, 2>(h, b, a);
-      else run_vec_modes<3, 8, 1, 0, PhysPoisson<3>, kTE, 2>(h, b, a);
+      if (b.nq == 8) run_vec_modes<3, 8, 1, 8, PhysPoisson<3>, kTE, kMinB1>(h, b, a);
+      else run_vec_modes<3, 8, 1, 0, PhysPoisson<3>, kTE, kMinB1>(h, b, a);
       break;
-    case FECB200_PHYS_LINEAR_ELASTIC: FEC_REQUIRE(h->nf == 3, "mechanics needs NF = ND"); vec8<PhysLinearElastic<3>, 3, 2>(h, b, a); break;
-    case FECB200_PHYS_NEOHOOKEAN: FEC_REQUIRE(h->nf == 3, "mechanics needs NF = ND"); vec8<PhysNeoHookean<3>, 3, 2>(h, b, a); break;
-    case FECB200_PHYS_NEOHOOKEAN_AS_WRITTEN: FEC_REQUIRE(h->nf == 3, "mechanics needs NF = ND"); vec8<PhysNeoHookeanAsWritten<3>, 3, 2>(h, b, a); break;
-    case FECB200_PHYS_J2_PLASTICITY: FEC_REQUIRE(h->nf == 3, "mechanics needs NF = ND"); vec8<PhysJ2<3>, 3, 2>(h, b, a); break;
+    case FECB200_PHYS_LINEAR_ELASTIC: FEC_REQUIRE(h->nf == 3, "mechanics needs NF = ND"); vec8<PhysLinearElastic<3>, 3, kMinB3>(h, b, a); break;
+    case FECB200_PHYS_NEOHOOKEAN: FEC_REQUIRE(h->nf == 3, "mechanics needs NF = ND"); vec8<PhysNeoHookean<3>, 3, kMinB3>(h, b, a); break;
+    case FECB200_PHYS_NEOHOOKEAN_AS_WRITTEN: FEC_REQUIRE(h->nf == 3, "mechanics needs NF = ND"); vec8<PhysNeoHookeanAsWritten<3>, 3, kMinB3>(h, b, a); break;
+    case FECB200_PHYS_J2_PLASTICITY: FEC_REQUIRE(h->nf == 3, "mechanics needs NF = ND"); vec8<PhysJ2<3>, 3, kMinB3>(h, b, a); break;
     default: throw Error("fecb200: unsupported physics for HEX8");
   }
 }

@@ -9,15 +9,15 @@ static void vec2d(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
   switch (b.physics) {
     case FECB200_PHYS_POISSON:
       FEC_REQUIRE(h->nf == 1, "Poisson needs NF = 1");
-      run_vec_modes<2, NNPE, 1, 0, PhysPoisson<2>, kTE, 2>(h, b, a);
+      run_vec_modes<2, NNPE, 1, 0, PhysPoisson<2>, kTE, kMinB1>(h, b, a);
       break;
     case FECB200_PHYS_LINEAR_ELASTIC:  // PlaneStrain (src/Formulations.jl:318-447)
       FEC_REQUIRE(h->nf == 2, "plane-strain mechanics needs NF = 2");
-      run_vec_modes<2, NNPE, 2, 0, PhysLinearElastic<2>, kTE, 2>(h, b, a);
+      run_vec_modes<2, NNPE, 2, 0, PhysLinearElastic<2>, kTE, kMinB1>(h, b, a);
       break;
     case FECB200_PHYS_NEOHOOKEAN:
       FEC_REQUIRE(h->nf == 2, "plane-strain mechanics needs NF = 2");
-      run_vec_modes<2, NNPE, 2, 0, PhysNeoHookean<2>, kTE, 2>(h, b, a);
+      run_vec_modes<2, NNPE, 2, 0, PhysNeoHookean<2>, kTE, kMinB1>(h, b, a);
       break;
     default: throw Error("fecb200: unsupported physics for QUAD4/TRI3");
   }

@@ -8,20 +8,20 @@ static void vec3d(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
   switch (b.physics) {
     case FECB200_PHYS_POISSON:
       FEC_REQUIRE(h->nf == 1, "Poisson needs NF = 1");
-      run_vec_modes<3, NNPE, 1, 0, PhysPoisson<3>, kTE, 2>(h, b, a);
+      run_vec_modes<3, NNPE, 1, 0, PhysPoisson<3>, kTE, kMinB1>(h, b, a);
       break;
     case FECB200_PHYS_LINEAR_ELASTIC:
       FEC_REQUIRE(h->nf == 3, "mechanics needs NF = ND");
-      run_vec_modes<3, NNPE, 3, 0, PhysLinearElastic<3>, kTE, 2>(h, b, a);
+      run_vec_modes<3, NNPE, 3, 0, PhysLinearElastic<3>, kTE, kMinB3>(h, b, a);
       break;
     case FECB200_PHYS_NEOHOOKEAN:
       FEC_REQUIRE(h->nf == 3, "mechanics needs NF = ND");
-      run_vec_modes<3, NNPE, 3, 0, PhysNeoHookean<3>, kTE, 2>(h, b, a);
+      run_vec_modes<3, NNPE, 3, 0, PhysNeoHookean<3>, kTE, kMinB3>(h, b, a);
       break;
     case FECB200_PHYS_J2_PLASTICITY:
       FEC_REQUIRE(h->nf == 3, "mechanics needs NF = ND");
-      if (b.nq == 4) run_vec_modes<3, NNPE, 3, 4, PhysJ2<3>, kTE, 2>(h, b, a);
-      else run_vec_modes<3, NNPE, 3, 0, PhysJ2<3>, kTE, 2>(h, b, a);
+      if (b.nq == 4) run_vec_modes<3, NNPE, 3, 4, PhysJ2<3>, kTE, kMinB3>(h, b, a);
+      else run_vec_modes<3, NNPE, 3, 0, PhysJ2<3>, kTE, kMinB3>(h, b, a);
       break;
     default: throw Error("fecb200: unsupported physics for TET4/TET10");
   }

@@ -1,0 +1,310 @@
+// kernel_mat2.cuh -- second-generation tangent kernel ("pair owner") for NF = ND mechanics.
+//
+// Why (ncu, profiles/r01a_kmat_details.txt): the first kernel (k_mat, one thread per block-column)
+// spends its time in the L1/TEX pipe -- 3.8e9 RED sectors (every lane of every RED its own 32 B
+// sector) plus 3.5e9 shared-memory wavefronts (108 LDS per 297 DFMA) -- with the FP64 pipe 37 % busy.
+//
+// Design:
+//   * NP = NF(NF+1)/2 threads per element, one per component pair (d1 <= d2); the tangents of all shipped
+//     physics have major symmetry (A_iJkL = A_kLiJ, checked in tests/test_oracle_pins.py), so pair (d1,d2)
+//     also yields its mirror.  Thread (d1,d2) owns M[a][b] = K_el[(a,d1),(b,d2)] for all NNPE^2 node
+//     pairs in registers and needs only dN_X (NNPE*ND) + its ND x ND block of A per quadrature point:
+//     33 LDS per 264 DFMA instead of 108 per 297.
+//   * 32/NP elements per warp; an element never leaves its warp, so the kernel needs __syncwarp only.
+//   * phase G: the element's threads split its quadrature points, compute dN_X and JxW*A once and park
+//     them in shared memory (A packed symmetric).
+//   * phase K: register accumulation over the quadrature points.
+//   * phase S: K_el is staged in shared memory in GLOBAL order (rows = dofs of the row node, columns
+//     sorted by global node id), then the warp issues REDs over flat (row, col) indices: consecutive
+//     lanes hit consecutive CSR slots (runs of NF * #adjacent nodes doubles), 4-5x fewer sectors per RED.
+//   * the element -> CSR slot map is one contiguous 240-byte record per element (row offsets, column offsets,
+//     masks, node ranks) built on the device at update_dofs (k_build_emeta) and fetched with cp.async.
+#pragma once
+#include "kernels.cuh"
+
+namespace fec {
+
+template <int ND, int NNPE, int NQT>
+struct Mat2Params {
+  const double* X;
+  const double* U;
+  double* nz;
+  const int32_t* conn;       // [ne*NNPE] tile-ordered global node ids
+  const unsigned char* emeta;  // [ne * REC] per-element scatter record, see Mat2Layout (built by k_build_emeta)
+  const double* state_old;
+  int32_t ne, nq;
+  double props[kMaxProps];
+  Tables<ND, NNPE, NQT> tab;
+};
+
+template <int N>
+__host__ __device__ constexpr int sym_index(int i, int j) {  // packed upper triangle, i <= j
+  return i * N - (i * (i - 1)) / 2 + (j - i);
+}
+
+template <int ND, int NNPE, int NF, int NQ>
+struct Mat2Layout {
+  static constexpr int NP = NF * (NF + 1) / 2;
+  static constexpr int EPW = 32 / NP;
+  static constexpr int NDF = NF * ND;
+  static constexpr int ASZ = NDF * (NDF + 1) / 2;
+  static constexpr int SLOT = NNPE * ND + ASZ;          // dN_X + packed JxW*A
+  static constexpr int NROW = NNPE * NF;
+  static constexpr int RSTRIDE = NROW + 1;              // padded row stride of the staged K_el
+  static constexpr int KSZ = NROW * RSTRIDE;
+  static constexpr int BODY = (NQ * SLOT > KSZ) ? NQ * SLOT : KSZ;
+  // per-element scatter record (global, contiguous; copied verbatim into shared memory with cp.async):
+  //   uint32 rowstart[NROW]  (0xFFFFFFFF = row eliminated)   CSR offset of the row of dof (b, d)
+  //   uint16 ecol[NNPE][NNPE]                                ecol[b][k]: column offset of the k-th sorted node in row node b
+  //   uint8  mask[NNPE]                                      kept-dof mask of the k-th sorted node
+  //   uint8  rank[NNPE]                                      rank of local node a among the element's sorted nodes
+  static constexpr int OFF_EC = NROW * 4;
+  static constexpr int OFF_MK = OFF_EC + NNPE * NNPE * 2;
+  static constexpr int OFF_RK = OFF_MK + NNPE;
+  static constexpr int REC = ((OFF_RK + NNPE + 15) / 16) * 16;
+  static constexpr int META = REC / 8;
+  static constexpr int BODY16 = ((BODY + 1) / 2) * 2;   // keep the record 16-byte aligned in shared memory
+  static constexpr int ELSM = BODY16 + META;            // 630 doubles for hex8/NF=3: 2*ELSM mod 32 = 12 -> no bank clashes
+  static_assert(ELSM % 2 == 0, "element stride must keep 16-byte alignment");
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void red_add_f64_pred(double* addr, double v, bool ok) {
+  asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p red.global.add.f64 [%0], %1; }" ::"l"(addr), "d"(v),
+               "r"((int)ok)
+               : "memory");
+}
+
+template <int ND, int NNPE, int NF, int NQT, class Phys, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat2Params<ND, NNPE, NQT> p) {
+  static_assert(NQT > 0, "k_mat2 is compiled for fixed quadrature rules");
+  using L = Mat2Layout<ND, NNPE, NF, NQT>;
+  constexpr int NP = L::NP, EPW = L::EPW, NDF = L::NDF, SLOT = L::SLOT, NROW = L::NROW, RS = L::RSTRIDE;
+  constexpr int NS = Phys::NS;
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int elw = lane / NP, t = lane % NP;
+  const bool lane_valid = elw < EPW;
+  const int e0 = (blockIdx.x * WARPS + warp) * EPW;      // first element of this warp
+  const int e = e0 + elw;
+  const bool active = lane_valid && e < p.ne;
+  double* wsm = smem + (size_t)warp * EPW * L::ELSM;
+  double* esm = wsm + (size_t)(lane_valid ? elw : 0) * L::ELSM;
+  // component pair of this thread: enumerate d1 <= d2
+  int d1 = 0, d2 = 0;
+  {
+    int k = t;
+#pragma unroll
+    for (int i = 0; i < NF; ++i)
+#pragma unroll
+      for (int j = i; j < NF; ++j) { if (k == 0) { d1 = i; d2 = j; } --k; }
+  }
+
+  // ---- meta: the warp's per-element scatter records are one contiguous run in global memory; fetch them
+  // asynchronously (LDGSTS) so the copy overlaps phase G.  Needed from phase S1 on.
+  {
+    const int nel = (p.ne - e0) < EPW ? (p.ne - e0) : EPW;
+    const unsigned char* g = p.emeta + (size_t)e0 * L::REC;
+    constexpr int CH = L::REC / 16;
+    for (int i = lane; i < nel * CH; i += 32) {
+      const int el = i / CH, r = i - el * CH;
+      cp_async16(reinterpret_cast<unsigned char*>(wsm + (size_t)el * L::ELSM + L::BODY16) + r * 16, g + (size_t)i * 16);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+
+  // ---- phase G: geometry + material tangent of the element's quadrature points, split over its threads
+  if (active) {
+    double x[NNPE][ND], u[NNPE][NF];
+#pragma unroll
+    for (int a = 0; a < NNPE; ++a) {
+      const int n = p.conn[(size_t)e * NNPE + a];
+#pragma unroll
+      for (int j = 0; j < ND; ++j) x[a][j] = p.X[(size_t)n * ND + j];
+#pragma unroll
+      for (int d = 0; d < NF; ++d) u[a][d] = p.U[(size_t)n * NF + d];
+    }
+    for (int q = t; q < NQT; q += NP) {
+      double J[ND][ND];
+#pragma unroll
+      for (int i = 0; i < ND; ++i)
+#pragma unroll
+        for (int j = 0; j < ND; ++j) {
+          double s = 0.0;
+#pragma unroll
+          for (int a = 0; a < NNPE; ++a) s = fma(x[a][i], p.tab.dN[q][a][j], s);
+          J[i][j] = s;
+        }
+      double Ji[ND][ND];
+      const double JxW = invert<ND>(J, Ji) * p.tab.w[q];
+      double* slot = esm + (size_t)q * SLOT;
+      double gu[NF][ND];
+#pragma unroll
+      for (int d = 0; d < NF; ++d)
+#pragma unroll
+        for (int k = 0; k < ND; ++k) gu[d][k] = 0.0;
+#pragma unroll
+      for (int a = 0; a < NNPE; ++a) {
+#pragma unroll
+        for (int k = 0; k < ND; ++k) {
+          double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < ND; ++j) s = fma(p.tab.dN[q][a][j], Ji[j][k], s);
+          slot[a * ND + k] = s;
+#pragma unroll
+          for (int d = 0; d < NF; ++d) gu[d][k] = fma(u[a][d], s, gu[d][k]);
+        }
+      }
+      double so[NS > 0 ? NS : 1];
+      if constexpr (NS > 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) so[s] = p.state_old[((size_t)s * p.nq + q) * p.ne + e];
+      }
+      double A[NDF][NDF];
+      Phys::tangent(gu, p.props, so, A);
+#pragma unroll
+      for (int i = 0; i < NDF; ++i)
+#pragma unroll
+        for (int j = i; j < NDF; ++j) slot[NNPE * ND + sym_index<NDF>(i, j)] = A[i][j] * JxW;
+    }
+  }
+  __syncwarp();
+
+  // ---- phase K: M[a][b] = sum_q sum_{j1,j2} dN_X[a][j1] A[(d1,j1)][(d2,j2)] dN_X[b][j2]
+  double M[NNPE][NNPE];
+#pragma unroll
+  for (int a = 0; a < NNPE; ++a)
+#pragma unroll
+    for (int b = 0; b < NNPE; ++b) M[a][b] = 0.0;
+  if (active) {
+    // packed indices of this thread's ND x ND block (d1 <= d2 so (d1,j1) <= (d2,j2) unless d1 == d2 and j1 > j2)
+    int aidx[ND][ND];
+#pragma unroll
+    for (int j1 = 0; j1 < ND; ++j1)
+#pragma unroll
+      for (int j2 = 0; j2 < ND; ++j2) {
+        const int i = d1 * ND + j1, j = d2 * ND + j2;
+        aidx[j1][j2] = NNPE * ND + (i <= j ? i * NDF - (i * (i - 1)) / 2 + (j - i) : j * NDF - (j * (j - 1)) / 2 + (i - j));
+      }
+#pragma unroll 1
+    for (int q = 0; q < NQT; ++q) {
+      const double* slot = esm + (size_t)q * SLOT;
+      double A9[ND][ND];
+#pragma unroll
+      for (int j1 = 0; j1 < ND; ++j1)
+#pragma unroll
+        for (int j2 = 0; j2 < ND; ++j2) A9[j1][j2] = slot[aidx[j1][j2]];
+      double g[NNPE][ND];
+#pragma unroll
+      for (int a = 0; a < NNPE; ++a)
+#pragma unroll
+        for (int k = 0; k < ND; ++k) g[a][k] = slot[a * ND + k];
+#pragma unroll
+      for (int b = 0; b < NNPE; ++b) {
+        double tb[ND];  // tb[j1] = sum_j2 A9[j1][j2] g[b][j2]
+#pragma unroll
+        for (int j1 = 0; j1 < ND; ++j1) {
+          double s = 0.0;
+#pragma unroll
+          for (int j2 = 0; j2 < ND; ++j2) s = fma(A9[j1][j2], g[b][j2], s);
+          tb[j1] = s;
+        }
+#pragma unroll
+        for (int a = 0; a < NNPE; ++a) {
+          double s = M[a][b];
+#pragma unroll
+          for (int j1 = 0; j1 < ND; ++j1) s = fma(g[a][j1], tb[j1], s);
+          M[a][b] = s;
+        }
+      }
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncwarp();  // every thread of the warp is done reading the slots (re-used as the K_el stage); records landed
+
+  // ---- phase S1: stage K_el in global order.  Storage row = dof of the ROW node, storage column =
+  // (rank of the column node among the element's sorted nodes, dof).  K_el is symmetric, so the reference's
+  // transposed COO convention and the CSR/CSC distinction do not change the values.
+  if (active) {
+    const uint8_t* rk = reinterpret_cast<const uint8_t*>(esm + L::BODY16) + L::OFF_RK;
+    int rnk[NNPE];
+#pragma unroll
+    for (int a = 0; a < NNPE; ++a) rnk[a] = rk[a];
+#pragma unroll
+    for (int a = 0; a < NNPE; ++a) {
+      const int ka = rnk[a];
+#pragma unroll
+      for (int b = 0; b < NNPE; ++b) {
+        const int kb = rnk[b];
+        // entry (row dof (a,d1), col dof (b,d2)) and its mirror (row (b,d2), col (a,d1))
+        esm[(a * NF + d1) * RS + kb * NF + d2] = M[a][b];
+        if (d1 != d2) esm[(b * NF + d2) * RS + ka * NF + d1] = M[a][b];
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- phase S2: REDs.  Lane = one storage column (sorted node rank k, dof dc) of the element; the warp walks
+  // the NROW rows, so one RED instruction covers one CSR row segment of the element: NROW consecutive-ish slots.
+  {
+    const int nel = (p.ne - e0) < EPW ? (p.ne - e0) : EPW;
+    const int col = lane < NROW ? lane : NROW - 1;
+    const int k = col / NF, dc = col - k * NF;
+    for (int el = 0; el < nel; ++el) {
+      const double* ks = wsm + (size_t)el * L::ELSM;
+      const unsigned char* rec = reinterpret_cast<const unsigned char*>(ks + L::BODY16);
+      const uint32_t* rs = reinterpret_cast<const uint32_t*>(rec);
+      const uint16_t* ec = reinterpret_cast<const uint16_t*>(rec + L::OFF_EC);
+      const unsigned mask = rec[L::OFF_MK + k];
+      const bool colok = (lane < NROW) && (mask & (1u << dc));
+      const int rank = __popc(mask & ((1u << dc) - 1u));
+      double* base = p.nz + rank;
+#pragma unroll
+      for (int b = 0; b < NNPE; ++b) {
+        double* cb = base + ec[b * NNPE + k];
+#pragma unroll
+        for (int dr = 0; dr < NF; ++dr) {
+          const int row = b * NF + dr;
+          const uint32_t r0 = rs[row];
+          red_add_f64_pred(cb + r0, ks[row * RS + col], colok && r0 != 0xFFFFFFFFu);
+        }
+      }
+    }
+  }
+}
+
+// element -> CSR column-offset table, rebuilt whenever update_dofs changes the kept-dof masks
+__global__ void k_build_emeta(const int32_t* conn, const uint8_t* epos, const int32_t* adjptr, const uint16_t* coloff,
+                              const uint8_t* freemask, const int64_t* rowstart, unsigned char* emeta, int nnpe, int nf,
+                              int rec, int64_t ne);
+
+template <int ND, int NNPE, int NF, int NQT, class Phys, int WARPS>
+void run_mat2(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
+  using L = Mat2Layout<ND, NNPE, NF, NQT>;
+  auto pp = std::make_unique<Mat2Params<ND, NNPE, NQT>>();
+  auto& p = *pp;
+  p.X = h->d_X.p; p.U = a.U; p.nz = a.nz;
+  FEC_REQUIRE(h->nnz < (int64_t)0xFFFFFFFFll, "k_mat2 needs nnz < 2^32 (32-bit row offsets in the scatter records)");
+  FEC_REQUIRE((int)b.emeta_rec == L::REC, "scatter record size mismatch");
+  p.conn = b.d_conn_perm.p; p.emeta = b.d_emeta.p;
+  p.state_old = b.d_state_old.p;
+  p.ne = (int32_t)b.ne; p.nq = b.nq;
+  for (int i = 0; i < kMaxProps; ++i) p.props[i] = i < (int)b.props.size() ? b.props[i] : 0.0;
+  fill_tables<ND, NNPE, NQT>(b, p.tab);
+  const size_t smem = (size_t)WARPS * L::EPW * L::ELSM * sizeof(double);
+  const int epc = WARPS * L::EPW;
+  const int grid = (int)((b.ne + epc - 1) / epc);
+  timing_begin(h);
+  // K_el is symmetric here, so CSR and CSC storage receive the same values through the same addressing
+  auto kern = k_mat2<ND, NNPE, NF, NQT, Phys, WARPS>;
+  FEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, WARPS * 32, smem, h->stream>>>(p);
+  FEC_CUDA(cudaGetLastError());
+  timing_end(h);
+  h->launches++;
+}
+
+}  // namespace fec

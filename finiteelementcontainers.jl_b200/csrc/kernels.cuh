@@ -584,6 +584,5 @@ void run_vec_modes(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
   }
 }
 
-constexpr int kTE = 256;  // elements per tile / threads per CTA of the vector kernels
 
 }  // namespace fec

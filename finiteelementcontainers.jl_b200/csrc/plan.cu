@@ -360,6 +360,7 @@ void build_dof_structures(fecb200_handle* h) {
   h->d_nz_mass.release();
   h->matrix_ready = true;
   h->stiff_adjusted = h->mass_adjusted = false;
+  build_ecol(h);
 }
 
 // rowptr/colval (CSR) or colptr/rowval (CSC), Int64 1-based, as SparseArrays.sparse! +
