@@ -19,6 +19,7 @@ OBJ = os.path.join(HERE, "build")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfecb200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+METIS = "/usr/local/cuda/targets/x86_64-linux/lib/libmetis_static.a"  # 64-bit idx_t build shipped with the toolkit
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp,-O3", "--expt-relaxed-constexpr"]
 # sweeps: FECB200_DEFINES="-DFEC_TE=128 -DFEC_MINB3=3" FECB200_VARIANT=te128_b3 python build.py
@@ -62,7 +63,7 @@ def build(force=False, jobs=None, verbose=True):
                     raise RuntimeError(f"nvcc failed on {src}")
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if todo or not os.path.exists(LIB):
-        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fopenmp", "-lgomp"]
+        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, METIS, "-Xcompiler", "-fopenmp", "-lgomp"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -6,6 +6,8 @@
 
 namespace fec {
 thread_local std::string g_last_error;
+int metis_mesh_dual(int64_t, int64_t, const int64_t*, const int64_t*, int64_t, int64_t, int64_t*, int64_t*);
+int metis_graph(int64_t, const int64_t*, const int64_t*, int64_t, int64_t*);
 
 void launch_vector(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
   switch (b.elem_type) {
@@ -55,6 +57,7 @@ static void assemble_vector_impl(fecb200_handle* h, int mode, const double* Uu_d
   if (Vu_dev) k_update_field(h, h->d_V.p, Vu_dev, false);  // V's BC slots stay 0 (Parameters.jl:415-425)
   h->last_ms = 0.f;
   for (auto& b : h->blocks) {
+    if (b.halo) continue;  // neighbour-owned elements: their contribution arrives through the halo exchange
     VecLaunch a{h->d_U.p, Vu_dev ? h->d_V.p : nullptr, out_field, mode};
     launch_vector(h, b, a);
   }
@@ -67,7 +70,7 @@ static double* nz_for_kind(fecb200_handle* h, int kind, bool alloc) {
   FEC_REQUIRE(h->matrix_ready, "matrix pattern not built");
   if (kind == FECB200_STIFFNESS) return h->d_nz_stiff.p;
   if (kind == FECB200_MASS) {
-    if (!h->d_nz_mass.p && alloc) { h->d_nz_mass.alloc(h->nnz); h->d_nz_mass.zero(h->stream); }
+    if (!h->d_nz_mass.p && alloc) { h->d_nz_mass.alloc(h->nnz + 32); h->d_nz_mass.zero(h->stream); }
     return h->d_nz_mass.p;
   }
   throw Error("fecb200: matrix kind must be FECB200_STIFFNESS or FECB200_MASS");
@@ -86,6 +89,7 @@ static void apply_operator(fecb200_handle* h, bool matrix_free, const double* x,
     FEC_CUDA(cudaMemsetAsync(h->d_Av.p, 0, h->ndof * sizeof(double), h->stream));
     k_update_field(h, h->d_V.p, x, false);
     for (auto& b : h->blocks) {
+      if (b.halo) continue;
       VecLaunch a{h->d_U.p, h->d_V.p, h->d_Av.p, MODE_ACTION_STIFFNESS};
       launch_vector(h, b, a);
     }
@@ -164,6 +168,7 @@ int fecb200_create(const fecb200_mesh_desc* mesh, const fecb200_opts* opts, fecb
   h->device = opts->device;
   h->opts = *opts;
   h->nd = mesh->ndim; h->nf = mesh->nf; h->nn = mesh->nnodes; h->ndof = h->nn * h->nf;
+  h->n_owned_nodes = h->nn;
   FEC_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   FEC_CUDA(cudaEventCreate(&h->ev0));
   FEC_CUDA(cudaEventCreate(&h->ev1));
@@ -480,6 +485,7 @@ int fecb200_assemble_action_full(fecb200_handle* h, int32_t kind, const double* 
   FEC_CUDA(cudaMemsetAsync(h->d_Av.p, 0, h->ndof * sizeof(double), h->stream));
   h->last_ms = 0.f;
   for (auto& b : h->blocks) {
+    if (b.halo) continue;
     VecLaunch a{h->d_U.p, h->d_V.p, h->d_Av.p, kind == FECB200_STIFFNESS ? MODE_ACTION_STIFFNESS : MODE_ACTION_MASS};
     launch_vector(h, b, a);
   }
@@ -589,6 +595,36 @@ int fecb200_newton_solve(fecb200_handle* h, double* Uu, int32_t max_iters, doubl
   FEC_API_END
 }
 
+int fecb200_metis_part_mesh_dual(int64_t ne, int64_t nn, const int64_t* eptr, const int64_t* eind, int64_t ncommon,
+                                 int64_t nparts, int64_t* epart, int64_t* npart) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(ne > 0 && nn > 0 && eptr && eind && epart && npart && nparts >= 1, "bad METIS arguments");
+  const int rc = metis_mesh_dual(ne, nn, eptr, eind, ncommon, nparts, epart, npart);
+  FEC_REQUIRE(rc == 1, "METIS_PartMeshDual failed");
+  FEC_API_END
+}
+
+int fecb200_metis_part_graph(int64_t nv, const int64_t* xadj, const int64_t* adjncy, int64_t nparts, int64_t* part) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(nv > 0 && xadj && adjncy && part && nparts >= 1, "bad METIS arguments");
+  const int rc = metis_graph(nv, xadj, adjncy, nparts, part);
+  FEC_REQUIRE(rc == 1, "METIS_PartGraphKway failed");
+  FEC_API_END
+}
+
+int fecb200_partition_setup(fecb200_handle* h, int64_t n_owned_nodes, const int32_t* block_is_halo) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h, "null handle");
+  FEC_REQUIRE(n_owned_nodes >= 0 && n_owned_nodes <= h->nn, "n_owned_nodes out of range");
+  FEC_CUDA(cudaSetDevice(h->device));
+  h->n_owned_nodes = n_owned_nodes;
+  for (size_t b = 0; b < h->blocks.size(); ++b) h->blocks[b].halo = block_is_halo && block_is_halo[b] != 0;
+  FEC_REQUIRE(h->opts.matrix_free || h->opts.matrix_type == FECB200_CSR, "partitioned assembly stores owned ROWS: use CSR");
+  build_matrix_structure(h);  // DOF maps and Dirichlet values are untouched
+  FEC_CUDA(cudaStreamSynchronize(h->stream));
+  FEC_API_END
+}
+
 int fecb200_halo_setup(fecb200_handle* h, int32_t n_neighbors, const int32_t* ranks, const int64_t* send_ptr,
                        const int64_t* send_nodes, const int64_t* recv_ptr, const int64_t* recv_nodes) {
   FEC_API_BEGIN
@@ -609,7 +645,6 @@ int fecb200_halo_setup(fecb200_handle* h, int32_t n_neighbors, const int32_t* ra
   }
   h->d_send_nodes.upload(sn, h->stream);
   h->d_recv_nodes.upload(rn, h->stream);
-  h->d_sendbuf.alloc(sn.size() * h->nf);
   FEC_API_END
 }
 
@@ -623,19 +658,24 @@ static double* field_ptr(fecb200_handle* h, int which) {
   }
 }
 
-int fecb200_halo_pack(fecb200_handle* h, int32_t which, double** sendbuf_dev, int64_t* n_doubles) {
+int fecb200_halo_pack(fecb200_handle* h, int32_t which, double* sendbuf_dev) {
   FEC_API_BEGIN
-  FEC_REQUIRE(h && sendbuf_dev, "null argument");
+  FEC_REQUIRE(h && (sendbuf_dev || h->d_send_nodes.n == 0), "null argument");
   FEC_CUDA(cudaSetDevice(h->device));
-  halo_pack(h, field_ptr(h, which), h->d_sendbuf.p);
-  *sendbuf_dev = h->d_sendbuf.p;
-  if (n_doubles) *n_doubles = (int64_t)h->d_sendbuf.n;
+  halo_pack(h, field_ptr(h, which), sendbuf_dev);
+  FEC_API_END
+}
+
+int fecb200_halo_send_size(fecb200_handle* h, int64_t* n_doubles) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && n_doubles, "null argument");
+  *n_doubles = (int64_t)h->d_send_nodes.n * h->nf;
   FEC_API_END
 }
 
 int fecb200_halo_unpack_add(fecb200_handle* h, int32_t which, const double* recvbuf_dev) {
   FEC_API_BEGIN
-  FEC_REQUIRE(h && recvbuf_dev, "null argument");
+  FEC_REQUIRE(h && (recvbuf_dev || h->d_recv_nodes.n == 0), "null argument");
   FEC_CUDA(cudaSetDevice(h->device));
   halo_unpack_add(h, field_ptr(h, which), recvbuf_dev);
   FEC_API_END

@@ -85,6 +85,7 @@ struct BlockPlan {
   std::vector<double> N, dN, w, props;
   std::vector<int32_t> conn0;  // [ne*nnpe] 0-based node ids, caller's element order
   // tiling (vector kernels): elements permuted into locality-ordered tiles of `te` elements
+  bool halo = false;  // neighbour-owned elements (partitioned runs): matrix assembly only
   int te = 0, ntiles = 0, max_tile_nodes = 0;
   std::vector<int32_t> perm;   // tile order -> original element index
   DevBuf<int32_t> d_perm;
@@ -107,6 +108,7 @@ struct fecb200_handle {
   fecb200_opts opts{};
   int nd = 0, nf = 0;
   int64_t nn = 0, ndof = 0;
+  int64_t n_owned_nodes = 0;  // == nn unless fecb200_partition_setup was called
   std::vector<fec::BlockPlan> blocks;
   double t = 0.0, dt = 0.0;
 
@@ -162,6 +164,7 @@ namespace fec {
 void build_block_tiles(fecb200_handle* h, BlockPlan& b, const double* coords);
 void build_adjacency(fecb200_handle* h);
 void build_dof_structures(fecb200_handle* h);
+void build_matrix_structure(fecb200_handle* h);
 void export_pattern(fecb200_handle* h, int64_t* ptr, int64_t* idx);
 
 // dispatch (one translation unit per element family)

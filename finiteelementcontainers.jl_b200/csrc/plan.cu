@@ -13,7 +13,42 @@
 #include <numeric>
 #include <omp.h>
 
+// METIS (libmetis_static.a shipped with the CUDA toolkit; 64-bit idx_t, 32-bit real_t; no metis.h in the image)
+extern "C" {
+int METIS_SetDefaultOptions(int64_t* options);
+int METIS_PartMeshDual(int64_t* ne, int64_t* nn, int64_t* eptr, int64_t* eind, int64_t* vwgt, int64_t* vsize,
+                       int64_t* ncommon, int64_t* nparts, float* tpwgts, int64_t* options, int64_t* objval,
+                       int64_t* epart, int64_t* npart);
+int METIS_PartGraphKway(int64_t* nvtxs, int64_t* ncon, int64_t* xadj, int64_t* adjncy, int64_t* vwgt, int64_t* vsize,
+                        int64_t* adjwgt, int64_t* nparts, float* tpwgts, float* ubvec, int64_t* options,
+                        int64_t* edgecut, int64_t* part);
+}
+
 namespace fec {
+
+int metis_mesh_dual(int64_t ne, int64_t nn, const int64_t* eptr, const int64_t* eind, int64_t ncommon, int64_t nparts,
+                    int64_t* epart, int64_t* npart) {
+  int64_t options[40];
+  METIS_SetDefaultOptions(options);
+  options[17] = 0;  // METIS_OPTION_NUMBERING = C-style
+  int64_t objval = 0;
+  if (nparts == 1) {
+    std::fill(epart, epart + ne, 0);
+    std::fill(npart, npart + nn, 0);
+    return 1;
+  }
+  return METIS_PartMeshDual(&ne, &nn, const_cast<int64_t*>(eptr), const_cast<int64_t*>(eind), nullptr, nullptr, &ncommon,
+                            &nparts, nullptr, options, &objval, epart, npart);
+}
+int metis_graph(int64_t nv, const int64_t* xadj, const int64_t* adjncy, int64_t nparts, int64_t* part) {
+  int64_t options[40];
+  METIS_SetDefaultOptions(options);
+  options[17] = 0;
+  int64_t ncon = 1, cut = 0;
+  if (nparts == 1) { std::fill(part, part + nv, 0); return 1; }
+  return METIS_PartGraphKway(&nv, &ncon, const_cast<int64_t*>(xadj), const_cast<int64_t*>(adjncy), nullptr, nullptr, nullptr,
+                             &nparts, nullptr, nullptr, options, &cut, part);
+}
 
 static inline uint64_t spread3(uint32_t v) {  // 21 bits -> every third bit
   uint64_t x = v & 0x1fffff;
@@ -303,6 +338,14 @@ void build_dof_structures(fecb200_handle* h) {
   h->d_Vu.alloc(ndof);
   h->d_out.alloc(ndof);
 
+  build_matrix_structure(h);
+}
+
+// dof-level CSR offsets on top of the node adjacency (rebuilt by update_dofs and partition_setup)
+void build_matrix_structure(fecb200_handle* h) {
+  const int nf = h->nf;
+  const int64_t nn = h->nn, ndof = h->ndof;
+  const std::vector<int64_t>& d2u = h->dof_to_unknown;
   // ---- CSR structure (matrix_free assemblers carry none: SparseMatrixAssembler.jl:82-88)
   h->matrix_ready = false;
   if (h->opts.matrix_free) return;
@@ -336,7 +379,7 @@ void build_dof_structures(fecb200_handle* h) {
   h->rowstart_h.assign(ndof, -1);
   std::vector<int64_t> diag(ndof, -1);
   int64_t pos = 0;
-  for (int64_t n = 0; n < nn; ++n) {
+  for (int64_t n = 0; n < h->n_owned_nodes; ++n) {  // ghost rows are not stored
     const unsigned m = h->freemask_h[n];
     // self position
     const int32_t* row = &h->adj[h->adjptr[n]];
@@ -350,12 +393,13 @@ void build_dof_structures(fecb200_handle* h) {
     }
   }
   h->nnz = pos;
-  h->nmat = condensed ? ndof : h->n_unknowns;
+  h->nmat = 0;
+  for (int64_t g = 0; g < h->n_owned_nodes * nf; ++g) h->nmat += (h->rowstart_h[g] >= 0);
   h->d_coloff.upload(coloff, h->stream);
   h->d_freemask.upload(h->freemask_h, h->stream);
   h->d_rowstart.upload(h->rowstart_h, h->stream);
   h->d_diagslot.upload(diag, h->stream);
-  h->d_nz_stiff.alloc(h->nnz);
+  h->d_nz_stiff.alloc(h->nnz + 32);  // + one dummy slot per lane for the branch-free RED stream of k_mat2
   h->d_nz_stiff.zero(h->stream);
   h->d_nz_mass.release();
   h->matrix_ready = true;
@@ -373,7 +417,7 @@ void export_pattern(fecb200_handle* h, int64_t* ptr, int64_t* idx) {
   const int64_t nn = h->nn;
   const bool condensed = h->opts.condensed != 0;
   int64_t row = 0;
-  for (int64_t n = 0; n < nn; ++n) {
+  for (int64_t n = 0; n < std::min(nn, h->n_owned_nodes); ++n) {
     const unsigned m = h->freemask_h[n];
     for (int d = 0; d < nf; ++d) {
       if (!(m & (1u << d))) continue;

@@ -18,5 +18,7 @@ from .assemblers import (SparseMatrixAssembler, Parameters, create_parameters, u
                          assemble_mass, assemble_matrix_action, assemble_matrix_free_action,
                          assemble_matrix_free_action_full, hvp, full_field)
 from .solvers import IterativeLinearSolver, NewtonSolver, QuasiStaticIntegrator
+from .partition import (Partition, partition_mesh, structured_brick_partition, metis_partition_elements,
+                        metis_partition_graph)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

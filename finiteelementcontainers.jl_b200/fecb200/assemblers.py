@@ -311,7 +311,8 @@ def _sparse(asm, kind):
     nz = np.empty(len(idx))
     check(lib.fecb200_matrix_values(asm._require(), kind, _lib.ptr(nz)))
     cls = sp.csr_matrix if asm.sparse_matrix_type == "csr" else sp.csc_matrix
-    return cls((nz, idx - 1, ptr - 1), shape=(n, n))
+    ncols = asm.sizes()[2]  # == n except for rank-local (partitioned) assemblers: owned rows x local columns
+    return cls((nz, idx - 1, ptr - 1), shape=(n, ncols) if asm.sparse_matrix_type == "csr" else (ncols, n))
 
 
 def _stiffness_accessor(asm):

@@ -1,0 +1,289 @@
+"""Domain decomposition for multi-GPU assembly (ext/PartitionedArraysExt.jl, ext/MetisExt.jl).
+
+One process per GPU.  The mesh is split by ELEMENTS (METIS k-way on the element dual graph, or bricks
+for structured meshes); a node is owned by the lowest rank among the owners of the elements that touch
+it (test/ext/script.jl:29-32 uses `minimum` the same way).  Every rank holds a rank-local mesh:
+
+    local nodes    = owned nodes first, then ghosts            (PartitionedArrays OwnAndGhostIndices)
+    block "owned"  = the elements this rank owns               -> residual / action assembly
+    block "halo"   = neighbour-owned elements touching an owned node -> only the Jacobian uses them,
+                     so each rank assembles ALL of its owned rows locally, with no exchange.
+
+Residual: contributions to ghost nodes are packed on the device, exchanged with NCCL send/recv and
+added into the owner's entries (the reverse halo / "assemble" step of PVector, :469-481).
+`local_to_global` / `local_to_owner` are exactly what `LocalIndices(n_global, rank, l2g, l2o)` takes
+(ext/PartitionedArraysExt.jl:228-232).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+from .fields import H1Field
+from .meshes import AbstractMesh
+
+
+def metis_partition_elements(mesh, nparts, ncommon=None):
+    """epart (0-based part id per element, blocks concatenated) from METIS_PartMeshDual."""
+    conns = [mesh.element_conns[b] - 1 for b in mesh.element_block_names]
+    ne = sum(c.shape[1] for c in conns)
+    nn = mesh.num_nodes()
+    eptr = np.zeros(ne + 1, dtype=np.int64)
+    eptr[1:] = np.cumsum(np.concatenate([np.full(c.shape[1], c.shape[0]) for c in conns]))
+    eind = np.concatenate([np.ascontiguousarray(c.T).reshape(-1) for c in conns]).astype(np.int64)
+    if ncommon is None:
+        ncommon = 2 if mesh.num_dimensions() == 2 else 3
+    epart = np.zeros(ne, dtype=np.int64)
+    npart = np.zeros(nn, dtype=np.int64)
+    check(lib.fecb200_metis_part_mesh_dual(ne, nn, _lib.i64(eptr)[1], _lib.i64(eind)[1], ncommon, nparts,
+                                           epart.ctypes.data_as(_lib.c_i64p), npart.ctypes.data_as(_lib.c_i64p)))
+    return epart
+
+
+def metis_partition_graph(xadj, adjncy, nparts):
+    """Metis.partition(graph, nparts) (ext/MetisExt.jl:6-14): 0-based CSR adjacency -> part ids."""
+    xadj, xp = _lib.i64(xadj)
+    adjncy, ap = _lib.i64(adjncy)
+    part = np.zeros(len(xadj) - 1, dtype=np.int64)
+    check(lib.fecb200_metis_part_graph(len(part), xp, ap, nparts, part.ctypes.data_as(_lib.c_i64p)))
+    return part
+
+
+class _LocalMesh(AbstractMesh):
+    pass
+
+
+class Partition:
+    """Rank-local decomposition data + halo exchange."""
+
+    def __init__(self, rank, nparts, local_to_global, local_to_owner, n_owned_nodes, n_owned_elements,
+                 n_global_elements, n_global_nodes, send, recv, has_halo_block):
+        self.rank, self.nparts = rank, nparts
+        self.local_to_global = np.asarray(local_to_global, dtype=np.int64)   # 1-based global node ids
+        self.local_to_owner = np.asarray(local_to_owner, dtype=np.int64)     # 0-based owner rank per local node
+        self.n_owned_nodes = int(n_owned_nodes)
+        self.n_owned_elements = int(n_owned_elements)
+        self.n_global_elements = int(n_global_elements)
+        self.n_global_nodes = int(n_global_nodes)
+        # {neighbour rank: 1-based local node ids}, both sorted by GLOBAL node id so the two sides agree
+        self.send = {int(r): np.asarray(v, dtype=np.int64) for r, v in sorted(send.items()) if len(v)}
+        self.recv = {int(r): np.asarray(v, dtype=np.int64) for r, v in sorted(recv.items()) if len(v)}
+        self.neighbors = sorted(set(self.send) | set(self.recv))
+        self.has_halo_block = has_halo_block
+        self._sendbuf = self._recvbuf = None
+        self._nf = None
+
+    # ---- library wiring ---------------------------------------------------------------------------
+    def attach(self, asm):
+        """partition_setup (ghost rows dropped, halo block skipped by vector assembly) + halo lists"""
+        h = asm._require()
+        nb = asm.dof.var.fspace.num_blocks()
+        flags = (C.c_int32 * nb)(*([0] + [1] * (nb - 1) if self.has_halo_block else [0] * nb))
+        check(lib.fecb200_partition_setup(h, self.n_owned_nodes, flags))
+        asm._pattern = None
+        nbrs = np.array(self.neighbors, dtype=np.int32)
+        sp = np.zeros(len(nbrs) + 1, dtype=np.int64)
+        rp = np.zeros(len(nbrs) + 1, dtype=np.int64)
+        sn, rn = [], []
+        for i, r in enumerate(nbrs):
+            s, v = self.send.get(int(r), np.zeros(0, dtype=np.int64)), self.recv.get(int(r), np.zeros(0, dtype=np.int64))
+            sn.append(s); rn.append(v)
+            sp[i + 1], rp[i + 1] = sp[i] + len(s), rp[i] + len(v)
+        sn = np.concatenate(sn) if sn else np.zeros(0, dtype=np.int64)
+        rn = np.concatenate(rn) if rn else np.zeros(0, dtype=np.int64)
+        check(lib.fecb200_halo_setup(h, len(nbrs), nbrs.ctypes.data_as(_lib.c_i32p), _lib.i64(sp)[1], _lib.i64(sn)[1],
+                                     _lib.i64(rp)[1], _lib.i64(rn)[1]))
+        self._nf = asm.dof.nf
+        self._send_counts = [int(sp[i + 1] - sp[i]) * self._nf for i in range(len(nbrs))]
+        self._recv_counts = [int(rp[i + 1] - rp[i]) * self._nf for i in range(len(nbrs))]
+
+    def halo_sum_residual(self, asm, stream=None, field=_lib.FIELD_RESIDUAL):
+        """ghost -> owner accumulation of the assembled residual (device pack, NCCL send/recv, device add)"""
+        import torch
+        h = asm._require()
+        if self._sendbuf is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            self._sendbuf = torch.empty(max(1, sum(self._send_counts)), dtype=torch.float64, device=dev)
+            self._recvbuf = torch.empty(max(1, sum(self._recv_counts)), dtype=torch.float64, device=dev)
+        ctx = torch.cuda.stream(stream) if stream is not None else _nullctx()
+        with ctx:
+            check(lib.fecb200_halo_pack(h, field, _lib.ptr(self._sendbuf)))
+            exchange(self.neighbors, self._sendbuf, self._send_counts, self._recvbuf, self._recv_counts)
+            check(lib.fecb200_halo_unpack_add(h, field, _lib.ptr(self._recvbuf)))
+
+
+class _nullctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def exchange(neighbors, sendbuf, send_counts, recvbuf, recv_counts):
+    """One batched point-to-point exchange with every neighbour (ncclGroupStart/Send/Recv/End under
+    torch.distributed; works with gloo on CPU tensors for the host-logic tests)."""
+    import torch.distributed as dist
+    ops, so, ro = [], 0, 0
+    for r, ns, nr in zip(neighbors, send_counts, recv_counts):
+        if ns:
+            ops.append(dist.P2POp(dist.isend, sendbuf[so:so + ns], r))
+        if nr:
+            ops.append(dist.P2POp(dist.irecv, recvbuf[ro:ro + nr], r))
+        so += ns
+        ro += nr
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+# --------------------------------------------------------------------------------------------------
+# general builder: any single-block mesh + an element partition (e.g. from METIS)
+# --------------------------------------------------------------------------------------------------
+def partition_mesh(mesh, epart, nparts, rank):
+    """Rank-local mesh + Partition from a global mesh and `epart` (0-based owner of every element).
+    Every rank can call this with the same global data (no communication needed)."""
+    assert len(mesh.element_block_names) == 1, "partition_mesh handles single-block meshes"
+    bname = mesh.element_block_names[0]
+    conn = mesh.element_conns[bname] - 1                     # (NNPE, NE) 0-based
+    nn = mesh.num_nodes()
+    epart = np.asarray(epart, dtype=np.int64)
+    owner = np.full(nn, nparts, dtype=np.int64)
+    np.minimum.at(owner, conn.reshape(-1), np.broadcast_to(epart, conn.shape).reshape(-1))
+    mine_e = np.nonzero(epart == rank)[0]
+    owned_nodes = np.nonzero(owner == rank)[0]
+    own_mask = np.zeros(nn, dtype=bool)
+    own_mask[owned_nodes] = True
+    halo_e = np.nonzero(own_mask[conn].any(axis=0) & (epart != rank))[0]
+    touched_own = np.unique(conn[:, mine_e])
+    all_local = np.unique(np.concatenate([touched_own, np.unique(conn[:, halo_e]) if len(halo_e) else touched_own,
+                                          owned_nodes]))
+    ghosts = all_local[~own_mask[all_local]]
+    l2g = np.concatenate([owned_nodes, ghosts])
+    g2l = np.full(nn, -1, dtype=np.int64)
+    g2l[l2g] = np.arange(len(l2g))
+    # halo lists (both sides sorted by global id)
+    res_ghosts = touched_own[~own_mask[touched_own]]
+    send = {int(r): g2l[res_ghosts[owner[res_ghosts] == r]] + 1 for r in np.unique(owner[res_ghosts])}
+    recv = {}
+    for r in range(nparts):
+        if r == rank:
+            continue
+        er = np.nonzero(epart == r)[0]
+        if not len(er):
+            continue
+        tr = np.unique(conn[:, er])
+        hit = tr[own_mask[tr]]
+        if len(hit):
+            recv[r] = g2l[hit] + 1
+    lm = _LocalMesh()
+    lm.nodal_coords = H1Field(np.asarray(mesh.nodal_coords)[:, l2g])
+    et = mesh.element_types[bname]
+    lm.element_block_names = ["owned"] + (["halo"] if len(halo_e) else [])
+    lm.element_types = {b: et for b in lm.element_block_names}
+    lm.element_conns = {"owned": g2l[conn[:, mine_e]] + 1}
+    if len(halo_e):
+        lm.element_conns["halo"] = g2l[conn[:, halo_e]] + 1
+
+    def restrict(sets):
+        out = {}
+        for k, v in sets.items():
+            loc = g2l[np.asarray(v, dtype=np.int64) - 1]
+            out[k] = loc[loc >= 0] + 1
+        return out
+
+    lm.nodeset_nodes = restrict(mesh.nodeset_nodes)
+    lm.sideset_nodes = restrict(mesh.sideset_nodes)
+    part = Partition(rank, nparts, l2g + 1, owner[l2g], len(owned_nodes), len(mine_e), conn.shape[1], nn, send, recv,
+                     bool(len(halo_e)))
+    part.owned_elements, part.halo_elements = mine_e, halo_e
+    return lm, part
+
+
+# --------------------------------------------------------------------------------------------------
+# structured bricks for the weak-scaling benchmark: every rank builds ONLY its own piece
+# --------------------------------------------------------------------------------------------------
+def structured_brick_partition(F, n, grid, rank):
+    """Rank-local hex8 mesh of the global (gx*n) x (gy*n) x (gz*n) element grid split into gx*gy*gz bricks
+    of n^3 elements (what METIS returns on this grid, without building the 57M-node global mesh on every
+    rank).  Global numbering = StructuredMesh's (nodes x fastest; elements ex outer, ez inner)."""
+    gx, gy, gz = grid
+    P = gx * gy * gz
+    px, py, pz = rank % gx, (rank // gx) % gy, rank // (gx * gy)
+    Ng = np.array([gx * n + 1, gy * n + 1, gz * n + 1], dtype=np.int64)
+    pc, g = np.array([px, py, pz]), np.array(grid)
+    lo = pc * n                                       # first global node index of the brick
+    hal = (pc < g - 1).astype(np.int64)               # one halo element layer on the high sides
+    nloc = n + 1 + hal                                # local node box
+    ii, jj, kk = np.meshgrid(np.arange(nloc[0]), np.arange(nloc[1]), np.arange(nloc[2]), indexing="ij")
+    ig, jg, kg = ii + lo[0], jj + lo[1], kk + lo[2]
+    gid = (ig + Ng[0] * (jg + Ng[1] * kg)).reshape(-1)   # 0-based global node id
+
+    def owner_of(i, j, k):
+        ox = np.minimum(np.maximum(0, (i - 1) // n), gx - 1)
+        oy = np.minimum(np.maximum(0, (j - 1) // n), gy - 1)
+        oz = np.minimum(np.maximum(0, (k - 1) // n), gz - 1)
+        return ox + gx * (oy + gy * oz)
+
+    own = owner_of(ig, jg, kg).reshape(-1)
+    is_own = own == rank
+    order = np.concatenate([np.nonzero(is_own)[0][np.argsort(gid[is_own], kind="stable")],
+                            np.nonzero(~is_own)[0][np.argsort(gid[~is_own], kind="stable")]])
+    box2loc = np.empty(len(gid), dtype=np.int64)
+    box2loc[order] = np.arange(len(gid))
+    l2g, l2o = gid[order], own[order]
+    n_owned = int(is_own.sum())
+    box = lambda i, j, k: (i * nloc[1] + j) * nloc[2] + k   # index into the meshgrid('ij') raveling
+
+    def conn_of(ex, ey, ez):  # local box element coordinates -> (8, NE) local node ids (1-based)
+        c = [box(ex, ey, ez), box(ex + 1, ey, ez), box(ex + 1, ey + 1, ez), box(ex, ey + 1, ez),
+             box(ex, ey, ez + 1), box(ex + 1, ey, ez + 1), box(ex + 1, ey + 1, ez + 1), box(ex, ey + 1, ez + 1)]
+        return box2loc[np.stack(c)] + 1
+
+    nel = nloc - 1
+    ex, ey, ez = np.meshgrid(np.arange(nel[0]), np.arange(nel[1]), np.arange(nel[2]), indexing="ij")
+    ex, ey, ez = ex.reshape(-1), ey.reshape(-1), ez.reshape(-1)
+    inside = (ex < n) & (ey < n) & (ez < n)
+    lm = _LocalMesh()
+    h = 1.0 / n
+    X = np.stack([ig.reshape(-1) * h, jg.reshape(-1) * h, kg.reshape(-1) * h])[:, order]
+    lm.nodal_coords = H1Field(X)
+    lm.element_block_names = ["owned"] + (["halo"] if (~inside).any() else [])
+    lm.element_types = {b: "HEX8" for b in lm.element_block_names}
+    lm.element_conns = {"owned": conn_of(ex[inside], ey[inside], ez[inside])}
+    if (~inside).any():
+        lm.element_conns["halo"] = conn_of(ex[~inside], ey[~inside], ez[~inside])
+    jgo, igo, kgo = jg.reshape(-1)[order], ig.reshape(-1)[order], kg.reshape(-1)[order]
+    loc = np.arange(1, len(l2g) + 1)
+    lm.nodeset_nodes = {"bottom": loc[jgo == 0], "top": loc[jgo == Ng[1] - 1], "left": loc[igo == 0],
+                        "right": loc[igo == Ng[0] - 1], "back": loc[kgo == 0], "front": loc[kgo == Ng[2] - 1]}
+    lm.sideset_nodes = dict(lm.nodeset_nodes)
+    # residual halo: ghosts touched by OWNED elements = nodes of the brick box not owned by this rank
+    inbrick = ((ii <= n) & (jj <= n) & (kk <= n)).reshape(-1)[order]
+    send = {}
+    cand = np.nonzero(inbrick & (l2o != rank))[0]
+    for r in np.unique(l2o[cand]):
+        sel = cand[l2o[cand] == r]
+        send[int(r)] = sel[np.argsort(l2g[sel], kind="stable")] + 1
+    # owned nodes that a neighbour's brick touches (that neighbour sends them to us)
+    recv = {}
+    for dz in (0, 1):
+        for dy in (0, 1):
+            for dx in (0, 1):
+                if dx == dy == dz == 0:
+                    continue
+                q = pc + np.array([dx, dy, dz])
+                if np.any(q >= g):
+                    continue
+                r = int(q[0] + gx * (q[1] + gy * q[2]))
+                qlo = q * n
+                sel = np.nonzero((l2o == rank) & (igo >= qlo[0]) & (igo <= qlo[0] + n) & (jgo >= qlo[1]) &
+                                 (jgo <= qlo[1] + n) & (kgo >= qlo[2]) & (kgo <= qlo[2] + n))[0]
+                if len(sel):
+                    recv[r] = sel[np.argsort(l2g[sel], kind="stable")] + 1
+    part = Partition(rank, P, l2g + 1, l2o, n_owned, int(inside.sum()), int(np.prod(g * n)), int(np.prod(Ng)), send, recv,
+                     bool((~inside).any()))
+    return lm, part

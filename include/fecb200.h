@@ -187,11 +187,27 @@ int fecb200_newton_solve(fecb200_handle* h, double* Uu, int32_t max_iters, doubl
  * rank-local mesh (owned nodes first, then ghosts).  The halo lists say which local nodes are
  * sent to / received from each neighbour rank.  Buffers are packed/unpacked on the device; the
  * exchange itself is driven by the host (NCCL send/recv or peer memory). ---------------------- */
+/* METIS k-way partition of the element dual graph (elements sharing >= ncommon nodes are adjacent).
+ * eptr[ne+1], eind: 0-based CSR element -> node lists; epart[ne], npart[nn] receive 0-based part ids.
+ * (The reference partitions with the SEACAS `decomp` tool, ext/PartitionedArraysExt.jl:41-49, or METIS on
+ * the DOF graph, ext/MetisExt.jl:6-14.)  Host-only; needs no handle. */
+int fecb200_metis_part_mesh_dual(int64_t ne, int64_t nn, const int64_t* eptr, const int64_t* eind, int64_t ncommon,
+                                 int64_t nparts, int64_t* epart, int64_t* npart);
+/* Metis.partition(graph, nparts) of ext/MetisExt.jl:6-14: xadj/adjncy 0-based CSR adjacency (no self loops) */
+int fecb200_metis_part_graph(int64_t nv, const int64_t* xadj, const int64_t* adjncy, int64_t nparts, int64_t* part);
+
+/* Rank-local view: local nodes [1, n_owned_nodes] are owned, the rest are ghosts (PartitionedArrays
+ * OwnAndGhostIndices order).  Blocks flagged in block_is_halo hold neighbour-owned elements that touch owned
+ * nodes: they are skipped by vector assembly (their residual arrives through the halo exchange) and included in
+ * matrix assembly, so every OWNED row of the Jacobian is complete without communication; ghost rows are not
+ * stored, ghost columns are.  Rebuilds the CSR structure. */
+int fecb200_partition_setup(fecb200_handle* h, int64_t n_owned_nodes, const int32_t* block_is_halo);
 int fecb200_halo_setup(fecb200_handle* h, int32_t n_neighbors, const int32_t* neighbor_ranks,
                        const int64_t* send_ptr, const int64_t* send_nodes,  /* ghosts I hold -> owner   */
                        const int64_t* recv_ptr, const int64_t* recv_nodes); /* my owned, ghosted by nbr */
-/* pack field values (NF per node) of the ghost nodes into a contiguous device buffer */
-int fecb200_halo_pack(fecb200_handle* h, int32_t which_field, double** sendbuf_dev, int64_t* n_doubles);
+/* pack field values (NF per node) of the send nodes into the caller's device buffer (halo_send_size doubles) */
+int fecb200_halo_pack(fecb200_handle* h, int32_t which_field, double* sendbuf_dev);
+int fecb200_halo_send_size(fecb200_handle* h, int64_t* n_doubles);
 /* owner side: add received ghost contributions into the owned entries */
 int fecb200_halo_unpack_add(fecb200_handle* h, int32_t which_field, const double* recvbuf_dev);
 int fecb200_halo_recv_size(fecb200_handle* h, int64_t* n_doubles);
