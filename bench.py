@@ -363,7 +363,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=int(os.environ.get("FECB200_BENCH_N", 192)), help="elements per axis per GPU")
+    ap.add_argument("--size", dest="n", type=int, default=int(os.environ.get("FECB200_BENCH_N", 192)), help="elements per axis per GPU")
     ap.add_argument("--cpu-n", type=int, default=48, help="elements per axis of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--report-nnz", action="store_true")
