@@ -29,10 +29,11 @@ sys.path.insert(0, os.path.join(ROOT, "finiteelementcontainers.jl_b200"))
 # algorithmic (compulsory) DRAM bytes per element, SURVEY.md 8(d) / DESIGN.md section 5
 BYTES_RESIDUAL = 136.0     # conn 64 + X 24 + U 24 + R 24
 BYTES_TANGENT = 2066.0     # conn 64 + X 24 + U 24 + CSR values 1954 (nnz/NE * 8)
+BYTES_FUSED = 2090.0       # tangent + R 24 (conn/X/U shared with the residual)
 BYTES_ACTION = 160.0
 # FP64 flops per element counted from the kernels' instruction mix
 FLOPS_RESIDUAL = 7.0e3
-FLOPS_TANGENT = 45.4e3
+FLOPS_TANGENT = 40.0e3      # fused k_mat2: FP64 warp-instructions x 64 / elements (ncu)
 NEO_PROPS = np.array([1e3, 10.0e6, 1.0e6])
 
 
@@ -147,16 +148,22 @@ def run_gpu(args):
             part.halo_sum_residual(asm, stream)
 
     def step_device():
+        # assemble_vector!(residual) + assemble_stiffness!(stiffness) at the same Uu, as solve! does
+        # (src/Solvers.jl:133-140), through the fused entry point; then the ghost->owner sum and residual(asm)
+        F.assemble_vector_and_stiffness(asm, F.residual, F.stiffness, dUu, p)
+        halo()
+        F.residual(asm, dR)
+
+    def step_unfused():
         F.assemble_vector(asm, F.residual, dUu, p)
         halo()
         F.residual(asm, dR)
         F.assemble_stiffness(asm, F.stiffness, dUu, p)
 
     def step_e2e():
-        F.assemble_vector(asm, F.residual, hUu, p)      # H2D of Uu inside
+        F.assemble_vector_and_stiffness(asm, F.residual, F.stiffness, hUu, p)  # H2D of Uu inside
         halo()
         F.residual(asm, hR)                             # D2H of the residual inside (synchronous)
-        F.assemble_stiffness(asm, F.stiffness, hUu, p)  # H2D of Uu inside
 
     def barrier():
         stream.synchronize()
@@ -209,6 +216,7 @@ def run_gpu(args):
         roof, ops = {}, {}
         if world == 1:
             Vu = torch.rand(N, dtype=torch.float64, device="cuda")
+            t_unf = op_ms(step_unfused)
             t_res = op_ms(lambda: F.assemble_vector(asm, F.residual, dUu, p))
             t_tan = op_ms(lambda: F.assemble_stiffness(asm, F.stiffness, dUu, p))
             t_act = op_ms(lambda: F.assemble_matrix_free_action(asm, F.stiffness_action, dUu, Vu, p))
@@ -217,7 +225,7 @@ def run_gpu(args):
             kms = []
             import ctypes as C
             for _ in range(5):
-                F.assemble_stiffness(asm, F.stiffness, dUu, p)
+                F.assemble_vector_and_stiffness(asm, F.residual, F.stiffness, dUu, p)
                 f = C.c_float()
                 check(lib.fecb200_last_kernel_ms(h, C.byref(f)))
                 kms.append(f.value)
@@ -229,7 +237,7 @@ def run_gpu(args):
                 kres.append(f.value)
             check(lib.fecb200_enable_timing(h, 0))
             k_tan, k_res = float(np.mean(kms[1:])), float(np.mean(kres[1:]))
-            ach = BYTES_TANGENT * ne_local / (k_tan * 1e-3) / 1e9
+            ach = BYTES_FUSED * ne_local / (k_tan * 1e-3) / 1e9
             # FP64 roof measured here with cuBLAS DGEMM (MEASURED_PEAKS.json has no FP64 entry)
             a = torch.randn(6144, 6144, dtype=torch.float64, device="cuda")
             torch.mm(a, a)
@@ -238,9 +246,9 @@ def run_gpu(args):
             e0.record(); torch.mm(a, a); torch.mm(a, a); e1.record(); torch.cuda.synchronize()
             fp64_peak = 2 * 2 * 6144 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
             del a
-            roof = {"bound": "hbm", "kernel": "k_mat<hex8,NF=3,neo-Hookean> (tangent -> CSR)", "achieved": round(ach, 1),
+            roof = {"bound": "hbm", "kernel": "k_mat2<hex8,NF=3,neo-Hookean,WITH_R> (fused residual + tangent -> CSR)", "achieved": round(ach, 1),
                     "peak": hbm, "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / hbm, 4), "traffic": None,
-                    "algorithmic_bytes_per_element": BYTES_TANGENT, "kernel_ms": round(k_tan, 4),
+                    "algorithmic_bytes_per_element": BYTES_FUSED, "kernel_ms": round(k_tan, 4),
                     "fp64": {"flops_per_element": FLOPS_TANGENT,
                              "achieved_tflops": round(FLOPS_TANGENT * ne_local / (k_tan * 1e-3) / 1e12, 2),
                              "peak_tflops_dgemm_measured": round(fp64_peak, 1),
@@ -253,6 +261,7 @@ def run_gpu(args):
             ops = {"residual_elements_per_s": round(ne_local / (t_res * 1e-3), 1),
                    "tangent_elements_per_s": round(ne_local / (t_tan * 1e-3), 1),
                    "action_elements_per_s": round(ne_local / (t_act * 1e-3), 1),
+                   "unfused_step_ms": round(t_unf, 4), "unfused_step_elements_per_s": round(ne_local / (t_unf * 1e-3), 1),
                    "residual_ms": round(t_res, 4), "tangent_ms": round(t_tan, 4), "action_ms": round(t_act, 4)}
         cpu = cpu_baseline(args.cpu_n) if (world == 1 and not args.no_cpu) else None
         out = {
@@ -267,7 +276,7 @@ def run_gpu(args):
                        "l2": "inputs and outputs larger than L2 (CSR values 13.8 GB at 192^3); no flush needed",
                        "setup_s": round(setup_s, 1)},
             "e2e": {"value": round(e2e_value, 1), "unit": "elements/s", "ms_per_step": round(ms_e2e / args.steps, 4),
-                    "h2d_bytes_per_step": int(2 * N * 8), "d2h_bytes_per_step": int(N * 8)},
+                    "h2d_bytes_per_step": int(N * 8), "d2h_bytes_per_step": int(N * 8)},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

@@ -144,6 +144,9 @@ using namespace fec;
 
 extern "C" {
 
+static void assemble_vector_and_matrix_impl(fecb200_handle* h, const double* u);
+static double* adjusted_values(fecb200_handle* h, int kind);
+
 const char* fecb200_last_error(void) { return fec::g_last_error.c_str(); }
 int fecb200_version(void) { return 100; }
 
@@ -436,6 +439,34 @@ int fecb200_assemble_matrix(fecb200_handle* h, int32_t kind, const double* Uu) {
   FEC_API_END
 }
 
+int fecb200_assemble_vector_and_matrix(fecb200_handle* h, const double* Uu) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && Uu, "null argument");
+  FEC_CUDA(cudaSetDevice(h->device));
+  const double* u = stage_in(h, Uu, h->d_Uu.p, len_Uu(h));
+  assemble_vector_and_matrix_impl(h, u);
+  FEC_API_END
+}
+
+static void assemble_vector_and_matrix_impl(fecb200_handle* h, const double* u) {
+  double* nz = nz_for_kind(h, FECB200_STIFFNESS, true);
+  FEC_CUDA(cudaMemsetAsync(h->d_R.p, 0, h->ndof * sizeof(double), h->stream));
+  FEC_CUDA(cudaMemsetAsync(nz, 0, h->nnz * sizeof(double), h->stream));
+  k_update_field(h, h->d_U.p, u, true);
+  h->last_ms = 0.f;
+  for (auto& b : h->blocks) {
+    if (!b.halo && matrix_kernel_fuses_residual(h, b)) {
+      MatLaunch a{h->d_U.p, nz, FECB200_STIFFNESS, h->d_R.p};
+      launch_matrix(h, b, a);
+    } else {
+      if (!b.halo) { VecLaunch v{h->d_U.p, nullptr, h->d_R.p, MODE_RESIDUAL}; launch_vector(h, b, v); }
+      MatLaunch a{h->d_U.p, nz, FECB200_STIFFNESS, nullptr};
+      launch_matrix(h, b, a);
+    }
+  }
+  h->stiff_adjusted = false;
+}
+
 static double* adjusted_values(fecb200_handle* h, int kind) {
   double* nz = nz_for_kind(h, kind, false);
   FEC_REQUIRE(nz, "matrix of this kind has not been assembled");
@@ -567,15 +598,14 @@ int fecb200_newton_solve(fecb200_handle* h, double* Uu, int32_t max_iters, doubl
   double* dU = h->d_cg_x.p;
   for (it = 1; it <= max_iters; ++it) {
     // solve!(IterativeLinearSolver) (Solvers.jl:128-153)
-    assemble_vector_impl(h, MODE_RESIDUAL, u, nullptr, h->d_R.p);
-    k_residual_accessor(h, Rb);
-    if (!matrix_free) {
-      double* nz = nz_for_kind(h, FECB200_STIFFNESS, true);
-      FEC_CUDA(cudaMemsetAsync(nz, 0, h->nnz * sizeof(double), h->stream));
-      for (auto& b : h->blocks) { MatLaunch a{h->d_U.p, nz, FECB200_STIFFNESS}; launch_matrix(h, b, a); }
-      h->stiff_adjusted = false;
-      adjusted_values(h, FECB200_STIFFNESS);
+    if (matrix_free) {
+      assemble_vector_impl(h, MODE_RESIDUAL, u, nullptr, h->d_R.p);
+    } else {
+      // residual and tangent at the same state: fused pass (see fecb200_assemble_vector_and_matrix)
+      assemble_vector_and_matrix_impl(h, u);
     }
+    k_residual_accessor(h, Rb);
+    if (!matrix_free) adjusted_values(h, FECB200_STIFFNESS);
     int64_t cgit = 0;
     cg_impl(h, Rb, dU, eps, eps, 2 * n, matrix_free != 0, &cgit, nullptr);
     cg_total += cgit;

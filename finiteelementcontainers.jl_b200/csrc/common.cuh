@@ -170,7 +170,8 @@ void export_pattern(fecb200_handle* h, int64_t* ptr, int64_t* idx);
 // dispatch (one translation unit per element family)
 enum { MODE_RESIDUAL = 0, MODE_ACTION_STIFFNESS = 1, MODE_ACTION_MASS = 2 };
 struct VecLaunch { const double* U; const double* V; double* out; int mode; };
-struct MatLaunch { const double* U; double* nz; int kind; };
+struct MatLaunch { const double* U; double* nz; int kind; double* R = nullptr; };  // R != null: fused residual
+bool matrix_kernel_fuses_residual(fecb200_handle* h, const BlockPlan& b);
 void launch_vector(fecb200_handle* h, BlockPlan& b, const VecLaunch& a);
 void launch_matrix(fecb200_handle* h, BlockPlan& b, const MatLaunch& a);
 void launch_vector_quad_tri(fecb200_handle* h, BlockPlan& b, const VecLaunch& a);

@@ -18,8 +18,15 @@ template <class Phys, int NF, int EPB>
 static void mat8(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   FEC_REQUIRE(b.nq == 8, "HEX8: this physics is compiled for 8-point quadrature rules only");
   // symmetric tangents (all shipped mechanics physics): pair-owner kernel with staged, coalesced REDs
-  if (a.kind == FECB200_STIFFNESS && !getenv("FECB200_KMAT1")) run_mat2<3, 8, NF, 8, Phys, FEC_MAT2_WARPS>(h, b, a);
+  if (a.kind == FECB200_STIFFNESS && matrix_kernel_fuses_residual(h, b)) run_mat2<3, 8, NF, 8, Phys, FEC_MAT2_WARPS>(h, b, a);
   else run_mat<3, 8, NF, 8, Phys, EPB>(h, b, a);
+}
+
+// true when launch_matrix for this block runs k_mat2, which can produce the residual in the same pass
+bool matrix_kernel_fuses_residual(fecb200_handle* h, const BlockPlan& b) {
+  return b.elem_type == FECB200_HEX8 && h->nf == 3 && b.nq == 8 && !getenv("FECB200_KMAT1") && h->nnz < (int64_t)0xFFFFFFFFll &&
+         (b.physics == FECB200_PHYS_LINEAR_ELASTIC || b.physics == FECB200_PHYS_NEOHOOKEAN ||
+          b.physics == FECB200_PHYS_NEOHOOKEAN_AS_WRITTEN || b.physics == FECB200_PHYS_J2_PLASTICITY);
 }
 
 void launch_vector_hex8(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {

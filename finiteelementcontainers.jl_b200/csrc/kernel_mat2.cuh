@@ -32,6 +32,8 @@ struct Mat2Params {
   const int32_t* conn;       // [ne*NNPE] tile-ordered global node ids
   const unsigned char* emeta;  // [ne * REC] per-element scatter record, see Mat2Layout (built by k_build_emeta)
   const double* state_old;
+  double* state_new;         // written when the residual is fused (stateful physics)
+  double* R;                 // fused residual target (full-length field) or nullptr
   int32_t ne, nq;
   double props[kMaxProps];
   Tables<ND, NNPE, NQT> tab;
@@ -42,13 +44,14 @@ __host__ __device__ constexpr int sym_index(int i, int j) {  // packed upper tri
   return i * N - (i * (i - 1)) / 2 + (j - i);
 }
 
-template <int ND, int NNPE, int NF, int NQ>
+template <int ND, int NNPE, int NF, int NQ, bool WITH_R>
 struct Mat2Layout {
   static constexpr int NP = NF * (NF + 1) / 2;
   static constexpr int EPW = 32 / NP;
   static constexpr int NDF = NF * ND;
   static constexpr int ASZ = NDF * (NDF + 1) / 2;
-  static constexpr int SLOT = NNPE * ND + ASZ;          // dN_X + packed JxW*A
+  static constexpr int OFF_P = NNPE * ND + ASZ;         // JxW * P (only when the residual is fused)
+  static constexpr int SLOT = OFF_P + (WITH_R ? NDF : 0); // dN_X + packed JxW*A [+ JxW*P]
   static constexpr int NROW = NNPE * NF;
   static constexpr int RSTRIDE = NROW + 1;              // padded row stride of the staged K_el
   static constexpr int KSZ = NROW * RSTRIDE;
@@ -78,10 +81,10 @@ __device__ __forceinline__ void red_add_f64_pred(double* addr, double v, bool ok
                : "memory");
 }
 
-template <int ND, int NNPE, int NF, int NQT, class Phys, int WARPS>
+template <int ND, int NNPE, int NF, int NQT, class Phys, int WARPS, bool WITH_R>
 __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat2Params<ND, NNPE, NQT> p) {
   static_assert(NQT > 0, "k_mat2 is compiled for fixed quadrature rules");
-  using L = Mat2Layout<ND, NNPE, NF, NQT>;
+  using L = Mat2Layout<ND, NNPE, NF, NQT, WITH_R>;
   constexpr int NP = L::NP, EPW = L::EPW, NDF = L::NDF, SLOT = L::SLOT, NROW = L::NROW, RS = L::RSTRIDE;
   constexpr int NS = Phys::NS;
   extern __shared__ __align__(16) double smem[];
@@ -169,6 +172,19 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
       for (int i = 0; i < NDF; ++i)
 #pragma unroll
         for (int j = i; j < NDF; ++j) slot[NNPE * ND + sym_index<NDF>(i, j)] = A[i][j] * JxW;
+      if constexpr (WITH_R) {
+        // fused residual: P at the same state (the compiler shares the kinematics with the tangent above)
+        double P[NF][ND], bsrc[NF], sn[NS > 0 ? NS : 1];
+        Phys::flux(gu, 0.0, p.props, so, NS > 0 ? sn : nullptr, P, bsrc);
+#pragma unroll
+        for (int d = 0; d < NF; ++d)
+#pragma unroll
+          for (int k = 0; k < ND; ++k) slot[L::OFF_P + d * ND + k] = P[d][k] * JxW;
+        if constexpr (NS > 0) {
+#pragma unroll
+          for (int s = 0; s < NS; ++s) p.state_new[((size_t)s * p.nq + q) * p.ne + e] = sn[s];
+        }
+      }
     }
   }
   __syncwarp();
@@ -179,6 +195,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
   for (int a = 0; a < NNPE; ++a)
 #pragma unroll
     for (int b = 0; b < NNPE; ++b) M[a][b] = 0.0;
+  double rr[WITH_R ? NNPE : 1];  // fused residual rows (a, d1) of the diagonal-pair threads (d1 == d2)
+#pragma unroll
+  for (int a = 0; a < (WITH_R ? NNPE : 1); ++a) rr[a] = 0.0;
   if (active) {
     // packed indices of this thread's ND x ND block (d1 <= d2 so (d1,j1) <= (d2,j2) unless d1 == d2 and j1 > j2)
     int aidx[ND][ND];
@@ -202,6 +221,17 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
       for (int a = 0; a < NNPE; ++a)
 #pragma unroll
         for (int k = 0; k < ND; ++k) g[a][k] = slot[a * ND + k];
+      if constexpr (WITH_R) {
+        if (d1 == d2) {  // R[a, d] += sum_j dN_X[a][j] (JxW P)[d][j]   (Formulations.jl:27-49)
+          double Pd[ND];
+#pragma unroll
+          for (int k = 0; k < ND; ++k) Pd[k] = slot[L::OFF_P + d1 * ND + k];
+#pragma unroll
+          for (int a = 0; a < NNPE; ++a)
+#pragma unroll
+            for (int k = 0; k < ND; ++k) rr[a] = fma(g[a][k], Pd[k], rr[a]);
+        }
+      }
 #pragma unroll
       for (int b = 0; b < NNPE; ++b) {
         double tb[ND];  // tb[j1] = sum_j2 A9[j1][j2] g[b][j2]
@@ -220,6 +250,13 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
           M[a][b] = s;
         }
       }
+    }
+  }
+  if constexpr (WITH_R) {
+    if (active && d1 == d2) {
+#pragma unroll
+      for (int a = 0; a < NNPE; ++a)
+        atomicAdd(&p.R[(size_t)p.conn[(size_t)e * NNPE + a] * NF + d1], rr[a]);  // 24 REDs per element
     }
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
@@ -281,15 +318,16 @@ __global__ void k_build_emeta(const int32_t* conn, const uint8_t* epos, const in
                               const uint8_t* freemask, const int64_t* rowstart, unsigned char* emeta, int nnpe, int nf,
                               int rec, int64_t ne);
 
-template <int ND, int NNPE, int NF, int NQT, class Phys, int WARPS>
-void run_mat2(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
-  using L = Mat2Layout<ND, NNPE, NF, NQT>;
+template <int ND, int NNPE, int NF, int NQT, class Phys, int WARPS, bool WITH_R>
+void run_mat2_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
+  using L = Mat2Layout<ND, NNPE, NF, NQT, WITH_R>;
   auto pp = std::make_unique<Mat2Params<ND, NNPE, NQT>>();
   auto& p = *pp;
   p.X = h->d_X.p; p.U = a.U; p.nz = a.nz;
   FEC_REQUIRE(h->nnz < (int64_t)0xFFFFFFFFll, "k_mat2 needs nnz < 2^32 (32-bit row offsets in the scatter records)");
   FEC_REQUIRE((int)b.emeta_rec == L::REC, "scatter record size mismatch");
   p.conn = b.d_conn_perm.p; p.emeta = b.d_emeta.p;
+  p.R = a.R; p.state_new = b.d_state_new.p;
   p.state_old = b.d_state_old.p;
   p.ne = (int32_t)b.ne; p.nq = b.nq;
   for (int i = 0; i < kMaxProps; ++i) p.props[i] = i < (int)b.props.size() ? b.props[i] : 0.0;
@@ -299,12 +337,18 @@ void run_mat2(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   const int grid = (int)((b.ne + epc - 1) / epc);
   timing_begin(h);
   // K_el is symmetric here, so CSR and CSC storage receive the same values through the same addressing
-  auto kern = k_mat2<ND, NNPE, NF, NQT, Phys, WARPS>;
+  auto kern = k_mat2<ND, NNPE, NF, NQT, Phys, WARPS, WITH_R>;
   FEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, WARPS * 32, smem, h->stream>>>(p);
   FEC_CUDA(cudaGetLastError());
   timing_end(h);
   h->launches++;
+}
+
+template <int ND, int NNPE, int NF, int NQT, class Phys, int WARPS>
+void run_mat2(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
+  if (a.R) run_mat2_t<ND, NNPE, NF, NQT, Phys, WARPS, true>(h, b, a);
+  else run_mat2_t<ND, NNPE, NF, NQT, Phys, WARPS, false>(h, b, a);
 }
 
 }  // namespace fec

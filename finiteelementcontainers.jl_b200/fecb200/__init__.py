@@ -15,7 +15,7 @@ from .physics import (AbstractPhysics, Poisson, Mechanics, NeoHookean, J2Plastic
                       stiffness_action_b, mass_action, mass_action_b)
 from .assemblers import (SparseMatrixAssembler, Parameters, create_parameters, update_dofs, update_bc_values,
                          update_time, create_field, create_unknowns, assemble_vector, assemble_stiffness,
-                         assemble_mass, assemble_matrix_action, assemble_matrix_free_action,
+                         assemble_mass, assemble_vector_and_stiffness, assemble_matrix_action, assemble_matrix_free_action,
                          assemble_matrix_free_action_full, hvp, full_field)
 from .solvers import IterativeLinearSolver, NewtonSolver, QuasiStaticIntegrator
 from .partition import (Partition, partition_mesh, structured_brick_partition, metis_partition_elements,

@@ -261,6 +261,15 @@ def assemble_stiffness(asm, func, Uu, p):
     check(lib.fecb200_assemble_matrix(asm._require(), _lib.STIFFNESS, _lib.ptr(Uu)))
 
 
+def assemble_vector_and_stiffness(asm, func_r, func_k, Uu, p):
+    """assemble_vector!(asm, residual, Uu, p); assemble_stiffness!(asm, stiffness, Uu, p) in one pass -- the pair
+    of calls solve!(::IterativeLinearSolver) makes at every Newton iteration (src/Solvers.jl:133-140)."""
+    _check_matrix_assembly_supported(asm, "assemble_stiffness!")
+    kind_of(func_r, (_lib.RESIDUAL,))
+    kind_of(func_k, (_lib.STIFFNESS,))
+    check(lib.fecb200_assemble_vector_and_matrix(asm._require(), _lib.ptr(Uu)))
+
+
 def assemble_mass(asm, func, Uu, p):
     """assemble_mass!(asm, mass, Uu, p)  (src/assemblers/Matrix.jl:1-10)"""
     _check_matrix_assembly_supported(asm, "assemble_mass!")

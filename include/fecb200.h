@@ -153,6 +153,12 @@ int fecb200_residual(fecb200_handle* h, double* out);
 /* assemble_stiffness!/assemble_mass! (src/assemblers/Matrix.jl:1-75) fused with the sparse!
  * realisation: values are accumulated straight into the CSR/CSC nzval (no COO is materialised). */
 int fecb200_assemble_matrix(fecb200_handle* h, int32_t kind, const double* Uu);
+/* Fused assemble_vector!(asm, residual, Uu, p) + assemble_stiffness!(asm, stiffness, Uu, p): what one Newton
+ * iteration of solve!(::IterativeLinearSolver) asks for back to back at the same Uu (src/Solvers.jl:133-140).
+ * One field update; blocks whose tangent kernel already holds dN_X and the constitutive state at every quadrature
+ * point produce the residual in the same pass.  Results are identical (to rounding) to the two separate calls;
+ * fecb200_residual / fecb200_matrix_values read them as usual. */
+int fecb200_assemble_vector_and_matrix(fecb200_handle* h, const double* Uu);
 /* stiffness(asm)/mass(asm) (Assemblers.jl:329-388): applies the condensed-mode constraint
  * adjustment (assemblers/Utils.jl:53-148: row/col scaling by (1-c), penalty 1e6*tr(K)/n on
  * constrained diagonals) and copies nzval [nnz] out. [host|device] */

@@ -332,3 +332,26 @@ def test_large_roundtrip_properties(F):
     F.assemble_vector(asm, F.residual, Uu, p)
     assert rel_err(F.residual(asm), K @ Uu) < 1e-12
     asm.close()
+
+
+@pytest.mark.parametrize("phys", ["neo", "linear"])
+def test_fused_residual_and_tangent(F, phys):
+    """fecb200_assemble_vector_and_matrix == the two separate calls (and the oracle)."""
+    n = 6
+    mesh = perturb(F.StructuredMesh("hex", (0, 0, 0), (1, 1, 1), (n + 1,) * 3), 0.15 / n)
+    props = np.array([1e3, 10e6, 1e6])
+    asm, p, oasm = build_pair(F, mesh, phys, props, condensed=False, matrix_type="csr",
+                              bc_nodes_1based=mesh.nodeset_nodes["bottom"], bc_value=0.01)
+    rng = np.random.default_rng(4)
+    Uu = 0.01 * rng.standard_normal(asm.sizes()[2])
+    F.assemble_vector(asm, F.residual, Uu, p)
+    R1 = F.residual(asm).copy()
+    F.assemble_stiffness(asm, F.stiffness, Uu, p)
+    K1 = F.stiffness(asm).data.copy()
+    F.assemble_vector_and_stiffness(asm, F.residual, F.stiffness, Uu, p)
+    R2, K2 = F.residual(asm), F.stiffness(asm).data
+    assert rel_err(R2, R1) < RTOL and rel_err(K2, K1) < RTOL
+    oasm.assemble_vector(Uu)
+    oasm.assemble_stiffness(Uu)
+    assert rel_err(R2, oasm.residual()) < RTOL and rel_err(K2, oasm.stiffness()[2]) < RTOL
+    asm.close()
