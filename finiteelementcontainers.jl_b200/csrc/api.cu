@@ -70,7 +70,7 @@ static double* nz_for_kind(fecb200_handle* h, int kind, bool alloc) {
   FEC_REQUIRE(h->matrix_ready, "matrix pattern not built");
   if (kind == FECB200_STIFFNESS) return h->d_nz_stiff.p;
   if (kind == FECB200_MASS) {
-    if (!h->d_nz_mass.p && alloc) { h->d_nz_mass.alloc(h->nnz + 32); h->d_nz_mass.zero(h->stream); }
+    if (!h->d_nz_mass.p && alloc) { h->d_nz_mass.alloc(h->nnz + 4096); h->d_nz_mass.zero(h->stream); }
     return h->d_nz_mass.p;
   }
   throw Error("fecb200: matrix kind must be FECB200_STIFFNESS or FECB200_MASS");

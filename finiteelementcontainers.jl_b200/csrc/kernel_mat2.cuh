@@ -34,6 +34,7 @@ struct Mat2Params {
   const double* state_old;
   double* state_new;         // written when the residual is fused (stateful physics)
   double* R;                 // fused residual target (full-length field) or nullptr
+  int64_t nnz;               // the trash region of the branch-free RED stream starts at nz[nnz]
   int32_t ne, nq;
   double props[kMaxProps];
   Tables<ND, NNPE, NQT> tab;
@@ -286,28 +287,32 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
 
   // ---- phase S2: REDs.  Lane = one storage column (sorted node rank k, dof dc) of the element; the warp walks
   // the NROW rows, so one RED instruction covers one CSR row segment of the element: NROW consecutive-ish slots.
-  {
+  // All shared-memory reads of an element are issued before its REDs so their latencies overlap (registers are
+  // free here: M is dead).  The RED stream is branch-free: entries of eliminated rows / columns (Dirichlet dofs,
+  // rare) are redirected into a 4096-slot trash region behind the matrix, hashed so they do not serialise.
+  if (lane < NROW) {
     const int nel = (p.ne - e0) < EPW ? (p.ne - e0) : EPW;
-    const int col = lane < NROW ? lane : NROW - 1;
-    const int k = col / NF, dc = col - k * NF;
+    const int k = lane / NF, dc = lane - k * NF;
     for (int el = 0; el < nel; ++el) {
       const double* ks = wsm + (size_t)el * L::ELSM;
       const unsigned char* rec = reinterpret_cast<const unsigned char*>(ks + L::BODY16);
       const uint32_t* rs = reinterpret_cast<const uint32_t*>(rec);
       const uint16_t* ec = reinterpret_cast<const uint16_t*>(rec + L::OFF_EC);
       const unsigned mask = rec[L::OFF_MK + k];
-      const bool colok = (lane < NROW) && (mask & (1u << dc));
+      const bool colok = (mask & (1u << dc)) != 0;
       const int rank = __popc(mask & ((1u << dc) - 1u));
-      double* base = p.nz + rank;
+      const uint32_t trash = (uint32_t)p.nnz + (((uint32_t)(e0 + el) * 613u + (uint32_t)lane * 29u) & 4095u);
+      uint32_t r0[NROW];
+      double val[NROW];
+      uint32_t off[NNPE];
 #pragma unroll
-      for (int b = 0; b < NNPE; ++b) {
-        double* cb = base + ec[b * NNPE + k];
+      for (int b = 0; b < NNPE; ++b) off[b] = ec[b * NNPE + k] + rank;
 #pragma unroll
-        for (int dr = 0; dr < NF; ++dr) {
-          const int row = b * NF + dr;
-          const uint32_t r0 = rs[row];
-          red_add_f64_pred(cb + r0, ks[row * RS + col], colok && r0 != 0xFFFFFFFFu);
-        }
+      for (int row = 0; row < NROW; ++row) { r0[row] = rs[row]; val[row] = ks[row * RS + lane]; }
+#pragma unroll
+      for (int row = 0; row < NROW; ++row) {
+        const uint32_t idx = (colok && r0[row] != 0xFFFFFFFFu) ? r0[row] + off[row / NF] : ((trash + row * 7u) & 4095u) + (uint32_t)p.nnz;
+        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p.nz + idx), "d"(val[row]));
       }
     }
   }
@@ -324,12 +329,12 @@ void run_mat2_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   auto pp = std::make_unique<Mat2Params<ND, NNPE, NQT>>();
   auto& p = *pp;
   p.X = h->d_X.p; p.U = a.U; p.nz = a.nz;
-  FEC_REQUIRE(h->nnz < (int64_t)0xFFFFFFFFll, "k_mat2 needs nnz < 2^32 (32-bit row offsets in the scatter records)");
+  FEC_REQUIRE(h->nnz + 4096 < (int64_t)0xFFFFFFFFll, "k_mat2 needs nnz < 2^32 (32-bit row offsets in the scatter records)");
   FEC_REQUIRE((int)b.emeta_rec == L::REC, "scatter record size mismatch");
   p.conn = b.d_conn_perm.p; p.emeta = b.d_emeta.p;
   p.R = a.R; p.state_new = b.d_state_new.p;
   p.state_old = b.d_state_old.p;
-  p.ne = (int32_t)b.ne; p.nq = b.nq;
+  p.ne = (int32_t)b.ne; p.nq = b.nq; p.nnz = h->nnz;
   for (int i = 0; i < kMaxProps; ++i) p.props[i] = i < (int)b.props.size() ? b.props[i] : 0.0;
   fill_tables<ND, NNPE, NQT>(b, p.tab);
   const size_t smem = (size_t)WARPS * L::EPW * L::ELSM * sizeof(double);
