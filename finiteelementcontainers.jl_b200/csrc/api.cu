@@ -38,12 +38,40 @@ static int phys_nstate(int p) { return p == FECB200_PHYS_J2_PLASTICITY ? 7 : 0; 
 // copy `n` doubles from a host-or-device pointer into device staging
 static const double* stage_in(fecb200_handle* h, const double* src, double* staging, int64_t n) {
   if (is_device_ptr(src)) return src;
+  if (h->async_copies) {
+    // H2D on its own stream: it overlaps whatever the main stream does until join_inputs() (e.g. the CSR memset)
+    if (h->in_consumed_valid) FEC_CUDA(cudaStreamWaitEvent(h->s_h2d, h->ev_in_consumed, 0));  // staging is free again
+    FEC_CUDA(cudaMemcpyAsync(staging, src, n * sizeof(double), cudaMemcpyHostToDevice, h->s_h2d));
+    FEC_CUDA(cudaEventRecord(h->ev_h2d, h->s_h2d));
+    h->h2d_pending = true;
+    return staging;
+  }
   FEC_CUDA(cudaMemcpyAsync(staging, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   return staging;
+}
+// main stream waits for pending H2D copies right before their first consumer
+static void join_inputs(fecb200_handle* h) {
+  if (h->h2d_pending) { FEC_CUDA(cudaStreamWaitEvent(h->stream, h->ev_h2d, 0)); h->h2d_pending = false; }
+}
+// record that the staged inputs have been consumed (the next H2D may overwrite the staging buffers)
+static void inputs_consumed(fecb200_handle* h) {
+  if (h->async_copies) { FEC_CUDA(cudaEventRecord(h->ev_in_consumed, h->stream)); h->in_consumed_valid = true; }
+}
+// before the main stream overwrites d_out: a D2H copy of its previous content may still be in flight
+static void wait_out_free(fecb200_handle* h) {
+  if (h->d2h_pending) { FEC_CUDA(cudaStreamWaitEvent(h->stream, h->ev_d2h, 0)); h->d2h_pending = false; }
 }
 static void copy_out(fecb200_handle* h, double* dst, const double* src_dev, int64_t n) {
   if (dst == src_dev) return;
   const bool dev = is_device_ptr(dst);
+  if (!dev && h->async_copies) {
+    FEC_CUDA(cudaEventRecord(h->ev_prod, h->stream));
+    FEC_CUDA(cudaStreamWaitEvent(h->s_d2h, h->ev_prod, 0));
+    FEC_CUDA(cudaMemcpyAsync(dst, src_dev, n * sizeof(double), cudaMemcpyDeviceToHost, h->s_d2h));
+    FEC_CUDA(cudaEventRecord(h->ev_d2h, h->s_d2h));
+    h->d2h_pending = true;  // caller reads dst after fecb200_synchronize
+    return;
+  }
   FEC_CUDA(cudaMemcpyAsync(dst, src_dev, n * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                            h->stream));
   if (!dev) FEC_CUDA(cudaStreamSynchronize(h->stream));
@@ -53,8 +81,10 @@ static int64_t len_Uu(fecb200_handle* h) { return h->opts.condensed ? h->ndof : 
 static void assemble_vector_impl(fecb200_handle* h, int mode, const double* Uu_dev, const double* Vu_dev,
                                  double* out_field) {
   FEC_CUDA(cudaMemsetAsync(out_field, 0, h->ndof * sizeof(double), h->stream));  // fill!(storage, 0)  Vector.jl:30
+  join_inputs(h);
   k_update_field(h, h->d_U.p, Uu_dev, true);
   if (Vu_dev) k_update_field(h, h->d_V.p, Vu_dev, false);  // V's BC slots stay 0 (Parameters.jl:415-425)
+  inputs_consumed(h);
   h->last_ms = 0.f;
   for (auto& b : h->blocks) {
     if (b.halo) continue;  // neighbour-owned elements: their contribution arrives through the halo exchange
@@ -228,6 +258,9 @@ int fecb200_destroy(fecb200_handle* h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     cudaStream_t s = h->own_stream ? h->stream : nullptr;
     cudaStreamSynchronize(h->stream);
+    if (h->s_h2d) { cudaStreamSynchronize(h->s_h2d); cudaStreamDestroy(h->s_h2d); }
+    if (h->s_d2h) { cudaStreamSynchronize(h->s_d2h); cudaStreamDestroy(h->s_d2h); }
+    for (cudaEvent_t ev : {h->ev_h2d, h->ev_in_consumed, h->ev_prod, h->ev_d2h}) if (ev) cudaEventDestroy(ev);
     delete h;
     if (s) cudaStreamDestroy(s);
   }
@@ -248,6 +281,28 @@ int fecb200_synchronize(fecb200_handle* h) {
   FEC_API_BEGIN
   FEC_REQUIRE(h, "null handle");
   FEC_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->s_h2d) FEC_CUDA(cudaStreamSynchronize(h->s_h2d));
+  if (h->s_d2h) FEC_CUDA(cudaStreamSynchronize(h->s_d2h));
+  h->d2h_pending = h->h2d_pending = false;
+  FEC_API_END
+}
+
+int fecb200_set_async(fecb200_handle* h, int32_t on) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h, "null handle");
+  FEC_CUDA(cudaSetDevice(h->device));
+  FEC_CUDA(cudaStreamSynchronize(h->stream));
+  if (on && !h->s_h2d) {
+    FEC_CUDA(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    FEC_CUDA(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    FEC_CUDA(cudaEventCreateWithFlags(&h->ev_h2d, cudaEventDisableTiming));
+    FEC_CUDA(cudaEventCreateWithFlags(&h->ev_in_consumed, cudaEventDisableTiming));
+    FEC_CUDA(cudaEventCreateWithFlags(&h->ev_prod, cudaEventDisableTiming));
+    FEC_CUDA(cudaEventCreateWithFlags(&h->ev_d2h, cudaEventDisableTiming));
+  }
+  if (!on && h->s_h2d) { FEC_CUDA(cudaStreamSynchronize(h->s_h2d)); FEC_CUDA(cudaStreamSynchronize(h->s_d2h)); }
+  h->async_copies = on != 0;
+  h->h2d_pending = h->d2h_pending = h->in_consumed_valid = false;
   FEC_API_END
 }
 
@@ -417,6 +472,7 @@ int fecb200_residual(fecb200_handle* h, double* out) {
   FEC_CUDA(cudaSetDevice(h->device));
   const bool dev = is_device_ptr(out);
   double* target = dev ? out : h->d_out.p;
+  if (!dev) wait_out_free(h);
   k_residual_accessor(h, target);
   if (!dev) copy_out(h, out, target, len_Uu(h));
   FEC_API_END
@@ -429,7 +485,9 @@ int fecb200_assemble_matrix(fecb200_handle* h, int32_t kind, const double* Uu) {
   double* nz = nz_for_kind(h, kind, true);
   const double* u = stage_in(h, Uu, h->d_Uu.p, len_Uu(h));
   FEC_CUDA(cudaMemsetAsync(nz, 0, h->nnz * sizeof(double), h->stream));  // fill!(storage, 0)  Matrix.jl:39
+  join_inputs(h);
   k_update_field(h, h->d_U.p, u, true);
+  inputs_consumed(h);
   h->last_ms = 0.f;
   for (auto& b : h->blocks) {
     MatLaunch a{h->d_U.p, nz, kind};
@@ -451,8 +509,10 @@ int fecb200_assemble_vector_and_matrix(fecb200_handle* h, const double* Uu) {
 static void assemble_vector_and_matrix_impl(fecb200_handle* h, const double* u) {
   double* nz = nz_for_kind(h, FECB200_STIFFNESS, true);
   FEC_CUDA(cudaMemsetAsync(h->d_R.p, 0, h->ndof * sizeof(double), h->stream));
-  FEC_CUDA(cudaMemsetAsync(nz, 0, h->nnz * sizeof(double), h->stream));
+  FEC_CUDA(cudaMemsetAsync(nz, 0, h->nnz * sizeof(double), h->stream));   // the H2D of Uu (async mode) overlaps this
+  join_inputs(h);
   k_update_field(h, h->d_U.p, u, true);
+  inputs_consumed(h);
   h->last_ms = 0.f;
   for (auto& b : h->blocks) {
     if (!b.halo && matrix_kernel_fuses_residual(h, b)) {
@@ -535,6 +595,8 @@ int fecb200_hvp(fecb200_handle* h, const double* v, double* out) {
   }
   const bool dev = is_device_ptr(out);
   double* target = dev ? out : h->d_out.p;
+  join_inputs(h);
+  if (!dev) wait_out_free(h);
   k_hvp_accessor(h, vd, target);
   if (!dev) copy_out(h, out, target, len_Uu(h));
   FEC_API_END

@@ -148,6 +148,12 @@ struct fecb200_handle {
   fec::DevBuf<int32_t> d_send_nodes, d_recv_nodes;
   fec::DevBuf<double> d_sendbuf;
 
+  // opt-in asynchronous host copies (fecb200_set_async): H2D / D2H run on their own streams, ordered with events
+  bool async_copies = false;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_h2d = nullptr, ev_in_consumed = nullptr, ev_prod = nullptr, ev_d2h = nullptr;
+  bool h2d_pending = false, d2h_pending = false, in_consumed_valid = false;
+
   // instrumentation
   int64_t launches = 0;
   bool timing = false;

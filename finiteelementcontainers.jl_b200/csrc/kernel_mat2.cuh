@@ -52,7 +52,14 @@ struct Mat2Layout {
   static constexpr int NDF = NF * ND;
   static constexpr int ASZ = NDF * (NDF + 1) / 2;
   static constexpr int OFF_P = NNPE * ND + ASZ;         // JxW * P (only when the residual is fused)
-  static constexpr int SLOT = OFF_P + (WITH_R ? NDF : 0); // dN_X + packed JxW*A [+ JxW*P]
+  static constexpr int SLOT_RAW = OFF_P + (WITH_R ? NDF : 0); // dN_X + packed JxW*A [+ JxW*P]
+#ifndef FEC_MAT2_NOPAD
+  // bank spreading (8-byte banks, 16 per wavefront): slot stride == 1 and element stride == NP (mod 16) put the
+  // EPW*NP lanes that store / load "the same field of different (element, quadrature point)" on distinct banks
+  static constexpr int SLOT = SLOT_RAW + (17 - SLOT_RAW % 16) % 16;
+#else
+  static constexpr int SLOT = SLOT_RAW;
+#endif
   static constexpr int NROW = NNPE * NF;
   static constexpr int RSTRIDE = NROW + 1;              // padded row stride of the staged K_el
   static constexpr int KSZ = NROW * RSTRIDE;
@@ -68,7 +75,11 @@ struct Mat2Layout {
   static constexpr int REC = ((OFF_RK + NNPE + 15) / 16) * 16;
   static constexpr int META = REC / 8;
   static constexpr int BODY16 = ((BODY + 1) / 2) * 2;   // keep the record 16-byte aligned in shared memory
-  static constexpr int ELSM = BODY16 + META;            // 630 doubles for hex8/NF=3: 2*ELSM mod 32 = 12 -> no bank clashes
+#ifndef FEC_MAT2_NOPAD
+  static constexpr int ELSM = BODY16 + META + ((NP + 16 - (BODY16 + META) % 16) % 16);
+#else
+  static constexpr int ELSM = BODY16 + META;
+#endif
   static_assert(ELSM % 2 == 0, "element stride must keep 16-byte alignment");
 };
 

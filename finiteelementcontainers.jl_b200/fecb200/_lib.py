@@ -66,6 +66,7 @@ SIGNATURES = {
     "fecb200_destroy": (C.c_int, [Handle]),
     "fecb200_set_stream": (C.c_int, [Handle, C.c_void_p]),
     "fecb200_synchronize": (C.c_int, [Handle]),
+    "fecb200_set_async": (C.c_int, [Handle, C.c_int32]),
     "fecb200_update_dofs": (C.c_int, [Handle, c_i64p, C.c_int64, c_i64p, c_i64p, C.c_int64]),
     "fecb200_sizes": (C.c_int, [Handle, c_i64p, c_i64p, c_i64p]),
     "fecb200_dof_maps_copy": (C.c_int, [Handle, c_i64p, c_i64p]),

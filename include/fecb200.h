@@ -106,6 +106,12 @@ int fecb200_destroy(fecb200_handle* h);
 /* use an existing CUDA stream (cudaStream_t) for all work of this handle; NULL = own stream */
 int fecb200_set_stream(fecb200_handle* h, void* cuda_stream);
 int fecb200_synchronize(fecb200_handle* h);
+/* Opt-in asynchronous HOST copies.  Default (off): every call is complete on return.  On: host inputs are uploaded
+ * and host outputs downloaded on dedicated copy streams, ordered against the compute stream with events, so the
+ * H2D of Uu overlaps the zero-fill of the CSR values and the D2H of a result overlaps the next assembly.  Host
+ * buffers should be page-locked; host OUTPUTS are valid only after fecb200_synchronize(); host INPUTS must stay
+ * untouched until then. */
+int fecb200_set_async(fecb200_handle* h, int32_t on);
 
 /* update_dofs!(asm, dbcs, pbcs)  (SparseMatrixAssembler.jl:228-274, DofManagers.jl:227-298,
  * SparsityPatterns.jl:160-231).  dirichlet_dofs need not be sorted/unique. */

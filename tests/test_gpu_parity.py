@@ -355,3 +355,32 @@ def test_fused_residual_and_tangent(F, phys):
     oasm.assemble_stiffness(Uu)
     assert rel_err(R2, oasm.residual()) < RTOL and rel_err(K2, oasm.stiffness()[2]) < RTOL
     asm.close()
+
+
+def test_async_host_copies(F):
+    """fecb200_set_async: pinned host inputs / outputs through the copy streams give the same numbers."""
+    import torch
+    from fecb200._lib import check, lib
+    n = 8
+    mesh = F.StructuredMesh("hex", (0, 0, 0), (1, 1, 1), (n + 1,) * 3)
+    asm, p, oasm = build_pair(F, mesh, "neo", np.array([1e3, 10e6, 1e6]), condensed=False, matrix_type="csr",
+                              bc_nodes_1based=mesh.nodeset_nodes["bottom"])
+    N = asm.sizes()[2]
+    rng = np.random.default_rng(8)
+    U1, U2 = 0.01 * rng.standard_normal(N), 0.01 * rng.standard_normal(N)
+    refs = []
+    for U in (U1, U2):
+        F.assemble_vector_and_stiffness(asm, F.residual, F.stiffness, U, p)
+        refs.append(F.residual(asm).copy())
+    h = asm._require()
+    check(lib.fecb200_set_async(h, 1))
+    hU = [torch.from_numpy(U).pin_memory() for U in (U1, U2)]
+    hR = [torch.empty(N, dtype=torch.float64).pin_memory() for _ in range(2)]
+    for i in range(2):                       # two back-to-back steps, no host synchronisation in between
+        F.assemble_vector_and_stiffness(asm, F.residual, F.stiffness, hU[i], p)
+        F.residual(asm, hR[i])
+    check(lib.fecb200_synchronize(h))
+    for i in range(2):
+        assert rel_err(hR[i].numpy(), refs[i]) < 1e-14
+    check(lib.fecb200_set_async(h, 0))
+    asm.close()
