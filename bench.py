@@ -143,24 +143,38 @@ def run_gpu(args):
     hR = torch.empty(N, dtype=torch.float64).pin_memory()
     stream.synchronize()
 
+    peer = part is not None and not args.nccl_halo
+    if peer:
+        # fused halo: ghost-node REDs go straight into the owner's residual over NVLink peer memory
+        with torch.cuda.stream(stream):
+            part.enable_peer_scatter(asm)
+        stream.synchronize()
+
     def halo():
         if part is not None:
-            part.halo_sum_residual(asm, stream)
+            part.halo_sum_residual(asm, stream)   # peer mode: a stream-ordered barrier; else pack / NCCL / unpack
+
+    def pre():
+        if peer:
+            part.barrier_on_stream(stream)        # every rank has read and re-zeroed its residual
 
     def step_device():
         # assemble_vector!(residual) + assemble_stiffness!(stiffness) at the same Uu, as solve! does
         # (src/Solvers.jl:133-140), through the fused entry point; then the ghost->owner sum and residual(asm)
+        pre()
         F.assemble_vector_and_stiffness(asm, F.residual, F.stiffness, dUu, p)
         halo()
         F.residual(asm, dR)
 
     def step_unfused():
+        pre()
         F.assemble_vector(asm, F.residual, dUu, p)
         halo()
         F.residual(asm, dR)
         F.assemble_stiffness(asm, F.stiffness, dUu, p)
 
     def step_e2e():
+        pre()
         F.assemble_vector_and_stiffness(asm, F.residual, F.stiffness, hUu, p)  # H2D of Uu inside
         halo()
         F.residual(asm, hR)                             # D2H of the residual inside (synchronous)
@@ -288,7 +302,7 @@ def run_gpu(args):
             "config": {"workload": f"neohookean_hex8_{n}^3_per_gpu residual+tangent(CSR) per Newton iteration",
                        "elements_per_gpu": int(ne_local), "elements_total": int(ne_total), "dofs_per_gpu": int(len(asm.dof)),
                        "csr_nnz_per_gpu": int(asm.pattern()[2].shape[0]) if args.report_nnz else None,
-                       "parallelism": f"domain decomposition x{world}" if world > 1 else "single GPU",
+                       "parallelism": (f"domain decomposition x{world}, halo = " + ("fused peer-memory REDs over NVLink" if peer else "NCCL send/recv")) if world > 1 else "single GPU",
                        "l2": "inputs and outputs larger than L2 (CSR values 13.8 GB at 192^3); no flush needed",
                        "setup_s": round(setup_s, 1)},
             "e2e": {"value": round(e2e_value, 1), "unit": "elements/s", "ms_per_step": round(ms_e2e / args.steps, 4),
@@ -391,6 +405,7 @@ def main():
     ap.add_argument("--size", dest="n", type=int, default=int(os.environ.get("FECB200_BENCH_N", 192)), help="elements per axis per GPU")
     ap.add_argument("--cpu-n", type=int, default=48, help="elements per axis of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--nccl-halo", action="store_true", help="N > 1: pack / NCCL send-recv / unpack instead of the fused peer-memory scatter")
     ap.add_argument("--report-nnz", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

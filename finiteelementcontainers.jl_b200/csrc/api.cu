@@ -77,10 +77,22 @@ static void copy_out(fecb200_handle* h, double* dst, const double* src_dev, int6
   if (!dev) FEC_CUDA(cudaStreamSynchronize(h->stream));
 }
 static int64_t len_Uu(fecb200_handle* h) { return h->opts.condensed ? h->ndof : h->n_unknowns; }
+static double* field_ptr(fecb200_handle* h, int which) {
+  switch (which) {
+    case FECB200_FIELD_U: return h->d_U.p;
+    case FECB200_FIELD_RESIDUAL: return h->d_R.p;
+    case FECB200_FIELD_ACTION: return h->d_Av.p;
+    case FECB200_FIELD_V: return h->d_V.p;
+    default: throw Error("fecb200: bad field selector");
+  }
+}
 
 static void assemble_vector_impl(fecb200_handle* h, int mode, const double* Uu_dev, const double* Vu_dev,
                                  double* out_field) {
-  FEC_CUDA(cudaMemsetAsync(out_field, 0, h->ndof * sizeof(double), h->stream));  // fill!(storage, 0)  Vector.jl:30
+  // fill!(storage, 0) (Vector.jl:30).  In peer-scatter mode the field is zeroed right after it is read instead
+  // (fecb200_residual): neighbours may already be adding into it when this call starts.
+  if (!(h->peer_enabled && out_field == field_ptr(h, h->peer_field)))
+    FEC_CUDA(cudaMemsetAsync(out_field, 0, h->ndof * sizeof(double), h->stream));
   join_inputs(h);
   k_update_field(h, h->d_U.p, Uu_dev, true);
   if (Vu_dev) k_update_field(h, h->d_V.p, Vu_dev, false);  // V's BC slots stay 0 (Parameters.jl:415-425)
@@ -258,6 +270,7 @@ int fecb200_destroy(fecb200_handle* h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     cudaStream_t s = h->own_stream ? h->stream : nullptr;
     cudaStreamSynchronize(h->stream);
+    for (void* pp : h->peer_opened) cudaIpcCloseMemHandle(pp);
     if (h->s_h2d) { cudaStreamSynchronize(h->s_h2d); cudaStreamDestroy(h->s_h2d); }
     if (h->s_d2h) { cudaStreamSynchronize(h->s_d2h); cudaStreamDestroy(h->s_d2h); }
     for (cudaEvent_t ev : {h->ev_h2d, h->ev_in_consumed, h->ev_prod, h->ev_d2h}) if (ev) cudaEventDestroy(ev);
@@ -474,6 +487,8 @@ int fecb200_residual(fecb200_handle* h, double* out) {
   double* target = dev ? out : h->d_out.p;
   if (!dev) wait_out_free(h);
   k_residual_accessor(h, target);
+  if (h->peer_enabled && h->peer_field == FECB200_FIELD_RESIDUAL)  // ready for the neighbours' next scatter
+    FEC_CUDA(cudaMemsetAsync(h->d_R.p, 0, h->ndof * sizeof(double), h->stream));
   if (!dev) copy_out(h, out, target, len_Uu(h));
   FEC_API_END
 }
@@ -508,7 +523,8 @@ int fecb200_assemble_vector_and_matrix(fecb200_handle* h, const double* Uu) {
 
 static void assemble_vector_and_matrix_impl(fecb200_handle* h, const double* u) {
   double* nz = nz_for_kind(h, FECB200_STIFFNESS, true);
-  FEC_CUDA(cudaMemsetAsync(h->d_R.p, 0, h->ndof * sizeof(double), h->stream));
+  if (!(h->peer_enabled && h->peer_field == FECB200_FIELD_RESIDUAL))
+    FEC_CUDA(cudaMemsetAsync(h->d_R.p, 0, h->ndof * sizeof(double), h->stream));
   FEC_CUDA(cudaMemsetAsync(nz, 0, h->nnz * sizeof(double), h->stream));   // the H2D of Uu (async mode) overlaps this
   join_inputs(h);
   k_update_field(h, h->d_U.p, u, true);
@@ -740,15 +756,6 @@ int fecb200_halo_setup(fecb200_handle* h, int32_t n_neighbors, const int32_t* ra
   FEC_API_END
 }
 
-static double* field_ptr(fecb200_handle* h, int which) {
-  switch (which) {
-    case FECB200_FIELD_U: return h->d_U.p;
-    case FECB200_FIELD_RESIDUAL: return h->d_R.p;
-    case FECB200_FIELD_ACTION: return h->d_Av.p;
-    case FECB200_FIELD_V: return h->d_V.p;
-    default: throw Error("fecb200: bad field selector");
-  }
-}
 
 int fecb200_halo_pack(fecb200_handle* h, int32_t which, double* sendbuf_dev) {
   FEC_API_BEGIN
@@ -777,6 +784,66 @@ int fecb200_halo_recv_size(fecb200_handle* h, int64_t* n_doubles) {
   FEC_API_BEGIN
   FEC_REQUIRE(h && n_doubles, "null argument");
   *n_doubles = (int64_t)h->d_recv_nodes.n * h->nf;
+  FEC_API_END
+}
+
+int fecb200_ipc_export(fecb200_handle* h, int32_t which, void* handle64) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && handle64, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  FEC_CUDA(cudaSetDevice(h->device));
+  cudaIpcMemHandle_t mh;
+  FEC_CUDA(cudaIpcGetMemHandle(&mh, field_ptr(h, which)));
+  memcpy(handle64, &mh, 64);
+  FEC_API_END
+}
+
+static void peer_detach_impl(fecb200_handle* h) {
+  for (void* p : h->peer_opened) cudaIpcCloseMemHandle(p);
+  h->peer_opened.clear();
+  h->peer_enabled = false;
+  h->peer = fec::PeerScatter{-1, nullptr, nullptr, {nullptr}};
+}
+
+int fecb200_peer_attach(fecb200_handle* h, int32_t which, int32_t n_peers, const void* handles64,
+                        const int32_t* ghost_peer, const int64_t* ghost_node, int64_t n_ghosts) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && (n_peers == 0 || handles64), "null argument");
+  FEC_REQUIRE(n_peers >= 0 && n_peers <= kMaxPeers, "too many peers");
+  FEC_REQUIRE(n_ghosts == h->nn - h->n_owned_nodes, "ghost arrays must cover every ghost node (call partition_setup first)");
+  FEC_REQUIRE(which == FECB200_FIELD_RESIDUAL || which == FECB200_FIELD_ACTION, "peer scatter targets the residual or action field");
+  FEC_CUDA(cudaSetDevice(h->device));
+  FEC_CUDA(cudaStreamSynchronize(h->stream));
+  peer_detach_impl(h);
+  h->peer.n_owned = h->n_owned_nodes;
+  for (int i = 0; i < n_peers; ++i) {
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, (const char*)handles64 + 64 * i, 64);
+    void* ptr = nullptr;
+    FEC_CUDA(cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_opened.push_back(ptr);
+    h->peer.base[i] = (double*)ptr;
+  }
+  std::vector<int32_t> gp(ghost_peer, ghost_peer + n_ghosts), gn(n_ghosts);
+  for (int64_t g = 0; g < n_ghosts; ++g) {
+    FEC_REQUIRE(gp[g] >= -1 && gp[g] < n_peers, "ghost_peer out of range");
+    gn[g] = gp[g] >= 0 ? (int32_t)ghost_node[g] : 0;
+  }
+  h->d_ghost_peer.upload(gp, h->stream);
+  h->d_ghost_node.upload(gn, h->stream);
+  h->peer.ghost_peer = h->d_ghost_peer.p;
+  h->peer.ghost_node = h->d_ghost_node.p;
+  h->peer_field = which;
+  h->peer_enabled = true;
+  FEC_API_END
+}
+
+int fecb200_peer_detach(fecb200_handle* h) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h, "null handle");
+  FEC_CUDA(cudaSetDevice(h->device));
+  FEC_CUDA(cudaStreamSynchronize(h->stream));
+  peer_detach_impl(h);
   FEC_API_END
 }
 

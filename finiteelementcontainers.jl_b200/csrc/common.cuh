@@ -76,6 +76,29 @@ constexpr int kTE = FEC_TE;        // elements per tile = threads per CTA of the
 constexpr int kMinB3 = FEC_MINB3;  // __launch_bounds__ min CTAs/SM for NF = 3 vector kernels
 constexpr int kMinB1 = FEC_MINB1;  // ... for NF <= 2
 constexpr int kMaxProps = 8;
+constexpr int kMaxPeers = 8;
+
+// Ghost-node scatter over NVLink peer memory (fecb200_peer_attach): contributions to a node this rank does not
+// own are added straight into the OWNER's field with system-scope REDs, instead of pack -> NCCL -> unpack.
+struct PeerScatter {
+  int64_t n_owned;              // local nodes >= n_owned are ghosts; < 0 disables the remote path
+  const int32_t* ghost_peer;    // [nn - n_owned] index into base[] (or -1: ghost never touched by owned elements)
+  const int32_t* ghost_node;    // [nn - n_owned] 0-based local node id on the owner
+  double* base[kMaxPeers];      // peer-mapped residual fields (cudaIpcOpenMemHandle)
+};
+
+__device__ __forceinline__ void scatter_add(const PeerScatter& ps, double* local, int64_t n, int nf, int d, double v) {
+  if (ps.n_owned >= 0 && n >= ps.n_owned) {
+    const int64_t g = n - ps.n_owned;
+    const int pr = ps.ghost_peer[g];
+    if (pr >= 0) {
+      double* dst = ps.base[pr] + (int64_t)ps.ghost_node[g] * nf + d;
+      asm volatile("red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(dst), "d"(v) : "memory");
+    }
+  } else {
+    atomicAdd(&local[n * nf + d], v);
+  }
+}
 constexpr int kMaxNQ = 27;  // runtime-NQ kernels (e.g. 3-point GLL on hex8)
 
 // One element block: FunctionSpace block + ReferenceFE tables + physics (host side of the plan)
@@ -140,6 +163,13 @@ struct fecb200_handle {
   fec::DevBuf<int64_t> d_rowstart, d_diagslot;
   fec::DevBuf<double> d_nz_stiff, d_nz_mass, d_scratch;
   bool stiff_adjusted = false, mass_adjusted = false;
+
+  // peer-memory halo (fecb200_peer_attach)
+  bool peer_enabled = false;
+  int peer_field = 0;
+  std::vector<void*> peer_opened;          // pointers returned by cudaIpcOpenMemHandle (closed in destroy)
+  fec::DevBuf<int32_t> d_ghost_peer, d_ghost_node;
+  fec::PeerScatter peer{-1, nullptr, nullptr, {nullptr}};
 
   // halo exchange
   int n_neighbors = 0;

@@ -35,6 +35,7 @@ struct Mat2Params {
   double* state_new;         // written when the residual is fused (stateful physics)
   double* R;                 // fused residual target (full-length field) or nullptr
   int64_t nnz;               // the trash region of the branch-free RED stream starts at nz[nnz]
+  PeerScatter peer;          // ghost rows of the fused residual go to their owner over NVLink
   int32_t ne, nq;
   double props[kMaxProps];
   Tables<ND, NNPE, NQT> tab;
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
     if (active && d1 == d2) {
 #pragma unroll
       for (int a = 0; a < NNPE; ++a)
-        atomicAdd(&p.R[(size_t)p.conn[(size_t)e * NNPE + a] * NF + d1], rr[a]);  // 24 REDs per element
+        scatter_add(p.peer, p.R, p.conn[(size_t)e * NNPE + a], NF, d1, rr[a]);  // 24 REDs per element
     }
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
@@ -344,6 +345,8 @@ void run_mat2_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   FEC_REQUIRE((int)b.emeta_rec == L::REC, "scatter record size mismatch");
   p.conn = b.d_conn_perm.p; p.emeta = b.d_emeta.p;
   p.R = a.R; p.state_new = b.d_state_new.p;
+  p.peer = h->peer;
+  if (!h->peer_enabled || h->peer_field != FECB200_FIELD_RESIDUAL) p.peer.n_owned = -1;
   p.state_old = b.d_state_old.p;
   p.ne = (int32_t)b.ne; p.nq = b.nq; p.nnz = h->nnz;
   for (int i = 0; i < kMaxProps; ++i) p.props[i] = i < (int)b.props.size() ? b.props[i] : 0.0;

@@ -52,6 +52,7 @@ struct VecParams {
   const double* state_old;
   double* state_new;
   const double* source;
+  PeerScatter peer;
   int32_t ne, nq;
   double props[kMaxProps];
   Tables<ND, NNPE, NQT> tab;
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(TE, MINB) k_vec(const __grid_constant__ VecPar
     }
     const int n = p.tile_nodes[nb + i];
 #pragma unroll
-    for (int d = 0; d < NF; ++d) atomicAdd(&p.out[(size_t)n * NF + d], acc[d]);  // RED.E.ADD.F64
+    for (int d = 0; d < NF; ++d) scatter_add(p.peer, p.out, n, NF, d, acc[d]);  // RED.E.ADD.F64 (local) / RED.SYS (ghost)
   }
 }
 
@@ -521,6 +522,8 @@ void run_vec(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
   p.tile_node_ptr = b.d_tile_node_ptr.p; p.tile_nodes = b.d_tile_nodes.p; p.lconn = b.d_lconn.p;
   p.inc_ptr = b.d_inc_ptr.p; p.inc = b.d_inc.p;
   p.state_old = b.d_state_old.p; p.state_new = b.d_state_new.p; p.source = b.d_source.p;
+  p.peer = h->peer;
+  if (!h->peer_enabled || a.out != (h->peer_field == FECB200_FIELD_RESIDUAL ? h->d_R.p : h->d_Av.p)) p.peer.n_owned = -1;
   p.ne = (int32_t)b.ne; p.nq = b.nq;
   for (int i = 0; i < kMaxProps; ++i) p.props[i] = i < (int)b.props.size() ? b.props[i] : 0.0;
   fill_tables<ND, NNPE, NQT>(b, p.tab);

@@ -100,6 +100,9 @@ SIGNATURES = {
     "fecb200_halo_send_size": (C.c_int, [Handle, c_i64p]),
     "fecb200_halo_unpack_add": (C.c_int, [Handle, C.c_int32, VP]),
     "fecb200_halo_recv_size": (C.c_int, [Handle, c_i64p]),
+    "fecb200_ipc_export": (C.c_int, [Handle, C.c_int32, C.c_void_p]),
+    "fecb200_peer_attach": (C.c_int, [Handle, C.c_int32, C.c_int32, C.c_void_p, c_i32p, c_i64p, C.c_int64]),
+    "fecb200_peer_detach": (C.c_int, [Handle]),
     "fecb200_launch_count": (C.c_int, [Handle, c_i64p]),
     "fecb200_enable_timing": (C.c_int, [Handle, C.c_int32]),
     "fecb200_last_kernel_ms": (C.c_int, [Handle, C.POINTER(C.c_float)]),

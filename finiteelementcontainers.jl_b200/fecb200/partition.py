@@ -100,9 +100,61 @@ class Partition:
         self._send_counts = [int(sp[i + 1] - sp[i]) * self._nf for i in range(len(nbrs))]
         self._recv_counts = [int(rp[i + 1] - rp[i]) * self._nf for i in range(len(nbrs))]
 
+    def enable_peer_scatter(self, asm):
+        """Switch the residual halo to the fused NVLink path: kernels add ghost contributions directly into the
+        owner's residual through peer-mapped memory (CUDA IPC).  Needs an initialised NCCL process group."""
+        import torch
+        import torch.distributed as dist
+        h = asm._require()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        sc = [len(self.send.get(r, ())) for r in self.neighbors]
+        rc = [len(self.recv.get(r, ())) for r in self.neighbors]
+        # owner-local ids of my ghosts: every neighbour tells me ITS local ids of the nodes it receives from me
+        mine = np.concatenate([self.recv[r] for r in self.neighbors if r in self.recv] or [np.zeros(0, dtype=np.int64)])
+        mine_t = torch.from_numpy(np.ascontiguousarray(mine)).to(dev)
+        theirs_t = torch.zeros(max(1, sum(sc)), dtype=torch.int64, device=dev)
+        exchange(self.neighbors, mine_t, rc, theirs_t, sc)
+        theirs = theirs_t.cpu().numpy()
+        # IPC handles of every rank's residual field
+        buf = (C.c_ubyte * 64)()
+        check(lib.fecb200_ipc_export(h, _lib.FIELD_RESIDUAL, C.cast(buf, C.c_void_p)))
+        mine_h = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+        allh = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(self.nparts)]
+        dist.all_gather(allh, mine_h)
+        peers = [r for r in self.neighbors if r in self.send]
+        assert len(peers) <= 8
+        handles = b"".join(bytes(allh[r].cpu().numpy().tolist()) for r in peers)
+        n_ghost = len(self.local_to_global) - self.n_owned_nodes
+        gpeer = np.full(n_ghost, -1, dtype=np.int32)
+        gnode = np.zeros(n_ghost, dtype=np.int64)
+        off = 0
+        for r, ns in zip(self.neighbors, sc):
+            if ns:
+                g = self.send[r] - 1 - self.n_owned_nodes
+                gpeer[g] = peers.index(r)
+                gnode[g] = theirs[off:off + ns] - 1
+            off += ns
+        hb = C.create_string_buffer(handles, max(64, len(handles)))
+        check(lib.fecb200_peer_attach(h, _lib.FIELD_RESIDUAL, len(peers), C.cast(hb, C.c_void_p),
+                                      gpeer.ctypes.data_as(_lib.c_i32p), gnode.ctypes.data_as(_lib.c_i64p), n_ghost))
+        self._peer = True
+        self._bar = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def barrier_on_stream(self, stream=None):
+        """stream-ordered cross-rank barrier (a 4-byte NCCL all-reduce): orders the peer scatter phases"""
+        import torch
+        import torch.distributed as dist
+        ctx = torch.cuda.stream(stream) if stream is not None else _nullctx()
+        with ctx:
+            dist.all_reduce(self._bar)
+
     def halo_sum_residual(self, asm, stream=None, field=_lib.FIELD_RESIDUAL):
         """ghost -> owner accumulation of the assembled residual (device pack, NCCL send/recv, device add)"""
         import torch
+        if getattr(self, "_peer", False):
+            # fused path: the kernels already added the ghost rows into their owners; just wait for everyone
+            self.barrier_on_stream(stream)
+            return
         h = asm._require()
         if self._sendbuf is None:
             dev = torch.device("cuda", torch.cuda.current_device())

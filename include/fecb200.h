@@ -224,6 +224,20 @@ int fecb200_halo_send_size(fecb200_handle* h, int64_t* n_doubles);
 int fecb200_halo_unpack_add(fecb200_handle* h, int32_t which_field, const double* recvbuf_dev);
 int fecb200_halo_recv_size(fecb200_handle* h, int64_t* n_doubles);
 
+/* Peer-memory halo (one process per GPU, NVLink / NVSwitch): instead of pack -> NCCL send/recv -> unpack, the
+ * assembly kernels add the contributions of ghost nodes straight into the OWNER's field with system-scope REDs
+ * over peer-mapped memory.
+ *   fecb200_ipc_export      64-byte cudaIpcMemHandle_t of this handle's field (host exchanges it, e.g. all_gather)
+ *   fecb200_peer_attach     open the neighbours' handles; ghost_peer[g] / ghost_node[g] give, for ghost g =
+ *                           local node n_owned + g, the index into `handles` (or -1) and the 0-based node id on
+ *                           the owner.  Needs fecb200_partition_setup first.
+ * The host must order steps across ranks: every rank's field is zeroed before any rank scatters, and all ranks
+ * finished scattering before an owner reads (two stream-ordered barriers per assembly). */
+int fecb200_ipc_export(fecb200_handle* h, int32_t which_field, void* handle64);
+int fecb200_peer_attach(fecb200_handle* h, int32_t which_field, int32_t n_peers, const void* handles64,
+                        const int32_t* ghost_peer, const int64_t* ghost_node, int64_t n_ghosts);
+int fecb200_peer_detach(fecb200_handle* h);
+
 /* ---- instrumentation: kernels launched by this handle since creation (bench `gpu_launches`) */
 int fecb200_launch_count(fecb200_handle* h, int64_t* n);
 /* last kernel timing (ms) measured with CUDA events on the handle's stream around the dominant

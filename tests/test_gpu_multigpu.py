@@ -1,0 +1,21 @@
+"""Multi-GPU check (needs >= 2 visible GPUs, skipped otherwise): the fused peer-memory halo (ghost-node REDs
+into the owner's residual over NVLink) against the NCCL pack / send-recv / unpack halo, under torchrun."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_peer_memory_halo_matches_nccl():
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(ROOT, "tests", "run_peer_check.py"), "16"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "OK" in out.stdout and "FAIL" not in out.stdout, out.stdout[-2000:]
