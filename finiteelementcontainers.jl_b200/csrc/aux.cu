@@ -108,7 +108,7 @@ void k_zero_bc_slots(fecb200_handle* h, double* field) {
 // ---- per-element scatter records for k_mat2 (layout: Mat2Layout in kernel_mat2.cuh); one thread per element
 __global__ void k_build_emeta(const int32_t* conn, const uint8_t* epos, const int32_t* adjptr, const uint16_t* coloff,
                               const uint8_t* freemask, const int64_t* rowstart, unsigned char* emeta, int nnpe, int nf,
-                              int rec, int64_t ne) {
+                              int rec, int64_t ne, int sorted_cols) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= ne) return;
   const int32_t* c = conn + e * nnpe;
@@ -121,9 +121,9 @@ __global__ void k_build_emeta(const int32_t* conn, const uint8_t* epos, const in
   for (int a = 0; a < nnpe; ++a) {
     int k = 0;
     for (int a2 = 0; a2 < nnpe; ++a2) k += (c[a2] < c[a]) || (c[a2] == c[a] && a2 < a);
-    rank[a] = k;
-    rk[a] = (uint8_t)k;
-    mk[k] = freemask[c[a]];
+    rank[a] = sorted_cols ? k : a;   // scalar kernel: columns stay indexed by local node
+    rk[a] = (uint8_t)rank[a];
+    mk[rank[a]] = freemask[c[a]];
   }
   for (int b = 0; b < nnpe; ++b) {
     for (int d = 0; d < nf; ++d) {
@@ -142,9 +142,10 @@ void build_ecol(fecb200_handle* h) {
     const size_t rec = (((size_t)b.nnpe * h->nf * 4 + (size_t)b.nnpe * b.nnpe * 2 + 2 * b.nnpe + 15) / 16) * 16;
     if (b.d_emeta.n != rec * b.ne) b.d_emeta.alloc(rec * b.ne);
     b.emeta_rec = rec;
+    b.emeta_sorted = h->nf > 1;  // k_mat2 wants address-sorted columns; the scalar kernel indexes by local node
     k_build_emeta<<<grid_for(b.ne), 256, 0, h->stream>>>(b.d_conn_perm.p, b.d_epos.p, h->d_adjptr.p, h->d_coloff.p,
                                                          h->d_freemask.p, h->d_rowstart.p, b.d_emeta.p, b.nnpe, h->nf,
-                                                         (int)rec, b.ne);
+                                                         (int)rec, b.ne, b.emeta_sorted ? 1 : 0);
     h->launches++;
   }
   FEC_CUDA(cudaGetLastError());

@@ -1,6 +1,7 @@
 // dispatch_hex8.cu -- HEX8 instantiations of the element kernels (3-D, 8 nodes).
 // Hot configurations (BASELINE.json configs 2, 3, 5): Poisson NF=1 and neo-Hookean NF=3 with 8-point rules.
 #include "kernel_mat2.cuh"
+#include "kernel_mat_scalar.cuh"
 
 #ifndef FEC_MAT2_WARPS
 #define FEC_MAT2_WARPS 4
@@ -48,7 +49,9 @@ void launch_matrix_hex8(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   switch (b.physics) {
     case FECB200_PHYS_POISSON:
       FEC_REQUIRE(h->nf == 1, "Poisson needs NF = 1");
-      if (b.nq == 8) run_mat<3, 8, 1, 8, PhysPoisson<3>, 32>(h, b, a);
+      if (b.nq == 8 && b.d_emeta.p && !b.emeta_sorted && h->nnz + 4096 < (int64_t)0xFFFFFFFFll && !getenv("FECB200_KMAT1"))
+        run_mat_scalar<3, 8, 8, PhysPoisson<3>>(h, b, a);   // register-resident thread-per-element kernel
+      else if (b.nq == 8) run_mat<3, 8, 1, 8, PhysPoisson<3>, 32>(h, b, a);
       else run_mat<3, 8, 1, 0, PhysPoisson<3>, 32>(h, b, a);
       break;
     case FECB200_PHYS_LINEAR_ELASTIC: mat8<PhysLinearElastic<3>, 3, 16>(h, b, a); break;

@@ -1,0 +1,141 @@
+// kernel_mat_scalar.cuh -- stiffness / mass -> CSR for scalar problems (NF = 1, e.g. Poisson, BASELINE config 2).
+//
+// One thread per element, everything in registers: no shared memory, no barriers.  The NNPE x NNPE element
+// matrix is accumulated over the quadrature points and written straight into the CSR values through the
+// per-element scatter record (row offsets u32, column offsets u16 indexed by LOCAL node -- see k_build_emeta with
+// sorted_cols = 0).  REDs are branch-free (eliminated rows / columns go to the hashed trash region behind nz).
+// Honours the reference's transposed COO convention (K[dof_b, dof_a] += K_el[a, b]) through TRANS.
+#pragma once
+#include "kernels.cuh"
+
+namespace fec {
+
+template <int ND, int NNPE, int NQT>
+struct MatSParams {
+  const double* X;
+  const double* U;
+  double* nz;
+  const int32_t* conn;
+  const unsigned char* emeta;
+  int64_t nnz;
+  int32_t ne, nq, rec;
+  double props[kMaxProps];
+  Tables<ND, NNPE, NQT> tab;
+};
+
+template <int ND, int NNPE, int NQT, class Phys, int KIND, bool TRANS>
+__global__ void __launch_bounds__(128) k_mat_scalar(const __grid_constant__ MatSParams<ND, NNPE, NQT> p) {
+  static_assert(Phys::NF == 1 && Phys::NS == 0, "scalar, stateless physics");
+  const int e = blockIdx.x * 128 + threadIdx.x;
+  if (e >= p.ne) return;
+  double x[NNPE][ND], u[NNPE][1];
+#pragma unroll
+  for (int a = 0; a < NNPE; ++a) {
+    const int n = p.conn[(size_t)e * NNPE + a];
+#pragma unroll
+    for (int j = 0; j < ND; ++j) x[a][j] = p.X[(size_t)n * ND + j];
+    u[a][0] = p.U[n];
+  }
+  double K[NNPE][NNPE];
+#pragma unroll
+  for (int a = 0; a < NNPE; ++a)
+#pragma unroll
+    for (int b = 0; b < NNPE; ++b) K[a][b] = 0.0;
+  const int nq = (NQT > 0) ? NQT : p.nq;
+#pragma unroll 1
+  for (int q = 0; q < nq; ++q) {
+    double J[ND][ND];
+#pragma unroll
+    for (int i = 0; i < ND; ++i)
+#pragma unroll
+      for (int j = 0; j < ND; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < NNPE; ++a) s = fma(x[a][i], p.tab.dN[q][a][j], s);
+        J[i][j] = s;
+      }
+    double Ji[ND][ND];
+    const double JxW = invert<ND>(J, Ji) * p.tab.w[q];
+    if constexpr (KIND == FECB200_MASS) {
+      const double rho = JxW * Phys::density(p.props);
+#pragma unroll
+      for (int a = 0; a < NNPE; ++a)
+#pragma unroll
+        for (int b = 0; b < NNPE; ++b) K[a][b] = fma(rho * p.tab.N[q][a], p.tab.N[q][b], K[a][b]);
+    } else {
+      double g[NNPE][ND], gu[1][ND];
+#pragma unroll
+      for (int k = 0; k < ND; ++k) gu[0][k] = 0.0;
+#pragma unroll
+      for (int a = 0; a < NNPE; ++a)
+#pragma unroll
+        for (int k = 0; k < ND; ++k) {
+          double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < ND; ++j) s = fma(p.tab.dN[q][a][j], Ji[j][k], s);
+          g[a][k] = s;
+          gu[0][k] = fma(u[a][0], s, gu[0][k]);
+        }
+      double A[ND][ND];
+      Phys::tangent(gu, p.props, nullptr, A);
+#pragma unroll
+      for (int b = 0; b < NNPE; ++b) {
+        double tb[ND];
+#pragma unroll
+        for (int j1 = 0; j1 < ND; ++j1) {
+          double s = 0.0;
+#pragma unroll
+          for (int j2 = 0; j2 < ND; ++j2) s = fma(A[j1][j2], g[b][j2], s);
+          tb[j1] = s * JxW;
+        }
+#pragma unroll
+        for (int a = 0; a < NNPE; ++a) {
+          double s = K[a][b];
+#pragma unroll
+          for (int j1 = 0; j1 < ND; ++j1) s = fma(g[a][j1], tb[j1], s);
+          K[a][b] = s;
+        }
+      }
+    }
+  }
+  // ---- scatter: record = u32 rowstart[NNPE] | u16 ecol[NNPE][NNPE] (by local node) | u8 mask[NNPE] | u8 rank[NNPE]
+  const unsigned char* rec = p.emeta + (size_t)e * p.rec;
+  uint32_t rs[NNPE];
+  unsigned mk[NNPE];
+#pragma unroll
+  for (int a = 0; a < NNPE; ++a) { rs[a] = reinterpret_cast<const uint32_t*>(rec)[a]; mk[a] = rec[NNPE * 4 + NNPE * NNPE * 2 + a]; }
+  const uint16_t* ec = reinterpret_cast<const uint16_t*>(rec + NNPE * 4);
+  const uint32_t trash = (uint32_t)p.nnz + (((uint32_t)e * 613u) & 4095u);
+#pragma unroll
+  for (int r = 0; r < NNPE; ++r)     // storage row node
+#pragma unroll
+    for (int c = 0; c < NNPE; ++c) { // storage column node
+      const bool ok = rs[r] != 0xFFFFFFFFu && (mk[c] & 1u);
+      const uint32_t idx = ok ? rs[r] + ec[r * NNPE + c] : (uint32_t)p.nnz + ((trash + r * 8u + c) & 4095u);
+      // CSR: K_glob[dof_r, dof_c] += K_el[c, r]; CSC storage holds the transpose of that
+      const double v = TRANS ? K[r][c] : K[c][r];
+      asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p.nz + idx), "d"(v));
+    }
+}
+
+template <int ND, int NNPE, int NQT, class Phys>
+void run_mat_scalar(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
+  auto pp = std::make_unique<MatSParams<ND, NNPE, NQT>>();
+  auto& p = *pp;
+  FEC_REQUIRE(h->nnz + 4096 < (int64_t)0xFFFFFFFFll && b.d_emeta.p && !b.emeta_sorted, "scalar matrix kernel: bad scatter records");
+  p.X = h->d_X.p; p.U = a.U; p.nz = a.nz; p.conn = b.d_conn_perm.p; p.emeta = b.d_emeta.p; p.nnz = h->nnz;
+  p.ne = (int32_t)b.ne; p.nq = b.nq; p.rec = (int32_t)b.emeta_rec;
+  for (int i = 0; i < kMaxProps; ++i) p.props[i] = i < (int)b.props.size() ? b.props[i] : 0.0;
+  fill_tables<ND, NNPE, NQT>(b, p.tab);
+  const int grid = (int)((b.ne + 127) / 128);
+  const bool trans = (h->opts.matrix_type == FECB200_CSC);
+  timing_begin(h);
+  if (a.kind == FECB200_MASS) k_mat_scalar<ND, NNPE, NQT, Phys, FECB200_MASS, false><<<grid, 128, 0, h->stream>>>(p);
+  else if (trans) k_mat_scalar<ND, NNPE, NQT, Phys, FECB200_STIFFNESS, true><<<grid, 128, 0, h->stream>>>(p);
+  else k_mat_scalar<ND, NNPE, NQT, Phys, FECB200_STIFFNESS, false><<<grid, 128, 0, h->stream>>>(p);
+  FEC_CUDA(cudaGetLastError());
+  timing_end(h);
+  h->launches++;
+}
+
+}  // namespace fec
