@@ -54,6 +54,7 @@ struct VecParams {
   const double* source;
   PeerScatter peer;
   int32_t ne, nq;
+  int32_t body_doubles, max_nodes;  // shared-memory layout: [node data | element-vector stage][node ids][inc_ptr][inc]
   double props[kMaxProps];
   Tables<ND, NNPE, NQT> tab;
 };
@@ -198,12 +199,19 @@ __global__ void __launch_bounds__(TE, MINB) k_vec(const __grid_constant__ VecPar
   const int nb = p.tile_node_ptr[tile];
   const int nn = p.tile_node_ptr[tile + 1] - nb;
 
-  // ---- 1. gather the tile's nodes once
+  // ---- 1. gather the tile's nodes once; the scatter metadata of phase 4 (node ids, incidence lists) is
+  // fetched now as well, so that phase has no global-load latency chain left (it was ~25 % of the kernel)
   double* sX = smem;
   double* sU = sX + nn * ND;
   double* sV = sU + nn * NF;
+  int32_t* sNode = reinterpret_cast<int32_t*>(smem + p.body_doubles);
+  int32_t* sIncPtr = sNode + p.max_nodes;
+  uint16_t* sInc = reinterpret_cast<uint16_t*>(sIncPtr + p.max_nodes + 1);
+  const int k_base = p.inc_ptr[nb];
   for (int i = tid; i < nn; i += TE) {
     const int n = p.tile_nodes[nb + i];
+    sNode[i] = n;
+    sIncPtr[i] = p.inc_ptr[nb + i] - k_base;
 #pragma unroll
     for (int j = 0; j < ND; ++j) sX[i * ND + j] = p.X[(size_t)n * ND + j];
 #pragma unroll
@@ -213,6 +221,9 @@ __global__ void __launch_bounds__(TE, MINB) k_vec(const __grid_constant__ VecPar
       for (int d = 0; d < NF; ++d) sV[i * NF + d] = p.V[(size_t)n * NF + d];
     }
   }
+  const int n_inc = p.inc_ptr[nb + nn] - k_base;
+  if (tid == 0) sIncPtr[nn] = n_inc;
+  for (int k = tid; k < n_inc; k += TE) sInc[k] = p.inc[k_base + k];
   __syncthreads();
 
   // ---- 2. element-level fields into registers (_element_level_fields_flat, Assemblers.jl:161-188)
@@ -276,13 +287,13 @@ __global__ void __launch_bounds__(TE, MINB) k_vec(const __grid_constant__ VecPar
     double acc[NF];
 #pragma unroll
     for (int d = 0; d < NF; ++d) acc[d] = 0.0;
-    const int k0 = p.inc_ptr[nb + i], k1 = p.inc_ptr[nb + i + 1];
+    const int k0 = sIncPtr[i], k1 = sIncPtr[i + 1];
     for (int k = k0; k < k1; ++k) {
-      const int s = p.inc[k];  // = a*NF*TE + t
+      const int s = sInc[k];  // = a*NF*TE + t
 #pragma unroll
       for (int d = 0; d < NF; ++d) acc[d] += sR[s + d * TE];
     }
-    const int n = p.tile_nodes[nb + i];
+    const int n = sNode[i];
 #pragma unroll
     for (int d = 0; d < NF; ++d) scatter_add(p.peer, p.out, n, NF, d, acc[d]);  // RED.E.ADD.F64 (local) / RED.SYS (ghost)
   }
@@ -530,7 +541,10 @@ void run_vec(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
   const int nfields = (MODE == MODE_RESIDUAL) ? 1 : 2;
   size_t sm_nodes = (size_t)b.max_tile_nodes * (ND + nfields * NF) * sizeof(double);
   size_t sm_stage = (size_t)NNPE * NF * TE * sizeof(double);
-  size_t smem = sm_nodes > sm_stage ? sm_nodes : sm_stage;
+  size_t body = sm_nodes > sm_stage ? sm_nodes : sm_stage;
+  p.body_doubles = (int32_t)(body / sizeof(double));
+  p.max_nodes = b.max_tile_nodes;
+  size_t smem = body + (size_t)(2 * b.max_tile_nodes + 1) * sizeof(int32_t) + (size_t)NNPE * TE * sizeof(uint16_t) + 8;
   auto kern = k_vec<ND, NNPE, NF, NQT, Phys, MODE, TE, MINB>;
   FEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   timing_begin(h);
