@@ -34,6 +34,9 @@ BYTES_ACTION = 160.0
 # FP64 flops per element counted from the kernels' instruction mix
 FLOPS_RESIDUAL = 7.0e3
 FLOPS_TANGENT = 40.0e3      # fused k_mat2: FP64 warp-instructions x 64 / elements (ncu)
+# DRAM bytes per launch of the dominant kernel from the `ncu --set full` capture of this same command
+# (profiles/r01h_fused_kmat2_details.txt: dram__bytes_read.sum 16.80 GB + dram__bytes_write.sum 14.45 GB at 192^3)
+TRAFFIC_NCU_BYTES_PER_ELEMENT = (16.796e9 + 14.452e9) / 7077888
 NEO_PROPS = np.array([1e3, 10.0e6, 1.0e6])
 
 
@@ -304,7 +307,8 @@ def run_gpu(args):
             fp64_peak = 2 * 2 * 6144 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
             del a
             roof = {"bound": "hbm", "kernel": "k_mat2<hex8,NF=3,neo-Hookean,WITH_R> (fused residual + tangent -> CSR)", "achieved": round(ach, 1),
-                    "peak": hbm, "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / hbm, 4), "traffic": None,
+                    "peak": hbm, "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / hbm, 4), "traffic": round(TRAFFIC_NCU_BYTES_PER_ELEMENT * ne_local),
+                    "traffic_note": "dram read+write bytes per launch, ncu --set full (profiles/r01h_fused_kmat2_details.txt); 2.1x algorithmic: zero-fill write-back + RED read-modify-write of the CSR values",
                     "algorithmic_bytes_per_element": BYTES_FUSED, "kernel_ms": round(k_tan, 4),
                     "fp64": {"flops_per_element": FLOPS_TANGENT,
                              "achieved_tflops": round(FLOPS_TANGENT * ne_local / (k_tan * 1e-3) / 1e12, 2),

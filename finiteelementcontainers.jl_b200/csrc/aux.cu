@@ -117,6 +117,7 @@ __global__ void k_build_emeta(const int32_t* conn, const uint8_t* epos, const in
   uint16_t* ec = reinterpret_cast<uint16_t*>(r + nnpe * nf * 4);
   uint8_t* mk = r + nnpe * nf * 4 + nnpe * nnpe * 2;
   uint8_t* rk = mk + nnpe;
+  uint32_t* nd = reinterpret_cast<uint32_t*>(rk + nnpe);
   int rank[16];
   for (int a = 0; a < nnpe; ++a) {
     int k = 0;
@@ -124,6 +125,7 @@ __global__ void k_build_emeta(const int32_t* conn, const uint8_t* epos, const in
     rank[a] = sorted_cols ? k : a;   // scalar kernel: columns stay indexed by local node
     rk[a] = (uint8_t)rank[a];
     mk[rank[a]] = freemask[c[a]];
+    nd[rank[a]] = (uint32_t)c[a];
   }
   for (int b = 0; b < nnpe; ++b) {
     for (int d = 0; d < nf; ++d) {
@@ -139,7 +141,7 @@ void build_ecol(fecb200_handle* h) {
   if (!h->matrix_ready || h->nnz >= (int64_t)0xFFFFFFFFll) return;
   for (auto& b : h->blocks) {
     if (b.nnpe > 16) continue;
-    const size_t rec = (((size_t)b.nnpe * h->nf * 4 + (size_t)b.nnpe * b.nnpe * 2 + 2 * b.nnpe + 15) / 16) * 16;
+    const size_t rec = (((size_t)b.nnpe * h->nf * 4 + (size_t)b.nnpe * b.nnpe * 2 + 2 * b.nnpe + 4 * b.nnpe + 15) / 16) * 16;
     if (b.d_emeta.n != rec * b.ne) b.d_emeta.alloc(rec * b.ne);
     b.emeta_rec = rec;
     b.emeta_sorted = h->nf > 1;  // k_mat2 wants address-sorted columns; the scalar kernel indexes by local node

@@ -64,7 +64,8 @@ struct Mat2Layout {
   static constexpr int NROW = NNPE * NF;
   static constexpr int RSTRIDE = NROW + 1;              // padded row stride of the staged K_el
   static constexpr int KSZ = NROW * RSTRIDE;
-  static constexpr int BODY = (NQ * SLOT > KSZ) ? NQ * SLOT : KSZ;
+  static constexpr int R_OFF = KSZ;                     // staged fused-residual row (NROW doubles) behind K_el
+  static constexpr int BODY = (NQ * SLOT > KSZ + NROW) ? NQ * SLOT : KSZ + NROW;
   // per-element scatter record (global, contiguous; copied verbatim into shared memory with cp.async):
   //   uint32 rowstart[NROW]  (0xFFFFFFFF = row eliminated)   CSR offset of the row of dof (b, d)
   //   uint16 ecol[NNPE][NNPE]                                ecol[b][k]: column offset of the k-th sorted node in row node b
@@ -73,7 +74,8 @@ struct Mat2Layout {
   static constexpr int OFF_EC = NROW * 4;
   static constexpr int OFF_MK = OFF_EC + NNPE * NNPE * 2;
   static constexpr int OFF_RK = OFF_MK + NNPE;
-  static constexpr int REC = ((OFF_RK + NNPE + 15) / 16) * 16;
+  static constexpr int OFF_ND = OFF_RK + NNPE;          //   uint32 node[NNPE]: global node id of the k-th sorted node
+  static constexpr int REC = ((OFF_ND + 4 * NNPE + 15) / 16) * 16;
   static constexpr int META = REC / 8;
   static constexpr int BODY16 = ((BODY + 1) / 2) * 2;   // keep the record 16-byte aligned in shared memory
 #ifndef FEC_MAT2_NOPAD
@@ -265,13 +267,6 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
       }
     }
   }
-  if constexpr (WITH_R) {
-    if (active && d1 == d2) {
-#pragma unroll
-      for (int a = 0; a < NNPE; ++a)
-        scatter_add(p.peer, p.R, p.conn[(size_t)e * NNPE + a], NF, d1, rr[a]);  // 24 REDs per element
-    }
-  }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncwarp();  // every thread of the warp is done reading the slots (re-used as the K_el stage); records landed
 
@@ -292,6 +287,12 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
         // entry (row dof (a,d1), col dof (b,d2)) and its mirror (row (b,d2), col (a,d1))
         esm[(a * NF + d1) * RS + kb * NF + d2] = M[a][b];
         if (d1 != d2) esm[(b * NF + d2) * RS + ka * NF + d1] = M[a][b];
+      }
+    }
+    if constexpr (WITH_R) {
+      if (d1 == d2) {
+#pragma unroll
+        for (int a = 0; a < NNPE; ++a) esm[L::R_OFF + rnk[a] * NF + d1] = rr[a];  // residual row, sorted like the columns
       }
     }
   }
@@ -325,6 +326,12 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
       for (int row = 0; row < NROW; ++row) {
         const uint32_t idx = (colok && r0[row] != 0xFFFFFFFFu) ? r0[row] + off[row / NF] : ((trash + row * 7u) & 4095u) + (uint32_t)p.nnz;
         asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p.nz + idx), "d"(val[row]));
+      }
+      if constexpr (WITH_R) {
+        // fused residual: lane (k, dc) adds the staged entry into R[node_k, dc] -- 3 consecutive doubles per node,
+        // nodes sorted by id (ghost nodes go to their owner over NVLink, see scatter_add)
+        const uint32_t n = reinterpret_cast<const uint32_t*>(rec + L::OFF_ND)[k];
+        scatter_add(p.peer, p.R, (int64_t)n, NF, dc, ks[L::R_OFF + lane]);
       }
     }
   }
