@@ -21,6 +21,7 @@
 //     masks, node ranks) built on the device at update_dofs (k_build_emeta) and fetched with cp.async.
 #pragma once
 #include "kernels.cuh"
+#include <cstdlib>
 
 namespace fec {
 
@@ -358,7 +359,8 @@ void run_mat2_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   p.ne = (int32_t)b.ne; p.nq = b.nq; p.nnz = h->nnz;
   for (int i = 0; i < kMaxProps; ++i) p.props[i] = i < (int)b.props.size() ? b.props[i] : 0.0;
   fill_tables<ND, NNPE, NQT>(b, p.tab);
-  const size_t smem = (size_t)WARPS * L::EPW * L::ELSM * sizeof(double);
+  size_t smem = (size_t)WARPS * L::EPW * L::ELSM * sizeof(double);
+  if (const char* pad = getenv("FECB200_MAT2_SMEM_PAD")) smem += (size_t)atoi(pad);  // occupancy experiments only
   const int epc = WARPS * L::EPW;
   const int grid = (int)((b.ne + epc - 1) / epc);
   timing_begin(h);
