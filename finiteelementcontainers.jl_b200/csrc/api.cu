@@ -112,7 +112,7 @@ static double* nz_for_kind(fecb200_handle* h, int kind, bool alloc) {
   FEC_REQUIRE(h->matrix_ready, "matrix pattern not built");
   if (kind == FECB200_STIFFNESS) return h->d_nz_stiff.p;
   if (kind == FECB200_MASS) {
-    if (!h->d_nz_mass.p && alloc) { h->d_nz_mass.alloc(h->nnz + 4096); h->d_nz_mass.zero(h->stream); }
+    if (!h->d_nz_mass.p && alloc) { h->d_nz_mass.alloc(nz_alloc_len(h)); h->d_nz_mass.zero(h->stream); }
     return h->d_nz_mass.p;
   }
   throw Error("fecb200: matrix kind must be FECB200_STIFFNESS or FECB200_MASS");
@@ -183,6 +183,35 @@ using namespace fec;
     fec::g_last_error = "fecb200: unknown exception";   \
     return 1;                                           \
   }
+
+// Double-buffered CSR values (fecb200_set_matrix_double_buffer): the assembly writes into the buffer the PREVIOUS
+// assembly's kernels cleared and clears the other one on the way (k_mat2, TMA bulk stores), so no stand-alone
+// fill!(storage, 0) pass (Matrix.jl:39) runs in steady state.  Each launch clears a share proportional to its elements.
+struct ZeroFillPlan {
+  bool on = false;
+  double* base = nullptr;
+  int64_t total16 = 0, ne_total = 0, ne_done = 0;
+  void next(const fec::BlockPlan& b, fec::MatLaunch& a) {
+    if (!on) return;
+    const int64_t beg = (int64_t)((__int128)total16 * ne_done / ne_total);
+    ne_done += b.ne;
+    const int64_t end = (int64_t)((__int128)total16 * ne_done / ne_total);
+    if (end > beg) { a.zf = base + 2 * beg; a.zf_n = 2 * (end - beg); }
+  }
+};
+
+static ZeroFillPlan begin_stiffness_fill(fecb200_handle* h) {
+  ZeroFillPlan z;
+  if (!h->double_buffer || !h->d_nz_stiff_alt.p) return z;
+  for (auto& b : h->blocks) z.ne_total += b.ne;  // every matrix kernel clears its share (zero_fill_begin, common.cuh)
+  if (z.ne_total == 0) return z;
+  if (!h->alt_clean) { h->d_nz_stiff_alt.zero(h->stream); h->alt_clean = true; }
+  std::swap(h->d_nz_stiff, h->d_nz_stiff_alt);  // d_nz_stiff is now the clean buffer; the kernels clear the other
+  z.on = true;
+  z.base = h->d_nz_stiff_alt.p;
+  z.total16 = (int64_t)(nz_alloc_len(h) / 2);
+  return z;
+}
 
 extern "C" {
 
@@ -497,15 +526,18 @@ int fecb200_assemble_matrix(fecb200_handle* h, int32_t kind, const double* Uu) {
   FEC_API_BEGIN
   FEC_REQUIRE(h && Uu, "null argument");
   FEC_CUDA(cudaSetDevice(h->device));
-  double* nz = nz_for_kind(h, kind, true);
+  nz_for_kind(h, kind, true);
   const double* u = stage_in(h, Uu, h->d_Uu.p, len_Uu(h));
-  FEC_CUDA(cudaMemsetAsync(nz, 0, h->nnz * sizeof(double), h->stream));  // fill!(storage, 0)  Matrix.jl:39
+  ZeroFillPlan zf = kind == FECB200_STIFFNESS ? begin_stiffness_fill(h) : ZeroFillPlan{};
+  double* nz = nz_for_kind(h, kind, true);
+  if (!zf.on) FEC_CUDA(cudaMemsetAsync(nz, 0, h->nnz * sizeof(double), h->stream));  // fill!(storage, 0)  Matrix.jl:39
   join_inputs(h);
   k_update_field(h, h->d_U.p, u, true);
   inputs_consumed(h);
   h->last_ms = 0.f;
   for (auto& b : h->blocks) {
     MatLaunch a{h->d_U.p, nz, kind};
+    zf.next(b, a);
     launch_matrix(h, b, a);
   }
   (kind == FECB200_STIFFNESS ? h->stiff_adjusted : h->mass_adjusted) = false;
@@ -521,11 +553,27 @@ int fecb200_assemble_vector_and_matrix(fecb200_handle* h, const double* Uu) {
   FEC_API_END
 }
 
+int fecb200_set_matrix_double_buffer(fecb200_handle* h, int32_t enable) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h, "null argument");
+  FEC_CUDA(cudaSetDevice(h->device));
+  h->double_buffer = enable != 0;
+  if (!h->double_buffer) { FEC_CUDA(cudaStreamSynchronize(h->stream)); h->d_nz_stiff_alt.release(); h->alt_clean = false; }
+  else if (h->matrix_ready && !h->opts.matrix_free && !h->d_nz_stiff_alt.p) {
+    h->d_nz_stiff_alt.alloc(nz_alloc_len(h));
+    h->d_nz_stiff_alt.zero(h->stream);
+    h->alt_clean = true;
+  }
+  FEC_API_END
+}
+
 static void assemble_vector_and_matrix_impl(fecb200_handle* h, const double* u) {
-  double* nz = nz_for_kind(h, FECB200_STIFFNESS, true);
+  nz_for_kind(h, FECB200_STIFFNESS, true);
+  ZeroFillPlan zf = begin_stiffness_fill(h);
+  double* nz = h->d_nz_stiff.p;
   if (!(h->peer_enabled && h->peer_field == FECB200_FIELD_RESIDUAL))
     FEC_CUDA(cudaMemsetAsync(h->d_R.p, 0, h->ndof * sizeof(double), h->stream));
-  FEC_CUDA(cudaMemsetAsync(nz, 0, h->nnz * sizeof(double), h->stream));   // the H2D of Uu (async mode) overlaps this
+  if (!zf.on) FEC_CUDA(cudaMemsetAsync(nz, 0, h->nnz * sizeof(double), h->stream));   // the H2D of Uu (async mode) overlaps this
   join_inputs(h);
   k_update_field(h, h->d_U.p, u, true);
   inputs_consumed(h);
@@ -533,10 +581,12 @@ static void assemble_vector_and_matrix_impl(fecb200_handle* h, const double* u) 
   for (auto& b : h->blocks) {
     if (!b.halo && matrix_kernel_fuses_residual(h, b)) {
       MatLaunch a{h->d_U.p, nz, FECB200_STIFFNESS, h->d_R.p};
+      zf.next(b, a);
       launch_matrix(h, b, a);
     } else {
       if (!b.halo) { VecLaunch v{h->d_U.p, nullptr, h->d_R.p, MODE_RESIDUAL}; launch_vector(h, b, v); }
       MatLaunch a{h->d_U.p, nz, FECB200_STIFFNESS, nullptr};
+      zf.next(b, a);
       launch_matrix(h, b, a);
     }
   }

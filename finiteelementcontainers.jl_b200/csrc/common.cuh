@@ -99,6 +99,36 @@ __device__ __forceinline__ void scatter_add(const PeerScatter& ps, double* local
     atomicAdd(&local[n * nf + d], v);
   }
 }
+// In-kernel zero-fill of the idle CSR value buffer (fecb200_set_matrix_double_buffer).  CTA i of a matrix kernel
+// clears 16-byte units [i*chunk16, min((i+1)*chunk16, total16)) of p: one thread queues bulk stores (TMA, async
+// proxy) from a shared-memory zero page; they drain to HBM underneath the element kernel without touching the
+// LSU / L1 data pipe its REDs are bound by.
+struct ZeroFill { double* p; int64_t total16; int32_t chunk16; };
+constexpr int kZeroPageBytes = 2048;
+
+// every thread of the CTA calls this (contains a CTA barrier when the fill is on); zp = kZeroPageBytes of shared memory
+__device__ __forceinline__ void zero_fill_begin(const ZeroFill& z, double* zp) {
+  if (z.p == nullptr) return;  // uniform
+  for (int i = threadIdx.x; i < kZeroPageBytes / 8; i += blockDim.x) zp[i] = 0.0;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int64_t beg = (int64_t)blockIdx.x * z.chunk16;
+    int64_t rem = (z.total16 - beg < z.chunk16 ? z.total16 - beg : (int64_t)z.chunk16) * 16;
+    char* g = reinterpret_cast<char*>(z.p) + beg * 16;
+    const unsigned zs = (unsigned)__cvta_generic_to_shared(zp);
+    for (; rem > 0; rem -= kZeroPageBytes, g += kZeroPageBytes) {
+      const unsigned nb = rem < kZeroPageBytes ? (unsigned)rem : (unsigned)kZeroPageBytes;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(zs), "r"(nb) : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+}
+// thread 0 calls this before it exits: the zero page must outlive the bulk stores' shared-memory reads
+__device__ __forceinline__ void zero_fill_end(const ZeroFill& z) {
+  if (z.p != nullptr && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 constexpr int kMaxNQ = 27;  // runtime-NQ kernels (e.g. 3-point GLL on hex8)
 
 // One element block: FunctionSpace block + ReferenceFE tables + physics (host side of the plan)
@@ -163,6 +193,8 @@ struct fecb200_handle {
   fec::DevBuf<uint8_t> d_freemask;
   fec::DevBuf<int64_t> d_rowstart, d_diagslot;
   fec::DevBuf<double> d_nz_stiff, d_nz_mass, d_scratch;
+  fec::DevBuf<double> d_nz_stiff_alt;  // fecb200_set_matrix_double_buffer: cleared by the kernel that fills the other one
+  bool double_buffer = false, alt_clean = false;
   bool stiff_adjusted = false, mass_adjusted = false;
 
   // peer-memory halo (fecb200_peer_attach)
@@ -197,6 +229,9 @@ struct fecb200_handle {
 
 namespace fec {
 
+// CSR value buffers: nnz values + the 4096-slot trash region of the branch-free RED streams, even length (16-byte units)
+inline size_t nz_alloc_len(const fecb200_handle* h) { return ((size_t)h->nnz + 4096 + 1) & ~(size_t)1; }
+
 // plan.cu
 void build_block_tiles(fecb200_handle* h, BlockPlan& b, const double* coords);
 void build_adjacency(fecb200_handle* h);
@@ -207,7 +242,21 @@ void export_pattern(fecb200_handle* h, int64_t* ptr, int64_t* idx);
 // dispatch (one translation unit per element family)
 enum { MODE_RESIDUAL = 0, MODE_ACTION_STIFFNESS = 1, MODE_ACTION_MASS = 2 };
 struct VecLaunch { const double* U; const double* V; double* out; int mode; };
-struct MatLaunch { const double* U; double* nz; int kind; double* R = nullptr; };  // R != null: fused residual
+struct MatLaunch {
+  const double* U; double* nz; int kind;
+  double* R = nullptr;                     // != null: fused residual
+  double* zf = nullptr; int64_t zf_n = 0;  // != null: the kernel also clears zf[0 .. zf_n) (double-buffered CSR values)
+};
+inline ZeroFill make_zero_fill(const MatLaunch& a, int grid) {
+  ZeroFill z{nullptr, 0, 0};
+  if (a.zf && a.zf_n > 0 && grid > 0) {
+    if (a.zf_n % 2 != 0 || (reinterpret_cast<uintptr_t>(a.zf) & 15) != 0) throw Error("fecb200: zero-fill range must be 16-byte aligned");
+    z.p = a.zf;
+    z.total16 = a.zf_n / 2;
+    z.chunk16 = (int32_t)((z.total16 + grid - 1) / grid);
+  }
+  return z;
+}
 bool matrix_kernel_fuses_residual(fecb200_handle* h, const BlockPlan& b);
 void launch_vector(fecb200_handle* h, BlockPlan& b, const VecLaunch& a);
 void launch_matrix(fecb200_handle* h, BlockPlan& b, const MatLaunch& a);

@@ -38,10 +38,10 @@ struct Mat2Params {
   int64_t nnz;               // the trash region of the branch-free RED stream starts at nz[nnz]
   PeerScatter peer;          // ghost rows of the fused residual go to their owner over NVLink
   int32_t ne, nq;
+  ZeroFill zf;               // in-kernel clear of the idle CSR value buffer (common.cuh)
   double props[kMaxProps];
   Tables<ND, NNPE, NQT> tab;
 };
-
 template <int N>
 __host__ __device__ constexpr int sym_index(int i, int j) {  // packed upper triangle, i <= j
   return i * N - (i * (i - 1)) / 2 + (j - i);
@@ -121,6 +121,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
 #pragma unroll
       for (int j = i; j < NF; ++j) { if (k == 0) { d1 = i; d2 = j; } --k; }
   }
+
+  __shared__ __align__(16) double zero_page[kZeroPageBytes / 8];
+  zero_fill_begin(p.zf, zero_page);
 
   // ---- meta: the warp's per-element scatter records are one contiguous run in global memory; fetch them
   // asynchronously (LDGSTS) so the copy overlaps phase G.  Needed from phase S1 on.
@@ -336,6 +339,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
       }
     }
   }
+  zero_fill_end(p.zf);
 }
 
 // element -> CSR column-offset table, rebuilt whenever update_dofs changes the kept-dof masks
@@ -360,9 +364,9 @@ void run_mat2_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   for (int i = 0; i < kMaxProps; ++i) p.props[i] = i < (int)b.props.size() ? b.props[i] : 0.0;
   fill_tables<ND, NNPE, NQT>(b, p.tab);
   size_t smem = (size_t)WARPS * L::EPW * L::ELSM * sizeof(double);
-  if (const char* pad = getenv("FECB200_MAT2_SMEM_PAD")) smem += (size_t)atoi(pad);  // occupancy experiments only
   const int epc = WARPS * L::EPW;
   const int grid = (int)((b.ne + epc - 1) / epc);
+  p.zf = make_zero_fill(a, grid);
   timing_begin(h);
   // K_el is symmetric here, so CSR and CSC storage receive the same values through the same addressing
   auto kern = k_mat2<ND, NNPE, NF, NQT, Phys, WARPS, WITH_R>;

@@ -19,6 +19,7 @@ struct MatSParams {
   const unsigned char* emeta;
   int64_t nnz;
   int32_t ne, nq, rec;
+  ZeroFill zf;
   double props[kMaxProps];
   Tables<ND, NNPE, NQT> tab;
 };
@@ -26,8 +27,10 @@ struct MatSParams {
 template <int ND, int NNPE, int NQT, class Phys, int KIND, bool TRANS>
 __global__ void __launch_bounds__(128) k_mat_scalar(const __grid_constant__ MatSParams<ND, NNPE, NQT> p) {
   static_assert(Phys::NF == 1 && Phys::NS == 0, "scalar, stateless physics");
+  __shared__ __align__(16) double zero_page[kZeroPageBytes / 8];
+  zero_fill_begin(p.zf, zero_page);
   const int e = blockIdx.x * 128 + threadIdx.x;
-  if (e >= p.ne) return;
+  if (e >= p.ne) return;   // never thread 0, which closes the zero-fill below
   double x[NNPE][ND], u[NNPE][1];
 #pragma unroll
   for (int a = 0; a < NNPE; ++a) {
@@ -116,6 +119,7 @@ __global__ void __launch_bounds__(128) k_mat_scalar(const __grid_constant__ MatS
       const double v = TRANS ? K[r][c] : K[c][r];
       asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p.nz + idx), "d"(v));
     }
+  zero_fill_end(p.zf);
 }
 
 template <int ND, int NNPE, int NQT, class Phys>
@@ -128,6 +132,7 @@ void run_mat_scalar(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   for (int i = 0; i < kMaxProps; ++i) p.props[i] = i < (int)b.props.size() ? b.props[i] : 0.0;
   fill_tables<ND, NNPE, NQT>(b, p.tab);
   const int grid = (int)((b.ne + 127) / 128);
+  p.zf = make_zero_fill(a, grid);
   const bool trans = (h->opts.matrix_type == FECB200_CSC);
   timing_begin(h);
   if (a.kind == FECB200_MASS) k_mat_scalar<ND, NNPE, NQT, Phys, FECB200_MASS, false><<<grid, 128, 0, h->stream>>>(p);

@@ -315,6 +315,7 @@ struct MatParams {
   const int64_t* rowstart;
   const double* state_old;
   int32_t ne, nq;
+  ZeroFill zf;
   double props[kMaxProps];
   Tables<ND, NNPE, NQT> tab;
 };
@@ -328,6 +329,8 @@ struct MatParams {
 template <int ND, int NNPE, int NF, int NQT, class Phys, int KIND, int EPB, bool TRANS>
 __global__ void __launch_bounds__(EPB * NNPE) k_mat(const __grid_constant__ MatParams<ND, NNPE, NQT> p) {
   extern __shared__ double smem[];
+  __shared__ __align__(16) double zero_page[kZeroPageBytes / 8];
+  zero_fill_begin(p.zf, zero_page);
   constexpr int NDF = NF * ND;
   constexpr int NS = Phys::NS;
   constexpr int SLOT = (KIND == FECB200_MASS) ? (NNPE + 1) : (NNPE * ND + NDF * NDF);
@@ -492,6 +495,7 @@ __global__ void __launch_bounds__(EPB * NNPE) k_mat(const __grid_constant__ MatP
       }
     }
   }
+  zero_fill_end(p.zf);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -571,6 +575,7 @@ void run_mat_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   auto kern = k_mat<ND, NNPE, NF, NQT, Phys, KIND, EPB, TRANS>;
   FEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)((b.ne + EPB - 1) / EPB);
+  p.zf = make_zero_fill(a, grid);
   timing_begin(h);
   kern<<<grid, EPB * NNPE, smem, h->stream>>>(p);
   FEC_CUDA(cudaGetLastError());

@@ -83,6 +83,7 @@ SIGNATURES = {
     "fecb200_residual": (C.c_int, [Handle, VP]),
     "fecb200_assemble_matrix": (C.c_int, [Handle, C.c_int32, VP]),
     "fecb200_assemble_vector_and_matrix": (C.c_int, [Handle, VP]),
+    "fecb200_set_matrix_double_buffer": (C.c_int, [Handle, C.c_int32]),
     "fecb200_matrix_values": (C.c_int, [Handle, C.c_int32, VP]),
     "fecb200_matrix_values_device": (C.c_int, [Handle, C.c_int32, C.POINTER(C.c_void_p)]),
     "fecb200_assemble_action": (C.c_int, [Handle, C.c_int32, VP, VP]),

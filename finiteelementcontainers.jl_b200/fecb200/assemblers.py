@@ -91,6 +91,11 @@ class SparseMatrixAssembler:
         except Exception:
             pass
 
+    def set_matrix_double_buffer(self, enable=True):
+        """Opt-in: keep two stiffness value arrays so the zero-fill of assemble_stiffness! (Matrix.jl:39) rides
+        inside the element kernel (fecb200_set_matrix_double_buffer)."""
+        check(lib.fecb200_set_matrix_double_buffer(self._require(), int(bool(enable))))
+
     # -- sizes / maps ----------------------------------------------------------------------------
     def sizes(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()

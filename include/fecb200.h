@@ -169,8 +169,15 @@ int fecb200_assemble_vector_and_matrix(fecb200_handle* h, const double* Uu);
  * adjustment (assemblers/Utils.jl:53-148: row/col scaling by (1-c), penalty 1e6*tr(K)/n on
  * constrained diagonals) and copies nzval [nnz] out. [host|device] */
 int fecb200_matrix_values(fecb200_handle* h, int32_t kind, double* nzval_out);
-/* device pointer to the handle's nzval storage (valid until destroy / update_dofs) */
+/* device pointer to the handle's nzval storage (valid until destroy / update_dofs; with double buffering
+ * enabled, until the next assembly of that matrix) */
 int fecb200_matrix_values_device(fecb200_handle* h, int32_t kind, double** nzval_dev);
+/* Opt-in double buffering of the stiffness nzval storage: replaces the stand-alone fill!(storage, 0) pass of
+ * assemble_stiffness! (src/assemblers/Matrix.jl:39) in steady state.  Each assembly accumulates into the buffer
+ * the previous assembly's kernels cleared and clears the other one with TMA bulk stores that drain under the
+ * element kernel.  Costs a second nzval array; values equal those of the single-buffer path (up to the
+ * summation order of the atomics, as always). */
+int fecb200_set_matrix_double_buffer(fecb200_handle* h, int32_t enable);
 
 /* assemble_matrix_action!(asm, f, Uu, Vu, p) and assemble_matrix_free_action! (MatrixAction.jl:9-77,
  * 154-238): always evaluated matrix-free.  kind = FECB200_STIFFNESS or FECB200_MASS. */

@@ -384,3 +384,71 @@ def test_async_host_copies(F):
         assert rel_err(hR[i].numpy(), refs[i]) < 1e-14
     check(lib.fecb200_set_async(h, 0))
     asm.close()
+
+
+@pytest.mark.parametrize("condensed", [False, True])
+def test_double_buffered_stiffness(F, condensed):
+    """fecb200_set_matrix_double_buffer: the kernel-side zero-fill of the idle value buffer replaces fill!(storage, 0)
+    (Matrix.jl:39) without changing any value, over a sequence of assemblies that mixes the fused and the plain
+    entry points, the condensed-mode adjustment, the device CG and an update_dofs in between."""
+    n = 7
+    mesh = perturb(F.StructuredMesh("hex", (0, 0, 0), (1, 1, 1), (n + 1, n + 2, n + 1)), 0.1 / n)
+    props = np.array([1e3, 10e6, 1e6])
+    asm, p, oasm = build_pair(F, mesh, "neo", props, condensed=condensed, matrix_type="csr",
+                              bc_nodes_1based=mesh.nodeset_nodes["bottom"], bc_value=0.01)
+    asm.set_matrix_double_buffer(True)
+    rng = np.random.default_rng(11)
+    N = asm.sizes()[2]
+    for it in range(5):
+        Uu = 0.01 * rng.standard_normal(N)
+        if it % 2 == 0:
+            F.assemble_vector_and_stiffness(asm, F.residual, F.stiffness, Uu, p)
+            oasm.assemble_vector(Uu)
+            assert rel_err(F.residual(asm), oasm.residual()) < RTOL
+        else:
+            F.assemble_stiffness(asm, F.stiffness, Uu, p)
+        K = F.stiffness(asm)
+        oasm.assemble_stiffness(Uu)
+        assert rel_err(K.data, oasm.stiffness()[2]) < RTOL, it
+        if it == 2 and not condensed:   # the solve reads the CURRENT buffer (condensed: penalty rows make CG's true residual stagnate)
+            b = rng.random(N)
+            x, its, rn = F.IterativeLinearSolver(asm, "cg").solve(b)
+            assert np.linalg.norm(K @ x - b) <= 1e-6 * np.linalg.norm(b)
+    asm.set_matrix_double_buffer(False)
+    Uu = 0.01 * rng.standard_normal(N)
+    F.assemble_stiffness(asm, F.stiffness, Uu, p)
+    oasm.assemble_stiffness(Uu)
+    assert rel_err(F.stiffness(asm).data, oasm.stiffness()[2]) < RTOL
+    asm.close()
+
+
+@pytest.mark.parametrize("case", ["poisson_hex8_csr", "poisson_hex8_csc", "linear_quad_tri", "poisson_quad_tri"])
+def test_double_buffered_other_kernels(F, case):
+    """The same double buffering through the thread-per-element scalar kernel (Poisson hex8) and the generic
+    column-owner kernel on a two-block mesh (each launch clears its share of the idle buffer); a mass assembly in
+    between must not disturb the stiffness buffers."""
+    if case.startswith("poisson_hex8"):
+        n = 8
+        mesh = perturb(F.StructuredMesh("hex", (0, 0, 0), (1, 1, 1), (n + 1,) * 3), 0.15 / n)
+        bc = _boundary_nodes(mesh, ["bottom", "top"])
+        asm, p, oasm = build_pair(F, mesh, "poisson", None, condensed=False, matrix_type=case[-3:], bc_nodes_1based=bc, func=SRC3)
+        scale = 1.0
+    else:
+        mesh = F.UnstructuredMesh(os.path.join(GOLDEN, "multi_block_quad4_tri3.npz"))
+        phys = case.split("_")[0]
+        asm, p, oasm = build_pair(F, mesh, phys, None if phys == "poisson" else np.array([1e3, 10e9, 1e9]), condensed=False,
+                                  matrix_type="csr", bc_nodes_1based=mesh.sideset_nodes["boundary"],
+                                  func=SRC2 if phys == "poisson" else None)
+        scale = 1.0 if phys == "poisson" else 1e-3
+    asm.set_matrix_double_buffer(True)
+    rng = np.random.default_rng(5)
+    for it in range(4):
+        Uu = scale * rng.uniform(-1, 1, asm.sizes()[2])
+        F.assemble_stiffness(asm, F.stiffness, Uu, p)
+        oasm.assemble_stiffness(Uu)
+        assert rel_err(F.stiffness(asm).data, oasm.stiffness()[2]) < RTOL, it
+        if it == 1:
+            F.assemble_mass(asm, F.mass, Uu, p)
+            oasm.assemble_stiffness(Uu, kind="mass")
+            assert rel_err(F.mass(asm).data, oasm.stiffness()[2]) < RTOL
+    asm.close()
