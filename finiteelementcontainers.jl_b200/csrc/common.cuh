@@ -104,14 +104,18 @@ __device__ __forceinline__ void scatter_add(const PeerScatter& ps, double* local
 // proxy) from a shared-memory zero page; they drain to HBM underneath the element kernel without touching the
 // LSU / L1 data pipe its REDs are bound by.
 struct ZeroFill { double* p; int64_t total16; int32_t chunk16; };
-constexpr int kZeroPageBytes = 2048;
+#ifndef FEC_ZPAGE
+#define FEC_ZPAGE 2048
+#endif
+constexpr int kZeroPageBytes = FEC_ZPAGE;
 
-// every thread of the CTA calls this (contains a CTA barrier when the fill is on); zp = kZeroPageBytes of shared memory
+// every thread of the CTA calls this; zp = kZeroPageBytes of shared memory.  Only warp 0 works: it clears the page,
+// then its lane 0 queues the CTA's stores (issuing from every warp measured slower: 19.13 vs 18.80 ms at 192^3).
 __device__ __forceinline__ void zero_fill_begin(const ZeroFill& z, double* zp) {
-  if (z.p == nullptr) return;  // uniform
-  for (int i = threadIdx.x; i < kZeroPageBytes / 8; i += blockDim.x) zp[i] = 0.0;
+  if (z.p == nullptr || threadIdx.x >= 32) return;
+  for (int i = threadIdx.x; i < kZeroPageBytes / 8; i += 32) zp[i] = 0.0;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncthreads();
+  __syncwarp();
   if (threadIdx.x == 0) {
     const int64_t beg = (int64_t)blockIdx.x * z.chunk16;
     int64_t rem = (z.total16 - beg < z.chunk16 ? z.total16 - beg : (int64_t)z.chunk16) * 16;

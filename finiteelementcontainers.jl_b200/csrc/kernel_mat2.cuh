@@ -123,7 +123,6 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
   }
 
   __shared__ __align__(16) double zero_page[kZeroPageBytes / 8];
-  zero_fill_begin(p.zf, zero_page);
 
   // ---- meta: the warp's per-element scatter records are one contiguous run in global memory; fetch them
   // asynchronously (LDGSTS) so the copy overlaps phase G.  Needed from phase S1 on.
@@ -139,8 +138,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
   }
 
   // ---- phase G: geometry + material tangent of the element's quadrature points, split over its threads
+  double x[NNPE][ND], u[NNPE][NF];
   if (active) {
-    double x[NNPE][ND], u[NNPE][NF];
 #pragma unroll
     for (int a = 0; a < NNPE; ++a) {
       const int n = p.conn[(size_t)e * NNPE + a];
@@ -149,6 +148,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
 #pragma unroll
       for (int d = 0; d < NF; ++d) u[a][d] = p.U[(size_t)n * NF + d];
     }
+  }
+  zero_fill_begin(p.zf, zero_page);   // queued while the gathers above are in flight (0.13 ms better than up front)
+  if (active) {
     for (int q = t; q < NQT; q += NP) {
       double J[ND][ND];
 #pragma unroll

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(128) k_mat_scalar(const __grid_constant__ MatS
   __shared__ __align__(16) double zero_page[kZeroPageBytes / 8];
   zero_fill_begin(p.zf, zero_page);
   const int e = blockIdx.x * 128 + threadIdx.x;
-  if (e >= p.ne) return;   // never thread 0, which closes the zero-fill below
+  if (e >= p.ne) { zero_fill_end(p.zf); return; }
   double x[NNPE][ND], u[NNPE][1];
 #pragma unroll
   for (int a = 0; a < NNPE; ++a) {
