@@ -191,6 +191,7 @@ struct fecb200_handle {
   fec::DevBuf<int32_t> d_adjptr, d_adj;
   bool matrix_ready = false;
   int64_t nmat = 0, nnz = 0;
+  int32_t max_rowlen = 0;            // longest node row (kept dofs), bounds the column offsets
   std::vector<int64_t> rowstart_h;   // per dof, -1 if the row is eliminated
   std::vector<uint8_t> freemask_h;   // per node
   fec::DevBuf<uint16_t> d_coloff;    // per adjacency entry: kept dofs before this neighbour in the row
@@ -233,8 +234,9 @@ struct fecb200_handle {
 
 namespace fec {
 
-// CSR value buffers: nnz values + the 4096-slot trash region of the branch-free RED streams, even length (16-byte units)
-inline size_t nz_alloc_len(const fecb200_handle* h) { return ((size_t)h->nnz + 4096 + 1) & ~(size_t)1; }
+// CSR value buffers: nnz values + the trash region of the branch-free RED streams (4096 hashed row starts, each
+// followed by up to one row of column offsets), even length (16-byte units)
+inline size_t nz_alloc_len(const fecb200_handle* h) { return ((size_t)h->nnz + 4096 + (size_t)h->max_rowlen + 8 + 1) & ~(size_t)1; }
 
 // plan.cu
 void build_block_tiles(fecb200_handle* h, BlockPlan& b, const double* coords);

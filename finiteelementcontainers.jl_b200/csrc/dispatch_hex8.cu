@@ -25,7 +25,7 @@ static void mat8(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
 
 // true when launch_matrix for this block runs k_mat2, which can produce the residual in the same pass
 bool matrix_kernel_fuses_residual(fecb200_handle* h, const BlockPlan& b) {
-  return b.elem_type == FECB200_HEX8 && h->nf == 3 && b.nq == 8 && !getenv("FECB200_KMAT1") && h->nnz < (int64_t)0xFFFFFFFFll &&
+  return b.elem_type == FECB200_HEX8 && h->nf == 3 && b.nq == 8 && !getenv("FECB200_KMAT1") && b.d_emeta.p && (int64_t)nz_alloc_len(h) < (int64_t)0xFFFFFFFFll &&
          (b.physics == FECB200_PHYS_LINEAR_ELASTIC || b.physics == FECB200_PHYS_NEOHOOKEAN ||
           b.physics == FECB200_PHYS_NEOHOOKEAN_AS_WRITTEN || b.physics == FECB200_PHYS_J2_PLASTICITY);
 }

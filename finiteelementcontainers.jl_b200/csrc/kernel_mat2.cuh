@@ -307,8 +307,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
   // ---- phase S2: REDs.  Lane = one storage column (sorted node rank k, dof dc) of the element; the warp walks
   // the NROW rows, so one RED instruction covers one CSR row segment of the element: NROW consecutive-ish slots.
   // All shared-memory reads of an element are issued before its REDs so their latencies overlap (registers are
-  // free here: M is dead).  The RED stream is branch-free: entries of eliminated rows / columns (Dirichlet dofs,
-  // rare) are redirected into a 4096-slot trash region behind the matrix, hashed so they do not serialise.
+  // free here: M is dead).  The RED stream has no per-entry tests: rows that are not stored (Dirichlet dofs, ghost
+  // rows) carry a row offset inside a 4096-slot hashed trash region behind the matrix, written by k_build_emeta.
   if (lane < NROW) {
     const int nel = (p.ne - e0) < EPW ? (p.ne - e0) : EPW;
     const int k = lane / NF, dc = lane - k * NF;
@@ -318,20 +318,18 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
       const uint32_t* rs = reinterpret_cast<const uint32_t*>(rec);
       const uint16_t* ec = reinterpret_cast<const uint16_t*>(rec + L::OFF_EC);
       const unsigned mask = rec[L::OFF_MK + k];
-      const bool colok = (mask & (1u << dc)) != 0;
-      const int rank = __popc(mask & ((1u << dc) - 1u));
-      const uint32_t trash = (uint32_t)p.nnz + (((uint32_t)(e0 + el) * 613u + (uint32_t)lane * 29u) & 4095u);
-      uint32_t r0[NROW];
-      double val[NROW];
-      uint32_t off[NNPE];
+      if (mask & (1u << dc)) {  // eliminated column (Dirichlet dof, rare): the lane sits this element out
+        const int rank = __popc(mask & ((1u << dc) - 1u));
+        uint32_t r0[NROW];
+        double val[NROW];
+        uint32_t off[NNPE];
 #pragma unroll
-      for (int b = 0; b < NNPE; ++b) off[b] = ec[b * NNPE + k] + rank;
+        for (int b = 0; b < NNPE; ++b) off[b] = ec[b * NNPE + k] + rank;
 #pragma unroll
-      for (int row = 0; row < NROW; ++row) { r0[row] = rs[row]; val[row] = ks[row * RS + lane]; }
+        for (int row = 0; row < NROW; ++row) { r0[row] = rs[row]; val[row] = ks[row * RS + lane]; }
 #pragma unroll
-      for (int row = 0; row < NROW; ++row) {
-        const uint32_t idx = (colok && r0[row] != 0xFFFFFFFFu) ? r0[row] + off[row / NF] : ((trash + row * 7u) & 4095u) + (uint32_t)p.nnz;
-        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p.nz + idx), "d"(val[row]));
+        for (int row = 0; row < NROW; ++row)  // rows that are not stored point into the trash region (k_build_emeta)
+          asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p.nz + (r0[row] + off[row / NF])), "d"(val[row]));
       }
       if constexpr (WITH_R) {
         // fused residual: lane (k, dc) adds the staged entry into R[node_k, dc] -- 3 consecutive doubles per node,
@@ -347,7 +345,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
 // element -> CSR column-offset table, rebuilt whenever update_dofs changes the kept-dof masks
 __global__ void k_build_emeta(const int32_t* conn, const uint8_t* epos, const int32_t* adjptr, const uint16_t* coloff,
                               const uint8_t* freemask, const int64_t* rowstart, unsigned char* emeta, int nnpe, int nf,
-                              int rec, int64_t ne, int sorted_cols);
+                              int rec, int64_t ne, int sorted_cols, int64_t nnz);
 
 template <int ND, int NNPE, int NF, int NQT, class Phys, int WARPS, bool WITH_R>
 void run_mat2_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
@@ -355,7 +353,7 @@ void run_mat2_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   auto pp = std::make_unique<Mat2Params<ND, NNPE, NQT>>();
   auto& p = *pp;
   p.X = h->d_X.p; p.U = a.U; p.nz = a.nz;
-  FEC_REQUIRE(h->nnz + 4096 < (int64_t)0xFFFFFFFFll, "k_mat2 needs nnz < 2^32 (32-bit row offsets in the scatter records)");
+  FEC_REQUIRE((int64_t)nz_alloc_len(h) < (int64_t)0xFFFFFFFFll, "k_mat2 needs nnz < 2^32 (32-bit row offsets in the scatter records)");
   FEC_REQUIRE((int)b.emeta_rec == L::REC, "scatter record size mismatch");
   p.conn = b.d_conn_perm.p; p.emeta = b.d_emeta.p;
   p.R = a.R; p.state_new = b.d_state_new.p;

@@ -375,7 +375,11 @@ void build_matrix_structure(fecb200_handle* h) {
     }
     rowlen[n] = off;
   }
-  for (int64_t n = 0; n < nn; ++n) FEC_REQUIRE(rowlen[n] < 65536, "row too long for 16-bit column offsets");
+  h->max_rowlen = 0;
+  for (int64_t n = 0; n < nn; ++n) {
+    FEC_REQUIRE(rowlen[n] < 65536, "row too long for 16-bit column offsets");
+    h->max_rowlen = std::max(h->max_rowlen, rowlen[n]);
+  }
   h->rowstart_h.assign(ndof, -1);
   std::vector<int64_t> diag(ndof, -1);
   int64_t pos = 0;
