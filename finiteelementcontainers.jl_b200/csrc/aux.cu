@@ -108,7 +108,7 @@ void k_zero_bc_slots(fecb200_handle* h, double* field) {
 // ---- per-element scatter records for k_mat2 (layout: Mat2Layout in kernel_mat2.cuh); one thread per element
 __global__ void k_build_emeta(const int32_t* conn, const uint8_t* epos, const int32_t* adjptr, const uint16_t* coloff,
                               const uint8_t* freemask, const int64_t* rowstart, unsigned char* emeta, int nnpe, int nf,
-                              int rec, int64_t ne, int sorted_cols, int64_t nnz) {
+                              int rec, int64_t ne, int sorted_cols, int64_t nnz, int trash_rows) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= ne) return;
   const int32_t* c = conn + e * nnpe;
@@ -132,7 +132,7 @@ __global__ void k_build_emeta(const int32_t* conn, const uint8_t* epos, const in
       const int64_t v = rowstart[(int64_t)c[b] * nf + d];
       // eliminated / not-stored rows: the scalar kernel tests for the sentinel; k_mat2 (sorted records) adds the
       // row blindly, so the row is pointed into the hashed trash region behind the values instead
-      const uint32_t dead = sorted_cols ? (uint32_t)nnz + (uint32_t)(((uint32_t)e * 613u + (uint32_t)(b * nf + d) * 97u) & 4095u) : 0xFFFFFFFFu;
+      const uint32_t dead = trash_rows ? (uint32_t)nnz + (uint32_t)(((uint32_t)e * 613u + (uint32_t)(b * nf + d) * 97u) & 4095u) : 0xFFFFFFFFu;
       rs[b * nf + d] = v < 0 ? dead : (uint32_t)v;
     }
     const int base = adjptr[c[b]];
@@ -147,10 +147,10 @@ void build_ecol(fecb200_handle* h) {
     const size_t rec = (((size_t)b.nnpe * h->nf * 4 + (size_t)b.nnpe * b.nnpe * 2 + 2 * b.nnpe + 4 * b.nnpe + 15) / 16) * 16;
     if (b.d_emeta.n != rec * b.ne) b.d_emeta.alloc(rec * b.ne);
     b.emeta_rec = rec;
-    b.emeta_sorted = h->nf > 1;  // k_mat2 wants address-sorted columns; the scalar kernel indexes by local node
+    b.emeta_sorted = h->nf > 1;  // k_mat2 records (dead rows point into the trash region); else scalar-kernel records
     k_build_emeta<<<grid_for(b.ne), 256, 0, h->stream>>>(b.d_conn_perm.p, b.d_epos.p, h->d_adjptr.p, h->d_coloff.p,
                                                          h->d_freemask.p, h->d_rowstart.p, b.d_emeta.p, b.nnpe, h->nf,
-                                                         (int)rec, b.ne, b.emeta_sorted ? 1 : 0, h->nnz);
+                                                         (int)rec, b.ne, 0, h->nnz, b.emeta_sorted ? 1 : 0);
     h->launches++;
   }
   FEC_CUDA(cudaGetLastError());

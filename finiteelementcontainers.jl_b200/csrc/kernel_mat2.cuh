@@ -63,19 +63,21 @@ struct Mat2Layout {
   static constexpr int SLOT = SLOT_RAW;
 #endif
   static constexpr int NROW = NNPE * NF;
-  static constexpr int RSTRIDE = NROW + 1;              // padded row stride of the staged K_el
+  // row stride of the staged K_el: a bank simulation of the S1 stores (lane = (element, pair), 8-byte banks) gives
+  // 384 wavefronts per warp for stride 24 against 512 for 25 with NROW = 24; the S2 loads are conflict-free either way
+  static constexpr int RSTRIDE = (NROW % 16 == 8) ? NROW : NROW + 1;
   static constexpr int KSZ = NROW * RSTRIDE;
   static constexpr int R_OFF = KSZ;                     // staged fused-residual row (NROW doubles) behind K_el
   static constexpr int BODY = (NQ * SLOT > KSZ + NROW) ? NQ * SLOT : KSZ + NROW;
   // per-element scatter record (global, contiguous; copied verbatim into shared memory with cp.async):
   //   uint32 rowstart[NROW]  (0xFFFFFFFF = row eliminated)   CSR offset of the row of dof (b, d)
-  //   uint16 ecol[NNPE][NNPE]                                ecol[b][k]: column offset of the k-th sorted node in row node b
-  //   uint8  mask[NNPE]                                      kept-dof mask of the k-th sorted node
-  //   uint8  rank[NNPE]                                      rank of local node a among the element's sorted nodes
+  //   uint16 ecol[NNPE][NNPE]                                ecol[b][k]: column offset of local node k in row node b
+  //   uint8  mask[NNPE]                                      kept-dof mask of local node k
+  //   uint8  rank[NNPE]                                      (unused: identity)
   static constexpr int OFF_EC = NROW * 4;
   static constexpr int OFF_MK = OFF_EC + NNPE * NNPE * 2;
   static constexpr int OFF_RK = OFF_MK + NNPE;
-  static constexpr int OFF_ND = OFF_RK + NNPE;          //   uint32 node[NNPE]: global node id of the k-th sorted node
+  static constexpr int OFF_ND = OFF_RK + NNPE;          //   uint32 node[NNPE]: global node id of local node k
   static constexpr int REC = ((OFF_ND + 4 * NNPE + 15) / 16) * 16;
   static constexpr int META = REC / 8;
   static constexpr int BODY16 = ((BODY + 1) / 2) * 2;   // keep the record 16-byte aligned in shared memory
@@ -276,35 +278,30 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncwarp();  // every thread of the warp is done reading the slots (re-used as the K_el stage); records landed
 
-  // ---- phase S1: stage K_el in global order.  Storage row = dof of the ROW node, storage column =
-  // (rank of the column node among the element's sorted nodes, dof).  K_el is symmetric, so the reference's
-  // transposed COO convention and the CSR/CSC distinction do not change the values.
+  // ---- phase S1: stage K_el.  Storage row = dof of the ROW node, storage column = (local column node, dof).
+  // K_el is symmetric, so the reference's transposed COO convention and the CSR/CSC distinction do
+  // not change the values.  (Sorting the columns by global node id was measured to make no difference: the RED
+  // coalescer merges a warp's lanes into sectors whatever their order, so all offsets here are static.)
   if (active) {
-    const uint8_t* rk = reinterpret_cast<const uint8_t*>(esm + L::BODY16) + L::OFF_RK;
-    int rnk[NNPE];
-#pragma unroll
-    for (int a = 0; a < NNPE; ++a) rnk[a] = rk[a];
 #pragma unroll
     for (int a = 0; a < NNPE; ++a) {
-      const int ka = rnk[a];
 #pragma unroll
       for (int b = 0; b < NNPE; ++b) {
-        const int kb = rnk[b];
         // entry (row dof (a,d1), col dof (b,d2)) and its mirror (row (b,d2), col (a,d1))
-        esm[(a * NF + d1) * RS + kb * NF + d2] = M[a][b];
-        if (d1 != d2) esm[(b * NF + d2) * RS + ka * NF + d1] = M[a][b];
+        esm[(a * NF + d1) * RS + b * NF + d2] = M[a][b];
+        if (d1 != d2) esm[(b * NF + d2) * RS + a * NF + d1] = M[a][b];
       }
     }
     if constexpr (WITH_R) {
       if (d1 == d2) {
 #pragma unroll
-        for (int a = 0; a < NNPE; ++a) esm[L::R_OFF + rnk[a] * NF + d1] = rr[a];  // residual row, sorted like the columns
+        for (int a = 0; a < NNPE; ++a) esm[L::R_OFF + a * NF + d1] = rr[a];  // residual row, laid out like the columns
       }
     }
   }
   __syncwarp();
 
-  // ---- phase S2: REDs.  Lane = one storage column (sorted node rank k, dof dc) of the element; the warp walks
+  // ---- phase S2: REDs.  Lane = one storage column (local node k, dof dc) of the element; the warp walks
   // the NROW rows, so one RED instruction covers one CSR row segment of the element: NROW consecutive-ish slots.
   // All shared-memory reads of an element are issued before its REDs so their latencies overlap (registers are
   // free here: M is dead).  The RED stream has no per-entry tests: rows that are not stored (Dirichlet dofs, ghost
@@ -332,8 +329,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
           asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p.nz + (r0[row] + off[row / NF])), "d"(val[row]));
       }
       if constexpr (WITH_R) {
-        // fused residual: lane (k, dc) adds the staged entry into R[node_k, dc] -- 3 consecutive doubles per node,
-        // nodes sorted by id (ghost nodes go to their owner over NVLink, see scatter_add)
+        // fused residual: lane (k, dc) adds the staged entry into R[node_k, dc] -- 3 consecutive doubles per node
+        // (ghost nodes go to their owner over NVLink, see scatter_add)
         const uint32_t n = reinterpret_cast<const uint32_t*>(rec + L::OFF_ND)[k];
         scatter_add(p.peer, p.R, (int64_t)n, NF, dc, ks[L::R_OFF + lane]);
       }
@@ -345,7 +342,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
 // element -> CSR column-offset table, rebuilt whenever update_dofs changes the kept-dof masks
 __global__ void k_build_emeta(const int32_t* conn, const uint8_t* epos, const int32_t* adjptr, const uint16_t* coloff,
                               const uint8_t* freemask, const int64_t* rowstart, unsigned char* emeta, int nnpe, int nf,
-                              int rec, int64_t ne, int sorted_cols, int64_t nnz);
+                              int rec, int64_t ne, int sorted_cols, int64_t nnz, int trash_rows);
 
 template <int ND, int NNPE, int NF, int NQT, class Phys, int WARPS, bool WITH_R>
 void run_mat2_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
