@@ -322,8 +322,19 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
         uint32_t off[NNPE];
 #pragma unroll
         for (int b = 0; b < NNPE; ++b) off[b] = ec[b * NNPE + k] + rank;
+        if constexpr (NROW % 4 == 0) {  // the row offsets are 16-byte aligned in the record: broadcast LDS.128
+          const uint4* rs4 = reinterpret_cast<const uint4*>(rec);
 #pragma unroll
-        for (int row = 0; row < NROW; ++row) { r0[row] = rs[row]; val[row] = ks[row * RS + lane]; }
+          for (int i = 0; i < NROW / 4; ++i) {
+            const uint4 v = rs4[i];
+            r0[4 * i] = v.x; r0[4 * i + 1] = v.y; r0[4 * i + 2] = v.z; r0[4 * i + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int row = 0; row < NROW; ++row) r0[row] = rs[row];
+        }
+#pragma unroll
+        for (int row = 0; row < NROW; ++row) val[row] = ks[row * RS + lane];
 #pragma unroll
         for (int row = 0; row < NROW; ++row)  // rows that are not stored point into the trash region (k_build_emeta)
           asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p.nz + (r0[row] + off[row / NF])), "d"(val[row]));
