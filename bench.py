@@ -33,10 +33,12 @@ BYTES_FUSED = 2090.0       # tangent + R 24 (conn/X/U shared with the residual)
 BYTES_ACTION = 160.0
 # FP64 flops per element counted from the kernels' instruction mix
 FLOPS_RESIDUAL = 7.0e3
-FLOPS_TANGENT = 40.0e3      # fused k_mat2: FP64 warp-instructions x 64 / elements (ncu)
-# DRAM bytes per launch of the dominant kernel from the `ncu --set full` capture of this same command
-# (profiles/r01h_fused_kmat2_details.txt: dram__bytes_read.sum 16.80 GB + dram__bytes_write.sum 14.45 GB at 192^3)
-TRAFFIC_NCU_BYTES_PER_ELEMENT = (16.796e9 + 14.452e9) / 7077888
+FLOPS_TANGENT = 36.6e3      # fused k_mat2: thread-level (2 DFMA + DMUL + DADD) per element, ncu r01m
+BYTES_ZERO_FILL = 1954.0   # fill!(storage, 0) of the CSR values (Matrix.jl:39): inside the kernel when double-buffered
+# DRAM bytes per launch of the dominant kernel from the `ncu --set full` capture of this same command at 192^3:
+#   double-buffered (default)  profiles/r01m_fused_kmat2_details.txt  dram__bytes_read.sum 17.30 GB + write 28.33 GB
+#   --single-buffer            profiles/r01h_fused_kmat2_details.txt  read 16.80 GB + write 14.45 GB (memset separate)
+TRAFFIC_NCU_BYTES_PER_ELEMENT = {True: (17.297e9 + 28.332e9) / 7077888, False: (16.796e9 + 14.452e9) / 7077888}
 NEO_PROPS = np.array([1e3, 10.0e6, 1.0e6])
 
 
@@ -307,7 +309,8 @@ def run_gpu(args):
                 kres.append(f.value)
             check(lib.fecb200_enable_timing(h, 0))
             k_tan, k_res = float(np.mean(kms[1:])), float(np.mean(kres[1:]))
-            ach = BYTES_FUSED * ne_local / (k_tan * 1e-3) / 1e9
+            bytes_el = BYTES_FUSED + (BYTES_ZERO_FILL if dbuf else 0.0)
+            ach = bytes_el * ne_local / (k_tan * 1e-3) / 1e9
             # FP64 roof measured here with cuBLAS DGEMM (MEASURED_PEAKS.json has no FP64 entry)
             a = torch.randn(6144, 6144, dtype=torch.float64, device="cuda")
             torch.mm(a, a)
@@ -316,10 +319,11 @@ def run_gpu(args):
             e0.record(); torch.mm(a, a); torch.mm(a, a); e1.record(); torch.cuda.synchronize()
             fp64_peak = 2 * 2 * 6144 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
             del a
-            roof = {"bound": "hbm", "kernel": "k_mat2<hex8,NF=3,neo-Hookean,WITH_R> (fused residual + tangent -> CSR)", "achieved": round(ach, 1),
-                    "peak": hbm, "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / hbm, 4), "traffic": round(TRAFFIC_NCU_BYTES_PER_ELEMENT * ne_local),
-                    "traffic_note": "dram read+write bytes per launch, ncu --set full (profiles/r01h_fused_kmat2_details.txt); 2.1x algorithmic: zero-fill write-back + RED read-modify-write of the CSR values",
-                    "algorithmic_bytes_per_element": BYTES_FUSED, "kernel_ms": round(k_tan, 4),
+            roof = {"bound": "hbm", "kernel": "k_mat2<hex8,NF=3,neo-Hookean,WITH_R> (fused residual + tangent -> CSR" + (" + zero-fill of the idle value array)" if dbuf else ")"), "achieved": round(ach, 1),
+                    "peak": hbm, "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / hbm, 4), "traffic": round(TRAFFIC_NCU_BYTES_PER_ELEMENT[dbuf] * ne_local),
+                    "traffic_note": ("dram read+write bytes per launch, ncu --set full (profiles/r01m_fused_kmat2_details.txt); 1.6x algorithmic: RED read-modify-write of the CSR values"
+                                     if dbuf else "dram read+write bytes per launch, ncu --set full (profiles/r01h_fused_kmat2_details.txt); 2.1x algorithmic: memset write-back + RED read-modify-write of the CSR values"),
+                    "algorithmic_bytes_per_element": bytes_el, "kernel_ms": round(k_tan, 4),
                     "fp64": {"flops_per_element": FLOPS_TANGENT,
                              "achieved_tflops": round(FLOPS_TANGENT * ne_local / (k_tan * 1e-3) / 1e12, 2),
                              "peak_tflops_dgemm_measured": round(fp64_peak, 1),
