@@ -116,16 +116,26 @@ def grid_for(world):
 def build_problem(F, n, rank, world, matrix_free=False):
     """Rank-local neo-Hookean problem.  N = 1: StructuredMesh('hex', (0,0,0), (1,1,1), (n+1,)*3) with the
     BCs of BASELINE config 3.  N > 1: this rank's brick of the global grid (see fecb200.partition)."""
+    verbose = bool(os.environ.get("FECB200_VERBOSE"))
+    tick = [time.time()]
+
+    def lap(name):
+        if verbose and rank == 0:
+            print(f"[bench setup] {name:28s} {time.time() - tick[0]:.3f} s", file=sys.stderr, flush=True)
+        tick[0] = time.time()
     if world == 1:
         mesh = F.StructuredMesh("hex", (0., 0., 0.), (1., 1., 1.), (n + 1, n + 1, n + 1))
         part = None
     else:
         from fecb200.partition import structured_brick_partition
         mesh, part = structured_brick_partition(F, n, grid_for(world), rank)
+    lap("mesh")
     V = F.FunctionSpace(mesh, F.H1Field, F.Lagrange, q_type="GaussLegendre", q_degree=2)
     u = F.VectorFunction(V, "displ")
+    lap("function space")
     asm = F.SparseMatrixAssembler(u, sparse_matrix_type="csr", use_condensed=False, matrix_free=matrix_free,
                                   device=int(os.environ.get("LOCAL_RANK", 0)))
+    lap("SparseMatrixAssembler")
     zero = lambda X, t: np.zeros(X.shape[0])
     pull = lambda X, t: np.full(X.shape[0], 0.1 * t)
     dbcs = [F.DirichletBC(c, zero, nodeset_name="bottom") for c in u.names()]
@@ -133,14 +143,17 @@ def build_problem(F, n, rank, world, matrix_free=False):
              F.DirichletBC("displ_y", pull, nodeset_name="top")]
     p = F.create_parameters(mesh, asm, F.NeoHookean(F.ThreeDimensional()), NEO_PROPS, dirichlet_bcs=dbcs,
                             times=F.TimeStepper(0.0, 1.0, 10))
+    lap("create_parameters")
     if part is not None:
         part.attach(asm)
+        lap("partition attach")
     # raw-throughput state: u = 0.02 (sin 2 pi y, sin 2 pi z, sin 2 pi x) + U(-1e-3,1e-3) h
     X = np.asarray(mesh.nodal_coords)
     rng = np.random.default_rng(42 + rank)
     U = 0.02 * np.stack([np.sin(2 * np.pi * X[1]), np.sin(2 * np.pi * X[2]), np.sin(2 * np.pi * X[0])])
     U += rng.uniform(-1e-3, 1e-3, U.shape) / n
     Uu = np.ascontiguousarray(U.reshape(-1, order="F")[asm.dof.unknown_dofs - 1])
+    lap("initial state")
     return mesh, asm, p, Uu, part
 
 

@@ -109,6 +109,7 @@ static double* nz_for_kind(fecb200_handle* h, int kind, bool alloc) {
   FEC_REQUIRE(!h->opts.matrix_free,
               "assemble_matrix! called on a matrix-free SparseMatrixAssembler.  Re-create the assembler with "
               "matrix_free=false to enable matrix assembly.");  // Matrix.jl:23-28
+  ensure_matrix_structure(h);
   FEC_REQUIRE(h->matrix_ready, "matrix pattern not built");
   if (kind == FECB200_STIFFNESS) return h->d_nz_stiff.p;
   if (kind == FECB200_MASS) {
@@ -223,6 +224,7 @@ int fecb200_version(void) { return 100; }
 
 int fecb200_create(const fecb200_mesh_desc* mesh, const fecb200_opts* opts, fecb200_handle** out) {
   FEC_API_BEGIN
+  PhaseTimer _pt("fecb200_create (total)");
   FEC_REQUIRE(mesh && opts && out, "null argument");
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -351,12 +353,14 @@ int fecb200_set_async(fecb200_handle* h, int32_t on) {
 int fecb200_update_dofs(fecb200_handle* h, const int64_t* dd, int64_t nd, const int64_t* pa, const int64_t* pb,
                         int64_t np) {
   FEC_API_BEGIN
+  PhaseTimer _pt("fecb200_update_dofs (total)");
   FEC_REQUIRE(h, "null handle");
   FEC_CUDA(cudaSetDevice(h->device));
   h->dirichlet_dofs.assign(dd, dd + nd);
   h->per_a.assign(pa, pa + np);
   h->per_b.assign(pb, pb + np);
   build_dof_structures(h);
+  ensure_matrix_structure(h);  // eager here: configuration errors (e.g. periodic BCs + matrix assembly) surface at update_dofs!
   FEC_CUDA(cudaStreamSynchronize(h->stream));
   FEC_API_END
 }
@@ -381,6 +385,8 @@ int fecb200_dof_maps_copy(fecb200_handle* h, int64_t* unknown_dofs, int64_t* dof
 int fecb200_pattern_sizes(fecb200_handle* h, int64_t* n, int64_t* nnz) {
   FEC_API_BEGIN
   FEC_REQUIRE(h, "null handle");
+  FEC_CUDA(cudaSetDevice(h->device));
+  ensure_matrix_structure(h);
   FEC_REQUIRE(h->matrix_ready, "no matrix pattern (matrix_free assembler)");
   if (n) *n = h->nmat;
   if (nnz) *nnz = h->nnz;
@@ -558,6 +564,7 @@ int fecb200_set_matrix_double_buffer(fecb200_handle* h, int32_t enable) {
   FEC_REQUIRE(h, "null argument");
   FEC_CUDA(cudaSetDevice(h->device));
   h->double_buffer = enable != 0;
+  ensure_matrix_structure(h);
   if (!h->double_buffer) { FEC_CUDA(cudaStreamSynchronize(h->stream)); h->d_nz_stiff_alt.release(); h->alt_clean = false; }
   else if (h->matrix_ready && !h->opts.matrix_free && !h->d_nz_stiff_alt.p) {
     h->d_nz_stiff_alt.alloc(nz_alloc_len(h));
@@ -691,7 +698,7 @@ int fecb200_cg_solve(fecb200_handle* h, const double* b, double* x, double atol,
   FEC_REQUIRE(h && b && x, "null argument");
   FEC_CUDA(cudaSetDevice(h->device));
   const int64_t n = len_Uu(h);
-  if (!matrix_free) FEC_REQUIRE(h->matrix_ready && !h->opts.matrix_free, "no assembled matrix for CG");
+  if (!matrix_free) { ensure_matrix_structure(h); FEC_REQUIRE(h->matrix_ready && !h->opts.matrix_free, "no assembled matrix for CG"); }
   ensure_cg(h);
   const double* bd = stage_in(h, b, h->d_Vu.p, n);
   const bool dev = is_device_ptr(x);
@@ -772,6 +779,7 @@ int fecb200_metis_part_graph(int64_t nv, const int64_t* xadj, const int64_t* adj
 
 int fecb200_partition_setup(fecb200_handle* h, int64_t n_owned_nodes, const int32_t* block_is_halo) {
   FEC_API_BEGIN
+  PhaseTimer _pt("fecb200_partition_setup (total)");
   FEC_REQUIRE(h, "null handle");
   FEC_REQUIRE(n_owned_nodes >= 0 && n_owned_nodes <= h->nn, "n_owned_nodes out of range");
   FEC_CUDA(cudaSetDevice(h->device));
@@ -786,6 +794,7 @@ int fecb200_partition_setup(fecb200_handle* h, int64_t n_owned_nodes, const int3
 int fecb200_halo_setup(fecb200_handle* h, int32_t n_neighbors, const int32_t* ranks, const int64_t* send_ptr,
                        const int64_t* send_nodes, const int64_t* recv_ptr, const int64_t* recv_nodes) {
   FEC_API_BEGIN
+  PhaseTimer _pt("fecb200_halo_setup (total)");
   FEC_REQUIRE(h, "null handle");
   FEC_CUDA(cudaSetDevice(h->device));
   h->n_neighbors = n_neighbors;

@@ -141,6 +141,7 @@ __global__ void k_build_emeta(const int32_t* conn, const uint8_t* epos, const in
 }
 
 void build_ecol(fecb200_handle* h) {
+  PhaseTimer _pt("build_ecol");
   if (!h->matrix_ready || (int64_t)nz_alloc_len(h) >= (int64_t)0xFFFFFFFFll) return;
   for (auto& b : h->blocks) {
     if (b.nnpe > 16) continue;

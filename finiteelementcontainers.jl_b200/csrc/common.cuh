@@ -1,5 +1,8 @@
 // common.cuh -- internal declarations of libfecb200 (not part of the C ABI).
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -60,6 +63,17 @@ struct DevBuf {  // owning device array
     }
   }
   void zero(cudaStream_t s) { if (n) FEC_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+};
+
+// FECB200_VERBOSE=1: wall time of the set-up phases on stderr
+struct PhaseTimer {
+  const char* name;
+  std::chrono::steady_clock::time_point t0;
+  bool on;
+  explicit PhaseTimer(const char* n) : name(n), t0(std::chrono::steady_clock::now()), on(getenv("FECB200_VERBOSE") != nullptr) {}
+  ~PhaseTimer() {
+    if (on) fprintf(stderr, "[fecb200] %-28s %.3f s\n", name, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+  }
 };
 
 // tuning knobs of the vector kernels (overridable at build time for sweeps)
@@ -190,6 +204,7 @@ struct fecb200_handle {
   std::vector<int32_t> adjptr, adj;  // host
   fec::DevBuf<int32_t> d_adjptr, d_adj;
   bool matrix_ready = false;
+  bool matrix_dirty = false;         // DOF maps changed since the CSR structure was built (built lazily after create)
   int64_t nmat = 0, nnz = 0;
   int32_t max_rowlen = 0;            // longest node row (kept dofs), bounds the column offsets
   std::vector<int64_t> rowstart_h;   // per dof, -1 if the row is eliminated
@@ -243,6 +258,7 @@ void build_block_tiles(fecb200_handle* h, BlockPlan& b, const double* coords);
 void build_adjacency(fecb200_handle* h);
 void build_dof_structures(fecb200_handle* h);
 void build_matrix_structure(fecb200_handle* h);
+void ensure_matrix_structure(fecb200_handle* h);
 void export_pattern(fecb200_handle* h, int64_t* ptr, int64_t* idx);
 
 // dispatch (one translation unit per element family)

@@ -73,6 +73,7 @@ static inline uint64_t spread2(uint32_t v) {
 // ~NE^(1/ND) cells per axis, so structured meshes -- StructuredMesh.jl enumerates ez fastest,
 // nodes x fastest -- fall into exact bricks: 256 elements = 8x8x4) and cut into tiles of `te`.
 void build_block_tiles(fecb200_handle* h, BlockPlan& b, const double* coords) {
+  PhaseTimer _pt("build_block_tiles");
   const int nd = h->nd, nnpe = b.nnpe, nf = h->nf;
   const int64_t ne = b.ne;
   const int te = b.te;
@@ -178,6 +179,7 @@ void build_block_tiles(fecb200_handle* h, BlockPlan& b, const double* coords) {
 // Node adjacency = sparsity pattern of the condensed operator at node granularity.
 // Row n lists, ascending, every node sharing an element with n (all blocks).
 void build_adjacency(fecb200_handle* h) {
+  PhaseTimer _pt("build_adjacency");
   const int64_t nn = h->nn;
   // node -> (block, element) incidence via counting sort
   std::vector<int64_t> nptr(nn + 1, 0);
@@ -257,6 +259,7 @@ void build_adjacency(fecb200_handle* h) {
 
 // DofManager maps + dof-level CSR offsets after update_dofs!.
 void build_dof_structures(fecb200_handle* h) {
+  PhaseTimer _pt("build_dof_structures");
   const int nf = h->nf;
   const int64_t nn = h->nn, ndof = h->ndof;
   // ---- update_dofs!(dof, dirichlet, per_a, per_b)  (DofManagers.jl:227-298)
@@ -338,11 +341,21 @@ void build_dof_structures(fecb200_handle* h) {
   h->d_Vu.alloc(ndof);
   h->d_out.alloc(ndof);
 
+  // the CSR structure depends on the kept dofs: rebuilt on demand (ensure_matrix_structure)
+  h->matrix_ready = false;
+  h->matrix_dirty = !h->opts.matrix_free;
+}
+
+void ensure_matrix_structure(fecb200_handle* h) {
+  if (!h->matrix_dirty) return;
+  h->matrix_dirty = false;
   build_matrix_structure(h);
 }
 
 // dof-level CSR offsets on top of the node adjacency (rebuilt by update_dofs and partition_setup)
 void build_matrix_structure(fecb200_handle* h) {
+  PhaseTimer _pt("build_matrix_structure");
+  h->matrix_dirty = false;
   const int nf = h->nf;
   const int64_t nn = h->nn, ndof = h->ndof;
   const std::vector<int64_t>& d2u = h->dof_to_unknown;
@@ -419,6 +432,7 @@ void build_matrix_structure(fecb200_handle* h) {
 // row/column, duplicates merged, explicit zeros kept.  The pattern is structurally symmetric, so
 // both formats share the arrays.
 void export_pattern(fecb200_handle* h, int64_t* ptr, int64_t* idx) {
+  ensure_matrix_structure(h);
   FEC_REQUIRE(h->matrix_ready, "no matrix pattern (matrix_free assembler or update_dofs not called)");
   const int nf = h->nf;
   const int64_t nn = h->nn;
