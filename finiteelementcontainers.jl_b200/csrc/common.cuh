@@ -119,7 +119,7 @@ __device__ __forceinline__ void scatter_add(const PeerScatter& ps, double* local
 // LSU / L1 data pipe its REDs are bound by.
 struct ZeroFill { double* p; int64_t total16; int32_t chunk16; };
 #ifndef FEC_ZPAGE
-#define FEC_ZPAGE 2048
+#define FEC_ZPAGE 1024
 #endif
 constexpr int kZeroPageBytes = FEC_ZPAGE;
 

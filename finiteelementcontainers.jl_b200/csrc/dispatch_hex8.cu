@@ -3,8 +3,11 @@
 #include "kernel_mat2.cuh"
 #include "kernel_mat_scalar.cuh"
 
+// Warps per k_mat2 CTA.  The warps of a CTA start together and walk the phases (FP64-bound G/K, RED-bound S) in
+// lockstep, so the FP64 pipes idle while a whole CTA scatters: one-shot CTAs of 8 / 4 / 2 / 1 warps measured
+// 22.9 / 17.9 / 16.8 / 17.2 ms for the fused kernel at 192^3 (same 8 warps per SM in every case).
 #ifndef FEC_MAT2_WARPS
-#define FEC_MAT2_WARPS 4
+#define FEC_MAT2_WARPS 2
 #endif
 #include <cstdlib>
 
