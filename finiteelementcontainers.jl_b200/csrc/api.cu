@@ -507,10 +507,30 @@ int fecb200_state_swap(fecb200_handle* h) {
 int fecb200_assemble_vector(fecb200_handle* h, int32_t kind, const double* Uu) {
   FEC_API_BEGIN
   FEC_REQUIRE(h && Uu, "null argument");
-  FEC_REQUIRE(kind == FECB200_RESIDUAL, "assemble_vector: kind must be FECB200_RESIDUAL");
+  int mode = -1;
+  switch (kind) {
+    case FECB200_RESIDUAL: mode = MODE_RESIDUAL; break;
+    case FECB200_LUMPED_MASS: mode = MODE_LUMPED_MASS; break;
+    case FECB200_DIAGONAL_STIFFNESS: mode = MODE_DIAG_STIFFNESS; break;
+    case FECB200_DIAGONAL_MASS: mode = MODE_DIAG_MASS; break;
+  }
+  FEC_REQUIRE(mode >= 0, "assemble_vector: kind must be FECB200_RESIDUAL, FECB200_LUMPED_MASS or FECB200_DIAGONAL_*");
   FEC_CUDA(cudaSetDevice(h->device));
   const double* u = stage_in(h, Uu, h->d_Uu.p, len_Uu(h));
-  assemble_vector_impl(h, MODE_RESIDUAL, u, nullptr, h->d_R.p);
+  assemble_vector_impl(h, mode, u, nullptr, h->d_R.p);
+  FEC_API_END
+}
+
+int fecb200_vector_values(fecb200_handle* h, double* out) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && out, "null argument");
+  FEC_CUDA(cudaSetDevice(h->device));
+  const bool dev = is_device_ptr(out);
+  double* target = dev ? out : h->d_out.p;
+  if (!dev) wait_out_free(h);
+  if (h->opts.condensed) FEC_CUDA(cudaMemcpyAsync(target, h->d_R.p, h->ndof * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  else k_extract_unknowns(h, h->d_R.p, target);
+  if (!dev) copy_out(h, out, target, len_Uu(h));
   FEC_API_END
 }
 

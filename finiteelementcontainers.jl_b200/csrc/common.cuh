@@ -262,7 +262,7 @@ void ensure_matrix_structure(fecb200_handle* h);
 void export_pattern(fecb200_handle* h, int64_t* ptr, int64_t* idx);
 
 // dispatch (one translation unit per element family)
-enum { MODE_RESIDUAL = 0, MODE_ACTION_STIFFNESS = 1, MODE_ACTION_MASS = 2 };
+enum { MODE_RESIDUAL = 0, MODE_ACTION_STIFFNESS = 1, MODE_ACTION_MASS = 2, MODE_LUMPED_MASS = 3, MODE_DIAG_MASS = 4, MODE_DIAG_STIFFNESS = 5 };
 struct VecLaunch { const double* U; const double* V; double* out; int mode; };
 struct MatLaunch {
   const double* U; double* nz; int kind;

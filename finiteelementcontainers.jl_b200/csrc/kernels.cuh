@@ -105,7 +105,19 @@ FEC_DEV void vec_qp(const Tab& tab, const int q, const double (&x)[NNPE][ND], co
   double Ji[ND][ND];
   const double JxW = invert<ND>(J, Ji) * tab.w[q];
 
-  if constexpr (MODE == MODE_ACTION_MASS) {
+  if constexpr (MODE == MODE_LUMPED_MASS || MODE == MODE_DIAG_MASS) {
+    // lumped_mass: rho JxW N[a] in every direction (row sum of the consistent element mass, partition of unity;
+    // LumpedMass.jl:1-30, TestMechanicsCommon.jl:98-125).  Diagonal of the consistent mass: rho JxW N[a]^2
+    // (assemble_diagonal!(asm, mass, ...), Diagonal.jl:1-14 + Assemblers.jl:42-45).
+    const double rho = Phys::density(props) * JxW;
+#pragma unroll
+    for (int a = 0; a < NNPE; ++a) {
+      const double m = rho * tab.N[q][a] * (MODE == MODE_DIAG_MASS ? tab.N[q][a] : 1.0);
+#pragma unroll
+      for (int d = 0; d < NF; ++d) r[a][d] += m;
+    }
+    return;
+  } else if constexpr (MODE == MODE_ACTION_MASS) {
     // mass_action: JxW rho N (N . v)   (TestPoissonCommon.jl:66-72, Formulations.jl:264-288)
     const double rho = Phys::density(props) * JxW;
 #pragma unroll
@@ -139,6 +151,33 @@ FEC_DEV void vec_qp(const Tab& tab, const int q, const double (&x)[NNPE][ND], co
         for (int j = 0; j < ND; ++j) s = fma(gx[d][j], Ji[j][k], s);
         gu[d][k] = s;
       }
+    if constexpr (MODE == MODE_DIAG_STIFFNESS) {
+      // diagonal of the element stiffness (Assemblers.jl:42-45 on K_q = G^T A G):
+      //   K_el[(a,d),(a,d)] += JxW sum_{j1,j2} dN_X[a][j1] A[(d,j1)][(d,j2)] dN_X[a][j2]
+      double A[NF * ND][NF * ND];
+      Phys::tangent(gu, props, so, A);
+#pragma unroll
+      for (int a = 0; a < NNPE; ++a) {
+        double g[ND];
+#pragma unroll
+        for (int k = 0; k < ND; ++k) {
+          double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < ND; ++j) s = fma(tab.dN[q][a][j], Ji[j][k], s);
+          g[k] = s;
+        }
+#pragma unroll
+        for (int d = 0; d < NF; ++d) {
+          double s = 0.0;
+#pragma unroll
+          for (int j1 = 0; j1 < ND; ++j1)
+#pragma unroll
+            for (int j2 = 0; j2 < ND; ++j2) s = fma(g[j1] * A[d * ND + j1][d * ND + j2], g[j2], s);
+          r[a][d] = fma(s, JxW, r[a][d]);
+        }
+      }
+      return;
+    }
     double P[NF][ND], b[NF];
     if constexpr (MODE == MODE_RESIDUAL) {
       Phys::flux(gu, fq, props, so, sn, P, b);
@@ -193,7 +232,7 @@ FEC_DEV void vec_qp(const Tab& tab, const int q, const double (&x)[NNPE][ND], co
 template <int ND, int NNPE, int NF, int NQT, class Phys, int MODE, int TE, int MINB>
 __global__ void __launch_bounds__(TE, MINB) k_vec(const __grid_constant__ VecParams<ND, NNPE, NQT> p) {
   extern __shared__ double smem[];
-  constexpr bool kNeedV = (MODE != MODE_RESIDUAL);
+  constexpr bool kNeedV = (MODE == MODE_ACTION_STIFFNESS || MODE == MODE_ACTION_MASS);
   constexpr int NS = Phys::NS;
   const int tile = blockIdx.x, tid = threadIdx.x;
   const int nb = p.tile_node_ptr[tile];
@@ -542,7 +581,7 @@ void run_vec(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
   p.ne = (int32_t)b.ne; p.nq = b.nq;
   for (int i = 0; i < kMaxProps; ++i) p.props[i] = i < (int)b.props.size() ? b.props[i] : 0.0;
   fill_tables<ND, NNPE, NQT>(b, p.tab);
-  const int nfields = (MODE == MODE_RESIDUAL) ? 1 : 2;
+  const int nfields = (MODE == MODE_ACTION_STIFFNESS || MODE == MODE_ACTION_MASS) ? 2 : 1;
   size_t sm_nodes = (size_t)b.max_tile_nodes * (ND + nfields * NF) * sizeof(double);
   size_t sm_stage = (size_t)NNPE * NF * TE * sizeof(double);
   size_t body = sm_nodes > sm_stage ? sm_nodes : sm_stage;
@@ -602,6 +641,9 @@ void run_vec_modes(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
     case MODE_RESIDUAL: run_vec<ND, NNPE, NF, NQT, Phys, MODE_RESIDUAL, TE, MINB>(h, b, a); break;
     case MODE_ACTION_STIFFNESS: run_vec<ND, NNPE, NF, NQT, Phys, MODE_ACTION_STIFFNESS, TE, MINB>(h, b, a); break;
     case MODE_ACTION_MASS: run_vec<ND, NNPE, NF, NQT, Phys, MODE_ACTION_MASS, TE, MINB>(h, b, a); break;
+    case MODE_LUMPED_MASS: run_vec<ND, NNPE, NF, NQT, Phys, MODE_LUMPED_MASS, TE, MINB>(h, b, a); break;
+    case MODE_DIAG_MASS: run_vec<ND, NNPE, NF, NQT, Phys, MODE_DIAG_MASS, TE, MINB>(h, b, a); break;
+    case MODE_DIAG_STIFFNESS: run_vec<ND, NNPE, NF, NQT, Phys, MODE_DIAG_STIFFNESS, TE, MINB>(h, b, a); break;
     default: throw Error("fecb200: bad vector mode");
   }
 }

@@ -253,6 +253,22 @@ def assemble_vector(asm, func, Uu, p):
     check(lib.fecb200_assemble_vector(asm._require(), kind, _lib.ptr(Uu)))
 
 
+def assemble_lumped_mass(asm, func, Uu, p):
+    """assemble_lumped_mass!(asm, lumped_mass, Uu, p)  (src/assemblers/LumpedMass.jl:32-60): row-sum mass
+    rho * JxW * N[a] per dof into the residual storage; read it with lumped_mass(asm)."""
+    kind_of(func, (_lib.LUMPED_MASS,))
+    check(lib.fecb200_assemble_vector(asm._require(), _lib.LUMPED_MASS, _lib.ptr(Uu)))
+
+
+def assemble_diagonal(asm, func, Uu, p):
+    """assemble_diagonal!(asm, stiffness | mass, Uu, p)  (src/assemblers/Diagonal.jl:16-74): the diagonal of the
+    element matrices summed into the residual storage, without assembling the sparse matrix; read it with
+    diagonal(asm)."""
+    kind = kind_of(func, (_lib.STIFFNESS, _lib.MASS))
+    check(lib.fecb200_assemble_vector(asm._require(), _lib.DIAGONAL_STIFFNESS if kind == _lib.STIFFNESS else _lib.DIAGONAL_MASS,
+                                      _lib.ptr(Uu)))
+
+
 def _check_matrix_assembly_supported(asm, fname):
     if asm.matrix_free:
         raise FECError(f"{fname} called on a matrix-free SparseMatrixAssembler.  Re-create the assembler with "
@@ -311,6 +327,16 @@ def _residual_accessor(asm, out=None):
     out = np.empty(asm.sizes()[2]) if out is None else out
     check(lib.fecb200_residual(asm._require(), _lib.ptr(out)))
     return out
+
+
+def _vector_values_accessor(asm, out=None):
+    """lumped_mass(asm) / diagonal(asm)  (LumpedMass.jl:70-80, Diagonal.jl:76-89): shares the residual storage."""
+    out = np.empty(asm.sizes()[2]) if out is None else out
+    check(lib.fecb200_vector_values(asm._require(), _lib.ptr(out)))
+    return out
+
+
+diagonal = _vector_values_accessor
 
 
 def hvp(asm, v, out=None):

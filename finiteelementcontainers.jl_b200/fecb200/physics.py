@@ -115,6 +115,7 @@ stiffness_action = _ElementFunction("stiffness_action", _lib.STIFFNESS, action=T
 stiffness_action_b = _ElementFunction("stiffness_action!", _lib.STIFFNESS, inplace=True, action=True)
 mass_action = _ElementFunction("mass_action", _lib.MASS, action=True)
 mass_action_b = _ElementFunction("mass_action!", _lib.MASS, inplace=True, action=True)
+lumped_mass = _ElementFunction("lumped_mass", _lib.LUMPED_MASS, "_vector_values_accessor")
 
 
 def kind_of(func, allowed):

@@ -9,6 +9,7 @@ module FECB200
 
 using FiniteElementContainers
 import FiniteElementContainers: AbstractAssembler, DofManager, assemble_vector!, assemble_stiffness!, assemble_mass!,
+                                assemble_lumped_mass!, assemble_diagonal!, lumped_mass, diagonal,
                                 assemble_matrix_action!, assemble_matrix_free_action!, residual, stiffness, mass, hvp,
                                 update_dofs!, create_unknowns, function_space
 using SparseArrays, SparseMatricesCSR
@@ -18,6 +19,7 @@ const LIB = get(ENV, "FECB200_LIB", joinpath(@__DIR__, "..", "lib", "libfecb200.
 # enums of include/fecb200.h
 const QUAD4, TRI3, HEX8, TET4, TET10 = Int32(1), Int32(2), Int32(3), Int32(4), Int32(5)
 const RESIDUAL, STIFFNESS, MASS = Int32(1), Int32(2), Int32(3)
+const LUMPED_MASS, DIAGONAL_STIFFNESS, DIAGONAL_MASS = Int32(4), Int32(5), Int32(6)
 const CSC, CSR = Int32(1), Int32(2)
 
 struct BlockDesc
@@ -109,6 +111,23 @@ _ptr(x) = reinterpret(Ptr{Float64}, pointer(x))          # CuArray: device point
 function assemble_vector!(asm::B200Assembler, f::F, Uu, p) where F <: Function
   GC.@preserve Uu check(ccall((:fecb200_assemble_vector, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}), asm.handle, kind(f), _ptr(Uu)))
 end
+# assemble_lumped_mass! (src/assemblers/LumpedMass.jl:32-60) / assemble_diagonal! (src/assemblers/Diagonal.jl:16-74)
+function assemble_lumped_mass!(asm::B200Assembler, f::F, Uu, p) where F <: Function
+  f === FiniteElementContainers.lumped_mass || error("fecb200 assembles only the shipped element functions; got $f")
+  GC.@preserve Uu check(ccall((:fecb200_assemble_vector, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}), asm.handle, LUMPED_MASS, _ptr(Uu)))
+end
+function assemble_diagonal!(asm::B200Assembler, f::F, Uu, p) where F <: Function
+  k = kind(f) == STIFFNESS ? DIAGONAL_STIFFNESS : kind(f) == MASS ? DIAGONAL_MASS : error("assemble_diagonal!: stiffness or mass")
+  GC.@preserve Uu check(ccall((:fecb200_assemble_vector, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}), asm.handle, k, _ptr(Uu)))
+end
+function _vector_values(asm::B200Assembler)
+  out = zeros(_sizes(asm)[3])
+  check(ccall((:fecb200_vector_values, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), asm.handle, out))
+  return out
+end
+lumped_mass(asm::B200Assembler) = _vector_values(asm)
+diagonal(asm::B200Assembler) = _vector_values(asm)
+
 function assemble_stiffness!(asm::B200Assembler, f::F, Uu, p) where F <: Function
   GC.@preserve Uu check(ccall((:fecb200_assemble_matrix, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}), asm.handle, STIFFNESS, _ptr(Uu)))
 end

@@ -48,7 +48,9 @@ enum {
 
 /* which element-level function is assembled: the `f` argument of assemble_vector! etc.
  * (mapped by identity on the Julia side: residual / stiffness / mass / stiffness_action) */
-enum { FECB200_RESIDUAL = 1, FECB200_STIFFNESS = 2, FECB200_MASS = 3 };
+enum { FECB200_RESIDUAL = 1, FECB200_STIFFNESS = 2, FECB200_MASS = 3,
+       /* vector flavours of fecb200_assemble_vector */
+       FECB200_LUMPED_MASS = 4, FECB200_DIAGONAL_STIFFNESS = 5, FECB200_DIAGONAL_MASS = 6 };
 
 /* sparse_matrix_type of SparseMatrixAssembler (src/assemblers/SparseMatrixAssembler.jl:64-76) */
 enum { FECB200_CSC = 1, FECB200_CSR = 2 };
@@ -152,6 +154,15 @@ int fecb200_state_swap(fecb200_handle* h); /* state_old <- state_new at the end 
  * _update_for_assembly! (Parameters.jl:404-413), element kernel, nodal scatter.
  * Uu [host|device], length len_Uu. */
 int fecb200_assemble_vector(fecb200_handle* h, int32_t kind, const double* Uu);
+/* The other vector flavours go through the same call and, like the reference, into the residual storage:
+ *   kind = FECB200_LUMPED_MASS         assemble_lumped_mass!(asm, lumped_mass, Uu, p)  (src/assemblers/LumpedMass.jl:32-60):
+ *                                      row-sum mass rho*JxW*N[a] per dof (partition of unity)
+ *   kind = FECB200_DIAGONAL_STIFFNESS  assemble_diagonal!(asm, stiffness, Uu, p)       (src/assemblers/Diagonal.jl:16-74,
+ *          FECB200_DIAGONAL_MASS       assemble_diagonal!(asm, mass, Uu, p)             Assemblers.jl:42-45): diag of K_el / M_el
+ * fecb200_vector_values = lumped_mass(asm) / diagonal(asm) (LumpedMass.jl:70-80, Diagonal.jl:76-89): the full
+ * storage (condensed) or its unknown-dof subset -- no constraint scaling, no periodic fold.  out [host|device],
+ * length len_Uu. */
+int fecb200_vector_values(fecb200_handle* h, double* out);
 /* residual(asm) (src/assemblers/Assemblers.jl:347-371): condensed -> R*(1-c); else periodic
  * fold + gather of unknowns.  out [host|device], length len_Uu. */
 int fecb200_residual(fecb200_handle* h, double* out);

@@ -476,6 +476,10 @@ class Poisson:
     def mass_q(self, N_q, X_q, dN_X, JxW, u_el, props, so, sn):
         return JxW[:, None, None] * (N_q[:, None] * N_q[None, :])[None]
 
+    def lumped_mass_q(self, N_q, X_q, dN_X, JxW, u_el, props, so, sn):
+        """row sum of mass_q (partition of unity: sum_b N_b = 1), density 1"""
+        return JxW[:, None] * N_q[None, :]
+
 
 def _sym(A):
     return 0.5 * (A + np.swapaxes(A, -1, -2))
@@ -519,6 +523,12 @@ class _Mechanics:
         NN = N_q[:, None] * N_q[None, :]
         M = np.einsum("ab,df->adbf", NN, np.eye(nd)).reshape(len(N_q) * nd, len(N_q) * nd)
         return (JxW * props[0])[:, None, None] * M[None]
+
+    def lumped_mass_q(self, N_q, X_q, dN_X, JxW, u_el, props, so, sn):
+        """lumped_mass(physics::Mechanics, ...) (test/mechanics/TestMechanicsCommon.jl:98-125):
+        m_el[NF a + d] = props[1] * JxW * N[a], identical in every direction."""
+        m = (JxW * props[0])[:, None] * N_q[None, :]          # (NE, NNPE)
+        return np.repeat(m, self.nd, axis=1)                    # interleaved dof order
 
 
 class LinearElastic(_Mechanics):
@@ -693,6 +703,28 @@ def assemble_vector(blocks, X, U, nf):
     return R
 
 
+def assemble_lumped_mass(blocks, X, U, nf):
+    """assemble_lumped_mass! (LumpedMass.jl:32-60): the AssembledVector path with func = lumped_mass."""
+    R = np.zeros(U.shape[0] * U.shape[1])
+    for b in blocks:
+        Me = _loop_q(b, X, U, "lumped_mass", False)
+        dc = _dof_conn(b.conn, nf)
+        np.add.at(R, (dc.T - 1).ravel(), Me.ravel())
+    return R
+
+
+def assemble_diagonal(blocks, X, U, nf, kind="stiffness"):
+    """assemble_diagonal! (Diagonal.jl:16-74): per quadrature point only diag(K_q) is accumulated
+    (Assemblers.jl:42-45), then the nodal scatter of a vector."""
+    R = np.zeros(U.shape[0] * U.shape[1])
+    for b in blocks:
+        Ke = _loop_q(b, X, U, kind, False)                      # (NE, NDOF, NDOF)
+        De = np.einsum("eii->ei", Ke)
+        dc = _dof_conn(b.conn, nf)
+        np.add.at(R, (dc.T - 1).ravel(), De.ravel())
+    return R
+
+
 def assemble_matrix_coo(blocks, X, U, nf, kind="stiffness"):
     """assemble_matrix! (Matrix.jl:35-75): COO storage, storage[(e)*NDOF^2 + k] = K_el.data[k]
     with K_el column-major (Assemblers.jl:109-124)."""
@@ -772,6 +804,20 @@ class OracleAssembler:
     def assemble_stiffness(self, Uu, kind="stiffness"):
         self._update_field(self.field, Uu)
         self.stiffness_storage = assemble_matrix_coo(self.blocks, self.X, self._U(), self.nf, kind)
+
+    # assemble_lumped_mass! / assemble_diagonal! write the residual storage (LumpedMass.jl:36, Diagonal.jl:19)
+    def assemble_lumped_mass(self, Uu):
+        self._update_field(self.field, Uu)
+        self.residual_storage = assemble_lumped_mass(self.blocks, self.X, self._U(), self.nf)
+
+    def assemble_diagonal(self, Uu, kind="stiffness"):
+        self._update_field(self.field, Uu)
+        self.residual_storage = assemble_diagonal(self.blocks, self.X, self._U(), self.nf, kind)
+
+    def vector_values(self):
+        """lumped_mass(asm) / diagonal(asm) (LumpedMass.jl:70-80, Diagonal.jl:76-89): no constraint scaling, no fold"""
+        R = self.residual_storage
+        return R if self.condensed else R[self.dof["unknown_dofs"] - 1]
 
     def assemble_matrix_action(self, Uu, Vu, kind="stiffness"):
         self._update_field(self.field, Uu)

@@ -452,3 +452,70 @@ def test_double_buffered_other_kernels(F, case):
             oasm.assemble_stiffness(Uu, kind="mass")
             assert rel_err(F.mass(asm).data, oasm.stiffness()[2]) < RTOL
     asm.close()
+
+
+@pytest.mark.parametrize("case", ["neo_hex8", "poisson_hex8", "linear_quad_tri", "poisson_quad_tri"])
+@pytest.mark.parametrize("condensed", [False, True])
+def test_lumped_mass_and_diagonal(F, case, condensed):
+    """assemble_lumped_mass! / assemble_diagonal! (LumpedMass.jl, Diagonal.jl) against the oracle,
+    plus the reference's own contract (TestAssemblers.jl:432-518): lumped mass = row sums of the consistent mass."""
+    if case.endswith("hex8"):
+        n = 6
+        mesh = perturb(F.StructuredMesh("hex", (0, 0, 0), (1, 1, 1), (n + 1, n + 2, n + 1)), 0.1 / n)
+        phys = case.split("_")[0]
+        props = np.array([1e3, 10e6, 1e6]) if phys == "neo" else None
+        asm, p, oasm = build_pair(F, mesh, phys, props, condensed=condensed, matrix_type="csr",
+                                  bc_nodes_1based=mesh.nodeset_nodes["bottom"], bc_value=0.01, func=SRC3 if phys == "poisson" else None)
+        scale = 0.01
+    else:
+        mesh = F.UnstructuredMesh(os.path.join(GOLDEN, "multi_block_quad4_tri3.npz"))
+        phys = case.split("_")[0]
+        asm, p, oasm = build_pair(F, mesh, phys, None if phys == "poisson" else np.array([1e3, 10e9, 1e9]), condensed=condensed,
+                                  matrix_type="csr", bc_nodes_1based=mesh.sideset_nodes["boundary"],
+                                  func=SRC2 if phys == "poisson" else None)
+        scale = 1.0 if phys == "poisson" else 1e-3
+    rng = np.random.default_rng(12)
+    Uu = scale * rng.uniform(-1, 1, asm.sizes()[2])
+    F.assemble_lumped_mass(asm, F.lumped_mass, Uu, p)
+    ml = F.lumped_mass(asm).copy()
+    oasm.assemble_lumped_mass(Uu)
+    assert rel_err(ml, oasm.vector_values()) < RTOL
+    for func, kind in ((F.stiffness, "stiffness"), (F.mass, "mass")):
+        F.assemble_diagonal(asm, func, Uu, p)
+        d = F.diagonal(asm).copy()
+        oasm.assemble_diagonal(Uu, kind=kind)
+        assert rel_err(d, oasm.vector_values()) < RTOL, kind
+        if not condensed:   # the true diagonal of the matrix the sparse path assembles
+            (F.assemble_stiffness if kind == "stiffness" else F.assemble_mass)(asm, func, Uu, p)
+            M = (F.stiffness if kind == "stiffness" else F.mass)(asm)
+            assert rel_err(d, M.diagonal()) < RTOL, kind
+    # the residual path is untouched by the shared storage
+    F.assemble_vector(asm, F.residual, Uu, p)
+    oasm.assemble_vector(Uu)
+    assert rel_err(F.residual(asm), oasm.residual()) < RTOL
+    asm.close()
+
+
+def test_diagonal_with_state_tet10(F):
+    """assemble_diagonal!(stiffness) reads state_old like assemble_stiffness! does (J2 tet10, yielded points)."""
+    mesh = perturb(F.KuhnTet10Mesh(2), 0.02)
+    props = np.array([1e3, 10e9, 1e9, 2e8, 1e8])
+    asm, p, oasm = build_pair(F, mesh, "j2", props, condensed=False, matrix_type="csr",
+                              bc_nodes_1based=mesh.nodeset_nodes["bottom"], matrix_free=True)
+    X = np.asarray(mesh.nodal_coords)
+    U = 0.15 * np.stack([X[1] ** 2, 0.5 * X[1] * X[0], -0.3 * X[1]])
+    Uu = U.reshape(-1, order="F")[asm.dof.unknown_dofs - 1]
+    rng = np.random.default_rng(6)
+    nq, ne = 4, mesh.element_conns["block_1"].shape[1]
+    so = np.zeros((7, nq, ne))
+    so[:2] = 1e-4 * rng.standard_normal((2, nq, ne)); so[2] = -so[0] - so[1]
+    so[3:6] = 1e-4 * rng.standard_normal((3, nq, ne)); so[6] = 1e-4 * rng.random((nq, ne))
+    p.set_state(so, which="old")
+    oasm.blocks[0].state_old[:] = so
+    F.assemble_diagonal(asm, F.stiffness, Uu, p)
+    oasm.assemble_diagonal(Uu, kind="stiffness")
+    assert rel_err(F.diagonal(asm), oasm.vector_values()) < 1e-11
+    F.assemble_lumped_mass(asm, F.lumped_mass, Uu, p)
+    oasm.assemble_lumped_mass(Uu)
+    assert rel_err(F.lumped_mass(asm), oasm.vector_values()) < RTOL
+    asm.close()

@@ -222,3 +222,58 @@ def test_action_equals_matrix_times_vector():
     Kv = asm.hvp(Vu)
     assert np.allclose(K @ Vu, Kv, rtol=1e-10, atol=1e-10 * np.abs(Kv).max())
     assert abs(K - K.T).max() < 1e-8 * abs(K).max()
+
+
+def test_lumped_mass_contract_of_the_reference():
+    """test/TestAssemblers.jl:432-518 ('test_lumped_mass_mechanics') restated on the oracle:
+    (a) fully-free dofs: lumped mass == row sums of the consistent mass matrix (partition of unity);
+    (b) with Dirichlet BCs: == (a) restricted to the free dofs;
+    (c) differs from M_red * 1 at free dofs next to constrained ones."""
+    m = O.structured_mesh("hex", (0., 0., 0.), (1., 2., 1.), (4, 5, 4))
+    rng = np.random.default_rng(9)
+    X = m["coords"] + 0.03 * rng.standard_normal(m["coords"].shape)
+    props = [2.5e3, 10e6, 1e6]
+
+    def make(dd):
+        blk = O.Block(m["conn"], O.ref_fe_tables("HEX8", "gauss2"), O.LinearElastic(3), props=props)
+        a = O.OracleAssembler(X, [blk], nf=3, condensed=False, matrix_type="csc")
+        a.update_dofs(dd)
+        return a
+    full = make([])
+    Uu = np.zeros(full.n)
+    full.assemble_stiffness(Uu, kind="mass")
+    row_sums = np.asarray(full.stiffness_scipy().sum(axis=1)).ravel()
+    full.assemble_lumped_mass(Uu)
+    ml = full.vector_values().copy()
+    assert np.allclose(ml, row_sums, rtol=1e-12, atol=1e-14)
+    # total mass = density * volume, once per direction
+    vol = abs(np.linalg.det(np.eye(3))) * 1.0 * 2.0 * 1.0
+    assert np.isclose(ml.sum(), 3 * props[0] * vol, rtol=0.05)   # perturbed interior nodes keep the boundary box
+    bc = make(np.concatenate([3 * (m["nodesets"]["bottom"] - 1) + d for d in (1, 2, 3)]))
+    Ub = np.zeros(bc.n)
+    bc.assemble_lumped_mass(Ub)
+    mb = bc.vector_values().copy()
+    unk = bc.dof["unknown_dofs"]
+    assert len(mb) == len(unk) and np.allclose(mb, row_sums[unk - 1], rtol=1e-12, atol=1e-14)
+    bc.assemble_stiffness(Ub, kind="mass")
+    buggy = np.asarray(bc.stiffness_scipy().sum(axis=1)).ravel()
+    assert not np.allclose(mb, buggy, rtol=1e-10, atol=1e-14)
+
+
+@pytest.mark.parametrize("kind", ["stiffness", "mass"])
+def test_diagonal_equals_diagonal_of_the_assembled_matrix(kind):
+    """assemble_diagonal! (Diagonal.jl:1-14): 'gives the true diagonal' of the matrix assemble_stiffness! /
+    assemble_mass! would build -- checked against the oracle's own sparse! path, free and constrained."""
+    m = O.structured_mesh("hex", (0., 0., 0.), (1., 1., 1.), (4, 4, 5))
+    rng = np.random.default_rng(10)
+    X = m["coords"] + 0.03 * rng.standard_normal(m["coords"].shape)
+    for dd in ([], np.concatenate([3 * (m["nodesets"]["top"] - 1) + d for d in (1, 3)])):
+        blk = O.Block(m["conn"], O.ref_fe_tables("HEX8", "gauss2"), O.NeoHookean(3), props=[1e3, 10e6, 1e6])
+        a = O.OracleAssembler(X, [blk], nf=3, condensed=False, matrix_type="csr")
+        a.update_dofs(dd)
+        Uu = 0.01 * rng.standard_normal(a.n)
+        a.assemble_stiffness(Uu, kind=kind)
+        d_ref = a.stiffness_scipy().diagonal()
+        a.assemble_diagonal(Uu, kind=kind)
+        d = a.vector_values()
+        assert np.allclose(d, d_ref, rtol=1e-12, atol=1e-12 * np.abs(d_ref).max())
