@@ -106,7 +106,7 @@ void k_zero_bc_slots(fecb200_handle* h, double* field) {
 }
 
 // ---- per-element scatter records for k_mat2 (layout: Mat2Layout in kernel_mat2.cuh); one thread per element
-__global__ void k_build_emeta(const int32_t* conn, const uint8_t* epos, const int32_t* adjptr, const uint16_t* coloff,
+__global__ void k_build_emeta(const int32_t* conn, const int32_t* gconn, const uint8_t* epos, const int32_t* adjptr, const uint16_t* coloff,
                               const uint8_t* freemask, const int64_t* rowstart, unsigned char* emeta, int nnpe, int nf,
                               int rec, int64_t ne, int sorted_cols, int64_t nnz, int trash_rows) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -125,7 +125,7 @@ __global__ void k_build_emeta(const int32_t* conn, const uint8_t* epos, const in
     rank[a] = sorted_cols ? k : a;   // scalar kernel: columns stay indexed by local node
     rk[a] = (uint8_t)rank[a];
     mk[rank[a]] = freemask[c[a]];
-    nd[rank[a]] = (uint32_t)c[a];
+    nd[rank[a]] = (uint32_t)gconn[e * nnpe + a];   // fused residual: the node the element really gathers from
   }
   for (int b = 0; b < nnpe; ++b) {
     for (int d = 0; d < nf; ++d) {
@@ -149,7 +149,7 @@ void build_ecol(fecb200_handle* h) {
     if (b.d_emeta.n != rec * b.ne) b.d_emeta.alloc(rec * b.ne);
     b.emeta_rec = rec;
     b.emeta_sorted = h->nf > 1;  // k_mat2 records (dead rows point into the trash region); else scalar-kernel records
-    k_build_emeta<<<grid_for(b.ne), 256, 0, h->stream>>>(b.d_conn_perm.p, b.d_epos.p, h->d_adjptr.p, h->d_coloff.p,
+    k_build_emeta<<<grid_for(b.ne), 256, 0, h->stream>>>(b.d_sconn_perm.p ? b.d_sconn_perm.p : b.d_conn_perm.p, b.d_conn_perm.p, b.d_epos.p, h->d_adjptr.p, h->d_coloff.p,
                                                          h->d_freemask.p, h->d_rowstart.p, b.d_emeta.p, b.nnpe, h->nf,
                                                          (int)rec, b.ne, 0, h->nnz, b.emeta_sorted ? 1 : 0);
     h->launches++;

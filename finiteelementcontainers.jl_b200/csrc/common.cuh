@@ -155,6 +155,7 @@ struct BlockPlan {
   int64_t ne = 0;
   std::vector<double> N, dN, w, props;
   std::vector<int32_t> conn0;  // [ne*nnpe] 0-based node ids, caller's element order
+  std::vector<int32_t> sconn0; // scatter connectivity: periodic side-b nodes folded into side a (empty = conn0)
   // tiling (vector kernels): elements permuted into locality-ordered tiles of `te` elements
   bool halo = false;  // neighbour-owned elements (partitioned runs): matrix assembly only
   int te = 0, ntiles = 0, max_tile_nodes = 0;
@@ -163,6 +164,7 @@ struct BlockPlan {
   DevBuf<int32_t> d_tile_node_ptr, d_tile_nodes, d_inc_ptr;
   DevBuf<uint16_t> d_lconn, d_inc;
   DevBuf<int32_t> d_conn_perm;  // [ne*nnpe] global node ids in tile order (matrix kernels)
+  DevBuf<int32_t> d_sconn_perm; // folded twin of d_conn_perm (only with periodic BCs)
   DevBuf<uint8_t> d_epos;       // [ne*nnpe*nnpe] position of node a in the adjacency row of node b
   DevBuf<unsigned char> d_emeta;  // [ne * emeta_rec] per-element scatter records of k_mat2 (kernel_mat2.cuh)
   size_t emeta_rec = 0;
@@ -204,6 +206,7 @@ struct fecb200_handle {
   std::vector<int32_t> adjptr, adj;  // host
   fec::DevBuf<int32_t> d_adjptr, d_adj;
   bool matrix_ready = false;
+  bool adj_folded = false;           // the node adjacency was built on the periodic-folded connectivity
   bool matrix_dirty = false;         // DOF maps changed since the CSR structure was built (built lazily after create)
   int64_t nmat = 0, nnz = 0;
   int32_t max_rowlen = 0;            // longest node row (kept dofs), bounds the column offsets

@@ -346,7 +346,8 @@ struct MatParams {
   const double* X;
   const double* U;
   double* nz;
-  const int32_t* conn;      // [ne*NNPE] tile-ordered global node ids
+  const int32_t* conn;      // [ne*NNPE] tile-ordered global node ids (gathers)
+  const int32_t* sconn;     // [ne*NNPE] the same with periodic side-b nodes replaced by their side-a node (scatter)
   const uint8_t* epos;      // [ne*NNPE*NNPE]  epos[(e*NNPE + b)*NNPE + a] = position of node a in adj row of node b
   const int32_t* adjptr;
   const uint16_t* coloff;
@@ -511,7 +512,8 @@ __global__ void __launch_bounds__(EPB * NNPE) k_mat(const __grid_constant__ MatP
 
   // ---- scatter block-row conn[r]: slot = rowstart[row dof] + coloff[adj entry] + rank of d1 among kept dofs
   if (active) {
-    const int nb = conn[r];
+    const int32_t* sc = p.sconn + (size_t)e * NNPE;  // == conn unless periodic BCs fold side b into side a
+    const int nb = sc[r];
     const int abase = p.adjptr[nb];
     const uint8_t* ep = p.epos + ((size_t)e * NNPE + r) * NNPE;
     int64_t rs[NF];
@@ -520,7 +522,7 @@ __global__ void __launch_bounds__(EPB * NNPE) k_mat(const __grid_constant__ MatP
 #pragma unroll
     for (int a = 0; a < NNPE; ++a) {
       const int off = p.coloff[abase + ep[a]];
-      const unsigned mask = p.freemask[conn[a]];
+      const unsigned mask = p.freemask[sc[a]];
 #pragma unroll
       for (int d2 = 0; d2 < NF; ++d2) {
         if (rs[d2] < 0) continue;
@@ -603,6 +605,7 @@ void run_mat_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   auto& p = *pp;
   p.X = h->d_X.p; p.U = a.U; p.nz = a.nz;
   p.conn = b.d_conn_perm.p; p.epos = b.d_epos.p;
+  p.sconn = b.d_sconn_perm.p ? b.d_sconn_perm.p : b.d_conn_perm.p;
   p.adjptr = h->d_adjptr.p; p.coloff = h->d_coloff.p; p.freemask = h->d_freemask.p; p.rowstart = h->d_rowstart.p;
   p.state_old = b.d_state_old.p;
   p.ne = (int32_t)b.ne; p.nq = b.nq;

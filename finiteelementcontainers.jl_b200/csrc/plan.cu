@@ -176,15 +176,18 @@ void build_block_tiles(fecb200_handle* h, BlockPlan& b, const double* coords) {
   b.d_conn_perm.upload(conn_perm, h->stream);
 }
 
+static inline const std::vector<int32_t>& scatter_conn(const BlockPlan& b) { return b.sconn0.empty() ? b.conn0 : b.sconn0; }
+
 // Node adjacency = sparsity pattern of the condensed operator at node granularity.
-// Row n lists, ascending, every node sharing an element with n (all blocks).
+// Row n lists, ascending, every node sharing an element with n (all blocks).  With periodic BCs the scatter
+// connectivity has side-b nodes replaced by their side-a node (dof_to_unknown_index, DofManagers.jl:188-201).
 void build_adjacency(fecb200_handle* h) {
   PhaseTimer _pt("build_adjacency");
   const int64_t nn = h->nn;
   // node -> (block, element) incidence via counting sort
   std::vector<int64_t> nptr(nn + 1, 0);
   for (auto& b : h->blocks)
-    for (size_t i = 0; i < b.conn0.size(); ++i) nptr[b.conn0[i] + 1]++;
+    for (size_t i = 0; i < b.conn0.size(); ++i) nptr[scatter_conn(b)[i] + 1]++;
   for (int64_t n = 0; n < nn; ++n) nptr[n + 1] += nptr[n];
   std::vector<int64_t> fill(nptr.begin(), nptr.end() - 1);
   struct Ref { int32_t blk; int32_t el; };
@@ -192,7 +195,7 @@ void build_adjacency(fecb200_handle* h) {
   for (size_t bi = 0; bi < h->blocks.size(); ++bi) {
     auto& b = h->blocks[bi];
     for (int64_t e = 0; e < b.ne; ++e)
-      for (int a = 0; a < b.nnpe; ++a) refs[fill[b.conn0[e * b.nnpe + a]]++] = {(int32_t)bi, (int32_t)e};
+      for (int a = 0; a < b.nnpe; ++a) refs[fill[scatter_conn(b)[e * b.nnpe + a]]++] = {(int32_t)bi, (int32_t)e};
   }
   h->adjptr.assign(nn + 1, 0);
   std::vector<int32_t> cnt(nn);
@@ -204,7 +207,7 @@ void build_adjacency(fecb200_handle* h) {
       tmp.clear();
       for (int64_t k = nptr[n]; k < nptr[n + 1]; ++k) {
         const auto& b = h->blocks[refs[k].blk];
-        const int32_t* c = &b.conn0[(size_t)refs[k].el * b.nnpe];
+        const int32_t* c = &scatter_conn(b)[(size_t)refs[k].el * b.nnpe];
         tmp.insert(tmp.end(), c, c + b.nnpe);
       }
       std::sort(tmp.begin(), tmp.end());
@@ -224,7 +227,7 @@ void build_adjacency(fecb200_handle* h) {
       tmp.clear();
       for (int64_t k = nptr[n]; k < nptr[n + 1]; ++k) {
         const auto& b = h->blocks[refs[k].blk];
-        const int32_t* c = &b.conn0[(size_t)refs[k].el * b.nnpe];
+        const int32_t* c = &scatter_conn(b)[(size_t)refs[k].el * b.nnpe];
         tmp.insert(tmp.end(), c, c + b.nnpe);
       }
       std::sort(tmp.begin(), tmp.end());
@@ -241,7 +244,7 @@ void build_adjacency(fecb200_handle* h) {
     bool ok = true;
 #pragma omp parallel for schedule(static) reduction(&& : ok)
     for (int64_t e = 0; e < b.ne; ++e) {
-      const int32_t* c = &b.conn0[(size_t)b.perm[e] * nnpe];
+      const int32_t* c = &scatter_conn(b)[(size_t)b.perm[e] * nnpe];
       for (int r = 0; r < nnpe; ++r) {
         const int32_t* row = &h->adj[h->adjptr[c[r]]];
         const int len = h->adjptr[c[r] + 1] - h->adjptr[c[r]];
@@ -352,6 +355,49 @@ void ensure_matrix_structure(fecb200_handle* h) {
   build_matrix_structure(h);
 }
 
+// Periodic BCs in the assembled matrix: _update_dofs! maps a side-b dof to the unknown of its side-a dof
+// (SparsityPatterns.jl:160-231 with dof_to_unknown_index, DofManagers.jl:188-201), i.e. rows / columns of b are
+// summed into those of a.  Here that is a node-level fold of the SCATTER connectivity: the adjacency, the position
+// bytes and the scatter records are rebuilt on it, the gathers keep the original connectivity.
+static void fold_periodic_nodes(fecb200_handle* h) {
+  const bool need = !h->per_b.empty();
+  if (!need && !h->adj_folded) return;
+  const int nf = h->nf;
+  std::vector<int32_t> rep;
+  if (need) {
+    FEC_REQUIRE(h->n_owned_nodes == h->nn, "periodic BCs are not supported on a partitioned handle");
+    rep.resize(h->nn);
+    std::iota(rep.begin(), rep.end(), 0);
+    std::vector<int32_t> cnt(h->nn, 0);
+    for (size_t i = 0; i < h->per_b.size(); ++i) {
+      const int64_t gb = h->per_b[i] - 1, ga = h->per_a[i] - 1;
+      const int64_t nb = gb / nf, na = ga / nf;
+      FEC_REQUIRE(gb % nf == ga % nf, "periodic pair couples different field components: not supported in matrix assembly");
+      FEC_REQUIRE(cnt[nb] == 0 || rep[nb] == (int32_t)na, "the dofs of a periodic side-b node map to different side-a nodes");
+      rep[nb] = (int32_t)na;
+      cnt[nb]++;
+    }
+    for (int64_t n = 0; n < h->nn; ++n)
+      FEC_REQUIRE(cnt[n] == 0 || cnt[n] == nf,
+                  "a node with only some components periodic is not supported in matrix assembly (use the matrix-free path)");
+  }
+  for (auto& b : h->blocks) {
+    if (need) {
+      b.sconn0.resize(b.conn0.size());
+      for (size_t i = 0; i < b.conn0.size(); ++i) b.sconn0[i] = rep[b.conn0[i]];
+      std::vector<int32_t> sp((size_t)b.ne * b.nnpe);
+      for (int64_t e = 0; e < b.ne; ++e)
+        for (int a = 0; a < b.nnpe; ++a) sp[(size_t)e * b.nnpe + a] = b.sconn0[(size_t)b.perm[e] * b.nnpe + a];
+      b.d_sconn_perm.upload(sp, h->stream);
+    } else {
+      b.sconn0.clear();
+      b.d_sconn_perm.release();
+    }
+  }
+  build_adjacency(h);
+  h->adj_folded = need;
+}
+
 // dof-level CSR offsets on top of the node adjacency (rebuilt by update_dofs and partition_setup)
 void build_matrix_structure(fecb200_handle* h) {
   PhaseTimer _pt("build_matrix_structure");
@@ -364,8 +410,7 @@ void build_matrix_structure(fecb200_handle* h) {
   if (h->opts.matrix_free) return;
   FEC_REQUIRE(h->per_b.empty() || h->opts.condensed == 0,
               "Currently not supported periodic bcs in condensed mode");  // SparseMatrixAssembler.jl:251
-  FEC_REQUIRE(h->per_b.empty(), "matrix assembly with periodic BCs is not implemented in libfecb200 yet "
-                                "(vector and matrix-free paths support them)");
+  fold_periodic_nodes(h);
   const bool condensed = h->opts.condensed != 0;
   h->freemask_h.assign(nn, 0);
   std::vector<uint8_t> nfree(nn);

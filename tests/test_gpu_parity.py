@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import fec_oracle as O
-from util_parity import GOLDEN, RTOL, build_pair, perturb, rel_err
+from util_parity import GOLDEN, RTOL, build_pair, perturb, product_physics, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -518,4 +518,117 @@ def test_diagonal_with_state_tet10(F):
     F.assemble_lumped_mass(asm, F.lumped_mass, Uu, p)
     oasm.assemble_lumped_mass(Uu)
     assert rel_err(F.lumped_mass(asm), oasm.vector_values()) < RTOL
+    asm.close()
+
+
+def _match_periodic(X, side_a, side_b, axis, tol=1e-9):
+    """PeriodicBCContainer (src/bcs/PeriodicBCs.jl:19-110): pair the nodes of two opposite sides by their
+    coordinates in the directions other than `axis` (host bookkeeping; the library receives dof pairs)."""
+    other = [j for j in range(X.shape[0]) if j != axis]
+    key = lambda n: tuple(np.round(X[other, n - 1] / tol).astype(np.int64))
+    lookup = {key(n): n for n in side_b}
+    a = np.asarray(side_a, dtype=np.int64)
+    return a, np.array([lookup[key(n)] for n in a], dtype=np.int64)
+
+
+@pytest.mark.parametrize("case", ["poisson_quad4", "poisson_quad4_xy", "poisson_quad4_thin", "poisson_hex8", "neo_hex8"])
+@pytest.mark.parametrize("matrix_type", ["csr", "csc"])
+def test_periodic_matrix_assembly(F, case, matrix_type):
+    """Periodic side-b dofs folded into their side-a unknown in the ASSEMBLED matrix (_update_dofs!,
+    SparsityPatterns.jl:160-231 with dof_to_unknown_index, DofManagers.jl:188-201): rowptr / colval bit-exact with the
+    oracle's sparse! path, values to 1e-12, through the generic, the scalar and the pair-owner kernels.
+    '_xy': two periodic directions with corner chains; '_thin': one element between the two sides, so an element
+    holds a node and its own periodic image."""
+    phys = case.split("_")[0]
+    if "quad4" in case:
+        nx = 1 if case.endswith("thin") else 5
+        mesh = F.StructuredMesh("quad", (0, 0), (1.3, 1), (nx + 1, 6))
+        nf, etype, props, func = 1, "QUAD4", None, SRC2
+    else:
+        mesh = F.StructuredMesh("hex", (0, 0, 0), (1.3, 1, 0.8), (5, 4, 6))
+        nf, etype = (1, "HEX8") if phys == "poisson" else (3, "HEX8")
+        props, func = (None, SRC3) if phys == "poisson" else (np.array([1e3, 10e6, 1e6]), None)
+    X = np.asarray(mesh.nodal_coords)
+    left, right = mesh.nodeset_nodes["left"], mesh.nodeset_nodes["right"]
+    interior = np.setdiff1d(np.arange(1, X.shape[1] + 1), np.concatenate([mesh.nodeset_nodes[k] for k in mesh.nodeset_nodes]))
+    X[:, interior - 1] += np.random.default_rng(3).uniform(-0.02, 0.02, (X.shape[0], len(interior)))  # non-constant Jacobians
+    bottom = set(mesh.nodeset_nodes["bottom"].tolist())
+    V = F.FunctionSpace(mesh, F.H1Field, F.Lagrange, q_type="GaussLegendre", q_degree=2)
+    u = F.ScalarFunction(V, "u") if nf == 1 else F.VectorFunction(V, "displ")
+    asm = F.SparseMatrixAssembler(u, sparse_matrix_type=matrix_type, use_condensed=False)
+    xy = case.endswith("xy")
+    dbcs = [] if xy else [F.DirichletBC(c, lambda X_, t: np.zeros(X_.shape[0]), nodeset_name="bottom") for c in u.names()]
+    ph = product_physics(F, phys, X.shape[0], func)
+    p = F.create_parameters(mesh, asm, ph, props, dirichlet_bcs=dbcs)
+    a_nodes, b_nodes = _match_periodic(X, [n for n in left if xy or n not in bottom], right, axis=0)
+    if xy:   # second direction: bottom -> top; the corners form chains that update_dofs! resolves
+        a2, b2 = _match_periodic(X, mesh.nodeset_nodes["bottom"], mesh.nodeset_nodes["top"], axis=1)
+        a_nodes, b_nodes = np.concatenate([a_nodes, a2]), np.concatenate([b_nodes, b2])
+    pa = np.concatenate([nf * (a_nodes - 1) + d + 1 for d in range(nf)])
+    pb = np.concatenate([nf * (b_nodes - 1) + d + 1 for d in range(nf)])
+    F.update_dofs(asm, p.dirichlet_bcs, periodic=(pa, pb))
+    blk = O.Block(mesh.element_conns["block_1"], O.ref_fe_tables(etype, "gauss2"),
+                  O.Poisson(func) if phys == "poisson" else O.NeoHookean(3), props=props if props is not None else ())
+    oasm = O.OracleAssembler(X, [blk], nf, condensed=False, matrix_type=matrix_type)
+    oasm.update_dofs(p.dirichlet_bcs.dirichlet_dofs() if dbcs else [], pa, pb)
+    _check_dof_maps(asm, oasm)
+    rng = np.random.default_rng(21)
+    Uu = (1.0 if phys == "poisson" else 0.01) * rng.uniform(-1, 1, asm.sizes()[2])
+    F.assemble_stiffness(asm, F.stiffness, Uu, p)
+    oasm.assemble_stiffness(Uu)
+    _check_pattern_and_values(F, asm, oasm, F.stiffness(asm))
+    F.assemble_vector(asm, F.residual, Uu, p)
+    oasm.assemble_vector(Uu)
+    assert rel_err(F.residual(asm), oasm.residual()) < RTOL
+    if phys == "neo":   # fused entry point: the residual rows still go to the ORIGINAL nodes, folded by the accessor
+        F.assemble_vector_and_stiffness(asm, F.residual, F.stiffness, Uu, p)
+        oasm.assemble_vector(Uu)    # residual(asm) folds side b into side a IN PLACE (Assemblers.jl:357-361): re-assemble
+        assert rel_err(F.residual(asm), oasm.residual()) < RTOL
+        assert rel_err(F.stiffness(asm).data, oasm.stiffness()[2]) < RTOL
+    F.assemble_mass(asm, F.mass, Uu, p)
+    oasm.assemble_stiffness(Uu, kind="mass")
+    assert rel_err(F.mass(asm).data, oasm.stiffness()[2]) < RTOL
+    # K v through the assembled matrix == the matrix-free action on the same periodic dof maps
+    K = F.stiffness(asm)
+    Vu = rng.uniform(0, 1, asm.sizes()[2])
+    F.assemble_matrix_action(asm, F.stiffness, Uu, Vu, p)
+    # (the action path folds nothing in hvp: compare against the oracle's own action instead of K v)
+    oasm.assemble_matrix_action(Uu, Vu)
+    assert rel_err(F.hvp(asm, Vu), oasm.hvp(Vu)) < RTOL
+    # removing the periodic pairs again restores the plain pattern
+    F.update_dofs(asm, p.dirichlet_bcs)
+    oasm.update_dofs(p.dirichlet_bcs.dirichlet_dofs() if dbcs else [])
+    Uu = (1.0 if phys == "poisson" else 0.01) * rng.uniform(-1, 1, asm.sizes()[2])
+    F.assemble_stiffness(asm, F.stiffness, Uu, p)
+    oasm.assemble_stiffness(Uu)
+    _check_pattern_and_values(F, asm, oasm, F.stiffness(asm))
+    asm.close()
+
+
+def test_poisson_periodic_regression(F):
+    """The reference's 'test_poisson_periodic' (test/poisson/TestPoissonPBCs.jl:86-127): poisson.g, periodic in x
+    (sset_1 <-> sset_3) and y (sset_4 <-> sset_2), no Dirichlet BC, NewtonSolver(IterativeLinearSolver(asm, :cg)) with an
+    ASSEMBLED csc matrix; every nodal value within 5e-4 of the analytic solution."""
+    mesh = F.UnstructuredMesh(os.path.join(GOLDEN, "poisson_g.npz"))
+    X = np.asarray(mesh.nodal_coords)
+    f = lambda Xq: ((2 * np.pi) ** 2 * np.cos(2 * np.pi * Xq[:, 0]) + 0.5 * (4 * np.pi) ** 2 * np.cos(4 * np.pi * Xq[:, 1])
+                    + 0.25 * ((2 * np.pi) ** 2 + (4 * np.pi) ** 2) * np.sin(2 * np.pi * Xq[:, 0]) * np.sin(4 * np.pi * Xq[:, 1]))
+    u_an = np.cos(2 * np.pi * X[0]) + 0.5 * np.cos(4 * np.pi * X[1]) + 0.25 * np.sin(2 * np.pi * X[0]) * np.sin(4 * np.pi * X[1])
+    V = F.FunctionSpace(mesh, F.H1Field, F.Lagrange)
+    u = F.ScalarFunction(V, "u")
+    asm = F.SparseMatrixAssembler(u, sparse_matrix_type="csc", use_condensed=False)
+    p = F.create_parameters(mesh, asm, F.Poisson(lambda Xq, t: f(Xq)), None, dirichlet_bcs=[])
+    ss = mesh.sideset_nodes
+    # which coordinate is constant on a side tells the periodic direction's partner
+    def axis_of(nodes):
+        return int(np.argmin(np.ptp(X[:, nodes - 1], axis=1)))
+    assert axis_of(ss["sset_1"]) == axis_of(ss["sset_3"]) and axis_of(ss["sset_4"]) == axis_of(ss["sset_2"])
+    a1, b1 = _match_periodic(X, ss["sset_1"], ss["sset_3"], axis=axis_of(ss["sset_1"]), tol=1e-6)
+    a2, b2 = _match_periodic(X, ss["sset_4"], ss["sset_2"], axis=axis_of(ss["sset_4"]), tol=1e-6)
+    F.update_dofs(asm, p.dirichlet_bcs, periodic=(np.concatenate([a1, a2]), np.concatenate([b1, b2])))
+    solver = F.NewtonSolver(F.IterativeLinearSolver(asm, "cg"))
+    integ = F.QuasiStaticIntegrator(solver)
+    integ.evolve(p)
+    err = np.abs(p.field.data_flat - u_an).max()
+    assert err < 5e-4, err
     asm.close()
