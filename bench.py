@@ -21,6 +21,11 @@ import sys
 import threading
 import time
 
+# torchrun exports OMP_NUM_THREADS=1 for every rank; the library's host-side set-up (tiling, adjacency, DOF maps) is
+# OpenMP code, so give each rank its share of the cores BEFORE libgomp is loaded (set-up only; nothing timed uses it)
+if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // int(os.environ.get("LOCAL_WORLD_SIZE", os.environ["WORLD_SIZE"]))))
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -157,6 +162,21 @@ def build_problem(F, n, rank, world, matrix_free=False):
     return mesh, asm, p, Uu, part
 
 
+def bind_to_gpu_numa_node(index):
+    """CPU affinity of this process = the cores NVML reports as local to the GPU (one process per GPU)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index), (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -167,6 +187,7 @@ def run_gpu(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     if world > 1:
+        bind_to_gpu_numa_node(local)   # pinned staging buffers of the e2e path land next to this rank's GPU
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import fecb200 as F
     from fecb200 import _lib
