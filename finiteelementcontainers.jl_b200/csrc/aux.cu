@@ -105,10 +105,13 @@ void k_zero_bc_slots(fecb200_handle* h, double* field) {
   h->launches++;
 }
 
-// ---- per-element scatter records for k_mat2 (layout: Mat2Layout in kernel_mat2.cuh); one thread per element
+// ---- per-element scatter records (layout: Mat2Layout in kernel_mat2.cuh); one thread per element.
+//   conn  = scatter connectivity (periodic side-b nodes folded into side a), gconn = the nodes the element gathers from
+//   trash_rows: rows that are not stored get an offset into the hashed trash region behind the values (k_mat2 adds
+//   rows without testing); otherwise the 0xFFFFFFFF sentinel the scalar kernel tests for
 __global__ void k_build_emeta(const int32_t* conn, const int32_t* gconn, const uint8_t* epos, const int32_t* adjptr, const uint16_t* coloff,
                               const uint8_t* freemask, const int64_t* rowstart, unsigned char* emeta, int nnpe, int nf,
-                              int rec, int64_t ne, int sorted_cols, int64_t nnz, int trash_rows) {
+                              int rec, int64_t ne, int64_t nnz, int trash_rows) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= ne) return;
   const int32_t* c = conn + e * nnpe;
@@ -116,27 +119,21 @@ __global__ void k_build_emeta(const int32_t* conn, const int32_t* gconn, const u
   uint32_t* rs = reinterpret_cast<uint32_t*>(r);
   uint16_t* ec = reinterpret_cast<uint16_t*>(r + nnpe * nf * 4);
   uint8_t* mk = r + nnpe * nf * 4 + nnpe * nnpe * 2;
-  uint8_t* rk = mk + nnpe;
+  uint8_t* rk = mk + nnpe;   // reserved (identity): columns are indexed by local node
   uint32_t* nd = reinterpret_cast<uint32_t*>(rk + nnpe);
-  int rank[16];
   for (int a = 0; a < nnpe; ++a) {
-    int k = 0;
-    for (int a2 = 0; a2 < nnpe; ++a2) k += (c[a2] < c[a]) || (c[a2] == c[a] && a2 < a);
-    rank[a] = sorted_cols ? k : a;   // scalar kernel: columns stay indexed by local node
-    rk[a] = (uint8_t)rank[a];
-    mk[rank[a]] = freemask[c[a]];
-    nd[rank[a]] = (uint32_t)gconn[e * nnpe + a];   // fused residual: the node the element really gathers from
+    rk[a] = (uint8_t)a;
+    mk[a] = freemask[c[a]];
+    nd[a] = (uint32_t)gconn[e * nnpe + a];   // fused residual: the node the element really gathers from
   }
   for (int b = 0; b < nnpe; ++b) {
     for (int d = 0; d < nf; ++d) {
       const int64_t v = rowstart[(int64_t)c[b] * nf + d];
-      // eliminated / not-stored rows: the scalar kernel tests for the sentinel; k_mat2 (sorted records) adds the
-      // row blindly, so the row is pointed into the hashed trash region behind the values instead
       const uint32_t dead = trash_rows ? (uint32_t)nnz + (uint32_t)(((uint32_t)e * 613u + (uint32_t)(b * nf + d) * 97u) & 4095u) : 0xFFFFFFFFu;
       rs[b * nf + d] = v < 0 ? dead : (uint32_t)v;
     }
     const int base = adjptr[c[b]];
-    for (int a = 0; a < nnpe; ++a) ec[b * nnpe + rank[a]] = coloff[base + epos[(e * nnpe + b) * nnpe + a]];
+    for (int a = 0; a < nnpe; ++a) ec[b * nnpe + a] = coloff[base + epos[(e * nnpe + b) * nnpe + a]];
   }
 }
 
@@ -148,10 +145,10 @@ void build_ecol(fecb200_handle* h) {
     const size_t rec = (((size_t)b.nnpe * h->nf * 4 + (size_t)b.nnpe * b.nnpe * 2 + 2 * b.nnpe + 4 * b.nnpe + 15) / 16) * 16;
     if (b.d_emeta.n != rec * b.ne) b.d_emeta.alloc(rec * b.ne);
     b.emeta_rec = rec;
-    b.emeta_sorted = h->nf > 1;  // k_mat2 records (dead rows point into the trash region); else scalar-kernel records
+    b.emeta_trash_rows = h->nf > 1;  // k_mat2 records (dead rows point into the trash region); else scalar-kernel records
     k_build_emeta<<<grid_for(b.ne), 256, 0, h->stream>>>(b.d_sconn_perm.p ? b.d_sconn_perm.p : b.d_conn_perm.p, b.d_conn_perm.p, b.d_epos.p, h->d_adjptr.p, h->d_coloff.p,
                                                          h->d_freemask.p, h->d_rowstart.p, b.d_emeta.p, b.nnpe, h->nf,
-                                                         (int)rec, b.ne, 0, h->nnz, b.emeta_sorted ? 1 : 0);
+                                                         (int)rec, b.ne, h->nnz, b.emeta_trash_rows ? 1 : 0);
     h->launches++;
   }
   FEC_CUDA(cudaGetLastError());

@@ -168,7 +168,7 @@ struct BlockPlan {
   DevBuf<uint8_t> d_epos;       // [ne*nnpe*nnpe] position of node a in the adjacency row of node b
   DevBuf<unsigned char> d_emeta;  // [ne * emeta_rec] per-element scatter records of k_mat2 (kernel_mat2.cuh)
   size_t emeta_rec = 0;
-  bool emeta_sorted = true;
+  bool emeta_trash_rows = true;  // which flavour of scatter record d_emeta holds (k_build_emeta)
   DevBuf<double> d_state_old, d_state_new;  // [(s*nq+q)*ne + e_tile_order]
   DevBuf<double> d_source;                  // [q*ne + e_tile_order]
 };

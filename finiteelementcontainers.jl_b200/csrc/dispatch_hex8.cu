@@ -52,7 +52,7 @@ void launch_matrix_hex8(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   switch (b.physics) {
     case FECB200_PHYS_POISSON:
       FEC_REQUIRE(h->nf == 1, "Poisson needs NF = 1");
-      if (b.nq == 8 && b.d_emeta.p && !b.emeta_sorted && h->nnz + 4096 < (int64_t)0xFFFFFFFFll && !getenv("FECB200_KMAT1"))
+      if (b.nq == 8 && b.d_emeta.p && !b.emeta_trash_rows && h->nnz + 4096 < (int64_t)0xFFFFFFFFll && !getenv("FECB200_KMAT1"))
         run_mat_scalar<3, 8, 8, PhysPoisson<3>>(h, b, a);   // register-resident thread-per-element kernel
       else if (b.nq == 8) run_mat<3, 8, 1, 8, PhysPoisson<3>, 32>(h, b, a);
       else run_mat<3, 8, 1, 0, PhysPoisson<3>, 32>(h, b, a);

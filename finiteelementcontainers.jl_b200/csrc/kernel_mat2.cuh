@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
 // element -> CSR column-offset table, rebuilt whenever update_dofs changes the kept-dof masks
 __global__ void k_build_emeta(const int32_t* conn, const int32_t* gconn, const uint8_t* epos, const int32_t* adjptr, const uint16_t* coloff,
                               const uint8_t* freemask, const int64_t* rowstart, unsigned char* emeta, int nnpe, int nf,
-                              int rec, int64_t ne, int sorted_cols, int64_t nnz, int trash_rows);
+                              int rec, int64_t ne, int64_t nnz, int trash_rows);
 
 template <int ND, int NNPE, int NF, int NQT, class Phys, int WARPS, bool WITH_R>
 void run_mat2_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {

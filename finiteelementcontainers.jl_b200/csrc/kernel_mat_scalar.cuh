@@ -3,7 +3,7 @@
 // One thread per element, everything in registers: no shared memory, no barriers.  The NNPE x NNPE element
 // matrix is accumulated over the quadrature points and written straight into the CSR values through the
 // per-element scatter record (row offsets u32, column offsets u16 indexed by LOCAL node -- see k_build_emeta with
-// sorted_cols = 0).  REDs are branch-free (eliminated rows / columns go to the hashed trash region behind nz).
+// trash_rows = 0).  REDs are branch-free (eliminated rows / columns go to the hashed trash region behind nz).
 // Honours the reference's transposed COO convention (K[dof_b, dof_a] += K_el[a, b]) through TRANS.
 #pragma once
 #include "kernels.cuh"
@@ -126,7 +126,7 @@ template <int ND, int NNPE, int NQT, class Phys>
 void run_mat_scalar(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   auto pp = std::make_unique<MatSParams<ND, NNPE, NQT>>();
   auto& p = *pp;
-  FEC_REQUIRE(h->nnz + 4096 < (int64_t)0xFFFFFFFFll && b.d_emeta.p && !b.emeta_sorted, "scalar matrix kernel: bad scatter records");
+  FEC_REQUIRE(h->nnz + 4096 < (int64_t)0xFFFFFFFFll && b.d_emeta.p && !b.emeta_trash_rows, "scalar matrix kernel: bad scatter records");
   p.X = h->d_X.p; p.U = a.U; p.nz = a.nz; p.conn = b.d_conn_perm.p; p.emeta = b.d_emeta.p; p.nnz = h->nnz;
   p.ne = (int32_t)b.ne; p.nq = b.nq; p.rec = (int32_t)b.emeta_rec;
   for (int i = 0; i < kMaxProps; ++i) p.props[i] = i < (int)b.props.size() ? b.props[i] : 0.0;
