@@ -150,7 +150,10 @@ def test_multi_block_quad4_tri3(F, phys, matrix_type, condensed):
 
 def test_poisson_gold_solve(F):
     """BASELINE config 1: test/poisson/poisson.g (16384 QUAD4) Newton + CG on the device against
-    test/poisson/poisson.gold (TestPoisson.jl:54-103; exodiff default tolerance)."""
+    test/poisson/poisson.gold (TestPoisson.jl:54-103; exodiff default tolerance).  The same numbers pin the
+    reference's 'Laplace with sources' regression (test/laplace_with_source/TestLaplace.jl:24-76): laplace.g / laplace.gold
+    are byte-identical to poisson.g / poisson.gold in mesh and nodal values, and its Source("u", f, "block_1") is the
+    quadrature-point source array this library receives through fecb200_set_source_q."""
     mesh = F.UnstructuredMesh(os.path.join(GOLDEN, "poisson_g.npz"))
     gold = np.load(os.path.join(GOLDEN, "poisson_g.npz"))["gold_u"]
     for condensed in (False, True):
