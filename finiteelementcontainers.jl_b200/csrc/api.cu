@@ -26,6 +26,15 @@ void launch_matrix(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   }
 }
 
+void launch_scalar(fecb200_handle* h, BlockPlan& b, const double* U) {
+  switch (b.elem_type) {
+    case FECB200_QUAD4: case FECB200_TRI3: launch_scalar_quad_tri(h, b, U); break;
+    case FECB200_HEX8: launch_scalar_hex8(h, b, U); break;
+    case FECB200_TET4: case FECB200_TET10: launch_scalar_tet(h, b, U); break;
+    default: throw Error("fecb200: unknown element type");
+  }
+}
+
 static int elem_nnpe(int t) {
   switch (t) {
     case FECB200_QUAD4: return 4; case FECB200_TRI3: return 3; case FECB200_HEX8: return 8;
@@ -518,6 +527,41 @@ int fecb200_assemble_vector(fecb200_handle* h, int32_t kind, const double* Uu) {
   FEC_CUDA(cudaSetDevice(h->device));
   const double* u = stage_in(h, Uu, h->d_Uu.p, len_Uu(h));
   assemble_vector_impl(h, mode, u, nullptr, h->d_R.p);
+  FEC_API_END
+}
+
+int fecb200_assemble_scalar(fecb200_handle* h, const double* Uu) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && Uu, "null argument");
+  FEC_CUDA(cudaSetDevice(h->device));
+  const double* u = stage_in(h, Uu, h->d_Uu.p, len_Uu(h));
+  join_inputs(h);
+  k_update_field(h, h->d_U.p, u, true);
+  inputs_consumed(h);
+  h->last_ms = 0.f;
+  for (auto& b : h->blocks) {
+    if (b.halo) continue;
+    launch_scalar(h, b, h->d_U.p);
+  }
+  FEC_API_END
+}
+
+int fecb200_scalar_values(fecb200_handle* h, int32_t block, double* out) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && out, "null argument");
+  FEC_REQUIRE(block >= 0 && block < (int32_t)h->blocks.size(), "bad block index");
+  FEC_CUDA(cudaSetDevice(h->device));
+  BlockPlan& b = h->blocks[block];
+  FEC_REQUIRE(b.d_scalar.p, "assemble_scalar! has not been called");
+  const size_t n = (size_t)b.nq * b.ne;
+  const bool dev = is_device_ptr(out);
+  if ((size_t)h->d_scratch.n < n) h->d_scratch.alloc(n);
+  double* target = dev ? out : h->d_scratch.p;
+  k_permute_scalar_out(h, b, b.d_scalar.p, target);  // [q*ne + e_tile] -> [q + NQ*e] in the caller's element order
+  if (!dev) {
+    FEC_CUDA(cudaMemcpyAsync(out, target, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    FEC_CUDA(cudaStreamSynchronize(h->stream));
+  }
   FEC_API_END
 }
 

@@ -346,6 +346,10 @@ void k_permute_state_out(fecb200_handle* h, BlockPlan& b, const double* src, dou
   const int64_t n = b.ne * b.nq * b.nstate;
   if (n) { k_state_out<<<grid_for(n), 256, 0, h->stream>>>(src, dst_dev, b.d_perm.p, b.nstate, b.nq, b.ne); h->launches++; }
 }
+void k_permute_scalar_out(fecb200_handle* h, BlockPlan& b, const double* src, double* dst_dev) {
+  const int64_t n = b.ne * b.nq;
+  if (n) { k_state_out<<<grid_for(n), 256, 0, h->stream>>>(src, dst_dev, b.d_perm.p, 1, b.nq, b.ne); h->launches++; }
+}
 void k_permute_source_in(fecb200_handle* h, BlockPlan& b, const double* src_dev, double* dst) {
   const int64_t n = b.ne * b.nq;
   if (n) { k_state_in<<<grid_for(n), 256, 0, h->stream>>>(src_dev, dst, b.d_perm.p, 1, b.nq, b.ne); h->launches++; }

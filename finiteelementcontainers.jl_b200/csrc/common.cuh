@@ -171,6 +171,7 @@ struct BlockPlan {
   bool emeta_trash_rows = true;  // which flavour of scatter record d_emeta holds (k_build_emeta)
   DevBuf<double> d_state_old, d_state_new;  // [(s*nq+q)*ne + e_tile_order]
   DevBuf<double> d_source;                  // [q*ne + e_tile_order]
+  DevBuf<double> d_scalar;                  // [q*ne + e_tile_order] assemble_scalar! storage (allocated on first use)
 };
 
 }  // namespace fec
@@ -285,6 +286,10 @@ inline ZeroFill make_zero_fill(const MatLaunch& a, int grid) {
 bool matrix_kernel_fuses_residual(fecb200_handle* h, const BlockPlan& b);
 void launch_vector(fecb200_handle* h, BlockPlan& b, const VecLaunch& a);
 void launch_matrix(fecb200_handle* h, BlockPlan& b, const MatLaunch& a);
+void launch_scalar(fecb200_handle* h, BlockPlan& b, const double* U);
+void launch_scalar_quad_tri(fecb200_handle* h, BlockPlan& b, const double* U);
+void launch_scalar_hex8(fecb200_handle* h, BlockPlan& b, const double* U);
+void launch_scalar_tet(fecb200_handle* h, BlockPlan& b, const double* U);
 void launch_vector_quad_tri(fecb200_handle* h, BlockPlan& b, const VecLaunch& a);
 void launch_matrix_quad_tri(fecb200_handle* h, BlockPlan& b, const MatLaunch& a);
 void launch_vector_hex8(fecb200_handle* h, BlockPlan& b, const VecLaunch& a);
@@ -301,6 +306,7 @@ void k_adjust_matrix(fecb200_handle* h, double* nz);
 void k_permute_state_in(fecb200_handle* h, BlockPlan& b, const double* src_dev, double* dst);
 void k_permute_state_out(fecb200_handle* h, BlockPlan& b, const double* src, double* dst_dev);
 void k_permute_source_in(fecb200_handle* h, BlockPlan& b, const double* src_dev, double* dst);
+void k_permute_scalar_out(fecb200_handle* h, BlockPlan& b, const double* src, double* dst_dev);
 void k_zero_bc_slots(fecb200_handle* h, double* field);
 void build_ecol(fecb200_handle* h);
 void spmv(fecb200_handle* h, const double* nz, const double* x, double* y);

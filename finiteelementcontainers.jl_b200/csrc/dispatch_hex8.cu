@@ -65,4 +65,15 @@ void launch_matrix_hex8(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   }
 }
 
+void launch_scalar_hex8(fecb200_handle* h, BlockPlan& b, const double* U) {
+  switch (b.physics) {
+    case FECB200_PHYS_POISSON: FEC_REQUIRE(h->nf == 1, "Poisson needs NF = 1"); run_energy<3, 8, 1, 0, PhysPoisson<3>>(h, b, U); break;
+    case FECB200_PHYS_LINEAR_ELASTIC: FEC_REQUIRE(h->nf == 3, "mechanics needs NF = ND"); run_energy<3, 8, 3, 0, PhysLinearElastic<3>>(h, b, U); break;
+    case FECB200_PHYS_NEOHOOKEAN: FEC_REQUIRE(h->nf == 3, "mechanics needs NF = ND"); run_energy<3, 8, 3, 0, PhysNeoHookean<3>>(h, b, U); break;
+    case FECB200_PHYS_NEOHOOKEAN_AS_WRITTEN: FEC_REQUIRE(h->nf == 3, "mechanics needs NF = ND"); run_energy<3, 8, 3, 0, PhysNeoHookeanAsWritten<3>>(h, b, U); break;
+    case FECB200_PHYS_J2_PLASTICITY: run_energy<3, 8, 3, 0, PhysJ2<3>>(h, b, U); break;
+    default: throw Error("fecb200: unsupported physics for HEX8");
+  }
+}
+
 }  // namespace fec

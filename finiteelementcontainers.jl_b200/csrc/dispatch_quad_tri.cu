@@ -41,6 +41,19 @@ static void mat2d(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   }
 }
 
+template <int NNPE>
+static void scalar2d(fecb200_handle* h, BlockPlan& b, const double* U) {
+  switch (b.physics) {
+    case FECB200_PHYS_POISSON: FEC_REQUIRE(h->nf == 1, "Poisson needs NF = 1"); run_energy<2, NNPE, 1, 0, PhysPoisson<2>>(h, b, U); break;
+    case FECB200_PHYS_LINEAR_ELASTIC: FEC_REQUIRE(h->nf == 2, "plane-strain mechanics needs NF = 2"); run_energy<2, NNPE, 2, 0, PhysLinearElastic<2>>(h, b, U); break;
+    case FECB200_PHYS_NEOHOOKEAN: FEC_REQUIRE(h->nf == 2, "plane-strain mechanics needs NF = 2"); run_energy<2, NNPE, 2, 0, PhysNeoHookean<2>>(h, b, U); break;
+    default: throw Error("fecb200: unsupported physics for QUAD4/TRI3");
+  }
+}
+void launch_scalar_quad_tri(fecb200_handle* h, BlockPlan& b, const double* U) {
+  if (b.elem_type == FECB200_QUAD4) scalar2d<4>(h, b, U); else scalar2d<3>(h, b, U);
+}
+
 void launch_vector_quad_tri(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
   if (b.elem_type == FECB200_QUAD4) vec2d<4>(h, b, a); else vec2d<3>(h, b, a);
 }

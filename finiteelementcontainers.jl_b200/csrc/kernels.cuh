@@ -339,6 +339,87 @@ __global__ void __launch_bounds__(TE, MINB) k_vec(const __grid_constant__ VecPar
 }
 
 // ------------------------------------------------------------------------------------------------
+// Quadrature-point scalars: assemble_scalar!(asm, energy, Uu, p)  (src/assemblers/QuadratureQuantity.jl:4-45):
+//   storage[1, q, e] = JxW * e_q   (_accumulate_q_value(::AssembledScalar, ...), Assemblers.jl:47-51) -- no scatter.
+// One thread per element, direct gathers; out is [q * ne + e] in tile order (coalesced), un-permuted at the ABI.
+// ------------------------------------------------------------------------------------------------
+template <int ND, int NNPE, int NQT>
+struct ScalarParams {
+  const double* X;
+  const double* U;
+  const int32_t* conn;       // [ne*NNPE] tile-ordered global node ids
+  const double* state_old;
+  const double* source;      // [q*ne + e] or nullptr
+  double* out;               // [q*ne + e]
+  int32_t ne, nq;
+  double props[kMaxProps];
+  Tables<ND, NNPE, NQT> tab;
+};
+
+template <int ND, int NNPE, int NF, int NQT, class Phys>
+__global__ void __launch_bounds__(128) k_energy(const __grid_constant__ ScalarParams<ND, NNPE, NQT> p) {
+  constexpr int NS = Phys::NS;
+  const int e = blockIdx.x * 128 + threadIdx.x;
+  if (e >= p.ne) return;
+  double x[NNPE][ND], u[NNPE][NF];
+#pragma unroll
+  for (int a = 0; a < NNPE; ++a) {
+    const int n = p.conn[(size_t)e * NNPE + a];
+#pragma unroll
+    for (int j = 0; j < ND; ++j) x[a][j] = p.X[(size_t)n * ND + j];
+#pragma unroll
+    for (int d = 0; d < NF; ++d) u[a][d] = p.U[(size_t)n * NF + d];
+  }
+  const int nq = (NQT > 0) ? NQT : p.nq;
+#pragma unroll 1
+  for (int q = 0; q < nq; ++q) {
+    double J[ND][ND];
+#pragma unroll
+    for (int i = 0; i < ND; ++i)
+#pragma unroll
+      for (int j = 0; j < ND; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < NNPE; ++a) s = fma(x[a][i], p.tab.dN[q][a][j], s);
+        J[i][j] = s;
+      }
+    double Ji[ND][ND];
+    const double JxW = invert<ND>(J, Ji) * p.tab.w[q];
+    double gx[NF][ND], gu[NF][ND], uq[NF];
+#pragma unroll
+    for (int d = 0; d < NF; ++d) {
+      double s0 = 0.0;
+#pragma unroll
+      for (int a = 0; a < NNPE; ++a) s0 = fma(p.tab.N[q][a], u[a][d], s0);
+      uq[d] = s0;
+#pragma unroll
+      for (int j = 0; j < ND; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < NNPE; ++a) s = fma(u[a][d], p.tab.dN[q][a][j], s);
+        gx[d][j] = s;
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < NF; ++d)
+#pragma unroll
+      for (int k = 0; k < ND; ++k) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < ND; ++j) s = fma(gx[d][j], Ji[j][k], s);
+        gu[d][k] = s;
+      }
+    double so[NS > 0 ? NS : 1];
+    if constexpr (NS > 0) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) so[s] = p.state_old[((size_t)s * p.nq + q) * p.ne + e];
+    }
+    const double fq = (Phys::kHasSource && p.source) ? p.source[(size_t)q * p.ne + e] : 0.0;
+    p.out[(size_t)q * p.ne + e] = JxW * Phys::energy(gu, uq, fq, p.props, so);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Matrix kernel
 // ------------------------------------------------------------------------------------------------
 template <int ND, int NNPE, int NQT>
@@ -597,6 +678,26 @@ void run_vec(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
   FEC_CUDA(cudaGetLastError());
   timing_end(h);
   h->launches++;
+}
+
+template <int ND, int NNPE, int NF, int NQT, class Phys>
+void run_energy(fecb200_handle* h, BlockPlan& b, const double* U) {
+  if constexpr (!Phys::kHasEnergy) {
+    throw Error("fecb200: no energy is defined for this physics");
+  } else {
+    auto pp = std::make_unique<ScalarParams<ND, NNPE, NQT>>();
+    auto& p = *pp;
+    if (b.d_scalar.n != (size_t)b.nq * b.ne) b.d_scalar.alloc((size_t)b.nq * b.ne);
+    p.X = h->d_X.p; p.U = U; p.conn = b.d_conn_perm.p; p.state_old = b.d_state_old.p; p.source = b.d_source.p;
+    p.out = b.d_scalar.p; p.ne = (int32_t)b.ne; p.nq = b.nq;
+    for (int i = 0; i < kMaxProps; ++i) p.props[i] = i < (int)b.props.size() ? b.props[i] : 0.0;
+    fill_tables<ND, NNPE, NQT>(b, p.tab);
+    timing_begin(h);
+    k_energy<ND, NNPE, NF, NQT, Phys><<<(int)((b.ne + 127) / 128), 128, 0, h->stream>>>(p);
+    FEC_CUDA(cudaGetLastError());
+    timing_end(h);
+    h->launches++;
+  }
 }
 
 template <int ND, int NNPE, int NF, int NQT, class Phys, int KIND, int EPB, bool TRANS>

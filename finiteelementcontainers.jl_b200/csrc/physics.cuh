@@ -86,6 +86,14 @@ struct PhysPoisson {
 #pragma unroll
       for (int j = 0; j < ND; ++j) A[i][j] = (i == j) ? 1.0 : 0.0;
   }
+  // energy density e_q = 1/2 grad u . grad u - u_q f(X_q)   (test/poisson/TestPoissonCommon.jl:8-16)
+  static constexpr bool kHasEnergy = true;
+  FEC_DEV static double energy(const double (&gu)[1][ND], const double (&uq)[1], double fq, const double*, const double*) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < ND; ++j) s = fma(gu[0][j], gu[0][j], s);
+    return 0.5 * s - uq[0] * fq;
+  }
 };
 
 // Shared plumbing of the mechanics physics: Impl works on 3x3 tensors.
@@ -111,6 +119,14 @@ struct PhysMech3 {
     Impl::dstress(G3, V3, props, so, D3);
     restrict3<ND, ND>(D3, dP);
   }
+  // strain energy density psi(grad u)  (energy(physics::Mechanics, ...), test/mechanics/TestMechanicsCommon.jl:38-50)
+  static constexpr bool kHasEnergy = Impl::kHasEnergy;
+  FEC_DEV static double energy(const double (&gu)[ND][ND], const double (&)[ND], double, const double* props, const double* so) {
+    double G3[3][3];
+    pad3<ND, ND>(gu, G3);
+    if constexpr (Impl::kHasEnergy) return Impl::energy(G3, props, so);
+    else return 0.0;
+  }
   // A[(d1*ND+j1)][(d2*ND+j2)]
   FEC_DEV static void tangent(const double (&gu)[ND][ND], const double* props, const double* so,
                               double (&A)[ND * ND][ND * ND]) {
@@ -135,7 +151,19 @@ struct PhysMech3 {
 // -------------------------------------------------------------------------------------------
 struct LinearElasticImpl {
   static constexpr int NS = 0;
+  static constexpr bool kHasEnergy = true;
   struct Pre { double K, G; };
+  // psi = 1/2 K tr(eps)^2 + G dev(eps):dev(eps)   (TestMechanicsCommon.jl:14-20)
+  FEC_DEV static double energy(const double (&g)[3][3], const double* props, const double*) {
+    const double K = props[1], G = props[2];
+    const double tr = g[0][0] + g[1][1] + g[2][2];
+    double ee = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { const double e = 0.5 * (g[i][j] + g[j][i]); ee = fma(e, e, ee); }
+    return 0.5 * K * tr * tr + G * (ee - tr * tr * (1.0 / 3.0));
+  }
   FEC_DEV static void stress(const double (&g)[3][3], const double* props, const double*, double*, double (&P)[3][3]) {
     const double K = props[1], G = props[2];
     const double tr = g[0][0] + g[1][1] + g[2][2];
@@ -173,7 +201,16 @@ struct LinearElasticImpl {
 template <bool AS_WRITTEN>
 struct NeoHookeanImpl {
   static constexpr int NS = 0;
+  static constexpr bool kHasEnergy = true;
   struct Pre { double F[3][3], H[3][3], J, I1, m, c, cpJ, G; };
+  // psi = 1/2 K U(J) + 1/2 G (J^-2/3 tr(F F^T) - 3)   (TestMechanicsLargeDeformation.jl:17-27; U: see prepare)
+  FEC_DEV static double energy(const double (&g)[3][3], const double* props, const double*) {
+    Pre p;
+    prepare(g, props, nullptr, p);
+    const double K = props[1];
+    const double U = AS_WRITTEN ? 0.5 * (p.J - 1.0) * (p.J - 1.0) - log(p.J) : 0.5 * (p.J * p.J - 1.0) - log(p.J);
+    return 0.5 * K * U + 0.5 * p.G * (p.m * p.I1 - 3.0);
+  }
   FEC_DEV static void prepare(const double (&g)[3][3], const double* props, const double*, Pre& p) {
     const double K = props[1];
     p.G = props[2];
@@ -264,6 +301,7 @@ struct NeoHookeanImpl {
 // -------------------------------------------------------------------------------------------
 struct J2Impl {
   static constexpr int NS = 7;
+  static constexpr bool kHasEnergy = false;  // no energy is defined for the (oracle-defined) J2 law
   struct Pre { double K, G, theta, thbar, n[3][3]; };
   struct RM { double tr, s[3][3], n[3][3], dg, q; bool yld; };
   FEC_DEV static void return_map(const double (&g)[3][3], const double* props, const double* so, RM& r) {

@@ -12,11 +12,11 @@ from .function_spaces import FunctionSpace, Lagrange, ScalarFunction, VectorFunc
 from .bcs import DirichletBC, DirichletBCs, TimeStepper
 from .physics import (AbstractPhysics, Poisson, Mechanics, NeoHookean, J2Plasticity, ThreeDimensional, PlaneStrain,
                       residual, residual_b, stiffness, stiffness_b, mass, mass_b, stiffness_action,
-                      stiffness_action_b, mass_action, mass_action_b, lumped_mass)
+                      stiffness_action_b, mass_action, mass_action_b, lumped_mass, energy)
 from .assemblers import (SparseMatrixAssembler, Parameters, create_parameters, update_dofs, update_bc_values,
                          update_time, create_field, create_unknowns, assemble_vector, assemble_stiffness,
                          assemble_mass, assemble_vector_and_stiffness, assemble_matrix_action, assemble_matrix_free_action,
-                         assemble_matrix_free_action_full, hvp, full_field, assemble_lumped_mass, assemble_diagonal, diagonal)
+                         assemble_matrix_free_action_full, hvp, full_field, assemble_lumped_mass, assemble_diagonal, diagonal, assemble_scalar, scalar_values)
 from .solvers import IterativeLinearSolver, NewtonSolver, QuasiStaticIntegrator
 from .partition import (Partition, partition_mesh, structured_brick_partition, metis_partition_elements,
                         metis_partition_graph)

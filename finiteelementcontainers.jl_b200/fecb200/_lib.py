@@ -32,6 +32,7 @@ QUAD4, TRI3, HEX8, TET4, TET10 = 1, 2, 3, 4, 5
 PHYS_POISSON, PHYS_LINEAR_ELASTIC, PHYS_NEOHOOKEAN, PHYS_NEOHOOKEAN_AS_WRITTEN, PHYS_J2_PLASTICITY = 1, 2, 3, 4, 5
 RESIDUAL, STIFFNESS, MASS = 1, 2, 3
 LUMPED_MASS, DIAGONAL_STIFFNESS, DIAGONAL_MASS = 4, 5, 6
+ENERGY = 7   # host-side token only (fecb200_assemble_scalar has no kind argument)
 CSC, CSR = 1, 2
 FIELD_U, FIELD_RESIDUAL, FIELD_ACTION, FIELD_V = 1, 2, 3, 4
 
@@ -83,6 +84,8 @@ SIGNATURES = {
     "fecb200_assemble_vector": (C.c_int, [Handle, C.c_int32, VP]),
     "fecb200_residual": (C.c_int, [Handle, VP]),
     "fecb200_vector_values": (C.c_int, [Handle, VP]),
+    "fecb200_assemble_scalar": (C.c_int, [Handle, VP]),
+    "fecb200_scalar_values": (C.c_int, [Handle, C.c_int32, VP]),
     "fecb200_assemble_matrix": (C.c_int, [Handle, C.c_int32, VP]),
     "fecb200_assemble_vector_and_matrix": (C.c_int, [Handle, VP]),
     "fecb200_set_matrix_double_buffer": (C.c_int, [Handle, C.c_int32]),

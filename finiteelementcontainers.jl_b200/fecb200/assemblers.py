@@ -78,6 +78,9 @@ class SparseMatrixAssembler:
         h = _lib.Handle()
         check(lib.fecb200_create(C.byref(mesh), C.byref(opts), C.byref(h)))
         self._h = h
+        # block_quadrature_sizes(fspace) (scalar_quadrature_storage, SparseMatrixAssembler.jl:104-108)
+        self.block_quadrature_sizes = [(fspace.ref_fes[b].num_quadrature_points, int(fspace.elem_conns.nelems[b])) for b in range(nb)]
+        self.mesh_block_names = list(getattr(fspace, "block_names", None) or [f"block_{b + 1}" for b in range(nb)])
         self._pattern = None
 
     def close(self):
@@ -267,6 +270,27 @@ def assemble_diagonal(asm, func, Uu, p):
     kind = kind_of(func, (_lib.STIFFNESS, _lib.MASS))
     check(lib.fecb200_assemble_vector(asm._require(), _lib.DIAGONAL_STIFFNESS if kind == _lib.STIFFNESS else _lib.DIAGONAL_MASS,
                                       _lib.ptr(Uu)))
+
+
+def assemble_scalar(asm, func, Uu, p):
+    """assemble_scalar!(asm, energy, Uu, p)  (src/assemblers/QuadratureQuantity.jl:4-14): JxW * energy at every
+    quadrature point of every block; read it with scalar_values(asm)."""
+    kind_of(func, (_lib.ENERGY,))
+    check(lib.fecb200_assemble_scalar(asm._require(), _lib.ptr(Uu)))
+
+
+def scalar_values(asm, block=None):
+    """asm.scalar_quadrature_storage: {block name: array (NQ, NE)} (block_view(storage, b)[1, :, :]) or one block."""
+    names = list(asm.mesh_block_names)
+    out = {}
+    for bi, name in enumerate(names):
+        if block is not None and block not in (bi, name):
+            continue
+        nq, ne = asm.block_quadrature_sizes[bi]
+        a = np.empty((ne, nq))
+        check(lib.fecb200_scalar_values(asm._require(), bi, _lib.ptr(a)))
+        out[name] = a.T          # (NQ, NE) view of the column-major [NQ, NE] buffer
+    return out if block is None else next(iter(out.values()))
 
 
 def _check_matrix_assembly_supported(asm, fname):

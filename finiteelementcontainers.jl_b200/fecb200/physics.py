@@ -116,6 +116,7 @@ stiffness_action_b = _ElementFunction("stiffness_action!", _lib.STIFFNESS, inpla
 mass_action = _ElementFunction("mass_action", _lib.MASS, action=True)
 mass_action_b = _ElementFunction("mass_action!", _lib.MASS, inplace=True, action=True)
 lumped_mass = _ElementFunction("lumped_mass", _lib.LUMPED_MASS, "_vector_values_accessor")
+energy = _ElementFunction("energy", _lib.ENERGY)
 
 
 def kind_of(func, allowed):

@@ -9,7 +9,7 @@ module FECB200
 
 using FiniteElementContainers
 import FiniteElementContainers: AbstractAssembler, DofManager, assemble_vector!, assemble_stiffness!, assemble_mass!,
-                                assemble_lumped_mass!, assemble_diagonal!, lumped_mass, diagonal,
+                                assemble_lumped_mass!, assemble_diagonal!, lumped_mass, diagonal, assemble_scalar!,
                                 assemble_matrix_action!, assemble_matrix_free_action!, residual, stiffness, mass, hvp,
                                 update_dofs!, create_unknowns, function_space
 using SparseArrays, SparseMatricesCSR
@@ -127,6 +127,17 @@ function _vector_values(asm::B200Assembler)
 end
 lumped_mass(asm::B200Assembler) = _vector_values(asm)
 diagonal(asm::B200Assembler) = _vector_values(asm)
+
+# assemble_scalar!(asm, energy, Uu, p) (src/assemblers/QuadratureQuantity.jl:4-14); values per block as [NQ, NE]
+function assemble_scalar!(asm::B200Assembler, f::F, Uu, p) where F <: Function
+  f === FiniteElementContainers.energy || error("fecb200 assembles only the shipped element functions; got $f")
+  GC.@preserve Uu check(ccall((:fecb200_assemble_scalar, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), asm.handle, _ptr(Uu)))
+end
+function scalar_values(asm::B200Assembler, b::Integer, nq::Integer, ne::Integer)
+  out = Matrix{Float64}(undef, nq, ne)
+  check(ccall((:fecb200_scalar_values, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}), asm.handle, Int32(b - 1), out))
+  return out
+end
 
 function assemble_stiffness!(asm::B200Assembler, f::F, Uu, p) where F <: Function
   GC.@preserve Uu check(ccall((:fecb200_assemble_matrix, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}), asm.handle, STIFFNESS, _ptr(Uu)))

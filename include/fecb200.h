@@ -163,6 +163,14 @@ int fecb200_assemble_vector(fecb200_handle* h, int32_t kind, const double* Uu);
  * storage (condensed) or its unknown-dof subset -- no constraint scaling, no periodic fold.  out [host|device],
  * length len_Uu. */
 int fecb200_vector_values(fecb200_handle* h, double* out);
+/* assemble_scalar!(asm, energy, Uu, p) (src/assemblers/QuadratureQuantity.jl:4-45): the quadrature-point values
+ * storage[1, q, e] = JxW * energy_q of every block (Assemblers.jl:47-51), no scatter.  Energies: Poisson
+ * 1/2 |grad u|^2 - u f (TestPoissonCommon.jl:8-16), linear elastic psi (TestMechanicsCommon.jl:14-50), neo-Hookean psi
+ * (TestMechanicsLargeDeformation.jl:17-27); the J2 law has none (error).
+ * fecb200_scalar_values copies block `block` (0-based) as [NQ, NE] column-major (q fastest) in the caller's element
+ * order = block_view(asm.scalar_quadrature_storage, b).  out [host|device], length NQ*NE of that block. */
+int fecb200_assemble_scalar(fecb200_handle* h, const double* Uu);
+int fecb200_scalar_values(fecb200_handle* h, int32_t block, double* out);
 /* residual(asm) (src/assemblers/Assemblers.jl:347-371): condensed -> R*(1-c); else periodic
  * fold + gather of unknowns.  out [host|device], length len_Uu. */
 int fecb200_residual(fecb200_handle* h, double* out);

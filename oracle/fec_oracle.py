@@ -480,6 +480,12 @@ class Poisson:
         """row sum of mass_q (partition of unity: sum_b N_b = 1), density 1"""
         return JxW[:, None] * N_q[None, :]
 
+    def energy_q(self, N_q, X_q, dN_X, JxW, u_el, props, so, sn):
+        """energy (test/poisson/TestPoissonCommon.jl:8-16): JxW (1/2 grad u . grad u - u_q f(X_q))"""
+        gu = np.einsum("ead,eaj->edj", u_el, dN_X)[:, 0, :]
+        u_q = np.einsum("a,ea->e", N_q, u_el[:, :, 0])
+        return JxW * (0.5 * np.einsum("ej,ej->e", gu, gu) - u_q * self.func(X_q))
+
 
 def _sym(A):
     return 0.5 * (A + np.swapaxes(A, -1, -2))
@@ -524,6 +530,10 @@ class _Mechanics:
         M = np.einsum("ab,df->adbf", NN, np.eye(nd)).reshape(len(N_q) * nd, len(N_q) * nd)
         return (JxW * props[0])[:, None, None] * M[None]
 
+    def energy_q(self, N_q, X_q, dN_X, JxW, u_el, props, so, sn):
+        """energy(physics::Mechanics, ...) (test/mechanics/TestMechanicsCommon.jl:38-50): JxW psi(grad u)"""
+        return JxW * self.energy(self._grad3(u_el, dN_X), props)
+
     def lumped_mass_q(self, N_q, X_q, dN_X, JxW, u_el, props, so, sn):
         """lumped_mass(physics::Mechanics, ...) (test/mechanics/TestMechanicsCommon.jl:98-125):
         m_el[NF a + d] = props[1] * JxW * N[a], identical in every direction."""
@@ -534,6 +544,14 @@ class _Mechanics:
 class LinearElastic(_Mechanics):
     """test/mechanics/TestMechanicsCommon.jl:3-236: psi = 1/2 K tr(eps)^2 + G dev eps:dev eps,
     props = (rho, K, G)."""
+
+    def energy(self, gu, props):
+        """strain_energy (test/mechanics/TestMechanicsCommon.jl:14-20): 1/2 K tr(eps)^2 + G dev(eps):dev(eps)"""
+        K, G = props[1], props[2]
+        eps = _sym(gu)
+        tr = np.trace(eps, axis1=1, axis2=2)
+        dev = eps - tr[:, None, None] / 3 * np.eye(3)
+        return 0.5 * K * tr ** 2 + G * np.einsum("eij,eij->e", dev, dev)
 
     def stress_tangent(self, gu, props, so, sn, need_A=True):
         K, G = props[1], props[2]
@@ -703,6 +721,21 @@ def assemble_vector(blocks, X, U, nf):
     return R
 
 
+def assemble_scalar(blocks, X, U):
+    """assemble_scalar!(asm, energy, ...) (QuadratureQuantity.jl:4-45): storage[1, q, e] = energy_q per block
+    (Assemblers.jl:47-51).  Returns one (NQ, NE) array per block."""
+    out = []
+    for b in blocks:
+        x_el, u_el = _gather(X, b.conn), _gather(U, b.conn)
+        vals = np.zeros((len(b.w), b.conn.shape[1]))
+        for q in range(len(b.w)):
+            X_q, dN_X, JxW = map_interpolants(b.N[q], b.dN[q], b.w[q], x_el)
+            so = b.state_old[:, q, :].T if b.physics.NS else None
+            vals[q] = b.physics.energy_q(b.N[q], X_q, dN_X, JxW, u_el, b.props, so, None)
+        out.append(vals)
+    return out
+
+
 def assemble_lumped_mass(blocks, X, U, nf):
     """assemble_lumped_mass! (LumpedMass.jl:32-60): the AssembledVector path with func = lumped_mass."""
     R = np.zeros(U.shape[0] * U.shape[1])
@@ -813,6 +846,10 @@ class OracleAssembler:
     def assemble_diagonal(self, Uu, kind="stiffness"):
         self._update_field(self.field, Uu)
         self.residual_storage = assemble_diagonal(self.blocks, self.X, self._U(), self.nf, kind)
+
+    def assemble_scalar(self, Uu):
+        self._update_field(self.field, Uu)
+        self.scalar_quadrature_storage = assemble_scalar(self.blocks, self.X, self._U())
 
     def vector_values(self):
         """lumped_mass(asm) / diagonal(asm) (LumpedMass.jl:70-80, Diagonal.jl:76-89): no constraint scaling, no fold"""

@@ -635,3 +635,41 @@ def test_poisson_periodic_regression(F):
     err = np.abs(p.field.data_flat - u_an).max()
     assert err < 5e-4, err
     asm.close()
+
+
+@pytest.mark.parametrize("case", ["neo_hex8", "linear_hex8", "poisson_hex8", "linear_quad_tri", "poisson_quad_tri"])
+def test_assemble_scalar_energy(F, case):
+    """assemble_scalar!(asm, energy, Uu, p) (QuadratureQuantity.jl:4-45): JxW * energy at every quadrature point of
+    every block, [NQ, NE] in the caller's element order, against the oracle."""
+    phys = case.split("_")[0]
+    if case.endswith("hex8"):
+        n = 5
+        mesh = perturb(F.StructuredMesh("hex", (0, 0, 0), (1, 1, 1), (n + 1, n + 2, n + 1)), 0.1 / n)
+        props = None if phys == "poisson" else np.array([1e3, 10e6, 1e6])
+        asm, p, oasm = build_pair(F, mesh, phys, props, condensed=False, matrix_type="csr", bc_nodes_1based=mesh.nodeset_nodes["bottom"],
+                                  bc_value=0.01, func=SRC3 if phys == "poisson" else None, matrix_free=True)
+        scale = 1.0 if phys == "poisson" else 0.02
+    else:
+        mesh = F.UnstructuredMesh(os.path.join(GOLDEN, "multi_block_quad4_tri3.npz"))
+        asm, p, oasm = build_pair(F, mesh, phys, None if phys == "poisson" else np.array([1e3, 10e9, 1e9]), condensed=False,
+                                  matrix_type="csr", bc_nodes_1based=mesh.sideset_nodes["boundary"],
+                                  func=SRC2 if phys == "poisson" else None, matrix_free=True)
+        scale = 1.0 if phys == "poisson" else 1e-3
+    Uu = scale * np.random.default_rng(17).uniform(-1, 1, asm.sizes()[2])
+    F.assemble_scalar(asm, F.energy, Uu, p)
+    vals = F.scalar_values(asm)
+    oasm.assemble_scalar(Uu)
+    assert list(vals) == list(mesh.element_block_names)
+    for name, ref in zip(mesh.element_block_names, oasm.scalar_quadrature_storage):
+        assert vals[name].shape == ref.shape
+        assert rel_err(vals[name], ref) < RTOL, name
+    asm.close()
+
+
+def test_assemble_scalar_without_energy_is_an_error(F):
+    mesh = F.KuhnTet10Mesh(2)
+    asm, p, oasm = build_pair(F, mesh, "j2", np.array([1e3, 10e9, 1e9, 2e8, 1e8]), condensed=False, matrix_type="csr",
+                              bc_nodes_1based=mesh.nodeset_nodes["bottom"], matrix_free=True)
+    with pytest.raises(F.FECError, match="no energy"):
+        F.assemble_scalar(asm, F.energy, np.zeros(asm.sizes()[2]), p)
+    asm.close()

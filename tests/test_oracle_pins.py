@@ -277,3 +277,32 @@ def test_diagonal_equals_diagonal_of_the_assembled_matrix(kind):
         a.assemble_diagonal(Uu, kind=kind)
         d = a.vector_values()
         assert np.allclose(d, d_ref, rtol=1e-12, atol=1e-12 * np.abs(d_ref).max())
+
+
+@pytest.mark.parametrize("phys", ["poisson", "linear", "neo"])
+def test_energy_is_the_potential_of_the_residual(phys):
+    """assemble_scalar!(energy): the sum of the quadrature-point energies is the potential whose gradient
+    assemble_vector!(residual) returns (central differences on a few dofs) -- ties the energy restatement
+    (TestPoissonCommon.jl:8-16, TestMechanicsCommon.jl:14-50, TestMechanicsLargeDeformation.jl:17-27) to the pinned residual."""
+    m = O.structured_mesh("hex", (0., 0., 0.), (1., 1., 1.), (3, 4, 3))
+    rng = np.random.default_rng(13)
+    X = m["coords"] + 0.03 * rng.standard_normal(m["coords"].shape)
+    src = lambda Xq: 3.0 + Xq[:, 0] * Xq[:, 1]
+    physics = {"poisson": O.Poisson(src), "linear": O.LinearElastic(3), "neo": O.NeoHookean(3)}[phys]
+    nf = physics.NF
+    props = () if phys == "poisson" else [1e3, 10e6, 1e6]
+    blk = O.Block(m["conn"], O.ref_fe_tables("HEX8", "gauss2"), physics, props=props)
+    a = O.OracleAssembler(X, [blk], nf=nf, condensed=False)
+    a.update_dofs([])
+    Uu = (1.0 if phys == "poisson" else 0.02) * rng.standard_normal(a.n)
+    a.assemble_vector(Uu)
+    R = a.residual().copy()
+
+    def total(U):
+        a.assemble_scalar(U)
+        return sum(v.sum() for v in a.scalar_quadrature_storage)
+    h = 1e-6
+    for k in rng.choice(a.n, 6, replace=False):
+        e = np.zeros(a.n); e[k] = h
+        fd = (total(Uu + e) - total(Uu - e)) / (2 * h)
+        assert abs(fd - R[k]) < 1e-6 * max(abs(R).max(), 1.0), (k, fd, R[k])
