@@ -673,3 +673,14 @@ def test_assemble_scalar_without_energy_is_an_error(F):
     with pytest.raises(F.FECError, match="no energy"):
         F.assemble_scalar(asm, F.energy, np.zeros(asm.sizes()[2]), p)
     asm.close()
+
+
+@pytest.mark.parametrize("script,args", [("neohookean_cube.py", ["6"]), ("poisson_periodic.py", ["32"])])
+def test_examples_run(script, args):
+    """examples/ (the shape of the reference's examples/mechanics/Cube.jl and examples/poisson/periodic_bc.jl)"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "examples", script), *args], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Newton iterations" in r.stdout
