@@ -12,6 +12,7 @@
 #include <cmath>
 #include <numeric>
 #include <omp.h>
+#include <parallel/algorithm>
 
 // METIS (libmetis_static.a shipped with the CUDA toolkit; 64-bit idx_t, 32-bit real_t; no metis.h in the image)
 extern "C" {
@@ -80,13 +81,20 @@ void build_block_tiles(fecb200_handle* h, BlockPlan& b, const double* coords) {
   FEC_REQUIRE((int64_t)nnpe * nf * te <= 65536, "tile too large for 16-bit incidence slots");
   // bounding box of the block's nodes
   double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-  for (int64_t i = 0; i < ne * nnpe; ++i) {
-    const int n = b.conn0[i];
-    for (int j = 0; j < nd; ++j) {
-      const double c = coords[(size_t)n * nd + j];
-      lo[j] = std::min(lo[j], c);
-      hi[j] = std::max(hi[j], c);
+#pragma omp parallel
+  {
+    double tlo[3] = {1e300, 1e300, 1e300}, thi[3] = {-1e300, -1e300, -1e300};
+#pragma omp for schedule(static) nowait
+    for (int64_t i = 0; i < ne * nnpe; ++i) {
+      const int n = b.conn0[i];
+      for (int j = 0; j < nd; ++j) {
+        const double c = coords[(size_t)n * nd + j];
+        tlo[j] = std::min(tlo[j], c);
+        thi[j] = std::max(thi[j], c);
+      }
     }
+#pragma omp critical
+    for (int j = 0; j < nd; ++j) { lo[j] = std::min(lo[j], tlo[j]); hi[j] = std::max(hi[j], thi[j]); }
   }
   int nbins = (int)std::llround(std::pow((double)ne, 1.0 / nd));
   const int maxbins = (nd == 3) ? (1 << 20) : (1 << 30);
@@ -108,8 +116,15 @@ void build_block_tiles(fecb200_handle* h, BlockPlan& b, const double* coords) {
                        : (spread2(ic[0]) | spread2(ic[1]) << 1);
   }
   b.perm.resize(ne);
-  std::iota(b.perm.begin(), b.perm.end(), 0);
-  std::stable_sort(b.perm.begin(), b.perm.end(), [&](int32_t x, int32_t y) { return key[x] < key[y]; });
+  {
+    // (key, original index) pairs: a plain lexicographic sort is the stable sort by key, and runs multi-threaded
+    std::vector<std::pair<uint64_t, int32_t>> ki(ne);
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < ne; ++e) ki[e] = {key[e], (int32_t)e};
+    __gnu_parallel::sort(ki.begin(), ki.end());
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < ne; ++e) b.perm[e] = ki[e].second;
+  }
 
   b.ntiles = (int)((ne + te - 1) / te);
   std::vector<int32_t> tile_node_ptr(b.ntiles + 1, 0);
@@ -186,16 +201,29 @@ void build_adjacency(fecb200_handle* h) {
   const int64_t nn = h->nn;
   // node -> (block, element) incidence via counting sort
   std::vector<int64_t> nptr(nn + 1, 0);
-  for (auto& b : h->blocks)
-    for (size_t i = 0; i < b.conn0.size(); ++i) nptr[scatter_conn(b)[i] + 1]++;
+  for (auto& b : h->blocks) {
+    const std::vector<int32_t>& c = scatter_conn(b);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)c.size(); ++i) {
+#pragma omp atomic
+      nptr[c[i] + 1]++;
+    }
+  }
   for (int64_t n = 0; n < nn; ++n) nptr[n + 1] += nptr[n];
   std::vector<int64_t> fill(nptr.begin(), nptr.end() - 1);
   struct Ref { int32_t blk; int32_t el; };
-  std::vector<Ref> refs(nptr[nn]);
+  std::vector<Ref> refs(nptr[nn]);   // order inside a node's list is irrelevant: the neighbour sets are sorted below
   for (size_t bi = 0; bi < h->blocks.size(); ++bi) {
     auto& b = h->blocks[bi];
+    const std::vector<int32_t>& c = scatter_conn(b);
+#pragma omp parallel for schedule(static)
     for (int64_t e = 0; e < b.ne; ++e)
-      for (int a = 0; a < b.nnpe; ++a) refs[fill[scatter_conn(b)[e * b.nnpe + a]]++] = {(int32_t)bi, (int32_t)e};
+      for (int a = 0; a < b.nnpe; ++a) {
+        int64_t pos;
+#pragma omp atomic capture
+        pos = fill[c[e * b.nnpe + a]]++;
+        refs[pos] = {(int32_t)bi, (int32_t)e};
+      }
   }
   h->adjptr.assign(nn + 1, 0);
   std::vector<int32_t> cnt(nn);
@@ -414,6 +442,7 @@ void build_matrix_structure(fecb200_handle* h) {
   const bool condensed = h->opts.condensed != 0;
   h->freemask_h.assign(nn, 0);
   std::vector<uint8_t> nfree(nn);
+#pragma omp parallel for schedule(static)
   for (int64_t n = 0; n < nn; ++n) {
     unsigned m = 0;
     for (int d = 0; d < nf; ++d)
@@ -440,13 +469,21 @@ void build_matrix_structure(fecb200_handle* h) {
   }
   h->rowstart_h.assign(ndof, -1);
   std::vector<int64_t> diag(ndof, -1);
-  int64_t pos = 0;
-  for (int64_t n = 0; n < h->n_owned_nodes; ++n) {  // ghost rows are not stored
+  // first value slot of every owned node (ghost rows are not stored): serial prefix sum, the rest in parallel
+  std::vector<int64_t> nodebase(h->n_owned_nodes + 1, 0);
+  int64_t nmat = 0;
+  for (int64_t n = 0; n < h->n_owned_nodes; ++n) {
+    nodebase[n + 1] = nodebase[n] + (int64_t)nfree[n] * rowlen[n];
+    nmat += nfree[n];
+  }
+#pragma omp parallel for schedule(static)
+  for (int64_t n = 0; n < h->n_owned_nodes; ++n) {
     const unsigned m = h->freemask_h[n];
     // self position
     const int32_t* row = &h->adj[h->adjptr[n]];
     const int len = h->adjptr[n + 1] - h->adjptr[n];
     const int ks = (int)(std::lower_bound(row, row + len, (int32_t)n) - row);
+    int64_t pos = nodebase[n];
     for (int d = 0; d < nf; ++d) {
       if (!(m & (1u << d))) continue;
       h->rowstart_h[n * nf + d] = pos;
@@ -454,9 +491,8 @@ void build_matrix_structure(fecb200_handle* h) {
       pos += rowlen[n];
     }
   }
-  h->nnz = pos;
-  h->nmat = 0;
-  for (int64_t g = 0; g < h->n_owned_nodes * nf; ++g) h->nmat += (h->rowstart_h[g] >= 0);
+  h->nnz = nodebase[h->n_owned_nodes];
+  h->nmat = nmat;
   h->d_coloff.upload(coloff, h->stream);
   h->d_freemask.upload(h->freemask_h, h->stream);
   h->d_rowstart.upload(h->rowstart_h, h->stream);
