@@ -227,11 +227,19 @@ void build_adjacency(fecb200_handle* h) {
   }
   h->adjptr.assign(nn + 1, 0);
   std::vector<int32_t> cnt(nn);
-#pragma omp parallel
+  // one pass: schedule(static) hands every thread ONE contiguous node range, so each thread appends its rows to a
+  // private buffer in node order; the buffers are then copied behind each other
+  const int nt = omp_get_max_threads();
+  std::vector<std::vector<int32_t>> tout(nt);
+  std::vector<int64_t> tfirst(nt, -1);
+#pragma omp parallel num_threads(nt)
   {
+    const int t = omp_get_thread_num();
+    std::vector<int32_t>& out = tout[t];
     std::vector<int32_t> tmp;
 #pragma omp for schedule(static)
     for (int64_t n = 0; n < nn; ++n) {
+      if (tfirst[t] < 0) tfirst[t] = n;
       tmp.clear();
       for (int64_t k = nptr[n]; k < nptr[n + 1]; ++k) {
         const auto& b = h->blocks[refs[k].blk];
@@ -239,7 +247,9 @@ void build_adjacency(fecb200_handle* h) {
         tmp.insert(tmp.end(), c, c + b.nnpe);
       }
       std::sort(tmp.begin(), tmp.end());
-      cnt[n] = (int32_t)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
+      const auto end = std::unique(tmp.begin(), tmp.end());
+      cnt[n] = (int32_t)(end - tmp.begin());
+      out.insert(out.end(), tmp.begin(), end);
     }
   }
   int64_t tot = 0;
@@ -247,22 +257,10 @@ void build_adjacency(fecb200_handle* h) {
   FEC_REQUIRE(tot < (int64_t)INT32_MAX, "node adjacency exceeds int32 range");
   h->adjptr[nn] = (int32_t)tot;
   h->adj.resize(tot);
-#pragma omp parallel
-  {
-    std::vector<int32_t> tmp;
-#pragma omp for schedule(static)
-    for (int64_t n = 0; n < nn; ++n) {
-      tmp.clear();
-      for (int64_t k = nptr[n]; k < nptr[n + 1]; ++k) {
-        const auto& b = h->blocks[refs[k].blk];
-        const int32_t* c = &scatter_conn(b)[(size_t)refs[k].el * b.nnpe];
-        tmp.insert(tmp.end(), c, c + b.nnpe);
-      }
-      std::sort(tmp.begin(), tmp.end());
-      auto end = std::unique(tmp.begin(), tmp.end());
-      std::copy(tmp.begin(), end, h->adj.begin() + h->adjptr[n]);
-    }
-  }
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+  for (int t = 0; t < nt; ++t)
+    if (tfirst[t] >= 0) std::copy(tout[t].begin(), tout[t].end(), h->adj.begin() + h->adjptr[tfirst[t]]);
+  tout.clear();
   h->d_adjptr.upload(h->adjptr, h->stream);
   h->d_adj.upload(h->adj, h->stream);
   // element -> adjacency-position bytes (the element -> CSR slot map)
