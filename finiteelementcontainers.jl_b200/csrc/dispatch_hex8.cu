@@ -1,6 +1,7 @@
 // dispatch_hex8.cu -- HEX8 instantiations of the element kernels (3-D, 8 nodes).
 // Hot configurations (BASELINE.json configs 2, 3, 5): Poisson NF=1 and neo-Hookean NF=3 with 8-point rules.
 #include "kernel_mat2.cuh"
+#include "kernel_mat2c.cuh"
 #include "kernel_mat_scalar.cuh"
 
 // Warps per k_mat2 CTA.  The warps of a CTA start together and walk the phases (FP64-bound G/K, RED-bound S) in
@@ -8,6 +9,17 @@
 // 22.9 / 17.9 / 16.8 / 17.2 ms for the fused kernel at 192^3 (same 8 warps per SM in every case).
 #ifndef FEC_MAT2_WARPS
 #define FEC_MAT2_WARPS 2
+#endif
+// Column-split variant (kernel_mat2c.cuh): FEC_MAT2C = 1 selects it, FEC_MAT2C_EPC elements per CTA (12 threads each),
+// FEC_MAT2C_MINB CTAs per SM (sets the register cap: 5 -> 136, 4 -> 168).
+#ifndef FEC_MAT2C
+#define FEC_MAT2C 0
+#endif
+#ifndef FEC_MAT2C_EPC
+#define FEC_MAT2C_EPC 8
+#endif
+#ifndef FEC_MAT2C_MINB
+#define FEC_MAT2C_MINB 5
 #endif
 #include <cstdlib>
 
@@ -22,7 +34,13 @@ template <class Phys, int NF, int EPB>
 static void mat8(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   FEC_REQUIRE(b.nq == 8, "HEX8: this physics is compiled for 8-point quadrature rules only");
   // symmetric tangents (all shipped mechanics physics): pair-owner kernel with staged, coalesced REDs
-  if (a.kind == FECB200_STIFFNESS && matrix_kernel_fuses_residual(h, b)) run_mat2<3, 8, NF, 8, Phys, FEC_MAT2_WARPS>(h, b, a);
+  if (a.kind == FECB200_STIFFNESS && matrix_kernel_fuses_residual(h, b)) {
+#if FEC_MAT2C
+    run_mat2c<3, 8, NF, 8, Phys, FEC_MAT2C_EPC, FEC_MAT2C_MINB>(h, b, a);
+#else
+    run_mat2<3, 8, NF, 8, Phys, FEC_MAT2_WARPS>(h, b, a);
+#endif
+  }
   else run_mat<3, 8, NF, 8, Phys, EPB>(h, b, a);
 }
 
