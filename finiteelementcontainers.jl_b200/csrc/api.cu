@@ -803,6 +803,8 @@ int fecb200_newton_solve(fecb200_handle* h, double* Uu, int32_t max_iters, doubl
       // residual and tangent at the same state: fused pass (see fecb200_assemble_vector_and_matrix)
       assemble_vector_and_matrix_impl(h, u);
     }
+    add_source_loads(h, h->d_R.p);    // assemble_vector_source!      (Solvers.jl:135)
+    add_neumann_loads(h, h->d_R.p);   // assemble_vector_neumann_bc!  (Solvers.jl:136)
     k_residual_accessor(h, Rb);
     if (!matrix_free) adjusted_values(h, FECB200_STIFFNESS);
     int64_t cgit = 0;

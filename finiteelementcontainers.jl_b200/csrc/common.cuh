@@ -172,6 +172,17 @@ struct BlockPlan {
   DevBuf<double> d_state_old, d_state_new;  // [(s*nq+q)*ne + e_tile_order]
   DevBuf<double> d_source;                  // [q*ne + e_tile_order]
   DevBuf<double> d_scalar;                  // [q*ne + e_tile_order] assemble_scalar! storage (allocated on first use)
+  DevBuf<double> d_body_force;              // [NF, NQ, NE] body-force values, caller's element order (Sources.jl:38-46)
+  DevBuf<double> d_tab;                     // N [nq*nnpe], dN [nq*nnpe*nd], w [nq] for the run-time-shaped load kernel
+};
+
+// One NeumannBCContainer (src/bcs/NeumannBCs.jl:29-48): the sides of a side set with their surface tables.
+struct SurfaceLoad {
+  int64_t nsides = 0;
+  int nnps = 0, nqs = 0;
+  DevBuf<int32_t> nodes;  // [nsides*nnps] 0-based node ids of each side (surface_connectivity)
+  DevBuf<double> tab;     // Ns [nqs*nnps], dNs [nqs*nnps*(nd-1)], ws [nqs]
+  DevBuf<double> vals;    // [NF, nqs, nsides] = Matrix{SVector{NF}}(nqs, nsides)
 };
 
 }  // namespace fec
@@ -220,6 +231,14 @@ struct fecb200_handle {
   fec::DevBuf<double> d_nz_stiff_alt;  // fecb200_set_matrix_double_buffer: cleared by the kernel that fills the other one
   bool double_buffer = false, alt_clean = false;
   bool stiff_adjusted = false, mass_adjusted = false;
+
+  // external loads (loads.cu): U-independent, so they are integrated once per value update into a cached nodal
+  // vector and every assemble_vector_neumann_bc! / assemble_vector_source! is one streaming add
+  std::vector<fec::SurfaceLoad> surface_loads;
+  fec::DevBuf<double> d_F_neumann, d_F_source;
+  bool neumann_dirty = false, source_dirty = false;
+  bool has_neumann() const { return !surface_loads.empty(); }
+  bool has_source() const { for (auto& b : blocks) if (b.d_body_force.p) return true; return false; }
 
   // peer-memory halo (fecb200_peer_attach)
   bool peer_enabled = false;
@@ -315,6 +334,10 @@ void axpy(fecb200_handle* h, double alpha, const double* x, double* y, int64_t n
 void xpay(fecb200_handle* h, const double* x, double beta, double* y, int64_t n);  // y = x + beta*y
 void halo_pack(fecb200_handle* h, const double* field, double* buf);
 void halo_unpack_add(fecb200_handle* h, double* field, const double* buf);
+
+// loads.cu
+void add_neumann_loads(fecb200_handle* h, double* field);   // field += int_Gamma N g      (WeaklyEnforcedBCs.jl:61-83)
+void add_source_loads(fecb200_handle* h, double* field);    // field += -int_Omega N b    (Source.jl:44-63)
 
 inline bool is_device_ptr(const void* p) {
   cudaPointerAttributes a{};

@@ -9,14 +9,15 @@ from .fields import H1Field, Connectivity
 from .meshes import StructuredMesh, UnstructuredMesh, KuhnTet10Mesh
 from .reference_fe import ReferenceFE
 from .function_spaces import FunctionSpace, Lagrange, ScalarFunction, VectorFunction, DofManager
-from .bcs import DirichletBC, DirichletBCs, TimeStepper
+from .bcs import DirichletBC, DirichletBCs, NeumannBC, NeumannBCs, Source, Sources, TimeStepper
 from .physics import (AbstractPhysics, Poisson, Mechanics, NeoHookean, J2Plasticity, ThreeDimensional, PlaneStrain,
                       residual, residual_b, stiffness, stiffness_b, mass, mass_b, stiffness_action,
                       stiffness_action_b, mass_action, mass_action_b, lumped_mass, energy)
 from .assemblers import (SparseMatrixAssembler, Parameters, create_parameters, update_dofs, update_bc_values,
                          update_time, create_field, create_unknowns, assemble_vector, assemble_stiffness,
                          assemble_mass, assemble_vector_and_stiffness, assemble_matrix_action, assemble_matrix_free_action,
-                         assemble_matrix_free_action_full, hvp, full_field, assemble_lumped_mass, assemble_diagonal, diagonal, assemble_scalar, scalar_values)
+                         assemble_matrix_free_action_full, hvp, full_field, assemble_lumped_mass, assemble_diagonal, diagonal, assemble_scalar, scalar_values,
+                         assemble_vector_neumann_bc, assemble_vector_source)
 from .solvers import IterativeLinearSolver, NewtonSolver, QuasiStaticIntegrator
 from .partition import (Partition, partition_mesh, structured_brick_partition, metis_partition_elements,
                         metis_partition_graph)

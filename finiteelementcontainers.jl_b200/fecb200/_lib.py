@@ -95,6 +95,12 @@ SIGNATURES = {
     "fecb200_assemble_action_full": (C.c_int, [Handle, C.c_int32, VP, VP]),
     "fecb200_hvp": (C.c_int, [Handle, VP, VP]),
     "fecb200_field_copy": (C.c_int, [Handle, C.c_int32, VP]),
+    "fecb200_set_neumann_bc": (C.c_int, [Handle, C.c_int32, C.c_int64, C.c_int32, C.c_int32, c_i64p, c_f64p, c_f64p, c_f64p]),
+    "fecb200_set_neumann_values": (C.c_int, [Handle, C.c_int32, VP]),
+    "fecb200_clear_neumann_bcs": (C.c_int, [Handle]),
+    "fecb200_assemble_vector_neumann_bc": (C.c_int, [Handle]),
+    "fecb200_set_source_values": (C.c_int, [Handle, C.c_int32, VP]),
+    "fecb200_assemble_vector_source": (C.c_int, [Handle]),
     "fecb200_cg_solve": (C.c_int, [Handle, VP, VP, C.c_double, C.c_double, C.c_int64, C.c_int32,
                                    c_i64p, c_f64p]),
     "fecb200_newton_solve": (C.c_int, [Handle, VP, C.c_int32, C.c_double, C.c_int32, c_i32p, c_i64p, c_f64p]),

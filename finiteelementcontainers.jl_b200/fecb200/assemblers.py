@@ -18,7 +18,7 @@ import scipy.sparse as sp
 
 from . import _lib
 from ._lib import FECError, check, lib
-from .bcs import DirichletBCs, TimeStepper
+from .bcs import DirichletBCs, NeumannBCs, Sources, TimeStepper
 from .fields import H1Field
 from .function_spaces import AbstractFunction, DofManager
 from .physics import AbstractPhysics, Poisson, kind_of
@@ -133,10 +133,11 @@ class Parameters:
     """The slice of Parameters (src/Parameters.jl:37-73) the hot path touches; device-resident
     fields live inside the handle (`p |> cuda`)."""
 
-    def __init__(self, mesh, asm, physics, props, dirichlet_bcs, times):
+    def __init__(self, mesh, asm, physics, props, dirichlet_bcs, times, neumann_bcs=None, sources=None):
         self.mesh, self.asm = mesh, asm
         self.physics, self.properties = physics, props
         self.dirichlet_bcs = dirichlet_bcs
+        self.neumann_bcs, self.sources = neumann_bcs, sources
         self.times = times
         self.coords = mesh.nodal_coords
 
@@ -168,8 +169,8 @@ def _per_block(x, nb, kind):
     return [x] * nb
 
 
-def create_parameters(mesh, asm, physics, props=None, *, dirichlet_bcs=(), times=None):
-    """create_parameters(mesh, asm, physics, props; dirichlet_bcs, times)  (src/Parameters.jl:288-302):
+def create_parameters(mesh, asm, physics, props=None, *, dirichlet_bcs=(), neumann_bcs=(), sources=(), times=None):
+    """create_parameters(mesh, asm, physics, props; dirichlet_bcs, neumann_bcs, sources, times)  (src/Parameters.jl:288-302):
     builds the device handle (the `|> cuda` step), the BC containers, and calls update_dofs!."""
     fspace = asm.dof.var.fspace
     nb = fspace.num_blocks()
@@ -190,8 +191,15 @@ def create_parameters(mesh, asm, physics, props=None, *, dirichlet_bcs=(), times
     asm._create_handle(fspace, physics_list, props_list)
     times = times if times is not None else TimeStepper(0.0, 0.0, 1)
     dbcs = DirichletBCs(mesh, asm.dof, list(dirichlet_bcs))
-    p = Parameters(mesh, asm, physics_list, props_list, dbcs, times)
+    nbcs = NeumannBCs(mesh, asm.dof, list(neumann_bcs))
+    srcs = Sources(mesh, asm.dof, list(sources))
+    p = Parameters(mesh, asm, physics_list, props_list, dbcs, times, nbcs, srcs)
     update_dofs(asm, dbcs)
+    for i, c in enumerate(nbcs.bc_caches):   # the side sets' geometry is uploaded once (`p |> cuda`)
+        sn, snp = _lib.i64(c["side_nodes"].reshape(-1, order="F"))
+        Ns, Nsp = _lib.f64(c["Ns"]); dNs, dNsp = _lib.f64(c["dNs"]); ws, wsp = _lib.f64(c["ws"])
+        check(lib.fecb200_set_neumann_bc(asm._require(), i, c["side_nodes"].shape[1], c["side_nodes"].shape[0], len(ws),
+                                         snp, Nsp, dNsp, wsp))
     update_bc_values(p)
     _upload_sources(p)
     return p
@@ -231,6 +239,16 @@ def update_bc_values(p):
     d, dp = _lib.i64(bcs.dofs)
     v, vp = _lib.f64(bcs.vals)
     check(lib.fecb200_set_dirichlet_values(p.asm._require(), dp, vp, len(d)))
+    if p.neumann_bcs is not None and len(p.neumann_bcs):     # update_bc_values!(p.neumann_bcs, asm, X, t)
+        p.neumann_bcs.update_bc_values(p.coords, p.times.time_current)
+        for i, c in enumerate(p.neumann_bcs.bc_caches):
+            v = np.ascontiguousarray(c["vals"].reshape(-1, order="F"))
+            check(lib.fecb200_set_neumann_values(p.asm._require(), i, _lib.ptr(v)))
+    if p.sources is not None and len(p.sources):             # _update_source_values! (Sources.jl:55-66)
+        p.sources.update_source_values(p.asm.dof.var.fspace, p.times.time_current)
+        for b, vals in zip(p.sources.blocks, p.sources.vals):
+            v = np.ascontiguousarray(vals.reshape(-1, order="F"))
+            check(lib.fecb200_set_source_values(p.asm._require(), b, _lib.ptr(v)))
 
 
 def update_time(p):
@@ -254,6 +272,19 @@ def assemble_vector(asm, func, Uu, p):
     """assemble_vector!(asm, residual, Uu, p)  (src/assemblers/Vector.jl:4-74)"""
     kind = kind_of(func, (_lib.RESIDUAL,))
     check(lib.fecb200_assemble_vector(asm._require(), kind, _lib.ptr(Uu)))
+
+
+def assemble_vector_neumann_bc(asm, Uu, p):
+    """assemble_vector_neumann_bc!(asm, Uu, p)  (src/assemblers/WeaklyEnforcedBCs.jl:4-15): adds the Neumann loads of
+    p.neumann_bcs to the residual storage (no zeroing).  The loads do not depend on Uu; the library integrates them
+    once per update_bc_values! and adds the cached vector."""
+    check(lib.fecb200_assemble_vector_neumann_bc(asm._require()))
+
+
+def assemble_vector_source(asm, Uu, p):
+    """assemble_vector_source!(asm, Uu, p)  (src/assemblers/Source.jl:10-42): adds -int N b of p.sources to the
+    residual storage (no zeroing)."""
+    check(lib.fecb200_assemble_vector_source(asm._require()))
 
 
 def assemble_lumped_mass(asm, func, Uu, p):

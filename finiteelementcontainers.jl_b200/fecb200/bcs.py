@@ -68,3 +68,100 @@ class TimeStepper:
         self.time_start, self.time_end = float(t0), float(t1)
         self.time_current = float(t0)
         self.dt = (float(t1) - float(t0)) / n if n else 0.0
+
+
+def _as_values(v, n, nf):
+    """func(X, t) may return (n, NF), (NF,), (n,) for NF = 1, or a scalar; -> (n, NF)"""
+    v = np.asarray(v, dtype=float)
+    if v.ndim == 2:
+        return np.ascontiguousarray(np.broadcast_to(v, (n, nf)))
+    if v.ndim == 1 and v.shape[0] == nf and (nf > 1 or n == 1):
+        return np.ascontiguousarray(np.broadcast_to(v[None, :], (n, nf)))
+    return np.ascontiguousarray(np.broadcast_to(v.reshape(-1, 1) if v.ndim else v, (n, nf)))
+
+
+class NeumannBC:
+    """NeumannBC(var_name, func, sset_name)  (src/bcs/NeumannBCs.jl:7-20).  `func(X, t)` returns the flux vector
+    (all NF components, `SVector{NF}` in the reference); it is called vectorised: X is (n, ND), result (n, NF).
+    Sign convention: the assembler ADDS +int g N dGamma to the residual (test/laplace_with_source/TestLaplace.jl:438-440)."""
+
+    def __init__(self, var_name, func, sset_name):
+        self.var_name, self.func, self.sset_name = var_name, func, sset_name
+
+
+class NeumannBCs:
+    """NeumannBCs(mesh, dof, neumann_bcs) (src/bcs/NeumannBCs.jl:78-131) with `_setup_sideset`
+    (src/bcs/BoundaryConditions.jl:337-411): one cache per BC holding the side set's elements (block-local), sides,
+    surface connectivity, the block's surface tables and `vals[NF, nqs, nsides]`."""
+
+    def __init__(self, mesh, dof, neumann_bcs):
+        fspace = dof.var.fspace
+        self.nf = dof.nf
+        self.bc_funcs, self.bc_caches, self.block_ids, self.block_names = [], [], [], []
+        offs = np.cumsum([0] + [mesh.element_conns[b].shape[1] for b in mesh.element_block_names])
+        for bc in neumann_bcs:
+            dof.dof_index(bc.var_name)  # ValueError if the variable does not exist (_dof_index_from_var_name)
+            el = np.asarray(mesh.sideset_elems[bc.sset_name], dtype=np.int64)
+            sd = np.asarray(mesh.sideset_sides[bc.sset_name], dtype=np.int64)
+            blocks = np.searchsorted(offs, el - 1, side="right") - 1
+            if len(np.unique(blocks)) > 1:
+                raise AssertionError("Sidesets need to be in a single block")
+            b = int(blocks[0]) if len(blocks) else 0
+            Ns, dNs, ws = fspace.ref_fes[b].surface_tables()
+            cache = dict(block=b, elements=el - offs[b], sides=sd,
+                         side_nodes=np.ascontiguousarray(mesh.sideset_side_nodes[bc.sset_name], dtype=np.int64),
+                         Ns=Ns, dNs=dNs, ws=ws, vals=np.zeros((self.nf, len(ws), len(sd)), order="F"))
+            self.bc_caches.append(cache)
+            self.bc_funcs.append(bc.func)
+            self.block_ids.append(b)
+            self.block_names.append(mesh.element_block_names[b])
+
+    def __len__(self):
+        return len(self.bc_caches)
+
+    def update_bc_values(self, X, t):
+        """update_bc_values!(bcs, asm, X, t) (:157-171, :60-71): vals[q, e] = func(X_q, t) at the surface points"""
+        X = np.asarray(X)
+        for func, c in zip(self.bc_funcs, self.bc_caches):
+            xs = X[:, c["side_nodes"] - 1]                               # (ND, nnps, nsides)
+            Xq = np.einsum("qa,dae->eqd", c["Ns"], xs)                   # (nsides, nqs, ND)
+            n = Xq.shape[0] * Xq.shape[1]
+            v = _as_values(func(Xq.reshape(n, -1), t), n, self.nf)       # (nsides*nqs, NF), q fastest
+            c["vals"] = np.asfortranarray(v.reshape(Xq.shape[0], Xq.shape[1], self.nf).transpose(2, 1, 0))
+
+
+class Source:
+    """Source(var_name, func, block_name)  (src/bcs/Sources.jl:17-27): body force density b(X, t) (all NF components)
+    on one element block; the assembler adds -int N b dOmega to the residual (:1-5)."""
+
+    def __init__(self, var_name, func, block_name):
+        self.var_name, self.func, self.block_name = var_name, func, block_name
+
+
+class Sources:
+    """Sources(mesh, dof, sources) (src/bcs/Sources.jl:80-257): per entry the block index and `vals[NF, NQ, NE]`."""
+
+    def __init__(self, mesh, dof, sources):
+        self.nf = dof.nf
+        self.funcs, self.blocks, self.vals = [], [], []
+        for s in sources:
+            dof.dof_index(s.var_name)
+            if s.block_name not in mesh.element_block_names:
+                raise KeyError(f"Block {s.block_name} not found in mesh")
+            self.funcs.append(s.func)
+            self.blocks.append(mesh.element_block_names.index(s.block_name))
+            self.vals.append(None)
+
+    def __len__(self):
+        return len(self.funcs)
+
+    def update_source_values(self, fspace, t):
+        """_update_source_values! (:55-66): vals[q, e] = func(X_q, t) at the cell quadrature points"""
+        X = np.asarray(fspace.coords)
+        for i, (func, b) in enumerate(zip(self.funcs, self.blocks)):
+            rf = fspace.ref_fes[b]
+            xe = X[:, fspace.elem_conns.block(b) - 1]                    # (ND, NNPE, NE)
+            Xq = np.einsum("qa,dae->eqd", rf.N, xe)                      # (NE, NQ, ND)
+            n = Xq.shape[0] * Xq.shape[1]
+            v = _as_values(func(Xq.reshape(n, -1), t), n, self.nf)
+            self.vals[i] = np.asfortranarray(v.reshape(Xq.shape[0], Xq.shape[1], self.nf).transpose(2, 1, 0))

@@ -31,6 +31,47 @@ class AbstractMesh:
     nodeset_nodes: dict
     sideset_nodes: dict
 
+    # side sets as (elements, sides, side_nodes), the fields of the reference's mesh structs
+    # (src/meshes/StructuredMesh.jl:21-25); elements are 1-based ids over the concatenated blocks
+    sideset_elems: dict
+    sideset_sides: dict
+    sideset_side_nodes: dict
+
+    def _set_sidesets(self, sets):
+        """sets: {name: (elements, sides)} -> sideset_elems / sideset_sides / sideset_side_nodes"""
+        self.sideset_elems, self.sideset_sides, self.sideset_side_nodes = {}, {}, {}
+        offs = np.cumsum([0] + [self.element_conns[b].shape[1] for b in self.element_block_names])
+        for name, (el, sd) in sets.items():
+            el, sd = np.asarray(el, dtype=np.int64), np.asarray(sd, dtype=np.int64)
+            cols = []
+            for e, s in zip(el, sd):
+                b = int(np.searchsorted(offs, e - 1, side="right") - 1)
+                bn = self.element_block_names[b]
+                cols.append(self.element_conns[bn][list(_SIDE_NODES[self.element_types[bn]][s - 1]), e - 1 - offs[b]])
+            self.sideset_elems[name], self.sideset_sides[name] = el, sd
+            self.sideset_side_nodes[name] = (np.stack(cols, axis=1) if cols else np.zeros((0, 0))).astype(np.int64)
+
+    def _sidesets_from_nodesets(self, nodesets):
+        """every element side whose nodes all belong to the node set (meshes without side-set records)"""
+        sets, off = {}, 0
+        per_block = []
+        for bn in self.element_block_names:
+            per_block.append((off, self.element_conns[bn], _SIDE_NODES[self.element_types[bn]]))
+            off += self.element_conns[bn].shape[1]
+        for name, nodes in nodesets.items():
+            mark = np.zeros(self.num_nodes() + 1, dtype=bool)
+            mark[np.asarray(nodes, dtype=np.int64)] = True
+            el, sd = [], []
+            for o, conn, tab in per_block:
+                for s, loc in enumerate(tab):
+                    hit = np.nonzero(mark[conn[list(loc)]].all(axis=0))[0]
+                    el.append(hit + 1 + o)
+                    sd.append(np.full(len(hit), s + 1))
+            el, sd = np.concatenate(el), np.concatenate(sd)
+            order = np.argsort(el, kind="stable")
+            sets[name] = (el[order], sd[order])
+        return sets
+
     def num_dimensions(self):
         return self.nodal_coords.shape[0]
 
@@ -78,6 +119,37 @@ class StructuredMesh(AbstractMesh):
         self.element_conns = {"block_1": conn}
         self.nodeset_nodes = nsets
         self.sideset_nodes = dict(nsets)  # node lists of the boundary sides == node sets
+        self._set_sidesets(self._structured_sidesets(et, counts))
+
+    @staticmethod
+    def _structured_sidesets(et, counts):
+        """(elements, sides) per named boundary.  QUAD4 / TRI3: the reference's loops (src/meshes/StructuredMesh.jl:
+        257-330, 355-431).  HEX8: the reference's `_hex8_ssets` (:133-230) is unfinished (side numbers that do not lie
+        on the named boundary, a loop over an undefined k, side-node matrices sized for one row of faces); the faces
+        that do lie on the boundary are used: bottom/top = y-min/max (sides 1/3), left/right = x-min/max (4/2),
+        back/front = z-min/max (5/6), consistent with the node sets (:452-470)."""
+        if et in ("QUAD4", "TRI3"):
+            Ex, Ey = counts[0] - 1, counts[1] - 1
+            quad = lambda i, j: (i - 1) * Ey + j
+            I, J = np.arange(1, Ex + 1), np.arange(1, Ey + 1)
+            if et == "QUAD4":
+                return {"bottom": (quad(I, 1), np.full(Ex, 1)), "right": (quad(Ex, J), np.full(Ey, 2)),
+                        "top": (quad(I, Ey), np.full(Ex, 3)), "left": (quad(1, J), np.full(Ey, 4))}
+            return {"bottom": (2 * quad(I, 1) - 1, np.full(Ex, 1)), "right": (2 * quad(Ex, J) - 1, np.full(Ey, 2)),
+                    "top": (2 * quad(I, Ey), np.full(Ex, 2)), "left": (2 * quad(1, J), np.full(Ey, 3))}
+        Ex, Ey, Ez = counts[0] - 1, counts[1] - 1, counts[2] - 1
+        elem = lambda i, j, k: (i - 1) * Ey * Ez + (j - 1) * Ez + k
+
+        def plane(f, A, B):
+            aa, bb = np.meshgrid(A, B, indexing="ij")
+            return f(aa.ravel(), bb.ravel())
+        I, J, K = np.arange(1, Ex + 1), np.arange(1, Ey + 1), np.arange(1, Ez + 1)
+        return {"bottom": (plane(lambda i, k: elem(i, 1, k), I, K), np.full(Ex * Ez, 1)),
+                "top": (plane(lambda i, k: elem(i, Ey, k), I, K), np.full(Ex * Ez, 3)),
+                "left": (plane(lambda j, k: elem(1, j, k), J, K), np.full(Ey * Ez, 4)),
+                "right": (plane(lambda j, k: elem(Ex, j, k), J, K), np.full(Ey * Ez, 2)),
+                "back": (plane(lambda i, j: elem(i, j, 1), I, J), np.full(Ex * Ey, 5)),
+                "front": (plane(lambda i, j: elem(i, j, Ez), I, J), np.full(Ex * Ey, 6))}
 
     @staticmethod
     def _quad4(mins, maxs, counts):
@@ -165,6 +237,7 @@ class KuhnTet10Mesh(AbstractMesh):
         self.nodeset_nodes = {"bottom": idx[j3 == 0] + 1, "top": idx[j3 == M - 1] + 1, "left": idx[i3 == 0] + 1,
                               "right": idx[i3 == M - 1] + 1, "back": idx[k3 == 0] + 1, "front": idx[k3 == M - 1] + 1}
         self.sideset_nodes = dict(self.nodeset_nodes)
+        self._set_sidesets(self._sidesets_from_nodesets(self.nodeset_nodes))
 
 
 class UnstructuredMesh(AbstractMesh):
@@ -180,6 +253,9 @@ class UnstructuredMesh(AbstractMesh):
         self.element_conns = {b: np.ascontiguousarray(c, dtype=np.int64) for b, c in zip(data["block_names"], data["conns"])}
         self.nodeset_nodes = dict(data["nodesets"])
         self.sideset_nodes = dict(data["sidesets"])
+        # Exodus files carry (elem_ss, side_ss); the .npz fixtures only node lists -> sides recovered from them
+        self._set_sidesets(data["sideset_records"] if "sideset_records" in data
+                           else self._sidesets_from_nodesets(self.sideset_nodes))
 
     @staticmethod
     def _read_npz(path):
@@ -215,10 +291,11 @@ class UnstructuredMesh(AbstractMesh):
         ssn = names("ss_names", nss, "sset", np.array(nc.variables["ss_prop1"].data)) if nss else []
         nodesets = {nsn[i]: np.array(nc.variables[f"node_ns{i+1}"].data, dtype=np.int64) for i in range(nns)}
         offs = np.cumsum([0] + [c.shape[1] for c in conns])
-        sidesets = {}
+        sidesets, records = {}, {}
         for i in range(nss):
             el = np.array(nc.variables[f"elem_ss{i+1}"].data, dtype=np.int64)
             sd = np.array(nc.variables[f"side_ss{i+1}"].data, dtype=np.int64)
+            records[ssn[i]] = (el, sd)
             nodes = []
             for e, s in zip(el, sd):
                 b = int(np.searchsorted(offs, e - 1, side="right") - 1)
@@ -226,4 +303,5 @@ class UnstructuredMesh(AbstractMesh):
                 nodes.extend(conns[b][list(loc), e - 1 - offs[b]].tolist())
             _, first = np.unique(nodes, return_index=True)
             sidesets[ssn[i]] = np.array(nodes, dtype=np.int64)[np.sort(first)]
-        return dict(coords=coords, block_names=bnames, types=types, conns=conns, nodesets=nodesets, sidesets=sidesets)
+        return dict(coords=coords, block_names=bnames, types=types, conns=conns, nodesets=nodesets, sidesets=sidesets,
+                    sideset_records=records)

@@ -65,6 +65,7 @@ class ReferenceFE:
     def __init__(self, elem_type: str, q_type: str = "GaussLegendre", q_degree: int = 2):
         self.elem_type = elem_type
         self.elem_id = ELEM_IDS[elem_type]
+        self.q_type = q_type
         if elem_type in ("QUAD4", "HEX8"):
             nd = 2 if elem_type == "QUAD4" else 3
             x, w = _line_rule(q_type, q_degree)
@@ -92,6 +93,25 @@ class ReferenceFE:
         self.N = np.ascontiguousarray(self.N)
         self.dN = np.ascontiguousarray(self.dN)
         self.w = np.ascontiguousarray(self.w, dtype=float)
+
+    def surface_tables(self, q_type=None, q_degree=2):
+        """(Ns[q,a], dNs[q,a,k], ws[q]) of one side of this element: the reduced shape functions
+        `interps.N_reduced` and the surface rule of MappedH1OrL2SurfaceInterpolants (ReferenceFiniteElements.jl,
+        un-vendored -- a Julia host passes its own tables).  2-node edges (QUAD4, TRI3), 4-node faces (HEX8),
+        3- / 6-node triangles (TETRA4 / TETRA10), node order = Exodus side order (meshes._SIDE_NODES)."""
+        q_type = q_type or getattr(self, "q_type", "GaussLegendre")
+        t = self.elem_type
+        if t in ("QUAD4", "TRI3"):
+            x, w = _line_rule(q_type, q_degree)
+            Ns = np.stack([0.5 * (1 - x), 0.5 * (1 + x)], axis=1)
+            dNs = np.broadcast_to(np.array([[-0.5], [0.5]]), (len(x), 2, 1)).copy()
+            return np.ascontiguousarray(Ns), dNs, np.ascontiguousarray(w, dtype=float)
+        if t == "HEX8":
+            f = ReferenceFE("QUAD4", q_type, q_degree)
+            return f.N, f.dN, f.w
+        xi, w = np.array([[1 / 6, 1 / 6], [2 / 3, 1 / 6], [1 / 6, 2 / 3]]), np.full(3, 1 / 6)
+        Ns, dNs = _simplex_shape(2, t == "TETRA10", xi)
+        return np.ascontiguousarray(Ns), np.ascontiguousarray(dNs), w
 
     @classmethod
     def from_tables(cls, elem_type, N, dN, w):

@@ -11,8 +11,10 @@ using FiniteElementContainers
 import FiniteElementContainers: AbstractAssembler, DofManager, assemble_vector!, assemble_stiffness!, assemble_mass!,
                                 assemble_lumped_mass!, assemble_diagonal!, lumped_mass, diagonal, assemble_scalar!,
                                 assemble_matrix_action!, assemble_matrix_free_action!, residual, stiffness, mass, hvp,
-                                update_dofs!, create_unknowns, function_space
+                                update_dofs!, create_unknowns, function_space, assemble_vector_neumann_bc!,
+                                assemble_vector_source!, surface_connectivity
 using SparseArrays, SparseMatricesCSR
+import ReferenceFiniteElements
 
 const LIB = get(ENV, "FECB200_LIB", joinpath(@__DIR__, "..", "lib", "libfecb200.so"))
 
@@ -138,6 +140,45 @@ function scalar_values(asm::B200Assembler, b::Integer, nq::Integer, ne::Integer)
   check(ccall((:fecb200_scalar_values, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}), asm.handle, Int32(b - 1), out))
   return out
 end
+
+# External loads of the residual (src/Solvers.jl:133-137).  The containers stay the reference's own
+# (p.neumann_bcs::NeumannBCs, p.sources::Sources, filled by update_bc_values! on the host); their geometry is pushed
+# once, their values whenever they change, and each assemble call adds the device-cached load vector.
+# surface_tables(ref_fe): (Ns[nnps, nqs], dNs[ND-1, nnps, nqs], ws[nqs]) read from ref_fe.surface_interps of
+# ReferenceFiniteElements (column-major Julia arrays are exactly the row-major [q][a][k] tables of the header)
+function surface_tables(ref_fe)
+  si = ref_fe.surface_interps
+  nqs = ReferenceFiniteElements.num_surface_quadrature_points(ref_fe)
+  Ns = reduce(hcat, [collect(si[q, 1].N_reduced) for q in 1:nqs])
+  dNs = cat([permutedims(collect(si[q, 1].∇N_ξ_reduced)) for q in 1:nqs]...; dims = 3)
+  ws = [si[q, 1].w for q in 1:nqs]
+  return Ns, dNs, ws
+end
+function push_neumann_bcs!(asm::B200Assembler, p)
+  fspace = function_space(asm.dof)
+  for (i, cache) in enumerate(p.neumann_bcs.bc_caches)
+    ref_fe = fspace.ref_fes[p.neumann_bcs.block_ids[i]]
+    nqs = size(cache.vals, 1); nsides = length(cache.sides)
+    snodes = reduce(hcat, [collect(surface_connectivity(ref_fe, cache.element_conns.data, cache.sides[e], e, 1)) for e in 1:nsides])
+    Ns, dNs, ws = surface_tables(ref_fe)   # N_reduced, its parametric gradient and the weights of the surface rule
+    check(ccall((:fecb200_set_neumann_bc, LIB), Cint,
+                (Ptr{Cvoid}, Int32, Int64, Int32, Int32, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                asm.handle, Int32(i - 1), nsides, Int32(size(snodes, 1)), Int32(nqs), Int64.(snodes), Ns, dNs, ws))
+    check(ccall((:fecb200_set_neumann_values, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}), asm.handle, Int32(i - 1),
+                reinterpret(Float64, vec(cache.vals))))
+  end
+end
+function push_source_values!(asm::B200Assembler, p)
+  for (b, block_id) in enumerate(p.sources.block_id_to_source)
+    block_id == -1 && continue
+    check(ccall((:fecb200_set_source_values, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}), asm.handle, Int32(b - 1),
+                reinterpret(Float64, vec(p.sources.source_caches[block_id].vals))))
+  end
+end
+assemble_vector_neumann_bc!(asm::B200Assembler, Uu, p) =
+  check(ccall((:fecb200_assemble_vector_neumann_bc, LIB), Cint, (Ptr{Cvoid},), asm.handle))
+assemble_vector_source!(asm::B200Assembler, Uu, p) =
+  check(ccall((:fecb200_assemble_vector_source, LIB), Cint, (Ptr{Cvoid},), asm.handle))
 
 function assemble_stiffness!(asm::B200Assembler, f::F, Uu, p) where F <: Function
   GC.@preserve Uu check(ccall((:fecb200_assemble_matrix, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}), asm.handle, STIFFNESS, _ptr(Uu)))

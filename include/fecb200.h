@@ -209,6 +209,30 @@ int fecb200_hvp(fecb200_handle* h, const double* v, double* out);
 /* copy of a full-length nodal field (p.field, residual_storage, stiffness_action_storage) */
 int fecb200_field_copy(fecb200_handle* h, int32_t which, double* out);
 
+/* ---- external loads of the residual: the two calls solve! makes right after
+ * assemble_vector! (src/Solvers.jl:66-69, 133-137).  Neither zeroes the residual storage, both add to it
+ * (Source.jl:1-5); fecb200_newton_solve applies them after every residual assembly, as solve! does.
+ *
+ * Neumann BCs = NeumannBCContainer (src/bcs/NeumannBCs.jl:29-48, _setup_sideset BoundaryConditions.jl:337-411):
+ *   id          0, 1, 2, ... in registration order (re-registering an id replaces it)
+ *   side_nodes  [nnps, nsides] column-major, Int64 1-based: surface_connectivity of every side
+ *   Ns, dNs, ws surface tables of the block's ReferenceFE (ReferenceFiniteElements.jl is un-vendored, so they
+ *               travel like the cell tables): Ns[q*nnps + a], dNs[(q*nnps + a)*(ND-1) + k], ws[q]
+ *   vals        [NF, nqs, nsides] = Matrix{SVector{NF,Float64}}(nqs, nsides): func(X_q, t) evaluated by the host
+ *               (update_bc_values!, NeumannBCs.jl:60-71, 157-171)  [host|device]
+ * assemble_vector_neumann_bc! (src/assemblers/WeaklyEnforcedBCs.jl:4-15, 61-83):
+ *   R[(n,d)] += sum_q JxW_s(q) Ns[q][n] vals[d,q,e],  JxW_s = |sum_a x_a dNs_a| ws (edges) or |t_0 x t_1| ws (faces). */
+int fecb200_set_neumann_bc(fecb200_handle* h, int32_t id, int64_t nsides, int32_t nnps, int32_t nqs,
+                           const int64_t* side_nodes, const double* Ns, const double* dNs, const double* ws);
+int fecb200_set_neumann_values(fecb200_handle* h, int32_t id, const double* vals);
+int fecb200_clear_neumann_bcs(fecb200_handle* h);
+int fecb200_assemble_vector_neumann_bc(fecb200_handle* h);
+/* Body forces = SourceContainer.vals (src/bcs/Sources.jl:38-66): vals [NF, NQ, NE] of one block, element order of
+ * the block's conn; NULL removes the block's source  [host|device].
+ * assemble_vector_source! (src/assemblers/Source.jl:10-64): R[(n,d)] += - sum_q JxW(q) N[q][n] vals[d,q,e]. */
+int fecb200_set_source_values(fecb200_handle* h, int32_t block, const double* vals);
+int fecb200_assemble_vector_source(fecb200_handle* h);
+
 /* ---- callers of the path: device-resident Krylov / Newton ---------------
  * krylov_solve!(ws, stiffness(asm), residual(asm)) with CG (src/Solvers.jl:128-153); Krylov.jl
  * defaults atol = rtol = sqrt(eps), itmax = 2n.  Solves K x = b on the device using the handle's

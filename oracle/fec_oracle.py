@@ -308,6 +308,127 @@ def ref_fe_tables(el_type: str, rule: str = "gauss2"):
 
 
 # --------------------------------------------------------------------------------------
+# Side sets and surface tables (src/meshes/StructuredMesh.jl:133-230, 257-330, 355-431;
+# surface_connectivity / MappedH1OrL2SurfaceInterpolants live in ReferenceFiniteElements.jl,
+# un-vendored: Exodus side numbering, surface Jacobian |dx/dxi| (edges) or |t_0 x t_1| (faces))
+# --------------------------------------------------------------------------------------
+
+SIDE_NODES = {  # Exodus side -> local nodes (0-based)
+    "QUAD4": [(0, 1), (1, 2), (2, 3), (3, 0)],
+    "TRI3": [(0, 1), (1, 2), (2, 0)],
+    "HEX8": [(0, 1, 5, 4), (1, 2, 6, 5), (2, 3, 7, 6), (0, 4, 7, 3), (0, 3, 2, 1), (4, 5, 6, 7)],
+    "TETRA4": [(0, 1, 3), (1, 2, 3), (0, 3, 2), (0, 2, 1)],
+    "TETRA10": [(0, 1, 3, 4, 8, 7), (1, 2, 3, 5, 9, 8), (0, 3, 2, 7, 9, 6), (0, 2, 1, 6, 5, 4)],
+}
+
+
+def structured_sidesets(el_type, counts):
+    """{name: (elements, sides)} 1-based, for StructuredMesh.  QUAD4 / TRI3 follow the reference loops verbatim
+    (StructuredMesh.jl:257-330, 355-431).  HEX8: the reference's `_hex8_ssets` (:133-230) is unfinished (its side
+    numbers name faces that do not lie on the named boundary, its `left` loop reads an undefined k, and its
+    side-node matrices are sized for one row of faces), so the geometrically correct faces are used instead:
+    bottom / top = y-min / y-max, left / right = x-min / x-max, back / front = z-min / z-max like the node sets."""
+    t = el_type.upper()
+    if t.startswith("QUAD") or t.startswith("TRI"):
+        Ex, Ey = counts[0] - 1, counts[1] - 1
+        quad = lambda i, j: (i - 1) * Ey + j
+        I, J = np.arange(1, Ex + 1), np.arange(1, Ey + 1)
+        if t.startswith("QUAD"):
+            return {"bottom": (quad(I, 1), np.full(Ex, 1)), "right": (quad(Ex, J), np.full(Ey, 2)),
+                    "top": (quad(I, Ey), np.full(Ex, 3)), "left": (quad(1, J), np.full(Ey, 4))}
+        a, b = (lambda q: 2 * q - 1), (lambda q: 2 * q)
+        return {"bottom": (a(quad(I, 1)), np.full(Ex, 1)), "right": (a(quad(Ex, J)), np.full(Ey, 2)),
+                "top": (b(quad(I, Ey)), np.full(Ex, 2)), "left": (b(quad(1, J)), np.full(Ey, 3))}
+    Ex, Ey, Ez = counts[0] - 1, counts[1] - 1, counts[2] - 1
+    elem = lambda i, j, k: (i - 1) * Ey * Ez + (j - 1) * Ez + k
+
+    def plane(f, A, B):
+        aa, bb = np.meshgrid(A, B, indexing="ij")
+        return f(aa.ravel(), bb.ravel())
+    I, J, K = np.arange(1, Ex + 1), np.arange(1, Ey + 1), np.arange(1, Ez + 1)
+    return {"bottom": (plane(lambda i, k: elem(i, 1, k), I, K), np.full(Ex * Ez, 1)),
+            "top": (plane(lambda i, k: elem(i, Ey, k), I, K), np.full(Ex * Ez, 3)),
+            "left": (plane(lambda j, k: elem(1, j, k), J, K), np.full(Ey * Ez, 4)),
+            "right": (plane(lambda j, k: elem(Ex, j, k), J, K), np.full(Ey * Ez, 2)),
+            "back": (plane(lambda i, j: elem(i, j, 1), I, J), np.full(Ex * Ey, 5)),
+            "front": (plane(lambda i, j: elem(i, j, Ez), I, J), np.full(Ex * Ey, 6))}
+
+
+def side_nodes(el_type, conn, elements, sides):
+    """surface_connectivity of every (element, side): (nnps, nsides) 1-based global node ids."""
+    canon = {"QUAD": "QUAD4", "TRI": "TRI3", "HEX": "HEX8", "TET4": "TETRA4", "TET10": "TETRA10"}
+    tab = SIDE_NODES[canon.get(el_type.upper(), el_type.upper())]
+    return np.stack([conn[list(tab[s - 1]), e - 1] for e, s in zip(elements, sides)], axis=1).astype(np.int64)
+
+
+def surface_tables(el_type: str, rule: str = "gauss2"):
+    """(Ns[q,a], dNs[q,a,k], ws[q]) of the sides of an element type: 2-node edges (QUAD4, TRI3), 4-node faces
+    (HEX8), 3- / 6-node triangles (TETRA4 / TETRA10)."""
+    t = el_type.upper()
+    if t in ("QUAD4", "QUAD", "TRI3", "TRI"):
+        x, w = (_gauss_1d(int(rule[5:])) if rule.startswith("gauss") else _gll_1d(int(rule[3:]))) if rule[0] == "g" else _gauss_1d(2)
+        N = np.stack([0.5 * (1 - x), 0.5 * (1 + x)], axis=1)
+        dN = np.broadcast_to(np.array([[-0.5], [0.5]]), (len(x), 2, 1)).copy()
+        return N, dN, np.asarray(w, dtype=float)
+    if t in ("HEX8", "HEX"):
+        return ref_fe_tables("QUAD4", rule)
+    pts, wts = [(1 / 6, 1 / 6), (2 / 3, 1 / 6), (1 / 6, 2 / 3)], [1 / 6] * 3
+    if t in ("TET4", "TETRA4", "TETRA", "TET"):
+        return ref_fe_tables("TRI3", "tri3")
+    N, dN = [], []
+    for xi in pts:  # 6-node triangle, nodes (v0, v1, v2, m01, m12, m20)
+        L = np.array([1 - xi[0] - xi[1], xi[0], xi[1]])
+        dL = np.array([[-1.0, -1.0], [1.0, 0.0], [0.0, 1.0]])
+        n = [L[a] * (2 * L[a] - 1) for a in range(3)] + [4 * L[a] * L[b] for a, b in ((0, 1), (1, 2), (2, 0))]
+        d = [(4 * L[a] - 1) * dL[a] for a in range(3)] + [4 * (L[a] * dL[b] + L[b] * dL[a]) for a, b in ((0, 1), (1, 2), (2, 0))]
+        N.append(n); dN.append(d)
+    return np.array(N), np.array(dN), np.array(wts)
+
+
+def surface_jxw(dNs_q, w_q, x_s):
+    """x_s (nsides, nnps, ND) -> JxW (nsides,) of one surface quadrature point."""
+    t = np.einsum("eai,ak->eki", x_s, dNs_q)       # tangents (nsides, ND-1, ND)
+    if x_s.shape[2] == 2:
+        return np.linalg.norm(t[:, 0, :], axis=1) * w_q
+    return np.linalg.norm(np.cross(t[:, 0, :], t[:, 1, :]), axis=1) * w_q
+
+
+def surface_quadrature_points(snodes, tables, X):
+    """X_q of every (q, side): (nqs, nsides, ND)   (interps.X_q in _update_bc_values!, NeumannBCs.jl:60-71)"""
+    x_s = np.transpose(X[:, snodes - 1], (2, 1, 0))
+    return np.einsum("qa,eai->qei", tables[0], x_s)
+
+
+def assemble_vector_neumann_bc(R, snodes, tables, vals, X, nf):
+    """_assemble_block_vector_weakly_enforced_bc! (WeaklyEnforcedBCs.jl:61-83): R[(n,d)] += JxW Ns[n] vals[d,q,e].
+    snodes (nnps, nsides) 1-based; vals (NF, nqs, nsides).  Adds in place (no zeroing, :33)."""
+    Ns, dNs, ws = tables
+    x_s = np.transpose(X[:, snodes - 1], (2, 1, 0))
+    for q in range(len(ws)):
+        JxW = surface_jxw(dNs[q], ws[q], x_s)
+        contrib = JxW[:, None, None] * Ns[q][None, :, None] * vals[:, q, :].T[:, None, :]   # (nsides, nnps, NF)
+        dofs = nf * (snodes.T - 1)[:, :, None] + np.arange(nf)[None, None, :]
+        np.add.at(R, dofs.ravel(), contrib.ravel())
+    return R
+
+
+def cell_quadrature_points(block, X):
+    """X_q of every (q, e): (NQ, NE, ND)   (_update_source_values!, Sources.jl:55-66)"""
+    return np.einsum("qa,eai->qei", block.N, _gather(X, block.conn))
+
+
+def assemble_vector_source(R, block, vals, X, nf):
+    """_assemble_block_vector_source! (Source.jl:44-63): R[(n,d)] += -JxW N[n] vals[d,q,e]; vals (NF, NQ, NE)."""
+    x_el = _gather(X, block.conn)
+    for q in range(len(block.w)):
+        _, _, JxW = map_interpolants(block.N[q], block.dN[q], block.w[q], x_el)
+        contrib = -JxW[:, None, None] * block.N[q][None, :, None] * vals[:, q, :].T[:, None, :]
+        dofs = nf * (block.conn.T - 1)[:, :, None] + np.arange(nf)[None, None, :]
+        np.add.at(R, dofs.ravel(), contrib.ravel())
+    return R
+
+
+# --------------------------------------------------------------------------------------
 # DofManager maps  (src/DofManagers.jl:227-298)
 # --------------------------------------------------------------------------------------
 
@@ -834,6 +955,24 @@ class OracleAssembler:
         self._update_field(self.field, Uu)
         self.residual_storage = assemble_vector(self.blocks, self.X, self._U(), self.nf)
 
+    # external loads: p.neumann_bcs / p.sources (Parameters.jl:37-73); values are set by the caller like
+    # update_bc_values! does (NeumannBCs.jl:157-171, Sources.jl:55-66)
+    def add_neumann_bc(self, snodes, tables, vals):
+        self.neumann = getattr(self, "neumann", []) + [(np.asarray(snodes, dtype=np.int64), tables, np.asarray(vals, dtype=float))]
+
+    def add_source(self, block_index, vals):
+        self.sources = getattr(self, "sources", []) + [(block_index, np.asarray(vals, dtype=float))]
+
+    def assemble_vector_neumann_bc(self, Uu=None):
+        """assemble_vector_neumann_bc!(asm, Uu, p) (WeaklyEnforcedBCs.jl:4-15): adds to the residual storage"""
+        for snodes, tables, vals in getattr(self, "neumann", []):
+            assemble_vector_neumann_bc(self.residual_storage, snodes, tables, vals, self.X, self.nf)
+
+    def assemble_vector_source(self, Uu=None):
+        """assemble_vector_source!(asm, Uu, p) (Source.jl:10-42): adds to the residual storage"""
+        for b, vals in getattr(self, "sources", []):
+            assemble_vector_source(self.residual_storage, self.blocks[b], vals, self.X, self.nf)
+
     def assemble_stiffness(self, Uu, kind="stiffness"):
         self._update_field(self.field, Uu)
         self.stiffness_storage = assemble_matrix_coo(self.blocks, self.X, self._U(), self.nf, kind)
@@ -955,6 +1094,8 @@ def newton_solve(asm: OracleAssembler, Uu, max_iters=10, abs_tol=1e-12, rel_tol=
     hist, cgits = [], []
     for it in range(1, max_iters + 1):
         asm.assemble_vector(Uu)
+        asm.assemble_vector_source(Uu)       # Solvers.jl:135
+        asm.assemble_vector_neumann_bc(Uu)   # Solvers.jl:136
         R = asm.residual().copy()
         asm.assemble_stiffness(Uu)
         K = asm.stiffness_scipy()

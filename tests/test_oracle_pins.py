@@ -306,3 +306,86 @@ def test_energy_is_the_potential_of_the_residual(phys):
         e = np.zeros(a.n); e[k] = h
         fd = (total(Uu + e) - total(Uu - e)) / (2 * h)
         assert abs(fd - R[k]) < 1e-6 * max(abs(R).max(), 1.0), (k, fd, R[k])
+
+
+# ---- external loads: Neumann BCs and body-force sources (the two calls solve! makes after assemble_vector!) ----
+
+@pytest.mark.parametrize("el,rule", [("quad", "gauss2"), ("tri", "tri3")])
+def test_neumann_known_answer_of_the_reference(el, rule):
+    """test/laplace_with_source/TestLaplace.jl:429-545 (and test/poisson/TestPoisson.jl:605-721): Laplace on
+    StructuredMesh(el, (0,0), (1,1), (11,11)), u = 0 on `left`, NeumannBC g = -1 on `right` -> u(x, y) = x exactly:
+    `maximum(p.field) ~ 1.0`, `minimum ~ 0.0` (atol 1e-6).  Pins the oracle's surface connectivity (Exodus side
+    numbering + the reference's structured side sets), surface Jacobian and the +int g N sign convention."""
+    m = O.structured_mesh(el, (0., 0.), (1., 1.), (11, 11))
+    X, conn = m["coords"], m["conn"]
+    blk = O.Block(conn, O.ref_fe_tables(m["el_type"], rule), O.Poisson(lambda X: np.zeros(len(X))))
+    for condensed in (False, True):
+        asm = O.OracleAssembler(X, [blk], 1, condensed=condensed, matrix_type="csc")
+        asm.update_dofs(m["nodesets"]["left"])
+        elems, sides = O.structured_sidesets(el, (11, 11))["right"]
+        sn = O.side_nodes(m["el_type"], conn, elems, sides)
+        tabs = O.surface_tables(m["el_type"], "gauss2")
+        assert np.allclose(O.surface_quadrature_points(sn, tabs, X)[..., 0], 1.0)   # the sides lie on x = 1
+        asm.add_neumann_bc(sn, tabs, -np.ones((1, len(tabs[2]), sn.shape[1])))
+        Uu, nits, _, _ = O.newton_solve(asm, asm.create_unknowns(), direct=True)
+        asm._update_field(asm.field, Uu)
+        assert abs(asm.field.max() - 1.0) < 1e-6 and abs(asm.field.min()) < 1e-6
+        assert np.abs(asm.field - X[0]).max() < 1e-6
+        assert nits <= 3
+
+
+def test_source_reproduces_the_laplace_gold():
+    """test/laplace_with_source/TestLaplace.jl:24-76: Laplace physics + Source("u", f, "block_1") against laplace.gold,
+    which is byte-identical to poisson.gold (same mesh, same nodal values): the body-force path
+    (-int N b, Source.jl:44-63) must reproduce the gold exactly like Poisson's built-in f does."""
+    g = np.load(os.path.join(GOLDEN, "poisson_g.npz"))
+    f = lambda X: 2 * np.pi ** 2 * np.sin(np.pi * X[:, 0]) * np.sin(np.pi * X[:, 1])
+    blk = O.Block(g["conn_0"], O.ref_fe_tables("QUAD4", "gauss2"), O.Poisson(lambda X: np.zeros(len(X))))
+    bc_nodes = np.unique(np.concatenate([g[f"sideset_nodes_{i}"] for i in range(4)]))
+    asm = O.OracleAssembler(g["coords"], [blk], nf=1, condensed=False, matrix_type="csr")
+    asm.update_dofs(bc_nodes)
+    Xq = O.cell_quadrature_points(blk, g["coords"])                   # (NQ, NE, ND)
+    vals = f(Xq.reshape(-1, 2)).reshape(1, Xq.shape[0], Xq.shape[1])  # [NF, NQ, NE]
+    asm.add_source(0, vals)
+    Uu, nits, _, _ = O.newton_solve(asm, asm.create_unknowns(), direct=True)
+    asm._update_field(asm.field, Uu)
+    assert np.abs(asm.field - g["gold_u"]).max() < 1e-12
+    assert nits <= 3
+
+
+@pytest.mark.parametrize("el", ["HEX8", "TETRA10", "QUAD4"])
+def test_surface_and_body_loads_integrate_area_and_volume(el):
+    """size-independent properties of the load vectors on perturbed meshes: sum_n R_n of a unit Neumann flux = area of
+    the side set, sum_n R_n of a unit body force = -volume (partition of unity), per component."""
+    rng = np.random.default_rng(5)
+    if el == "HEX8":
+        m = O.structured_mesh("hex", (0., 0., 0.), (1., 2., 3.), (4, 3, 5))
+        counts, area, vol, nf, rule = (4, 3, 5), {"top": 3.0, "right": 6.0, "back": 2.0}, 6.0, 3, "gauss2"
+        conn = m["conn"]
+    elif el == "QUAD4":
+        m = O.structured_mesh("quad", (0., 0.), (2., 1.), (5, 4))
+        counts, area, vol, nf, rule = (5, 4), {"top": 2.0, "left": 1.0}, 2.0, 1, "gauss2"
+        conn = m["conn"]
+    else:
+        m = O.kuhn_tet10_mesh(2)
+        counts, area, vol, nf, rule, conn = None, {"top": 1.0, "left": 1.0}, 1.0, 3, "tet4", m["conn"]
+    X = m["coords"].copy()
+    interior = np.ones(X.shape[1], dtype=bool)
+    for nodes in m["nodesets"].values():
+        interior[np.asarray(nodes) - 1] = False
+    X[:, interior] += rng.uniform(-0.03, 0.03, (X.shape[0], interior.sum()))     # boundary stays planar
+    blk = O.Block(conn, O.ref_fe_tables(el, rule), O.Poisson(lambda X: np.zeros(len(X))) if nf == 1 else O.LinearElastic(3))
+    tabs = O.surface_tables(el, "gauss2")
+    for name, a in area.items():
+        if counts is not None:
+            elems, sides = O.structured_sidesets(el, counts)[name]
+            sn = O.side_nodes(el, conn, elems, sides)
+        else:  # all faces whose nodes lie in the node set
+            mark = np.zeros(X.shape[1] + 1, dtype=bool); mark[m["nodesets"][name]] = True
+            cols = [conn[list(loc)][:, mark[conn[list(loc)]].all(axis=0)] for loc in O.SIDE_NODES["TETRA10"]]
+            sn = np.concatenate(cols, axis=1)
+        R = O.assemble_vector_neumann_bc(np.zeros(nf * X.shape[1]), sn, tabs, np.ones((nf, len(tabs[2]), sn.shape[1])), X, nf)
+        assert np.allclose(R.reshape(-1, nf).sum(axis=0), a, rtol=1e-12), (name, R.reshape(-1, nf).sum(axis=0))
+    R = O.assemble_vector_source(np.zeros(nf * X.shape[1]), blk, np.ones((nf, len(blk.w), conn.shape[1])), X, nf)
+    # curved (perturbed mid-edge) TETRA10 cells have a cubic det J, which the degree-2 rule integrates only approximately
+    assert np.allclose(R.reshape(-1, nf).sum(axis=0), -vol, rtol=1e-4 if el == "TETRA10" else 1e-12)
