@@ -63,15 +63,25 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self._halt = index, [], set(), threading.Event()
         self.max_mhz = None
+        # NVML is initialised HERE, before the timed region: on a fresh box `import pynvml` + nvmlInit take longer than
+        # the 10 timed steps, and a sampler that starts late reports no clocks at all
+        self._nv = self._h = None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self._h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM))
+            nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+            self._nv = nv
+        except Exception:
+            self._nv = self._h = None
 
     def _run_nvml(self):
-        import pynvml as nv
-        nv.nvmlInit()
-        uuid = None
-        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-        idx = int(vis.split(",")[self.index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.index
-        h = nv.nvmlDeviceGetHandleByIndex(idx)
-        self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        nv, h = self._nv, self._h
+        if nv is None:
+            raise RuntimeError("NVML unavailable")
         bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
                 "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
         get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
@@ -358,6 +368,7 @@ def run_gpu(args):
                     "traffic_note": ("dram read+write bytes per launch, ncu --set full (profiles/r01p_fused_kmat2_details.txt); 1.6x algorithmic: RED read-modify-write of the CSR values"
                                      if dbuf else "dram read+write bytes per launch, ncu --set full (profiles/r01h_fused_kmat2_details.txt); 2.1x algorithmic: memset write-back + RED read-modify-write of the CSR values"),
                     "algorithmic_bytes_per_element": bytes_el, "kernel_ms": round(k_tan, 4),
+                    "binding_resource": "on-chip, not HBM: l1tex LSU data-pipe wavefronts 70 % of peak (shared-memory operand / staging traffic + REDs), FP64 pipe 55 % busy (ncu, profiles/r01p_fused_kmat2_details.txt, r01s_kmat2c_*; DESIGN.md section 5)",
                     "fp64": {"flops_per_element": FLOPS_TANGENT,
                              "achieved_tflops": round(FLOPS_TANGENT * ne_local / (k_tan * 1e-3) / 1e12, 2),
                              "peak_tflops_dgemm_measured": round(fp64_peak, 1),
