@@ -38,10 +38,19 @@ struct Mat2Params {
   int64_t nnz;               // the trash region of the branch-free RED stream starts at nz[nnz]
   PeerScatter peer;          // ghost rows of the fused residual go to their owner over NVLink
   int32_t ne, nq;
+  int32_t ko;                // knock-out mask of the phase-cost experiment (only read when built with -DFEC_MAT2_KO)
   ZeroFill zf;               // in-kernel clear of the idle CSR value buffer (common.cuh)
   double props[kMaxProps];
   Tables<ND, NNPE, NQT> tab;
 };
+// Phase-cost experiment (tools/ko_sweep.py): -DFEC_MAT2_KO compiles run-time predicates into k_mat2 that skip one
+// phase at a time (FECB200_KO = 1 REDs, 2 scatter read-back + REDs, 4 staging + scatter, 8 phase K, 16 phase G, 32
+// zero-fill), so the cost of each phase in the overlapped steady state can be measured.  Results are wrong by design.
+#ifdef FEC_MAT2_KO
+#define FEC_KO(bit) ((p.ko & (bit)) != 0)
+#else
+#define FEC_KO(bit) false
+#endif
 template <int N>
 __host__ __device__ constexpr int sym_index(int i, int j) {  // packed upper triangle, i <= j
   return i * N - (i * (i - 1)) / 2 + (j - i);
@@ -141,7 +150,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
 
   // ---- phase G: geometry + material tangent of the element's quadrature points, split over its threads
   double x[NNPE][ND], u[NNPE][NF];
-  if (active) {
+  if (active && !FEC_KO(16)) {
 #pragma unroll
     for (int a = 0; a < NNPE; ++a) {
       const int n = p.conn[(size_t)e * NNPE + a];
@@ -151,8 +160,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
       for (int d = 0; d < NF; ++d) u[a][d] = p.U[(size_t)n * NF + d];
     }
   }
-  zero_fill_begin(p.zf, zero_page);   // queued while the gathers above are in flight (0.13 ms better than up front)
-  if (active) {
+  if (!FEC_KO(32)) zero_fill_begin(p.zf, zero_page);   // queued while the gathers above are in flight (0.13 ms better than up front)
+  if (active && !FEC_KO(16)) {
     for (int q = t; q < NQT; q += NP) {
       double J[ND][ND];
 #pragma unroll
@@ -221,7 +230,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
   double rr[WITH_R ? NNPE : 1];  // fused residual rows (a, d1) of the diagonal-pair threads (d1 == d2)
 #pragma unroll
   for (int a = 0; a < (WITH_R ? NNPE : 1); ++a) rr[a] = 0.0;
-  if (active) {
+  if (active && !FEC_KO(8)) {
     // packed indices of this thread's ND x ND block (d1 <= d2 so (d1,j1) <= (d2,j2) unless d1 == d2 and j1 > j2)
     int aidx[ND][ND];
 #pragma unroll
@@ -282,7 +291,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
   // K_el is symmetric, so the reference's transposed COO convention and the CSR/CSC distinction do
   // not change the values.  (Sorting the columns by global node id was measured to make no difference: the RED
   // coalescer merges a warp's lanes into sectors whatever their order, so all offsets here are static.)
-  if (active) {
+  if (active && !FEC_KO(4)) {
 #pragma unroll
     for (int a = 0; a < NNPE; ++a) {
 #pragma unroll
@@ -306,7 +315,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
   // All shared-memory reads of an element are issued before its REDs so their latencies overlap (registers are
   // free here: M is dead).  The RED stream has no per-entry tests: rows that are not stored (Dirichlet dofs, ghost
   // rows) carry a row offset inside a 4096-slot hashed trash region behind the matrix, written by k_build_emeta.
-  if (lane < NROW) {
+  if (lane < NROW && !FEC_KO(2 | 4)) {
     const int nel = (p.ne - e0) < EPW ? (p.ne - e0) : EPW;
     const int k = lane / NF, dc = lane - k * NF;
     for (int el = 0; el < nel; ++el) {
@@ -335,9 +344,19 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
         }
 #pragma unroll
         for (int row = 0; row < NROW; ++row) val[row] = ks[row * RS + lane];
+        if (!FEC_KO(1)) {
 #pragma unroll
-        for (int row = 0; row < NROW; ++row)  // rows that are not stored point into the trash region (k_build_emeta)
-          asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p.nz + (r0[row] + off[row / NF])), "d"(val[row]));
+          for (int row = 0; row < NROW; ++row)  // rows that are not stored point into the trash region (k_build_emeta)
+            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p.nz + (r0[row] + off[row / NF])), "d"(val[row]));
+        }
+#ifdef FEC_MAT2_KO
+        else {  // keep the loads alive
+          double sacc = 0.0;
+#pragma unroll
+          for (int row = 0; row < NROW; ++row) sacc += val[row] + (double)(r0[row] + off[row / NF]);
+          if (sacc == 1.234567e300) p.nz[0] = sacc;
+        }
+#endif
       }
       if constexpr (WITH_R) {
         // fused residual: lane (k, dc) adds the staged entry into R[node_k, dc] -- 3 consecutive doubles per node
@@ -347,7 +366,17 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
       }
     }
   }
-  zero_fill_end(p.zf);
+  if (!FEC_KO(32)) zero_fill_end(p.zf);
+#ifdef FEC_MAT2_KO
+  if (FEC_KO(4)) {  // staging knocked out: keep phase K alive
+    double sacc = 0.0;
+#pragma unroll
+    for (int a = 0; a < NNPE; ++a)
+#pragma unroll
+      for (int b = 0; b < NNPE; ++b) sacc += M[a][b];
+    if (sacc == 1.234567e300) p.nz[0] = sacc;
+  }
+#endif
 }
 
 // element -> CSR column-offset table, rebuilt whenever update_dofs changes the kept-dof masks
@@ -371,6 +400,9 @@ void run_mat2_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   p.ne = (int32_t)b.ne; p.nq = b.nq; p.nnz = h->nnz;
   for (int i = 0; i < kMaxProps; ++i) p.props[i] = i < (int)b.props.size() ? b.props[i] : 0.0;
   fill_tables<ND, NNPE, NQT>(b, p.tab);
+#ifdef FEC_MAT2_KO
+  p.ko = getenv("FECB200_KO") ? atoi(getenv("FECB200_KO")) : 0;
+#endif
   size_t smem = (size_t)WARPS * L::EPW * L::ELSM * sizeof(double);
   const int epc = WARPS * L::EPW;
   const int grid = (int)((b.ne + epc - 1) / epc);

@@ -202,7 +202,8 @@ template <bool AS_WRITTEN>
 struct NeoHookeanImpl {
   static constexpr int NS = 0;
   static constexpr bool kHasEnergy = true;
-  struct Pre { double F[3][3], H[3][3], J, I1, m, c, cpJ, G; };
+  // Hs, Hg, Hb: the three coefficient-scaled copies of H / F the tangent is built from (see A below)
+  struct Pre { double F[3][3], H[3][3], Hs[3][3], Hg[3][3], Hb[3][3], J, I1, m, c, cpJ, G, gm; };
   // psi = 1/2 K U(J) + 1/2 G (J^-2/3 tr(F F^T) - 3)   (TestMechanicsLargeDeformation.jl:17-27; U: see prepare)
   FEC_DEV static double energy(const double (&g)[3][3], const double* props, const double*) {
     Pre p;
@@ -224,7 +225,7 @@ struct NeoHookeanImpl {
     for (int i = 0; i < 3; ++i)
 #pragma unroll
       for (int j = 0; j < 3; ++j) p.I1 = fma(p.F[i][j], p.F[i][j], p.I1);
-    p.m = 1.0 / cbrt(p.J * p.J);
+    p.m = rcbrt(p.J * p.J);   // J^(-2/3): one routine instead of cbrt + a division on the dependent chain
     if (AS_WRITTEN) {
       p.c = 0.5 * K * (p.J * p.J - p.J - 1.0);
       p.cpJ = 0.5 * K * (2.0 * p.J - 1.0) * p.J;
@@ -232,6 +233,21 @@ struct NeoHookeanImpl {
       p.c = 0.5 * K * (p.J * p.J - 1.0);
       p.cpJ = K * p.J * p.J;
     }
+    // A_iJkL = Hs_iJ H_kL + Hg_iJ F_kL + Hb_iL H_kJ + gm d_ik d_JL   with
+    //   Hs = (c'J + 2/9 gm I1) H - 2/3 gm F,  Hg = -2/3 gm H,  Hb = (gm I1/3 - c) H
+    // (the formula in the header comment with the common factors collected: 3 FP64 instructions per entry).
+    // Dead code in the residual / action paths, which never read these fields.
+    const double third = 1.0 / 3.0;
+    p.gm = p.G * p.m;
+    const double as = p.cpJ + (2.0 * third * third) * p.gm * p.I1, ag = -(2.0 * third) * p.gm, ab = p.gm * p.I1 * third - p.c;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        p.Hs[i][j] = fma(as, p.H[i][j], ag * p.F[i][j]);
+        p.Hg[i][j] = ag * p.H[i][j];
+        p.Hb[i][j] = ab * p.H[i][j];
+      }
   }
   FEC_DEV static void stress(const double (&g)[3][3], const double* props, const double*, double*, double (&P)[3][3]) {
     Pre p;
@@ -283,12 +299,10 @@ struct NeoHookeanImpl {
         D[i][j] = aH * p.H[i][j] + aF * p.F[i][j] + aT * T[i][j] + gm * dF[i][j];
   }
   FEC_DEV static double A(const Pre& p, int i, int j, int k, int l) {
-    const double third = 1.0 / 3.0, gm = p.G * p.m;
-    const double dev_ij = p.F[i][j] - p.I1 * third * p.H[i][j];
-    double a = p.cpJ * p.H[i][j] * p.H[k][l] - p.c * p.H[i][l] * p.H[k][j];
-    a += gm * (-(2.0 * third) * dev_ij * p.H[k][l] + ((i == k && j == l) ? 1.0 : 0.0) -
-               (2.0 * third) * p.H[i][j] * p.F[k][l] + p.I1 * third * p.H[i][l] * p.H[k][j]);
-    return a;
+    double a = p.Hs[i][j] * p.H[k][l];
+    a = fma(p.Hg[i][j], p.F[k][l], a);
+    a = fma(p.Hb[i][l], p.H[k][j], a);
+    return (i == k && j == l) ? a + p.gm : a;
   }
 };
 
