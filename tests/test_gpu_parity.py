@@ -839,3 +839,38 @@ def test_newton_with_traction_and_gravity_matches_oracle(F):
     assert solver.iterations == nits, (solver.iterations, nits)
     assert rel_err(integ.solution, oUu) < 1e-8
     asm.close()
+
+
+def test_external_load_error_behaviour(F):
+    """error paths of the load entry points: unknown variable (the reference's `_dof_index_from_var_name` throws),
+    values never pushed, ids out of order, and no-ops when nothing is registered (Source.jl:21 returns early)."""
+    from fecb200 import _lib
+    from fecb200._lib import lib
+    mesh = F.StructuredMesh("quad", (0., 0.), (1., 1.), (4, 4))
+    V = F.FunctionSpace(mesh, F.H1Field, F.Lagrange)
+    u = F.ScalarFunction(V, "u")
+    asm = F.SparseMatrixAssembler(u, sparse_matrix_type="csr")
+    with pytest.raises(ValueError):
+        F.create_parameters(mesh, asm, F.Poisson(None), None, neumann_bcs=[F.NeumannBC("nope", lambda X, t: X[:, :1], "top")])
+    with pytest.raises(KeyError):
+        F.create_parameters(mesh, asm, F.Poisson(None), None, sources=[F.Source("u", lambda X, t: X[:, :1], "block_9")])
+    p = F.create_parameters(mesh, asm, F.Poisson(None), None)
+    Uu = np.zeros(asm.sizes()[2])
+    F.assemble_vector(asm, F.residual, Uu, p)
+    F.assemble_vector_neumann_bc(asm, Uu, p)     # nothing registered: no-ops
+    F.assemble_vector_source(asm, Uu, p)
+    assert np.abs(F.full_field(asm, "residual")).max() == 0.0
+    h = asm._require()
+    sn, snp = _lib.i64(np.array([1, 2], dtype=np.int64))
+    t, tp = _lib.f64(np.array([0.5, 0.5]))
+    assert lib.fecb200_set_neumann_bc(h, 3, 1, 2, 1, snp, tp, tp, tp) != 0                 # ids must be 0, 1, 2, ...
+    assert lib.fecb200_set_neumann_values(h, 0, None) != 0                                   # unknown id
+    assert lib.fecb200_set_neumann_bc(h, 0, 1, 2, 1, snp, tp, tp, tp) == 0
+    assert lib.fecb200_assemble_vector_neumann_bc(h) != 0                                    # values never set
+    assert b"values were never set" in lib.fecb200_last_error()
+    bad, badp = _lib.i64(np.array([1, 99], dtype=np.int64))
+    assert lib.fecb200_set_neumann_bc(h, 0, 1, 2, 1, badp, tp, tp, tp) != 0                  # node id out of range
+    assert lib.fecb200_clear_neumann_bcs(h) == 0
+    assert lib.fecb200_assemble_vector_neumann_bc(h) == 0
+    assert lib.fecb200_set_source_values(h, 5, None) != 0                                    # bad block index
+    asm.close()

@@ -1,5 +1,5 @@
 """Small end-to-end case for compute-sanitizer runs (memcheck / racecheck): exercises k_vec (residual, action),
-k_mat2 (tangent, fused), k_mat (mass), k_mat_scalar (Poisson), the accessors and the device CG."""
+k_mat2 (tangent, fused), k_mat (mass), k_mat_scalar (Poisson), the load kernels (loads.cu), the accessors and the device CG."""
 import os
 import sys
 
@@ -18,12 +18,17 @@ for phys in ("neo", "poisson", "j2"):
     dbcs = [F.DirichletBC(c, lambda X, t: np.zeros(X.shape[0]), nodeset_name="bottom") for c in u.names()]
     ph = {"neo": F.NeoHookean(F.ThreeDimensional()), "poisson": F.Poisson(lambda X, t: X[:, 0]), "j2": F.J2Plasticity(F.ThreeDimensional())}[phys]
     props = {"neo": np.array([1e3, 1e7, 1e6]), "poisson": None, "j2": np.array([1e3, 1e10, 1e9, 2e8, 1e8])}[phys]
-    p = F.create_parameters(mesh, asm, ph, props, dirichlet_bcs=dbcs)
+    nfld = len(u.names())
+    nbcs = [F.NeumannBC(u.names()[0], lambda X, t: np.ones((X.shape[0], nfld)), "top")]
+    srcs = [F.Source(u.names()[0], lambda X, t: np.tile(np.arange(1.0, nfld + 1.0), (X.shape[0], 1)), "block_1")]
+    p = F.create_parameters(mesh, asm, ph, props, dirichlet_bcs=dbcs, neumann_bcs=nbcs, sources=srcs)
     if phys != "j2":
         asm.set_matrix_double_buffer(True)      # TMA zero-fill of the idle value array inside the matrix kernels
     N = asm.sizes()[2]
     rng = np.random.default_rng(0)
     Uu, Vu = 0.01 * rng.standard_normal(N), rng.random(N)
+    F.assemble_vector(asm, F.residual, Uu, p)
+    F.assemble_vector_source(asm, Uu, p); F.assemble_vector_neumann_bc(asm, Uu, p)   # loads.cu
     F.assemble_vector(asm, F.residual, Uu, p); R = F.residual(asm)
     F.assemble_matrix_action(asm, F.stiffness, Uu, Vu, p); Kv = F.hvp(asm, Vu)
     if phys != "j2":
