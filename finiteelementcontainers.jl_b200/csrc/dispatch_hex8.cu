@@ -2,6 +2,7 @@
 // Hot configurations (BASELINE.json configs 2, 3, 5): Poisson NF=1 and neo-Hookean NF=3 with 8-point rules.
 #include "kernel_mat2.cuh"
 #include "kernel_mat2c.cuh"
+#include "kernel_mat2w.cuh"
 #include "kernel_mat_scalar.cuh"
 
 // Warps per k_mat2 CTA.  The warps of a CTA start together and walk the phases (FP64-bound G/K, RED-bound S) in
@@ -21,6 +22,23 @@
 #ifndef FEC_MAT2C_MINB
 #define FEC_MAT2C_MINB 5
 #endif
+// Warp-specialised persistent variant (kernel_mat2w.cuh): FEC_MAT2W = 1 selects it; producer teams, consumer teams,
+// ring stages and the register cap are FEC_MAT2W_PT / _CT / _NST / _REG.
+#ifndef FEC_MAT2W
+#define FEC_MAT2W 0
+#endif
+#ifndef FEC_MAT2W_PT
+#define FEC_MAT2W_PT 3
+#endif
+#ifndef FEC_MAT2W_CT
+#define FEC_MAT2W_CT 3
+#endif
+#ifndef FEC_MAT2W_NST
+#define FEC_MAT2W_NST 5
+#endif
+#ifndef FEC_MAT2W_REG
+#define FEC_MAT2W_REG 128
+#endif
 #include <cstdlib>
 
 namespace fec {
@@ -35,7 +53,9 @@ static void mat8(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   FEC_REQUIRE(b.nq == 8, "HEX8: this physics is compiled for 8-point quadrature rules only");
   // symmetric tangents (all shipped mechanics physics): pair-owner kernel with staged, coalesced REDs
   if (a.kind == FECB200_STIFFNESS && matrix_kernel_fuses_residual(h, b)) {
-#if FEC_MAT2C
+#if FEC_MAT2W
+    run_mat2w<3, 8, NF, 8, Phys, Mat2wShape<FEC_MAT2W_PT, FEC_MAT2W_CT, FEC_MAT2W_NST>, FEC_MAT2W_REG>(h, b, a);
+#elif FEC_MAT2C
     run_mat2c<3, 8, NF, 8, Phys, FEC_MAT2C_EPC, FEC_MAT2C_MINB>(h, b, a);
 #else
     run_mat2<3, 8, NF, 8, Phys, FEC_MAT2_WARPS>(h, b, a);
