@@ -13,6 +13,10 @@ namespace fec {
 
 static inline int grid_for(int64_t n, int bs = 256) { return (int)((n + bs - 1) / bs); }
 
+__global__ void k_fill_indexed(double* f, const int32_t* idx, double v, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) f[idx[i]] = v;
+}
 __global__ void k_set_indexed(double* f, const int32_t* idx, const double* vals, int64_t n) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) f[idx[i]] = vals[i];
@@ -363,6 +367,9 @@ __global__ void k_pack(const double* f, const int32_t* nodes, double* buf, int64
 __global__ void k_unpack_add(double* f, const int32_t* nodes, const double* buf, int64_t n, int nf) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n * nf) atomicAdd(&f[(int64_t)nodes[i / nf] * nf + i % nf], buf[i]);
+}
+void fill_indexed(fecb200_handle* h, double* field, const int32_t* idx, double v, int64_t n) {
+  if (n) { k_fill_indexed<<<grid_for(n), 256, 0, h->stream>>>(field, idx, v, n); h->launches++; }
 }
 void halo_pack(fecb200_handle* h, const double* field, double* buf) {
   const int64_t n = (int64_t)h->d_send_nodes.n;

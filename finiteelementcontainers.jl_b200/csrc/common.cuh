@@ -332,6 +332,7 @@ void spmv(fecb200_handle* h, const double* nz, const double* x, double* y);
 double dot(fecb200_handle* h, const double* a, const double* b, int64_t n);
 void axpy(fecb200_handle* h, double alpha, const double* x, double* y, int64_t n);
 void xpay(fecb200_handle* h, const double* x, double beta, double* y, int64_t n);  // y = x + beta*y
+void fill_indexed(fecb200_handle* h, double* field, const int32_t* idx, double v, int64_t n);  // field[idx[i]] = v
 void halo_pack(fecb200_handle* h, const double* field, double* buf);
 void halo_unpack_add(fecb200_handle* h, double* field, const double* buf);
 

@@ -328,9 +328,29 @@ void build_dof_structures(fecb200_handle* h) {
   d2u.assign(ndof, 0);
   for (int64_t d : dd) d2u[d - 1] = -1;
   for (int64_t d : h->per_b) d2u[d - 1] = -2;
-  h->unknown_dofs.clear();
-  for (int64_t g = 0; g < ndof; ++g)
-    if (d2u[g] == 0) { h->unknown_dofs.push_back(g + 1); d2u[g] = (int64_t)h->unknown_dofs.size(); }
+  // unknown ids in ascending dof order: chunked count / prefix / fill (21.6 M dofs at 192^3)
+  {
+    const int nth = omp_get_max_threads();
+    std::vector<int64_t> cnt(nth + 1, 0);
+    const int64_t chunk = (ndof + nth - 1) / nth;
+#pragma omp parallel num_threads(nth)
+    {
+      const int t = omp_get_thread_num();
+      const int64_t lo = std::min<int64_t>(ndof, t * chunk), hi = std::min<int64_t>(ndof, lo + chunk);
+      int64_t c = 0;
+      for (int64_t g = lo; g < hi; ++g) c += d2u[g] == 0;
+      cnt[t + 1] = c;
+#pragma omp barrier
+#pragma omp single
+      {
+        for (int i = 0; i < nth; ++i) cnt[i + 1] += cnt[i];
+        h->unknown_dofs.resize(cnt[nth]);
+      }
+      int64_t k = cnt[t];
+      for (int64_t g = lo; g < hi; ++g)
+        if (d2u[g] == 0) { h->unknown_dofs[k] = g + 1; d2u[g] = ++k; }
+    }
+  }
   h->n_unknowns = (int64_t)h->unknown_dofs.size();
   h->b2a_unknown.assign(ndof, 0);
   for (size_t i = 0; i < h->per_a.size(); ++i) {
@@ -340,15 +360,26 @@ void build_dof_structures(fecb200_handle* h) {
   // device copies
   {
     std::vector<int32_t> ud(h->n_unknowns);
+#pragma omp parallel for schedule(static)
     for (int64_t k = 0; k < h->n_unknowns; ++k) ud[k] = (int32_t)(h->unknown_dofs[k] - 1);
     h->d_unknown_dofs.upload(ud, h->stream);
     std::vector<int32_t> d2ui(ndof);
+#pragma omp parallel for schedule(static)
     for (int64_t g = 0; g < ndof; ++g)
       d2ui[g] = h->opts.condensed ? (int32_t)g : (d2u[g] > 0 ? (int32_t)(d2u[g] - 1) : -1);
     h->d_d2u.upload(d2ui, h->stream);
-    std::vector<double> c(ndof, 0.0);
-    for (int64_t d : dd) c[d - 1] = 1.0;
-    h->d_constraint.upload(c, h->stream);
+    // constraint_storage: 1.0 at the Dirichlet dofs (SparseMatrixAssembler.jl:93-94): cleared on the device, the few
+    // non-zeros set by index
+    if ((int64_t)h->d_constraint.n != ndof) h->d_constraint.alloc(ndof);
+    h->d_constraint.zero(h->stream);
+    if (!dd.empty()) {
+      std::vector<int32_t> di(dd.size());
+      for (size_t i = 0; i < dd.size(); ++i) di[i] = (int32_t)(dd[i] - 1);
+      DevBuf<int32_t> ddev;
+      ddev.upload(di, h->stream);
+      fill_indexed(h, h->d_constraint.p, ddev.p, 1.0, (int64_t)di.size());
+      FEC_CUDA(cudaStreamSynchronize(h->stream));
+    }
     std::vector<int32_t> pa(h->per_a.size()), pb(h->per_b.size());
     for (size_t i = 0; i < pa.size(); ++i) { pa[i] = (int32_t)(h->per_a[i] - 1); pb[i] = (int32_t)(h->per_b[i] - 1); }
     h->n_per = (int64_t)pa.size();
@@ -366,9 +397,10 @@ void build_dof_structures(fecb200_handle* h) {
     std::vector<double> bv(dd.size(), 0.0);
     h->d_bc_vals.upload(bv, h->stream);
   }
-  h->d_Uu.alloc(ndof);
-  h->d_Vu.alloc(ndof);
-  h->d_out.alloc(ndof);
+  // staging vectors: kept across update_dofs calls (cudaFree / cudaMalloc of 3 x 173 MB at 192^3 is not free)
+  if ((int64_t)h->d_Uu.n != ndof) h->d_Uu.alloc(ndof);
+  if ((int64_t)h->d_Vu.n != ndof) h->d_Vu.alloc(ndof);
+  if ((int64_t)h->d_out.n != ndof) h->d_out.alloc(ndof);
 
   // the CSR structure depends on the kept dofs: rebuilt on demand (ensure_matrix_structure)
   h->matrix_ready = false;
