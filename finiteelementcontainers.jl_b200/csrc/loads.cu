@@ -92,19 +92,28 @@ __global__ void k_add_field(double* __restrict__ dst, const double* __restrict__
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) dst[i] += src[i];
 }
+// fused peer halo: entries of ghost nodes go straight into the owner's field over NVLink, like the element kernels do
+__global__ void k_add_field_peer(double* dst, const double* __restrict__ src, int64_t ndof, int nf, PeerScatter peer) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= ndof) return;
+  const double v = src[i];
+  if (v != 0.0) scatter_add(peer, dst, i / nf, nf, (int)(i % nf), v);
+}
 
 static PeerScatter local_only(const fecb200_handle* h) {
   PeerScatter ps = h->peer;
-  ps.n_owned = -1;   // the cached vector is rank-local; ghost entries travel with the residual's halo sum
+  ps.n_owned = -1;   // the cached vector is rank-local: ghost entries are forwarded when it is added (add_cached)
   return ps;
 }
 
 static void add_cached(fecb200_handle* h, double* field, const double* cache) {
-  // ghost-node entries: with the fused peer halo the residual's ghost slots are not exchanged, so they are sent to the
-  // owner here; otherwise they stay local and the pack / NCCL / unpack-add halo sum carries them
+  // ghost-node entries: with the NCCL halo they stay in the local field and the pack / send-recv / unpack-add sum carries
+  // them to the owner; with the fused peer halo the field's ghost slots are never exchanged, so they are RED-added into
+  // the owner's field here (between the same two stream-ordered barriers as the element kernels' ghost REDs)
   if (h->peer_enabled && h->peer_field == FECB200_FIELD_RESIDUAL && field == h->d_R.p && h->n_owned_nodes < h->nn)
-    throw Error("fecb200: external loads with the fused peer halo are not supported; use the NCCL halo path");
-  k_add_field<<<grid_for(h->ndof, 256), 256, 0, h->stream>>>(field, cache, h->ndof);
+    k_add_field_peer<<<grid_for(h->ndof, 256), 256, 0, h->stream>>>(field, cache, h->ndof, h->nf, h->peer);
+  else
+    k_add_field<<<grid_for(h->ndof, 256), 256, 0, h->stream>>>(field, cache, h->ndof);
   FEC_CUDA(cudaGetLastError());
   h->launches++;
 }

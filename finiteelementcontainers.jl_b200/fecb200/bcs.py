@@ -108,8 +108,10 @@ class NeumannBCs:
                 raise AssertionError("Sidesets need to be in a single block")
             b = int(blocks[0]) if len(blocks) else 0
             Ns, dNs, ws = fspace.ref_fes[b].surface_tables()
-            cache = dict(block=b, elements=el - offs[b], sides=sd,
-                         side_nodes=np.ascontiguousarray(mesh.sideset_side_nodes[bc.sset_name], dtype=np.int64),
+            sn = np.ascontiguousarray(mesh.sideset_side_nodes[bc.sset_name], dtype=np.int64)
+            if not len(sd):                       # e.g. a rank-local mesh that does not touch this boundary
+                sn = np.zeros((Ns.shape[1], 0), dtype=np.int64)
+            cache = dict(block=b, elements=el - offs[b], sides=sd, side_nodes=sn,
                          Ns=Ns, dNs=dNs, ws=ws, vals=np.zeros((self.nf, len(ws), len(sd)), order="F"))
             self.bc_caches.append(cache)
             self.bc_funcs.append(bc.func)
@@ -123,6 +125,8 @@ class NeumannBCs:
         """update_bc_values!(bcs, asm, X, t) (:157-171, :60-71): vals[q, e] = func(X_q, t) at the surface points"""
         X = np.asarray(X)
         for func, c in zip(self.bc_funcs, self.bc_caches):
+            if c["side_nodes"].shape[1] == 0:
+                continue
             xs = X[:, c["side_nodes"] - 1]                               # (ND, nnps, nsides)
             Xq = np.einsum("qa,dae->eqd", c["Ns"], xs)                   # (nsides, nqs, ND)
             n = Xq.shape[0] * Xq.shape[1]

@@ -51,12 +51,14 @@ class AbstractMesh:
             self.sideset_elems[name], self.sideset_sides[name] = el, sd
             self.sideset_side_nodes[name] = (np.stack(cols, axis=1) if cols else np.zeros((0, 0))).astype(np.int64)
 
-    def _sidesets_from_nodesets(self, nodesets):
-        """every element side whose nodes all belong to the node set (meshes without side-set records)"""
+    def _sidesets_from_nodesets(self, nodesets, blocks=None):
+        """every element side whose nodes all belong to the node set (meshes without side-set records);
+        `blocks` restricts the search (rank-local meshes: only the `owned` block carries surface loads)"""
         sets, off = {}, 0
         per_block = []
         for bn in self.element_block_names:
-            per_block.append((off, self.element_conns[bn], _SIDE_NODES[self.element_types[bn]]))
+            if blocks is None or bn in blocks:
+                per_block.append((off, self.element_conns[bn], _SIDE_NODES[self.element_types[bn]]))
             off += self.element_conns[bn].shape[1]
         for name, nodes in nodesets.items():
             mark = np.zeros(self.num_nodes() + 1, dtype=bool)

@@ -53,7 +53,20 @@ def metis_partition_graph(xadj, adjncy, nparts):
 
 
 class _LocalMesh(AbstractMesh):
-    pass
+    """Rank-local mesh: block `owned` (+ `halo`: neighbour-owned elements, matrix assembly only).  Side sets are the
+    faces of OWNED elements lying in the node sets, built on first use (surface loads of halo elements belong to their
+    owner rank)."""
+
+    def _lazy_sidesets(self):
+        if "_ss" not in self.__dict__:
+            self.__dict__["_ss"] = True
+            self._set_sidesets(self._sidesets_from_nodesets(self.sideset_nodes, blocks=["owned"]))
+
+    def __getattr__(self, name):
+        if name in ("sideset_elems", "sideset_sides", "sideset_side_nodes"):
+            self._lazy_sidesets()
+            return self.__dict__[name]
+        raise AttributeError(name)
 
 
 class Partition:

@@ -19,3 +19,15 @@ def test_peer_memory_halo_matches_nccl():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "OK" in out.stdout and "FAIL" not in out.stdout, out.stdout[-2000:]
+
+
+def test_partitioned_loads_match_serial():
+    """body force + tractions on a 2-rank partition (NCCL halo and fused peer halo) against the serial assembly"""
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29543", os.path.join(ROOT, "tests", "run_loads_check.py"), "8"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "OK" in out.stdout and "FAIL" not in out.stdout, out.stdout[-2000:]
