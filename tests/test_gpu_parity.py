@@ -675,7 +675,7 @@ def test_assemble_scalar_without_energy_is_an_error(F):
     asm.close()
 
 
-@pytest.mark.parametrize("script,args", [("neohookean_cube.py", ["6"]), ("poisson_periodic.py", ["32"])])
+@pytest.mark.parametrize("script,args", [("neohookean_cube.py", ["6"]), ("poisson_periodic.py", ["32"]), ("cantilever_gravity.py", ["3"])])
 def test_examples_run(script, args):
     """examples/ (the shape of the reference's examples/mechanics/Cube.jl and examples/poisson/periodic_bc.jl)"""
     import subprocess
