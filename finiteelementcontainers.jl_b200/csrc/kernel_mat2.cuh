@@ -199,11 +199,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
         for (int s = 0; s < NS; ++s) so[s] = p.state_old[((size_t)s * p.nq + q) * p.ne + e];
       }
       double A[NDF][NDF];
-      Phys::tangent(gu, p.props, so, A);
+      Phys::tangent_scaled(gu, p.props, so, JxW, A);   // JxW * A (folded into the law's coefficients where possible)
 #pragma unroll
       for (int i = 0; i < NDF; ++i)
 #pragma unroll
-        for (int j = i; j < NDF; ++j) slot[NNPE * ND + sym_index<NDF>(i, j)] = A[i][j] * JxW;
+        for (int j = i; j < NDF; ++j) slot[NNPE * ND + sym_index<NDF>(i, j)] = A[i][j];
       if constexpr (WITH_R) {
         // fused residual: P at the same state (the compiler shares the kinematics with the tangent above)
         double P[NF][ND], bsrc[NF], sn[NS > 0 ? NS : 1];

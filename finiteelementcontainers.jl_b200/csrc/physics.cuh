@@ -134,6 +134,7 @@ struct PhysMech3 {
     pad3<ND, ND>(gu, G3);
     typename Impl::Pre pre;
     Impl::prepare(G3, props, so, pre);
+    if constexpr (Impl::kScalesTangent) Impl::scale_tangent(pre, 1.0);
 #pragma unroll
     for (int i = 0; i < ND; ++i)
 #pragma unroll
@@ -143,6 +144,27 @@ struct PhysMech3 {
 #pragma unroll
           for (int l = 0; l < ND; ++l) A[i * ND + j][k * ND + l] = Impl::A(pre, i, j, k, l);
   }
+  // scale * A (the matrix kernels need JxW * A): constitutive laws whose tangent is a sum of coefficient-scaled
+  // products fold the factor into the coefficients (Impl::scale_tangent), the others multiply the entries
+  FEC_DEV static void tangent_scaled(const double (&gu)[ND][ND], const double* props, const double* so, const double scale,
+                                     double (&A)[ND * ND][ND * ND]) {
+    double G3[3][3];
+    pad3<ND, ND>(gu, G3);
+    typename Impl::Pre pre;
+    Impl::prepare(G3, props, so, pre);
+    if constexpr (Impl::kScalesTangent) Impl::scale_tangent(pre, scale);
+#pragma unroll
+    for (int i = 0; i < ND; ++i)
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+#pragma unroll
+        for (int k = 0; k < ND; ++k)
+#pragma unroll
+          for (int l = 0; l < ND; ++l) {
+            const double a = Impl::A(pre, i, j, k, l);
+            A[i * ND + j][k * ND + l] = Impl::kScalesTangent ? a : a * scale;
+          }
+  }
 };
 
 // -------------------------------------------------------------------------------------------
@@ -151,6 +173,7 @@ struct PhysMech3 {
 // -------------------------------------------------------------------------------------------
 struct LinearElasticImpl {
   static constexpr int NS = 0;
+  static constexpr bool kScalesTangent = false;
   static constexpr bool kHasEnergy = true;
   struct Pre { double K, G; };
   // psi = 1/2 K tr(eps)^2 + G dev(eps):dev(eps)   (TestMechanicsCommon.jl:14-20)
@@ -233,21 +256,6 @@ struct NeoHookeanImpl {
       p.c = 0.5 * K * (p.J * p.J - 1.0);
       p.cpJ = K * p.J * p.J;
     }
-    // A_iJkL = Hs_iJ H_kL + Hg_iJ F_kL + Hb_iL H_kJ + gm d_ik d_JL   with
-    //   Hs = (c'J + 2/9 gm I1) H - 2/3 gm F,  Hg = -2/3 gm H,  Hb = (gm I1/3 - c) H
-    // (the formula in the header comment with the common factors collected: 3 FP64 instructions per entry).
-    // Dead code in the residual / action paths, which never read these fields.
-    const double third = 1.0 / 3.0;
-    p.gm = p.G * p.m;
-    const double as = p.cpJ + (2.0 * third * third) * p.gm * p.I1, ag = -(2.0 * third) * p.gm, ab = p.gm * p.I1 * third - p.c;
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        p.Hs[i][j] = fma(as, p.H[i][j], ag * p.F[i][j]);
-        p.Hg[i][j] = ag * p.H[i][j];
-        p.Hb[i][j] = ab * p.H[i][j];
-      }
   }
   FEC_DEV static void stress(const double (&g)[3][3], const double* props, const double*, double*, double (&P)[3][3]) {
     Pre p;
@@ -298,6 +306,25 @@ struct NeoHookeanImpl {
       for (int j = 0; j < 3; ++j)
         D[i][j] = aH * p.H[i][j] + aF * p.F[i][j] + aT * T[i][j] + gm * dF[i][j];
   }
+  static constexpr bool kScalesTangent = true;
+  // A_iJkL = Hs_iJ H_kL + Hg_iJ F_kL + Hb_iL H_kJ + gm d_ik d_JL   with
+  //   Hs = (c'J + 2/9 gm I1) H - 2/3 gm F,  Hg = -2/3 gm H,  Hb = (gm I1/3 - c) H
+  // (the formula in the header comment with the common factors collected: 3 FP64 instructions per entry).  `s` scales the
+  // whole tangent (the matrix kernels need JxW * A): it is folded into the four coefficients.
+  FEC_DEV static void scale_tangent(Pre& p, const double s) {
+    const double third = 1.0 / 3.0;
+    const double gm = p.G * p.m;
+    p.gm = gm * s;
+    const double as = (p.cpJ + (2.0 * third * third) * gm * p.I1) * s, ag = -(2.0 * third) * p.gm, ab = (gm * p.I1 * third - p.c) * s;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        p.Hs[i][j] = fma(as, p.H[i][j], ag * p.F[i][j]);
+        p.Hg[i][j] = ag * p.H[i][j];
+        p.Hb[i][j] = ab * p.H[i][j];
+      }
+  }
   FEC_DEV static double A(const Pre& p, int i, int j, int k, int l) {
     double a = p.Hs[i][j] * p.H[k][l];
     a = fma(p.Hg[i][j], p.F[k][l], a);
@@ -315,6 +342,7 @@ struct NeoHookeanImpl {
 // -------------------------------------------------------------------------------------------
 struct J2Impl {
   static constexpr int NS = 7;
+  static constexpr bool kScalesTangent = false;
   static constexpr bool kHasEnergy = false;  // no energy is defined for the (oracle-defined) J2 law
   struct Pre { double K, G, theta, thbar, n[3][3]; };
   struct RM { double tr, s[3][3], n[3][3], dg, q; bool yld; };
