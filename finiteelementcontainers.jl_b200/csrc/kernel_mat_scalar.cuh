@@ -30,11 +30,11 @@ __global__ void __launch_bounds__(128) k_mat_scalar(const __grid_constant__ MatS
   __shared__ __align__(16) double zero_page[kZeroPageBytes / 8];
   zero_fill_begin(p.zf, zero_page);
   const int e = blockIdx.x * 128 + threadIdx.x;
-  if (e >= p.ne) { zero_fill_end(p.zf); return; }
+  const bool live = e < p.ne;   // the whole warp takes part in the staged scatter
   double x[NNPE][ND], u[NNPE][1];
 #pragma unroll
   for (int a = 0; a < NNPE; ++a) {
-    const int n = p.conn[(size_t)e * NNPE + a];
+    const int n = live ? p.conn[(size_t)e * NNPE + a] : 0;
 #pragma unroll
     for (int j = 0; j < ND; ++j) x[a][j] = p.X[(size_t)n * ND + j];
     u[a][0] = p.U[n];
@@ -102,23 +102,50 @@ __global__ void __launch_bounds__(128) k_mat_scalar(const __grid_constant__ MatS
     }
   }
   // ---- scatter: record = u32 rowstart[NNPE] | u16 ecol[NNPE][NNPE] (by local node) | u8 mask[NNPE] | u8 rank[NNPE]
-  const unsigned char* rec = p.emeta + (size_t)e * p.rec;
-  uint32_t rs[NNPE];
-  unsigned mk[NNPE];
+  // One RED per lane straight from the registers puts every lane of an instruction into its own 32-byte sector (64
+  // sectors per element; the L2 atomic units were the limiter, 131 G sectors/s at 128^3).  Instead every warp stages its 32
+  // element matrices and records in shared memory and walks them element by element with lane = (row r of 4, column c):
+  // the 8 columns of a row are 4 runs of two x-adjacent nodes, i.e. 16 instead of 32 sectors per RED instruction.
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  constexpr int KST = NNPE * NNPE + 1;                       // odd stride: conflict-free staging stores
+  constexpr int RECB = NNPE * 4 + NNPE * NNPE * 2 + 2 * NNPE;  // bytes of a record (rowstart | ecol | mask | rank)
+  constexpr int RECS = ((RECB + 15) / 16) * 16;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* kst = reinterpret_cast<double*>(sm_raw) + (size_t)warp * 32 * KST;
+  unsigned char* rst = sm_raw + (size_t)(blockDim.x >> 5) * 32 * KST * sizeof(double) + (size_t)warp * 32 * RECS;
+  if (live) {
 #pragma unroll
-  for (int a = 0; a < NNPE; ++a) { rs[a] = reinterpret_cast<const uint32_t*>(rec)[a]; mk[a] = rec[NNPE * 4 + NNPE * NNPE * 2 + a]; }
-  const uint16_t* ec = reinterpret_cast<const uint16_t*>(rec + NNPE * 4);
-  const uint32_t trash = (uint32_t)p.nnz + (((uint32_t)e * 613u) & 4095u);
+    for (int r = 0; r < NNPE; ++r)
 #pragma unroll
-  for (int r = 0; r < NNPE; ++r)     // storage row node
+      for (int c = 0; c < NNPE; ++c) kst[lane * KST + r * NNPE + c] = TRANS ? K[r][c] : K[c][r];   // storage (row r, col c)
+    const uint4* src = reinterpret_cast<const uint4*>(p.emeta + (size_t)e * p.rec);
+    uint4* dst = reinterpret_cast<uint4*>(rst + (size_t)lane * RECS);
 #pragma unroll
-    for (int c = 0; c < NNPE; ++c) { // storage column node
-      const bool ok = rs[r] != 0xFFFFFFFFu && (mk[c] & 1u);
-      const uint32_t idx = ok ? rs[r] + ec[r * NNPE + c] : (uint32_t)p.nnz + ((trash + r * 8u + c) & 4095u);
-      // CSR: K_glob[dof_r, dof_c] += K_el[c, r]; CSC storage holds the transpose of that
-      const double v = TRANS ? K[r][c] : K[c][r];
-      asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p.nz + idx), "d"(v));
+    for (int i = 0; i < RECS / 16; ++i) dst[i] = src[i];
+  }
+  __syncwarp();
+  {
+    const int e0 = blockIdx.x * 128 + warp * 32;
+    const int nel = (p.ne - e0) < 32 ? (p.ne - e0) : 32;
+    static_assert(NNPE == 8 || NNPE == 4, "lane = (row of 32 / NNPE, column)");
+    constexpr int RPI = 32 / NNPE;                           // rows per RED instruction
+    const int c = lane % NNPE, rl = lane / NNPE;
+    for (int el = 0; el < nel; ++el) {
+      const unsigned char* rec = rst + (size_t)el * RECS;
+      const uint32_t* rs = reinterpret_cast<const uint32_t*>(rec);
+      const uint16_t* ec = reinterpret_cast<const uint16_t*>(rec + NNPE * 4);
+      const bool colok = rec[NNPE * 4 + NNPE * NNPE * 2 + c] & 1u;
+      const uint32_t trash = (uint32_t)p.nnz + (((uint32_t)(e0 + el) * 613u) & 4095u);
+#pragma unroll
+      for (int it = 0; it < NNPE / RPI; ++it) {
+        const int r = it * RPI + rl;
+        const uint32_t rsr = rs[r];
+        const bool ok = rsr != 0xFFFFFFFFu && colok;
+        const uint32_t idx = ok ? rsr + ec[r * NNPE + c] : (uint32_t)p.nnz + ((trash + r * 8u + c) & 4095u);
+        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p.nz + idx), "d"(kst[el * KST + r * NNPE + c]));
+      }
     }
+  }
   zero_fill_end(p.zf);
 }
 
@@ -134,10 +161,17 @@ void run_mat_scalar(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   const int grid = (int)((b.ne + 127) / 128);
   p.zf = make_zero_fill(a, grid);
   const bool trans = (h->opts.matrix_type == FECB200_CSC);
+  constexpr int RECS = ((NNPE * 4 + NNPE * NNPE * 2 + 2 * NNPE + 15) / 16) * 16;
+  FEC_REQUIRE((int)b.emeta_rec >= RECS && b.emeta_rec % 16 == 0, "scalar matrix kernel: scatter record size mismatch");
+  const size_t smem = 128 * ((size_t)(NNPE * NNPE + 1) * sizeof(double) + RECS);
+  auto launch = [&](auto kern) {
+    FEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 128, smem, h->stream>>>(p);
+  };
   timing_begin(h);
-  if (a.kind == FECB200_MASS) k_mat_scalar<ND, NNPE, NQT, Phys, FECB200_MASS, false><<<grid, 128, 0, h->stream>>>(p);
-  else if (trans) k_mat_scalar<ND, NNPE, NQT, Phys, FECB200_STIFFNESS, true><<<grid, 128, 0, h->stream>>>(p);
-  else k_mat_scalar<ND, NNPE, NQT, Phys, FECB200_STIFFNESS, false><<<grid, 128, 0, h->stream>>>(p);
+  if (a.kind == FECB200_MASS) launch(k_mat_scalar<ND, NNPE, NQT, Phys, FECB200_MASS, false>);
+  else if (trans) launch(k_mat_scalar<ND, NNPE, NQT, Phys, FECB200_STIFFNESS, true>);
+  else launch(k_mat_scalar<ND, NNPE, NQT, Phys, FECB200_STIFFNESS, false>);
   FEC_CUDA(cudaGetLastError());
   timing_end(h);
   h->launches++;
