@@ -41,9 +41,10 @@ FLOPS_RESIDUAL = 7.0e3
 FLOPS_TANGENT = 34.0e3      # fused k_mat2: thread-level (2 DFMA + DMUL + DADD) per element, ncu r01z (36.6e3 before the tangent was re-factored)
 BYTES_ZERO_FILL = 1954.0   # fill!(storage, 0) of the CSR values (Matrix.jl:39): inside the kernel when double-buffered
 # DRAM bytes per launch of the dominant kernel from the `ncu --set full` capture of this same command at 192^3:
-#   double-buffered (default)  profiles/r01z_fused_kmat2_details.txt  dram__bytes_read.sum 17.30 GB + write 28.33 GB
+#   double-buffered (default)  profiles/r01zz_dram_compression.txt: dram__bytes_read.sum 8.68 GB + write 19.90 GB with the
+#                              compressible CSR value arrays (17.30 + 28.33 GB without, profiles/r01z_fused_kmat2_details.txt)
 #   --single-buffer            profiles/r01h_fused_kmat2_details.txt  read 16.80 GB + write 14.45 GB (memset separate)
-TRAFFIC_NCU_BYTES_PER_ELEMENT = {True: (17.298e9 + 28.329e9) / 7077888, False: (16.796e9 + 14.452e9) / 7077888}
+TRAFFIC_NCU_BYTES_PER_ELEMENT = {True: (8.68e9 + 19.90e9) / 7077888, False: (16.796e9 + 14.452e9) / 7077888}
 NEO_PROPS = np.array([1e3, 10.0e6, 1.0e6])
 
 
@@ -365,7 +366,7 @@ def run_gpu(args):
             del a
             roof = {"bound": "hbm", "kernel": "k_mat2<hex8,NF=3,neo-Hookean,WITH_R> (fused residual + tangent -> CSR" + (" + zero-fill of the idle value array)" if dbuf else ")"), "achieved": round(ach, 1),
                     "peak": hbm, "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / hbm, 4), "traffic": round(TRAFFIC_NCU_BYTES_PER_ELEMENT[dbuf] * ne_local),
-                    "traffic_note": ("dram read+write bytes per launch, ncu --set full (profiles/r01z_fused_kmat2_details.txt); 1.6x algorithmic: RED read-modify-write of the CSR values"
+                    "traffic_note": ("dram read+write bytes per launch, ncu (profiles/r01zz_dram_compression.txt): 1.0x algorithmic with the compressible CSR value arrays (zeros of the clear and of the first RED read stay compressed in HBM); 1.6x without"
                                      if dbuf else "dram read+write bytes per launch, ncu --set full (profiles/r01h_fused_kmat2_details.txt); 2.1x algorithmic: memset write-back + RED read-modify-write of the CSR values"),
                     "algorithmic_bytes_per_element": bytes_el, "kernel_ms": round(k_tan, 4),
                     "binding_resource": "on-chip, not HBM: l1tex LSU data-pipe wavefronts 74 % of peak (shared-memory operand / staging traffic + REDs), FP64 pipe 52 % busy, DRAM side alone 12.3 ms of the 16.0 (ncu profiles/r01z_fused_kmat2_details.txt, knock-out sweep profiles/r01u_ko_sweep.txt; DESIGN.md section 5)",

@@ -29,7 +29,7 @@ if VARIANT:
     OBJ = os.path.join(HERE, "build", VARIANT)
     LIB = os.path.join(LIBDIR, f"libfecb200_{VARIANT}.so")
 
-SOURCES = ["api.cu", "aux.cu", "plan.cu", "loads.cu", "dispatch_hex8.cu", "dispatch_quad_tri.cu", "dispatch_tet.cu"]
+SOURCES = ["api.cu", "aux.cu", "plan.cu", "loads.cu", "vmm.cu", "dispatch_hex8.cu", "dispatch_quad_tri.cu", "dispatch_tet.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", "kernel_mat2.cuh", "kernel_mat2c.cuh", "kernel_mat2w.cuh", "kernel_mat_scalar.cuh", "physics.cuh", os.path.join("..", "..", "include", "fecb200.h")]
 
 
@@ -63,7 +63,7 @@ def build(force=False, jobs=None, verbose=True):
                     raise RuntimeError(f"nvcc failed on {src}")
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if todo or not os.path.exists(LIB):
-        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, METIS, "-Xcompiler", "-fopenmp", "-lgomp"]
+        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, METIS, "-Xcompiler", "-fopenmp", "-lgomp", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -631,7 +631,7 @@ int fecb200_set_matrix_double_buffer(fecb200_handle* h, int32_t enable) {
   ensure_matrix_structure(h);
   if (!h->double_buffer) { FEC_CUDA(cudaStreamSynchronize(h->stream)); h->d_nz_stiff_alt.release(); h->alt_clean = false; }
   else if (h->matrix_ready && !h->opts.matrix_free && !h->d_nz_stiff_alt.p) {
-    h->d_nz_stiff_alt.alloc(nz_alloc_len(h));
+    h->d_nz_stiff_alt.alloc_compressible(nz_alloc_len(h), h->device);
     h->d_nz_stiff_alt.zero(h->stream);
     h->alt_clean = true;
   }

@@ -36,20 +36,44 @@ struct Error : std::runtime_error {
     if (!(cond)) throw fec::Error(std::string("fecb200: ") + (msg));                       \
   } while (0)
 
+// vmm.cu: compressible allocations through the driver's virtual-memory API (nullptr = not available)
+void* vmm_alloc_compressible(int device, size_t bytes, size_t* mapped, unsigned long long* handle);
+void vmm_free(void* p, size_t mapped, unsigned long long handle);
+
 template <class T>
 struct DevBuf {  // owning device array
   T* p = nullptr;
   size_t n = 0;
+  size_t vmm_bytes = 0;              // != 0: p came from vmm_alloc_compressible
+  unsigned long long vmm_handle = 0;
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), vmm_bytes(o.vmm_bytes), vmm_handle(o.vmm_handle) { o.p = nullptr; o.n = 0; o.vmm_bytes = 0; }
   DevBuf& operator=(DevBuf&& o) noexcept {
-    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    if (this != &o) {
+      release();
+      p = o.p; n = o.n; vmm_bytes = o.vmm_bytes; vmm_handle = o.vmm_handle;
+      o.p = nullptr; o.n = 0; o.vmm_bytes = 0;
+    }
     return *this;
   }
   ~DevBuf() { release(); }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() {
+    if (p) { if (vmm_bytes) vmm_free(p, vmm_bytes, vmm_handle); else cudaFree(p); }
+    p = nullptr; n = 0; vmm_bytes = 0;
+  }
+  // a compressible allocation when the driver offers one (see vmm.cu; FECB200_COMPRESS=0 opts out), cudaMalloc otherwise
+  void alloc_compressible(size_t count, int device) {
+    release();
+    const char* env = getenv("FECB200_COMPRESS");
+    if (count && !(env && env[0] == '0')) {
+      void* q = vmm_alloc_compressible(device, count * sizeof(T), &vmm_bytes, &vmm_handle);
+      if (q) { p = static_cast<T*>(q); n = count; return; }
+      vmm_bytes = 0;
+    }
+    alloc(count);
+  }
   void alloc(size_t count) {
     release();
     n = count;

@@ -527,11 +527,11 @@ void build_matrix_structure(fecb200_handle* h) {
   h->d_freemask.upload(h->freemask_h, h->stream);
   h->d_rowstart.upload(h->rowstart_h, h->stream);
   h->d_diagslot.upload(diag, h->stream);
-  h->d_nz_stiff.alloc(nz_alloc_len(h));
+  h->d_nz_stiff.alloc_compressible(nz_alloc_len(h), h->device);
   h->d_nz_stiff.zero(h->stream);
   h->d_nz_stiff_alt.release();
   h->alt_clean = false;
-  if (h->double_buffer) { h->d_nz_stiff_alt.alloc(nz_alloc_len(h)); h->d_nz_stiff_alt.zero(h->stream); h->alt_clean = true; }
+  if (h->double_buffer) { h->d_nz_stiff_alt.alloc_compressible(nz_alloc_len(h), h->device); h->d_nz_stiff_alt.zero(h->stream); h->alt_clean = true; }
   h->d_nz_mass.release();
   h->matrix_ready = true;
   h->stiff_adjusted = h->mass_adjusted = false;
