@@ -143,3 +143,71 @@ def test_element_function_tokens():
         kind_of(lambda *a: 0, (_lib.RESIDUAL,))
     with pytest.raises(ValueError):
         kind_of(F.stiffness, (_lib.RESIDUAL,))
+
+
+# ---- side sets, surface tables and the load containers of the host mirror (no GPU needed) ----------------------
+
+@pytest.mark.parametrize("el,counts", [("quad", (6, 4)), ("tri", (5, 7)), ("hex", (4, 3, 5))])
+def test_structured_sidesets_match_the_oracle_and_the_nodesets(el, counts):
+    """QUAD4 / TRI3: the reference's own loops (src/meshes/StructuredMesh.jl:257-330, 355-431); HEX8: the faces that lie on
+    the named boundary.  Every side's nodes are in the node set of the same name, and the generic finder
+    (_sidesets_from_nodesets, used for meshes without side-set records) recovers the same sides."""
+    nd = len(counts)
+    m = F.StructuredMesh(el, (0.,) * nd, (1.,) * nd, counts)
+    osets = O.structured_sidesets(el, counts)
+    conn = m.element_conns["block_1"]
+    found = m._sidesets_from_nodesets(m.nodeset_nodes)
+    for name, (oe, os_) in osets.items():
+        assert np.array_equal(m.sideset_elems[name], oe) and np.array_equal(m.sideset_sides[name], os_)
+        sn = O.side_nodes(m.element_types["block_1"], conn, oe, os_)
+        assert np.array_equal(m.sideset_side_nodes[name], sn)
+        assert set(np.unique(sn)) == set(m.nodeset_nodes[name].tolist())
+        fe, fs = found[name]
+        assert sorted(zip(fe.tolist(), fs.tolist())) == sorted(zip(oe.tolist(), os_.tolist()))
+
+
+@pytest.mark.parametrize("et", ["QUAD4", "TRI3", "HEX8", "TETRA4", "TETRA10"])
+def test_surface_tables_match_the_oracle_and_integrate_exactly(et):
+    """the host's surface tables (what a Julia host reads from ReferenceFiniteElements) against the oracle's: partition of
+    unity, zero-sum gradients, weights = measure of the reference side (2 for [-1,1], 4 for [-1,1]^2, 1/2 for the triangle)"""
+    Ns, dNs, ws = F.ReferenceFE(et).surface_tables()
+    oN, odN, ow = O.surface_tables(et, "gauss2")
+    assert np.allclose(Ns, oN, atol=1e-15) and np.allclose(dNs, odN, atol=1e-15) and np.allclose(ws, ow, atol=1e-15)
+    assert np.allclose(Ns.sum(axis=1), 1.0) and np.allclose(dNs.sum(axis=1), 0.0, atol=1e-14)
+    assert np.isclose(ws.sum(), {"QUAD4": 2.0, "TRI3": 2.0, "HEX8": 4.0, "TETRA4": 0.5, "TETRA10": 0.5}[et])
+
+
+def test_neumann_and_source_containers_evaluate_at_the_oracles_points():
+    """NeumannBCs / Sources (src/bcs/NeumannBCs.jl:60-71,157-171, Sources.jl:55-66): vals[d, q, e] = func(X_q, t)[d] at the
+    same quadrature points, in the same [NF, NQ, n] layout, as the oracle's restatement."""
+    m = F.StructuredMesh("hex", (0., 0., 0.), (1., 2., 1.5), (4, 3, 5))
+    rng = np.random.default_rng(2)
+    X = np.asarray(m.nodal_coords)
+    X += rng.uniform(-0.02, 0.02, X.shape)
+    V = F.FunctionSpace(m, F.H1Field, F.Lagrange)
+    dof = F.DofManager(F.VectorFunction(V, "displ"))
+    f = lambda X, t: np.stack([X[:, 0] + t, X[:, 1] * X[:, 2], np.sin(X[:, 0]) - t], axis=1)
+    nb = F.NeumannBCs(m, dof, [F.NeumannBC("displ_y", f, "top"), F.NeumannBC("displ_x", f, "left")])
+    nb.update_bc_values(X, 0.3)
+    tabs = O.surface_tables("HEX8", "gauss2")
+    for c, name in zip(nb.bc_caches, ("top", "left")):
+        sn = np.asarray(m.sideset_side_nodes[name])
+        Xq = O.surface_quadrature_points(sn, tabs, X)                          # (nqs, nsides, ND)
+        want = f(Xq.reshape(-1, 3), 0.3).reshape(Xq.shape[0], Xq.shape[1], 3).transpose(2, 0, 1)
+        assert c["vals"].shape == want.shape and np.allclose(c["vals"], want, rtol=1e-14, atol=1e-14)
+        assert c["vals"].flags.f_contiguous                                     # [NF, nqs, nsides] as the ABI expects
+    src = F.Sources(m, dof, [F.Source("displ_x", f, "block_1")])
+    src.update_source_values(V, 0.3)
+    blk = O.Block(m.element_conns["block_1"], O.ref_fe_tables("HEX8", "gauss2"), O.LinearElastic(3))
+    Xq = O.cell_quadrature_points(blk, X)
+    want = f(Xq.reshape(-1, 3), 0.3).reshape(Xq.shape[0], Xq.shape[1], 3).transpose(2, 0, 1)
+    assert np.allclose(src.vals[0], want, rtol=1e-14, atol=1e-14)
+    with pytest.raises(ValueError):
+        F.NeumannBCs(m, dof, [F.NeumannBC("nope", f, "top")])
+    with pytest.raises(KeyError):
+        F.Sources(m, dof, [F.Source("displ_x", f, "block_7")])
+    # scalar-valued functions broadcast for NF = 1
+    dof1 = F.DofManager(F.ScalarFunction(V, "u"))
+    nb1 = F.NeumannBCs(m, dof1, [F.NeumannBC("u", lambda X, t: -1.0, "right")])
+    nb1.update_bc_values(X, 0.0)
+    assert nb1.bc_caches[0]["vals"].shape[0] == 1 and np.all(nb1.bc_caches[0]["vals"] == -1.0)
