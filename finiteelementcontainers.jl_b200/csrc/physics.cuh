@@ -173,7 +173,7 @@ struct PhysMech3 {
 // -------------------------------------------------------------------------------------------
 struct LinearElasticImpl {
   static constexpr int NS = 0;
-  static constexpr bool kScalesTangent = false;
+  static constexpr bool kScalesTangent = true;    // A is linear in (K, G): a scale factor goes into the two moduli
   static constexpr bool kHasEnergy = true;
   struct Pre { double K, G; };
   // psi = 1/2 K tr(eps)^2 + G dev(eps):dev(eps)   (TestMechanicsCommon.jl:14-20)
@@ -205,6 +205,7 @@ struct LinearElasticImpl {
   FEC_DEV static void prepare(const double (&)[3][3], const double* props, const double*, Pre& p) {
     p.K = props[1]; p.G = props[2];
   }
+  FEC_DEV static void scale_tangent(Pre& p, const double s) { p.K *= s; p.G *= s; }
   FEC_DEV static double A(const Pre& p, int i, int j, int k, int l) {
     const double dij = (i == j), dkl = (k == l), dik = (i == k), djl = (j == l), dil = (i == l), djk = (j == k);
     return (p.K - 2.0 * p.G / 3.0) * dij * dkl + p.G * (dik * djl + dil * djk);
