@@ -158,3 +158,42 @@ def test_brick_partition_matches_general_builder():
             return {tuple(sorted(p.local_to_global[c - 1])) for c in lm.element_conns[blk].T} if blk in lm.element_conns else set()
         assert gl(lm_b, pb, "owned") == gl(lm_g, pg, "owned") and gl(lm_b, pb, "halo") == gl(lm_g, pg, "halo")
         assert np.allclose(np.asarray(lm_b.nodal_coords)[:, :pb.n_owned_nodes], np.asarray(lm_g.nodal_coords)[:, :pg.n_owned_nodes])
+
+
+@pytest.mark.parametrize("how", ["bricks", "metis"])
+def test_rank_local_sidesets_tile_the_global_ones(how):
+    """surface loads on a partition: the side sets of the rank-local meshes are faces of OWNED elements only and,
+    mapped back to global node ids, tile the global side set exactly once (no face lost, none counted twice), so
+    summing the ranks' Neumann vectors over the halo gives the serial vector."""
+    n, grid, P = 4, (2, 1, 1), 2
+    gmesh = F.StructuredMesh("hex", (0., 0., 0.), (2., 1., 1.), (2 * n + 1, n + 1, n + 1))
+    locals_ = []
+    if how == "bricks":
+        for r in range(P):
+            locals_.append(structured_brick_partition(F, n, grid, r))
+    else:
+        epart = metis_partition_elements(gmesh, P)
+        for r in range(P):
+            locals_.append(partition_mesh(gmesh, epart, P, r))
+    tabs = O.surface_tables("HEX8", "gauss2")
+    Xg = np.asarray(gmesh.nodal_coords)
+    for name in ("top", "right", "front", "left"):
+        key = lambda cols: sorted(tuple(sorted(c)) for c in cols.T.tolist())
+        want = key(np.asarray(gmesh.sideset_side_nodes[name]))
+        got = []
+        Rsum = np.zeros(3 * gmesh.num_nodes())
+        for lm, part in locals_:
+            sn = np.asarray(lm.sideset_side_nodes[name])
+            n_owned_el = lm.element_conns["owned"].shape[1]
+            assert np.all(np.asarray(lm.sideset_elems[name]) <= n_owned_el)          # faces of owned elements only
+            if sn.size:
+                gsn = part.local_to_global[sn - 1]
+                got += key(gsn)
+                # the rank's Neumann vector, scattered to global numbering (what the halo sum + owner add up to)
+                Xl = np.asarray(lm.nodal_coords)
+                Rl = O.assemble_vector_neumann_bc(np.zeros(3 * Xl.shape[1]), sn, tabs, np.ones((3, 4, sn.shape[1])), Xl, 3)
+                np.add.at(Rsum.reshape(-1, 3), part.local_to_global - 1, Rl.reshape(-1, 3))
+        assert sorted(got) == want
+        Rg = O.assemble_vector_neumann_bc(np.zeros(3 * gmesh.num_nodes()), np.asarray(gmesh.sideset_side_nodes[name]), tabs,
+                                          np.ones((3, 4, len(want))), Xg, 3)
+        assert np.allclose(Rsum, Rg, rtol=1e-13, atol=1e-15)
