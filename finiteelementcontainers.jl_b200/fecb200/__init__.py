@@ -8,7 +8,8 @@ from ._lib import FECError
 from .fields import H1Field, Connectivity
 from .meshes import StructuredMesh, UnstructuredMesh, KuhnTet10Mesh
 from .reference_fe import ReferenceFE
-from .function_spaces import FunctionSpace, Lagrange, ScalarFunction, VectorFunction, DofManager
+from .function_spaces import (FunctionSpace, Lagrange, ScalarFunction, VectorFunction, DofManager, update_field_unknowns,
+                              extract_field_unknowns, update_field_dirichlet_bcs)
 from .bcs import DirichletBC, DirichletBCs, NeumannBC, NeumannBCs, Source, Sources, TimeStepper
 from .physics import (AbstractPhysics, Poisson, Mechanics, NeoHookean, J2Plasticity, ThreeDimensional, PlaneStrain,
                       residual, residual_b, stiffness, stiffness_b, mass, mass_b, stiffness_action,

@@ -85,3 +85,36 @@ class DofManager:
 
     def dof_index(self, var_name):
         return self.var.names().index(var_name)  # 0-based component
+
+
+# ---- host-side field helpers of the DofManager (src/DofManagers.jl:203-213, 349-411, src/bcs/DirichletBCs.jl:411-418) --
+# Inside every assemble_* call the library does these three steps on the device (k_update_field); the functions below
+# are the same index copies for a caller's own HOST fields (post-processing, initial guesses), like the reference's CPU
+# methods.  `U` is an H1Field (or its flat data), indices are the DofManager's 1-based dof ids.
+
+def _flat(U):
+    return U.data_flat if hasattr(U, "data_flat") else np.asarray(U).reshape(-1)
+
+
+def update_field_unknowns(U, dof, Uu):
+    """update_field_unknowns!(U, dof, Uu): U[unknown_dofs] = Uu (non-condensed) or Uu[unknown_dofs] (condensed)"""
+    f, ud = _flat(U), np.asarray(dof.unknown_dofs) - 1
+    Uu = np.asarray(Uu)
+    if dof.condensed:
+        assert Uu.shape[0] == f.shape[0]
+        f[ud] = Uu[ud]
+    else:
+        assert Uu.shape[0] == len(ud)
+        f[ud] = Uu
+
+
+def extract_field_unknowns(Uu, dof, U):
+    """extract_field_unknowns!(Uu, dof, U): Uu[n] = U[unknown_dofs[n]]"""
+    Uu[:len(dof.unknown_dofs)] = _flat(U)[np.asarray(dof.unknown_dofs) - 1]
+
+
+def update_field_dirichlet_bcs(U, bcs):
+    """update_field_dirichlet_bcs!(U, bcs): U[dofs[i]] = vals[i], in order (a later BC wins on a shared dof)"""
+    f = _flat(U)
+    for d, v in zip(np.asarray(bcs.dofs) - 1, np.asarray(bcs.vals)):
+        f[d] = v

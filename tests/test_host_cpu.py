@@ -211,3 +211,40 @@ def test_neumann_and_source_containers_evaluate_at_the_oracles_points():
     nb1 = F.NeumannBCs(m, dof1, [F.NeumannBC("u", lambda X, t: -1.0, "right")])
     nb1.update_bc_values(X, 0.0)
     assert nb1.bc_caches[0]["vals"].shape[0] == 1 and np.all(nb1.bc_caches[0]["vals"] == -1.0)
+
+
+def test_field_helpers_of_the_dofmanager():
+    """update_field_unknowns! / extract_field_unknowns! / update_field_dirichlet_bcs! on host fields
+    (src/DofManagers.jl:203-213, 349-411; src/bcs/DirichletBCs.jl:411-418) against the oracle's _update_field."""
+    m = F.StructuredMesh("quad", (0., 0.), (1., 1.), (5, 4))
+    V = F.FunctionSpace(m, F.H1Field, F.Lagrange)
+    u = F.VectorFunction(V, "displ")
+    rng = np.random.default_rng(4)
+    for condensed in (False, True):
+        dof = F.DofManager(u, use_condensed=condensed)
+        dbcs = F.DirichletBCs(m, dof, [F.DirichletBC("displ_x", lambda X, t: X[:, 1] + t, nodeset_name="left"),
+                                       F.DirichletBC("displ_y", lambda X, t: np.full(len(X), 2.0), nodeset_name="left"),
+                                       F.DirichletBC("displ_x", lambda X, t: np.full(len(X), 7.0), nodeset_name="bottom")])
+        dbcs.update_bc_values(m.nodal_coords, 0.5)
+        dd = dbcs.dirichlet_dofs()
+        od = O.update_dofs(2, m.num_nodes(), dd)
+        dof.unknown_dofs, dof.dof_to_unknown, dof.dirichlet_dofs = od["unknown_dofs"], od["dof_to_unknown"], dd
+        n = len(dof) if condensed else len(dof.unknown_dofs)
+        Uu = rng.standard_normal(n)
+        U = F.H1Field.zeros(2, m.num_nodes())
+        F.update_field_dirichlet_bcs(U, dbcs)
+        F.update_field_unknowns(U, dof, Uu)
+        blk = O.Block(m.element_conns["block_1"], O.ref_fe_tables("QUAD4", "gauss2"), O.LinearElastic(2))
+        oasm = O.OracleAssembler(np.asarray(m.nodal_coords), [blk], 2, condensed=condensed)
+        oasm.update_dofs(dd)
+        vals = np.zeros(len(dd))
+        for d, v in zip(dbcs.dofs, dbcs.vals):                 # later BCs win on shared dofs (bottom-left corner)
+            vals[np.searchsorted(dd, d)] = v
+        oasm.bc_vals[:] = vals
+        oasm._update_field(oasm.field, Uu)
+        assert np.array_equal(U.data_flat, oasm.field)
+        back = np.zeros(n)
+        F.extract_field_unknowns(back, dof, U)
+        ud = dof.unknown_dofs - 1
+        assert np.array_equal(back[:len(ud)], U.data_flat[ud])
+        assert U[0, m.nodeset_nodes["bottom"][0] - 1] == 7.0      # corner node: the bottom BC was applied last
