@@ -389,3 +389,21 @@ def test_surface_and_body_loads_integrate_area_and_volume(el):
     R = O.assemble_vector_source(np.zeros(nf * X.shape[1]), blk, np.ones((nf, len(blk.w), conn.shape[1])), X, nf)
     # curved (perturbed mid-edge) TETRA10 cells have a cubic det J, which the degree-2 rule integrates only approximately
     assert np.allclose(R.reshape(-1, nf).sum(axis=0), -vol, rtol=1e-4 if el == "TETRA10" else 1e-12)
+
+
+def test_surface_loads_are_linear_and_rotation_invariant():
+    """properties of the oracle's surface integrals that do not depend on the mesh size: linear in the flux values, and
+    the total load of a constant normal-free flux is unchanged by a rigid rotation of the mesh (|t_0 x t_1| is)."""
+    rng = np.random.default_rng(9)
+    m = O.structured_mesh("hex", (0., 0., 0.), (1., 1.5, 2.), (4, 4, 3))
+    X, conn = m["coords"].copy(), m["conn"]
+    X += rng.uniform(-0.04, 0.04, X.shape)
+    el, sd = O.structured_sidesets("hex", (4, 4, 3))["front"]
+    sn = O.side_nodes("HEX8", conn, el, sd)
+    tabs = O.surface_tables("HEX8", "gauss2")
+    v1, v2 = rng.standard_normal((3, 4, sn.shape[1])), rng.standard_normal((3, 4, sn.shape[1]))
+    R = lambda v, XX: O.assemble_vector_neumann_bc(np.zeros(3 * XX.shape[1]), sn, tabs, v, XX, 3)
+    assert np.allclose(R(2.0 * v1 - 0.5 * v2, X), 2.0 * R(v1, X) - 0.5 * R(v2, X), rtol=1e-13, atol=1e-15)
+    Q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+    ones = np.ones((3, 4, sn.shape[1]))
+    assert np.allclose(R(ones, X).reshape(-1, 3).sum(axis=0), R(ones, Q @ X).reshape(-1, 3).sum(axis=0), rtol=1e-12)
