@@ -248,3 +248,54 @@ def test_field_helpers_of_the_dofmanager():
         ud = dof.unknown_dofs - 1
         assert np.array_equal(back[:len(ud)], U.data_flat[ud])
         assert U[0, m.nodeset_nodes["bottom"][0] - 1] == 7.0      # corner node: the bottom BC was applied last
+
+
+def test_postprocessor_writes_a_readable_exodus_file(tmp_path):
+    """PostProcessor / write_times / write_field / close (src/PostProcessors.jl:27-49, src/meshes/Exodus.jl:148-282), the
+    output side of the reference's regression tests (TestPoisson.jl:88-97): the file is Exodus II over NetCDF classic and
+    reads back -- mesh, sets and the nodal field -- through this package's own Exodus reader."""
+    from scipy.io import netcdf_file
+    g = np.load(os.path.join(GOLDEN, "poisson_g.npz"))
+    mesh = F.UnstructuredMesh(os.path.join(GOLDEN, "poisson_g.npz"))
+    V = F.FunctionSpace(mesh, F.H1Field, F.Lagrange)
+    u = F.ScalarFunction(V, "u")
+    out = str(tmp_path / "poisson_out.e")
+    pp = F.PostProcessor(mesh, out, u)
+    F.write_times(pp, 1, 0.0)
+    F.write_field(pp, 1, ("u",), F.H1Field(g["gold_u"]))
+    F.write_times(pp, 2, 0.5)
+    F.write_field(pp, 2, ("u",), F.H1Field(2.0 * g["gold_u"]))
+    with pytest.raises(KeyError):
+        F.write_field(pp, 1, ("v",), F.H1Field(g["gold_u"]))
+    F.close(pp)
+    assert open(out, "rb").read(4) == b"CDF\x02"
+    back = F.UnstructuredMesh(out)
+    assert np.array_equal(np.asarray(back.nodal_coords), np.asarray(mesh.nodal_coords))
+    assert back.element_block_names == mesh.element_block_names and back.element_types == mesh.element_types
+    assert np.array_equal(back.element_conns["block_1"], mesh.element_conns["block_1"])
+    for k in mesh.sideset_elems:
+        assert np.array_equal(back.sideset_elems[k], mesh.sideset_elems[k]) and np.array_equal(back.sideset_sides[k], mesh.sideset_sides[k])
+    nc = netcdf_file(out, "r", mmap=False)
+    assert b"".join(nc.variables["name_nod_var"].data[0]).split(b"\x00")[0] == b"u"
+    assert np.allclose(nc.variables["time_whole"].data, [0.0, 0.5])
+    vals = np.array(nc.variables["vals_nod_var1"].data)
+    assert vals.shape == (2, mesh.num_nodes()) and np.array_equal(vals[0], g["gold_u"]) and np.array_equal(vals[1], 2.0 * g["gold_u"])
+    assert nc.variables["connect1"].elem_type.decode().strip() == "QUAD4"
+    nc.close()
+    # vector functions: one variable per component, 3-D structured mesh with generated side sets
+    m3 = F.StructuredMesh("hex", (0., 0., 0.), (1., 1., 1.), (3, 4, 3))
+    d3 = F.VectorFunction(F.FunctionSpace(m3, F.H1Field, F.Lagrange), "displ")
+    out3 = str(tmp_path / "cube.exo")
+    pp = F.PostProcessor(m3, out3, d3, extra_nodal_names=["pressure"])
+    assert pp.nodal_names == ["displ_x", "displ_y", "displ_z", "pressure"]
+    U = F.H1Field(np.arange(3.0 * m3.num_nodes()).reshape(3, -1, order="F"))
+    F.write_field(pp, 1, d3.names(), U)
+    pp.close()
+    b3 = F.UnstructuredMesh(out3)
+    assert np.array_equal(b3.element_conns["block_1"], m3.element_conns["block_1"])
+    assert set(b3.sideset_elems) == set(m3.sideset_elems)
+    nc = netcdf_file(out3, "r", mmap=False)
+    assert np.array_equal(np.array(nc.variables["vals_nod_var2"].data)[0], np.asarray(U)[1])
+    nc.close()
+    with pytest.raises(RuntimeError):
+        F.PostProcessor(m3, str(tmp_path / "cube.vtk"), d3)
