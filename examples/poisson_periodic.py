@@ -22,20 +22,11 @@ u_exact = np.cos(2 * np.pi * X[0]) + 0.5 * np.cos(4 * np.pi * X[1]) + 0.25 * np.
 V = F.FunctionSpace(mesh, F.H1Field, F.Lagrange)
 u = F.ScalarFunction(V, "u")
 asm = F.SparseMatrixAssembler(u, sparse_matrix_type="csc", use_condensed=False)
-p = F.create_parameters(mesh, asm, F.Poisson(f), None, dirichlet_bcs=[])
-
-
-def pairs(side_a, side_b, axis):
-    """host-side PeriodicBC bookkeeping (src/bcs/PeriodicBCs.jl): match nodes by the other coordinate"""
-    other = 1 - axis
-    lookup = {round(float(X[other, b - 1]), 9): b for b in mesh.nodeset_nodes[side_b]}
-    a = mesh.nodeset_nodes[side_a]
-    return a, np.array([lookup[round(float(X[other, n_ - 1]), 9)] for n_ in a])
-
-
-a1, b1 = pairs("left", "right", 0)
-a2, b2 = pairs("bottom", "top", 1)
-F.update_dofs(asm, p.dirichlet_bcs, periodic=(np.concatenate([a1, a2]), np.concatenate([b1, b2])))
+# PeriodicBC(var, direction, func, side_a, side_b) (src/bcs/PeriodicBCs.jl:1-15): `direction` is the coordinate along which the
+# two sides run and by which their nodes are matched; func is the jump U[b] = U[a] + func(X_b, t)
+zero = lambda X, t: np.zeros(len(X))
+pbcs = [F.PeriodicBC("u", "y", zero, "left", "right"), F.PeriodicBC("u", "x", zero, "bottom", "top")]
+p = F.create_parameters(mesh, asm, F.Poisson(f), None, dirichlet_bcs=[], periodic_bcs=pbcs)
 solver = F.NewtonSolver(F.IterativeLinearSolver(asm, "cg"))
 F.QuasiStaticIntegrator(solver).evolve(p)
 err = np.abs(p.field.data_flat - u_exact).max()

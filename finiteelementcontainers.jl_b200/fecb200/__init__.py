@@ -10,7 +10,8 @@ from .meshes import StructuredMesh, UnstructuredMesh, KuhnTet10Mesh
 from .reference_fe import ReferenceFE
 from .function_spaces import (FunctionSpace, Lagrange, ScalarFunction, VectorFunction, DofManager, update_field_unknowns,
                               extract_field_unknowns, update_field_dirichlet_bcs)
-from .bcs import DirichletBC, DirichletBCs, NeumannBC, NeumannBCs, Source, Sources, TimeStepper
+from .bcs import (DirichletBC, DirichletBCs, NeumannBC, NeumannBCs, PeriodicBC, PeriodicBCs, Source, Sources,
+                  TimeStepper)
 from .physics import (AbstractPhysics, Poisson, Mechanics, NeoHookean, J2Plasticity, ThreeDimensional, PlaneStrain,
                       residual, residual_b, stiffness, stiffness_b, mass, mass_b, stiffness_action,
                       stiffness_action_b, mass_action, mass_action_b, lumped_mass, energy)

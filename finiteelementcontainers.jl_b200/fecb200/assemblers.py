@@ -18,7 +18,7 @@ import scipy.sparse as sp
 
 from . import _lib
 from ._lib import FECError, check, lib
-from .bcs import DirichletBCs, NeumannBCs, Sources, TimeStepper
+from .bcs import DirichletBCs, NeumannBCs, PeriodicBCs, Sources, TimeStepper
 from .fields import H1Field
 from .function_spaces import AbstractFunction, DofManager
 from .physics import AbstractPhysics, Poisson, kind_of
@@ -133,11 +133,12 @@ class Parameters:
     """The slice of Parameters (src/Parameters.jl:37-73) the hot path touches; device-resident
     fields live inside the handle (`p |> cuda`)."""
 
-    def __init__(self, mesh, asm, physics, props, dirichlet_bcs, times, neumann_bcs=None, sources=None):
+    def __init__(self, mesh, asm, physics, props, dirichlet_bcs, times, neumann_bcs=None, sources=None, periodic_bcs=None):
         self.mesh, self.asm = mesh, asm
         self.physics, self.properties = physics, props
         self.dirichlet_bcs = dirichlet_bcs
         self.neumann_bcs, self.sources = neumann_bcs, sources
+        self.periodic_bcs = periodic_bcs
         self.times = times
         self.coords = mesh.nodal_coords
 
@@ -169,7 +170,8 @@ def _per_block(x, nb, kind):
     return [x] * nb
 
 
-def create_parameters(mesh, asm, physics, props=None, *, dirichlet_bcs=(), neumann_bcs=(), sources=(), times=None):
+def create_parameters(mesh, asm, physics, props=None, *, dirichlet_bcs=(), neumann_bcs=(), sources=(), periodic_bcs=(),
+                      times=None):
     """create_parameters(mesh, asm, physics, props; dirichlet_bcs, neumann_bcs, sources, times)  (src/Parameters.jl:288-302):
     builds the device handle (the `|> cuda` step), the BC containers, and calls update_dofs!."""
     fspace = asm.dof.var.fspace
@@ -193,8 +195,9 @@ def create_parameters(mesh, asm, physics, props=None, *, dirichlet_bcs=(), neuma
     dbcs = DirichletBCs(mesh, asm.dof, list(dirichlet_bcs))
     nbcs = NeumannBCs(mesh, asm.dof, list(neumann_bcs))
     srcs = Sources(mesh, asm.dof, list(sources))
-    p = Parameters(mesh, asm, physics_list, props_list, dbcs, times, nbcs, srcs)
-    update_dofs(asm, dbcs)
+    pbcs = PeriodicBCs(mesh, asm.dof, list(periodic_bcs))
+    p = Parameters(mesh, asm, physics_list, props_list, dbcs, times, nbcs, srcs, pbcs)
+    update_dofs(asm, dbcs, periodic=pbcs.periodic_dofs())      # update_dofs!(asm, dbcs, pbcs) (Parameters.jl:118-125)
     for i, c in enumerate(nbcs.bc_caches):   # the side sets' geometry is uploaded once (`p |> cuda`)
         sn, snp = _lib.i64(c["side_nodes"].reshape(-1, order="F"))
         Ns, Nsp = _lib.f64(c["Ns"]); dNs, dNsp = _lib.f64(c["dNs"]); ws, wsp = _lib.f64(c["ws"])
@@ -228,6 +231,7 @@ def update_dofs(asm, dbcs, periodic=((), ())):
     pb, pbp = _lib.i64(periodic[1])
     check(lib.fecb200_update_dofs(asm._require(), ddp, len(dd), pap, pbp, len(pa)))
     asm.dof.dirichlet_dofs = dd
+    asm.dof.periodic_side_a_dofs, asm.dof.periodic_side_b_dofs = pa, pb
     asm._refresh_dof_maps()
     asm._pattern = None
 
@@ -239,6 +243,14 @@ def update_bc_values(p):
     d, dp = _lib.i64(bcs.dofs)
     v, vp = _lib.f64(bcs.vals)
     check(lib.fecb200_set_dirichlet_values(p.asm._require(), dp, vp, len(d)))
+    if getattr(p, "periodic_bcs", None) is not None and len(p.periodic_bcs):    # jump values U[b] = U[a] + val
+        p.periodic_bcs.update_bc_values(p.coords, p.times.time_current)
+        # the library keeps one value per (de-duplicated, chain-resolved) pair in registration order and checks the count;
+        # all-zero jumps (the default inside the library) need no call
+        pv = p.periodic_bcs.values()
+        if np.any(pv != 0.0):
+            v, vp = _lib.f64(pv)
+            check(lib.fecb200_set_periodic_values(p.asm._require(), vp, len(v)))
     if p.neumann_bcs is not None and len(p.neumann_bcs):     # update_bc_values!(p.neumann_bcs, asm, X, t)
         p.neumann_bcs.update_bc_values(p.coords, p.times.time_current)
         for i, c in enumerate(p.neumann_bcs.bc_caches):

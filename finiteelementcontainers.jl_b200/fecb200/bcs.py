@@ -169,3 +169,65 @@ class Sources:
             n = Xq.shape[0] * Xq.shape[1]
             v = _as_values(func(Xq.reshape(n, -1), t), n, self.nf)
             self.vals[i] = np.asfortranarray(v.reshape(Xq.shape[0], Xq.shape[1], self.nf).transpose(2, 1, 0))
+
+
+class PeriodicBC:
+    """PeriodicBC(var_name, direction, func, side_a_sset, side_b_sset)  (src/bcs/PeriodicBCs.jl:1-15).  `direction` is the
+    coordinate ALONG which the two sides run and by which their nodes are matched (:62-81: key = round(X[dir, node] / tol));
+    `func(X, t)` is the jump U[b] = U[a] + func(X_b, t) (:253-262)."""
+
+    def __init__(self, var_name, direction, func, side_a_sset, side_b_sset):
+        self.var_name, self.direction, self.func = var_name, direction, func
+        self.side_a_sset, self.side_b_sset = side_a_sset, side_b_sset
+
+
+class PeriodicBCs:
+    """PeriodicBCs(mesh, dof, periodic_bcs) (src/bcs/PeriodicBCs.jl:17-110): per BC the side-a dofs / nodes (sorted, unique)
+    and the side-b dofs / nodes matched to them.  In 3-D the reference's single-coordinate key cannot tell apart the nodes
+    of a face (its `_transverse_key` is commented out, :63,:69); here every coordinate except the one the two sides differ
+    in is part of the key, which is the same thing in 2-D."""
+
+    def __init__(self, mesh, dof, pbcs, tolerance=1.0e-6):
+        X = np.asarray(mesh.nodal_coords)
+        nd, nf = X.shape[0], dof.nf
+        self.bc_funcs, self.bc_caches = [], []
+        for bc in pbcs:
+            if bc.direction not in "xyz"[:nd]:
+                raise AssertionError(f"direction {bc.direction} on a {nd}-D mesh")
+            d = dof.dof_index(bc.var_name)
+            a_nodes = np.unique(np.asarray(mesh.sideset_nodes[bc.side_a_sset], dtype=np.int64))   # _unique_sort_perm
+            b_nodes = np.asarray(mesh.sideset_nodes[bc.side_b_sset], dtype=np.int64)
+            dir_id = "xyz".index(bc.direction)
+            if nd == 2:
+                axes = [dir_id]
+            else:
+                normal = int(np.argmax(np.abs(X[:, a_nodes - 1].mean(axis=1) - X[:, b_nodes - 1].mean(axis=1))))
+                axes = [i for i in range(nd) if i != normal]
+            key = lambda n: tuple(np.rint(X[axes, n - 1] / tolerance).astype(np.int64))
+            to_b = {key(n): n for n in b_nodes}
+            if len({key(n) for n in a_nodes}) != len(to_b):
+                raise AssertionError("Side a and side b have different numbers of nodes")
+            matched = np.array([to_b[key(n)] for n in a_nodes], dtype=np.int64)
+            self.bc_caches.append(dict(side_a_nodes=a_nodes, side_b_nodes=matched, side_a_dofs=nf * (a_nodes - 1) + d + 1,
+                                       side_b_dofs=nf * (matched - 1) + d + 1, vals=np.zeros(len(a_nodes))))
+            self.bc_funcs.append(bc.func)
+
+    def __len__(self):
+        return len(self.bc_caches)
+
+    def periodic_dofs(self):
+        """(side_a_dofs, side_b_dofs) of all BCs concatenated (:240-250): what update_dofs! consumes"""
+        if not self.bc_caches:
+            return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+        return (np.concatenate([c["side_a_dofs"] for c in self.bc_caches]),
+                np.concatenate([c["side_b_dofs"] for c in self.bc_caches]))
+
+    def update_bc_values(self, X, t):
+        """update_bc_values!(bcs, X, t) (:252-257, :128-143): vals[n] = func(X[:, side_b_nodes[n]], t)"""
+        X = np.asarray(X)
+        for func, c in zip(self.bc_funcs, self.bc_caches):
+            v = func(X[:, c["side_b_nodes"] - 1].T, t)
+            c["vals"] = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=float), (len(c["side_b_nodes"]),)))
+
+    def values(self):
+        return np.concatenate([c["vals"] for c in self.bc_caches]) if self.bc_caches else np.zeros(0)

@@ -299,3 +299,36 @@ def test_postprocessor_writes_a_readable_exodus_file(tmp_path):
     nc.close()
     with pytest.raises(RuntimeError):
         F.PostProcessor(m3, str(tmp_path / "cube.vtk"), d3)
+
+
+def test_periodic_bc_container_matches_nodes_like_the_reference():
+    """PeriodicBCs (src/bcs/PeriodicBCs.jl:17-110): side-a nodes sorted and unique, side-b nodes matched through the
+    coordinate along the sides; the pairs feed update_dofs! (same maps as the oracle's), jumps come from func(X_b, t)."""
+    m = F.StructuredMesh("quad", (0., 0.), (1., 1.), (6, 5))
+    V = F.FunctionSpace(m, F.H1Field, F.Lagrange)
+    dof = F.DofManager(F.ScalarFunction(V, "u"))
+    X = np.asarray(m.nodal_coords)
+    pb = F.PeriodicBCs(m, dof, [F.PeriodicBC("u", "y", lambda X, t: 0.25 * X[:, 1] + t, "left", "right"),
+                                F.PeriodicBC("u", "x", lambda X, t: np.zeros(len(X)), "bottom", "top")])
+    c = pb.bc_caches[0]
+    assert np.array_equal(c["side_a_nodes"], np.sort(m.nodeset_nodes["left"]))
+    assert np.allclose(X[1, c["side_a_nodes"] - 1], X[1, c["side_b_nodes"] - 1])          # matched by y along the side
+    assert np.allclose(X[0, c["side_b_nodes"] - 1], 1.0) and np.allclose(X[0, c["side_a_nodes"] - 1], 0.0)
+    c2 = pb.bc_caches[1]
+    assert np.allclose(X[0, c2["side_a_nodes"] - 1], X[0, c2["side_b_nodes"] - 1]) and np.allclose(X[1, c2["side_b_nodes"] - 1], 1.0)
+    pa, pbd = pb.periodic_dofs()
+    assert len(pa) == len(pbd) == 6 + 5 and np.array_equal(pa[:5], c["side_a_dofs"])
+    od = O.update_dofs(1, m.num_nodes(), [], pa, pbd)                                       # the chains resolve (corner nodes)
+    assert len(od["unknown_dofs"]) == m.num_nodes() - len(np.unique(pbd))
+    pb.update_bc_values(X, 0.5)
+    assert np.allclose(pb.bc_caches[0]["vals"], 0.25 * X[1, c["side_b_nodes"] - 1] + 0.5)
+    with pytest.raises(AssertionError):
+        F.PeriodicBCs(m, dof, [F.PeriodicBC("u", "z", lambda X, t: 0.0, "left", "right")])
+    # 3-D: both transverse coordinates take part in the match
+    m3 = F.StructuredMesh("hex", (0., 0., 0.), (1., 1., 1.), (4, 3, 5))
+    d3 = F.DofManager(F.VectorFunction(F.FunctionSpace(m3, F.H1Field, F.Lagrange), "displ"))
+    p3 = F.PeriodicBCs(m3, d3, [F.PeriodicBC("displ_y", "y", lambda X, t: 0.0, "left", "right")])
+    X3 = np.asarray(m3.nodal_coords)
+    a, b = p3.bc_caches[0]["side_a_nodes"], p3.bc_caches[0]["side_b_nodes"]
+    assert np.allclose(X3[1:, a - 1], X3[1:, b - 1]) and len(np.unique(b)) == len(b) == 15
+    assert np.array_equal(p3.bc_caches[0]["side_b_dofs"], 3 * (b - 1) + 2)
