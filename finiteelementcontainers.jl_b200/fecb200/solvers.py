@@ -7,7 +7,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import check, lib
+from ._lib import FECError, check, lib
 from .assemblers import update_bc_values, update_time
 
 
@@ -31,6 +31,34 @@ class IterativeLinearSolver:
         return x, its.value, rn.value
 
 
+class DirectLinearSolver:
+    """DirectLinearSolver(asm) + solve!(solver, Uu, p) (src/Solvers.jl:37-86): residual (+ source + Neumann loads) and
+    stiffness assembled on the device, the sparse direct solve of K x = R on the host -- exactly where the reference does it ("currently doesn't
+    work on GPU", Solvers.jl:81; Robin terms are out of scope).  Uu is updated in place."""
+
+    def __init__(self, assembler):
+        if assembler.matrix_free:
+            raise FECError("DirectLinearSolver needs an assembled matrix (matrix_free=false)")
+        self.assembler = assembler
+        self.matrix_free = False
+        self.dUu = None
+
+    def solve(self, Uu, p):
+        import scipy.sparse.linalg as spla
+        from . import assemblers as A
+        from .physics import residual, stiffness
+        asm = self.assembler
+        A.assemble_vector(asm, residual, Uu, p)
+        A.assemble_vector_source(asm, Uu, p)
+        A.assemble_vector_neumann_bc(asm, Uu, p)
+        A.assemble_stiffness(asm, stiffness, Uu, p)
+        R = A._residual_accessor(asm)
+        K = A._stiffness_accessor(asm)
+        self.dUu = -spla.spsolve(K.tocsc(), R)
+        Uu += self.dUu
+        return Uu
+
+
 class NewtonSolver:
     """NewtonSolver(linear_solver) (src/Solvers.jl:178-220): <= 10 iterations, tolerances 1e-12."""
 
@@ -43,6 +71,22 @@ class NewtonSolver:
 
     def solve(self, Uu, p):
         asm = self.linear_solver.assembler
+        if isinstance(self.linear_solver, DirectLinearSolver):
+            # solve!(::NewtonSolver) (src/Solvers.jl:193-220) around the host-side direct solve
+            from . import assemblers as A
+            r0 = 0.0
+            for n in range(1, self.max_iters + 1):
+                self.linear_solver.solve(Uu, p)
+                n_du = float(np.linalg.norm(self.linear_solver.dUu))
+                n_r = float(np.linalg.norm(A._residual_accessor(asm)))
+                if n == 1:
+                    r0 = n_r
+                rel = n_r / r0 if r0 > 0.0 else n_r
+                self.iterations, self.residual_norm = n, n_r
+                if n_du < self.tol or n_r < self.tol or rel < self.tol:
+                    break
+            self.cg_iterations = 0
+            return Uu
         nit, cgit, rn = C.c_int32(), C.c_int64(), C.c_double()
         check(lib.fecb200_newton_solve(asm._require(), _lib.ptr(Uu), self.max_iters, self.tol,
                                        int(self.linear_solver.matrix_free), C.byref(nit), C.byref(cgit), C.byref(rn)))

@@ -874,3 +874,31 @@ def test_external_load_error_behaviour(F):
     assert lib.fecb200_assemble_vector_neumann_bc(h) == 0
     assert lib.fecb200_set_source_values(h, 5, None) != 0                                    # bad block index
     asm.close()
+
+
+def test_direct_linear_solver_reproduces_the_gold_and_the_neumann_answer(F):
+    """NewtonSolver(DirectLinearSolver(asm)) (src/Solvers.jl:37-86, 193-220; the reference's regression tests run both
+    linear solvers): device assembly + host `K \\ R`.  poisson.gold to 1e-12 (the direct solve has no Krylov tolerance),
+    and the Laplace / Neumann known answer u = x."""
+    mesh = F.UnstructuredMesh(os.path.join(GOLDEN, "poisson_g.npz"))
+    gold = np.load(os.path.join(GOLDEN, "poisson_g.npz"))["gold_u"]
+    V = F.FunctionSpace(mesh, F.H1Field, F.Lagrange)
+    u = F.ScalarFunction(V, "u")
+    asm = F.SparseMatrixAssembler(u, sparse_matrix_type="csc", use_condensed=False)
+    dbcs = [F.DirichletBC("u", lambda X, t: np.zeros(X.shape[0]), sideset_name=f"sset_{i}") for i in (1, 2, 3, 4)]
+    p = F.create_parameters(mesh, asm, F.Poisson(lambda X, t: SRC2(X)), None, dirichlet_bcs=dbcs)
+    solver = F.NewtonSolver(F.DirectLinearSolver(asm))
+    F.QuasiStaticIntegrator(solver).evolve(p)
+    assert np.abs(p.field.data_flat - gold).max() < 1e-12
+    assert solver.iterations <= 3
+    asm.close()
+    m2 = F.StructuredMesh("quad", (0., 0.), (1., 1.), (11, 11))
+    u2 = F.ScalarFunction(F.FunctionSpace(m2, F.H1Field, F.Lagrange), "u")
+    asm2 = F.SparseMatrixAssembler(u2, sparse_matrix_type="csc", use_condensed=True)
+    p2 = F.create_parameters(m2, asm2, F.Poisson(None), None,
+                             dirichlet_bcs=[F.DirichletBC("u", lambda X, t: np.zeros(X.shape[0]), sideset_name="left")],
+                             neumann_bcs=[F.NeumannBC("u", lambda X, t: -np.ones((X.shape[0], 1)), "right")])
+    s2 = F.NewtonSolver(F.DirectLinearSolver(asm2))
+    F.QuasiStaticIntegrator(s2).evolve(p2)
+    assert np.abs(p2.field.data_flat - np.asarray(m2.nodal_coords)[0]).max() < 1e-9
+    asm2.close()
