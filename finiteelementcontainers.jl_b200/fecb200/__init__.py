@@ -10,8 +10,8 @@ from .meshes import StructuredMesh, UnstructuredMesh, KuhnTet10Mesh
 from .reference_fe import ReferenceFE
 from .function_spaces import (FunctionSpace, Lagrange, ScalarFunction, VectorFunction, DofManager, update_field_unknowns,
                               extract_field_unknowns, update_field_dirichlet_bcs)
-from .bcs import (DirichletBC, DirichletBCs, NeumannBC, NeumannBCs, PeriodicBC, PeriodicBCs, Source, Sources,
-                  TimeStepper)
+from .bcs import (DirichletBC, DirichletBCs, InitialCondition, InitialConditions, NeumannBC, NeumannBCs, PeriodicBC,
+                  PeriodicBCs, Source, Sources, TimeStepper)
 from .physics import (AbstractPhysics, Poisson, Mechanics, NeoHookean, J2Plasticity, ThreeDimensional, PlaneStrain,
                       residual, residual_b, stiffness, stiffness_b, mass, mass_b, stiffness_action,
                       stiffness_action_b, mass_action, mass_action_b, lumped_mass, energy)
@@ -24,5 +24,66 @@ from .solvers import DirectLinearSolver, IterativeLinearSolver, NewtonSolver, Qu
 from .postprocessors import PostProcessor, write_times, write_field, close
 from .partition import (Partition, partition_mesh, structured_brick_partition, metis_partition_elements,
                         metis_partition_graph)
+
+
+
+# small accessors the reference exports as functions (src/FiniteElementContainers.jl:35-171)
+def num_dimensions(mesh):
+    return mesh.num_dimensions()
+
+
+def num_nodes(mesh):
+    return mesh.num_nodes()
+
+
+def nodal_coordinates(mesh):
+    return mesh.nodal_coords
+
+
+def element_blocks(mesh):
+    return list(mesh.element_block_names)
+
+
+def nodesets(mesh):
+    return mesh.nodeset_nodes
+
+
+def sidesets(mesh):
+    return mesh.sideset_nodes
+
+
+def num_fields(x):
+    """num_fields(field | function | dof)"""
+    return x.num_fields() if hasattr(x, "num_fields") else (x.nf if hasattr(x, "nf") else x.shape[0])
+
+
+def num_entities(field):
+    return field.shape[1]
+
+
+def connectivity(conn, b):
+    """connectivity(conn, b) with the reference's 1-based block index (src/Fields.jl:163-168)"""
+    return conn.block(b - 1)
+
+
+def num_elements(fspace, b=None):
+    return sum(fspace.elem_conns.nelems) if b is None else fspace.elem_conns.nelems[b - 1]
+
+
+def current_time(times):
+    return times.time_current
+
+
+def dirichlet_dofs(bcs):
+    return bcs.dirichlet_dofs()
+
+
+def update_ic_values(ics, X):
+    ics.update_ic_values(X)
+
+
+def update_field_ics(U, ics):
+    ics.update_field_ics(U)
+
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -231,3 +231,51 @@ class PeriodicBCs:
 
     def values(self):
         return np.concatenate([c["vals"] for c in self.bc_caches]) if self.bc_caches else np.zeros(0)
+
+
+class InitialCondition:
+    """InitialCondition(var_name, func; block_name | nodeset_name | sideset_name)  (src/InitialConditions.jl:10-46).
+    `func(X)` is called vectorised: X is (n, ND), returns (n,) or a scalar."""
+
+    def __init__(self, var_name, func, *, block_name=None, nodeset_name=None, sideset_name=None):
+        given = [x is not None for x in (block_name, nodeset_name, sideset_name)]
+        if sum(given) == 0:
+            raise ValueError("block_name, nodeset_name, or sideset_name required as input arguments in DirichletBC")
+        if sum(given) != 1:
+            raise ValueError("More than one entity type specificed in DirichletBC")
+        self.var_name, self.func = var_name, func
+        self.block_name, self.nset_name, self.sset_name = block_name, nodeset_name, sideset_name
+
+
+class InitialConditions:
+    """InitialConditions(mesh, dof, ics) (src/InitialConditions.jl:48-224): per IC the dofs / nodes it sets and their
+    values; `update_ic_values(X)` evaluates the functions, `update_field_ics(U)` writes U[dofs] = vals (host field --
+    e.g. the starting point handed to the integrator through extract_field_unknowns)."""
+
+    def __init__(self, mesh, dof, ics):
+        self.ic_funcs, self.ic_caches = [], []
+        nf = dof.nf
+        for ic in ics:
+            d = dof.dof_index(ic.var_name)
+            if ic.block_name is not None:
+                n = np.unique(mesh.element_conns[ic.block_name])
+            elif ic.nset_name is not None:
+                n = np.unique(np.asarray(mesh.nodeset_nodes[ic.nset_name], dtype=np.int64))
+            else:
+                n = np.unique(np.asarray(mesh.sideset_nodes[ic.sset_name], dtype=np.int64))
+            self.ic_caches.append(dict(dofs=nf * (n - 1) + d + 1, locations=n, vals=np.zeros(len(n))))
+            self.ic_funcs.append(ic.func)
+
+    def __len__(self):
+        return len(self.ic_caches)
+
+    def update_ic_values(self, X):
+        X = np.asarray(X)
+        for func, c in zip(self.ic_funcs, self.ic_caches):
+            v = func(X[:, c["locations"] - 1].T)
+            c["vals"] = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=float), (len(c["locations"]),)))
+
+    def update_field_ics(self, U):
+        f = U.data_flat if hasattr(U, "data_flat") else np.asarray(U).reshape(-1)
+        for c in self.ic_caches:
+            f[c["dofs"] - 1] = c["vals"]

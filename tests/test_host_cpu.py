@@ -332,3 +332,27 @@ def test_periodic_bc_container_matches_nodes_like_the_reference():
     a, b = p3.bc_caches[0]["side_a_nodes"], p3.bc_caches[0]["side_b_nodes"]
     assert np.allclose(X3[1:, a - 1], X3[1:, b - 1]) and len(np.unique(b)) == len(b) == 15
     assert np.array_equal(p3.bc_caches[0]["side_b_dofs"], 3 * (b - 1) + 2)
+
+
+def test_initial_conditions_and_accessors():
+    """InitialCondition(s) (src/InitialConditions.jl) and the small accessor functions the reference exports."""
+    m = F.StructuredMesh("hex", (0., 0., 0.), (1., 1., 1.), (3, 4, 3))
+    V = F.FunctionSpace(m, F.H1Field, F.Lagrange)
+    u = F.VectorFunction(V, "displ")
+    dof = F.DofManager(u)
+    ics = F.InitialConditions(m, dof, [F.InitialCondition("displ_y", lambda X: 0.1 * X[:, 1], block_name="block_1"),
+                                      F.InitialCondition("displ_x", lambda X: 2.0, nodeset_name="top")])
+    F.update_ic_values(ics, m.nodal_coords)
+    U = F.create_field_like(dof) if hasattr(F, "create_field_like") else F.H1Field.zeros(3, m.num_nodes())
+    F.update_field_ics(U, ics)
+    X = np.asarray(m.nodal_coords)
+    assert np.allclose(U[1], 0.1 * X[1]) and np.all(U[2] == 0.0)
+    top = m.nodeset_nodes["top"] - 1
+    assert np.all(U[0, top] == 2.0) and np.count_nonzero(U[0]) == len(top)
+    with pytest.raises(ValueError):
+        F.InitialCondition("displ_x", lambda X: 0.0)
+    assert F.num_dimensions(m) == 3 and F.num_nodes(m) == 36 and F.element_blocks(m) == ["block_1"]
+    assert F.num_fields(u) == 3 and F.num_fields(U) == 3 and F.num_entities(U) == 36 and F.num_fields(dof) == 3
+    assert F.connectivity(V.elem_conns, 1).shape == (8, 12) and F.num_elements(V) == 12 and F.num_elements(V, 1) == 12
+    assert F.current_time(F.TimeStepper(0.5, 1.0, 5)) == 0.5
+    assert np.array_equal(F.nodal_coordinates(m), m.nodal_coords) and "top" in F.nodesets(m) and "top" in F.sidesets(m)
