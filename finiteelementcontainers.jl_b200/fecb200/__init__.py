@@ -23,7 +23,7 @@ from .assemblers import (SparseMatrixAssembler, Parameters, create_parameters, u
 from .solvers import DirectLinearSolver, IterativeLinearSolver, NewtonSolver, QuasiStaticIntegrator
 from .postprocessors import PostProcessor, write_times, write_field, close
 from .partition import (Partition, partition_mesh, structured_brick_partition, metis_partition_elements,
-                        metis_partition_graph)
+                        metis_partition_graph, metis_partition_pattern)
 
 
 

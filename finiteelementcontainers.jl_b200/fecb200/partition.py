@@ -52,6 +52,19 @@ def metis_partition_graph(xadj, adjncy, nparts):
     return part
 
 
+def metis_partition_pattern(pattern, nparts):
+    """Metis.partition(pattern::SparseMatrixPattern, nparts) (ext/MetisExt.jl:6-14): partition of the DOF graph of the
+    sparsity pattern.  `pattern` is an assembler (its `pattern()` is used) or a `(n, ptr, idx)` triple, Int64 1-based as
+    the library returns it; the diagonal is dropped (METIS graphs have no self loops).  Returns 0-based part ids."""
+    n, ptr, idx = pattern.pattern() if hasattr(pattern, "pattern") else pattern
+    ptr, idx = np.asarray(ptr, dtype=np.int64) - 1, np.asarray(idx, dtype=np.int64) - 1
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(ptr))
+    keep = rows != idx
+    xadj = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(xadj, rows[keep] + 1, 1)
+    return metis_partition_graph(np.cumsum(xadj), idx[keep], nparts)
+
+
 class _LocalMesh(AbstractMesh):
     """Rank-local mesh: block `owned` (+ `halo`: neighbour-owned elements, matrix assembly only).  Side sets are the
     faces of OWNED elements lying in the node sets, built on first use (surface loads of halo elements belong to their

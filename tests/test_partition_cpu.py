@@ -197,3 +197,22 @@ def test_rank_local_sidesets_tile_the_global_ones(how):
         Rg = O.assemble_vector_neumann_bc(np.zeros(3 * gmesh.num_nodes()), np.asarray(gmesh.sideset_side_nodes[name]), tabs,
                                           np.ones((3, 4, len(want))), Xg, 3)
         assert np.allclose(Rsum, Rg, rtol=1e-13, atol=1e-15)
+
+
+def test_metis_partition_of_the_sparsity_pattern():
+    """Metis.partition(pattern, nparts) (ext/MetisExt.jl:6-14) on the DOF graph of the CSR pattern: balanced parts, every
+    dof assigned, edge cut well below a random assignment's."""
+    m = O.structured_mesh("quad", (0., 0.), (1., 1.), (17, 17))
+    dof = O.update_dofs(1, m["coords"].shape[1], [])
+    pat = O.matrix_pattern([m["conn"]], 1, dof, condensed=True)
+    n = m["coords"].shape[1]
+    colptr, rowval, _ = O.sparse_csc(pat["Is"], pat["Js"], np.ones(len(pat["Is"])), n)
+    part = F.metis_partition_pattern((n, colptr, rowval), 4)
+    assert part.shape == (n,) and set(np.unique(part)) == {0, 1, 2, 3}
+    counts = np.bincount(part, minlength=4)
+    assert counts.max() <= 1.1 * n / 4 + 2
+    rows = np.repeat(np.arange(n), np.diff(colptr))
+    cut = np.count_nonzero(part[rows] != part[rowval - 1])
+    rng = np.random.default_rng(0)
+    rnd = rng.integers(0, 4, n)
+    assert cut < 0.25 * np.count_nonzero(rnd[rows] != rnd[rowval - 1])
