@@ -269,8 +269,10 @@ def update_time(p):
     check(lib.fecb200_set_time(p.asm._require(), p.times.time_current, p.times.dt))
 
 
-def create_field(asm):
-    return H1Field.zeros(asm.dof.nf, asm.dof.nn)
+def create_field(asm_or_dof):
+    """create_field(dof) / create_field(asm) (src/DofManagers.jl:148-158)"""
+    dof = getattr(asm_or_dof, "dof", asm_or_dof)
+    return H1Field.zeros(dof.nf, dof.nn)
 
 
 def create_unknowns(asm):

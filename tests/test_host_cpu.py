@@ -356,3 +356,35 @@ def test_initial_conditions_and_accessors():
     assert F.connectivity(V.elem_conns, 1).shape == (8, 12) and F.num_elements(V) == 12 and F.num_elements(V, 1) == 12
     assert F.current_time(F.TimeStepper(0.5, 1.0, 5)) == 0.5
     assert np.array_equal(F.nodal_coordinates(m), m.nodal_coords) and "top" in F.nodesets(m) and "top" in F.sidesets(m)
+
+
+def test_reference_bc_tests_restated():
+    """test/TestBCs.jl:21-103 on the same mesh (poisson.g): DirichletBC input handling, container construction on a block /
+    node set / side set, the unknown-variable error, update_bc_values! with bc_func(_, t) = 2 t^2 at t = 3 -> 18, and
+    update_field_dirichlet_bcs!."""
+    mesh = F.UnstructuredMesh(os.path.join(GOLDEN, "poisson_g.npz"))
+    fspace = F.FunctionSpace(mesh, F.H1Field, F.Lagrange)
+    f1 = lambda X, t: 5.0 * t
+    with pytest.raises(ValueError):
+        F.DirichletBC("u", f1)
+    with pytest.raises(ValueError):
+        F.DirichletBC("u", f1, block_name="some_block", nodeset_name="some_nodeset")
+    bc = F.DirichletBC("my_var", f1, block_name="my_block")
+    assert (bc.block_name, bc.nset_name, bc.sset_name, bc.var_name, bc.func) == ("my_block", None, None, "my_var", f1)
+    bc = F.DirichletBC("my_var", f1, nodeset_name="my_nset")
+    assert (bc.block_name, bc.nset_name, bc.sset_name) == (None, "my_nset", None)
+    bc = F.DirichletBC("my_var", f1, sideset_name="my_sset")
+    assert (bc.block_name, bc.nset_name, bc.sset_name) == (None, None, "my_sset")
+    dof = F.DofManager(F.VectorFunction(fspace, "displ"))
+    F.DirichletBCs(mesh, dof, [F.DirichletBC("displ_x", f1, block_name="block_1")])
+    F.DirichletBCs(mesh, dof, [F.DirichletBC("displ_x", f1, sideset_name="sset_1")])
+    with pytest.raises(ValueError):
+        F.DirichletBCs(mesh, dof, [F.DirichletBC("bad_var_name", f1, sideset_name="sset_1")])
+    bcs = F.DirichletBCs(mesh, dof, [F.DirichletBC("displ_x", lambda X, t: 2.0 * t ** 2, sideset_name="sset_1")])
+    bcs.update_bc_values(mesh.nodal_coords, 3.0)
+    assert np.allclose(bcs.vals, 18.0)
+    U = F.create_field(dof)
+    F.update_field_dirichlet_bcs(U, bcs)
+    dd = F.dirichlet_dofs(bcs)
+    assert np.allclose(U.data_flat[dd - 1], 18.0) and np.count_nonzero(U.data_flat) == len(dd)
+    assert np.all((dd - 1) % 2 == 0)                      # displ_x dofs only: NF*(n-1) + 1
