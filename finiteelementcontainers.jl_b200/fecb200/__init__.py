@@ -8,7 +8,8 @@ from ._lib import FECError
 from .fields import H1Field, Connectivity
 from .meshes import StructuredMesh, UnstructuredMesh, KuhnTet10Mesh
 from .reference_fe import ReferenceFE
-from .function_spaces import (FunctionSpace, Lagrange, ScalarFunction, VectorFunction, DofManager, update_field_unknowns,
+from .function_spaces import (FunctionSpace, Lagrange, ScalarFunction, VectorFunction, TensorFunction,
+                              SymmetricTensorFunction, GeneralFunction, DofManager, update_field_unknowns,
                               extract_field_unknowns, update_field_dirichlet_bcs)
 from .bcs import (DirichletBC, DirichletBCs, InitialCondition, InitialConditions, NeumannBC, NeumannBCs, PeriodicBC,
                   PeriodicBCs, Source, Sources, TimeStepper)

@@ -44,6 +44,9 @@ class AbstractFunction:
     def num_fields(self):
         return len(self._names)
 
+    def __len__(self):
+        return len(self._names)
+
 
 class ScalarFunction(AbstractFunction):
     """ScalarFunction(V, name) (src/Functions.jl:36-51)"""
@@ -59,6 +62,37 @@ class VectorFunction(AbstractFunction):
     def __init__(self, fspace, name):
         self.fspace = fspace
         self._names = [f"{name}_{c}" for c in "xyz"[: fspace.num_dimensions()]]
+
+
+class SymmetricTensorFunction(AbstractFunction):
+    """SymmetricTensorFunction(V, name; use_spatial_dimension) (src/Functions.jl:120-150): Voigt order xx, yy, zz, yz, xz, xy
+    (always 3-D unless use_spatial_dimension: xx, yy, xy in 2-D)"""
+
+    def __init__(self, fspace, name, use_spatial_dimension=False):
+        self.fspace = fspace
+        nd = fspace.num_dimensions() if use_spatial_dimension else 3
+        comps = ["xx", "yy", "zz", "yz", "xz", "xy"] if nd == 3 else ["xx", "yy", "xy"]
+        self._names = [f"{name}_{c}" for c in comps]
+
+
+class TensorFunction(AbstractFunction):
+    """TensorFunction(V, name; use_spatial_dimension) (src/Functions.jl:89-118): xx, yy, zz, yz, xz, xy, zy, zx, yx
+    (xx, yy, xy, yx in 2-D with use_spatial_dimension)"""
+
+    def __init__(self, fspace, name, use_spatial_dimension=False):
+        self.fspace = fspace
+        nd = fspace.num_dimensions() if use_spatial_dimension else 3
+        comps = ["xx", "yy", "zz", "yz", "xz", "xy", "zy", "zx", "yx"] if nd == 3 else ["xx", "yy", "xy", "yx"]
+        self._names = [f"{name}_{c}" for c in comps]
+
+
+class GeneralFunction(AbstractFunction):
+    """GeneralFunction(u, v, ...) (src/Functions.jl:184-207): the fields of several functions on one space side by side"""
+
+    def __init__(self, *funcs):
+        assert funcs and all(f.fspace is funcs[0].fspace for f in funcs), "functions must share one FunctionSpace"
+        self.fspace = funcs[0].fspace
+        self._names = [n for f in funcs for n in f.names()]
 
 
 class DofManager:

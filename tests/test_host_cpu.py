@@ -388,3 +388,42 @@ def test_reference_bc_tests_restated():
     dd = F.dirichlet_dofs(bcs)
     assert np.allclose(U.data_flat[dd - 1], 18.0) and np.count_nonzero(U.data_flat) == len(dd)
     assert np.all((dd - 1) % 2 == 0)                      # displ_x dofs only: NF*(n-1) + 1
+
+
+def test_reference_function_dof_and_ic_tests_restated():
+    """test/TestFunctions.jl:1-45 (component names of every function type), test/TestDofManagers.jl:17-27 (sizes) and
+    test/TestICs.jl:9-60 (InitialCondition input, container init + update on block / node set / side set), on poisson.g."""
+    mesh = F.UnstructuredMesh(os.path.join(GOLDEN, "poisson_g.npz"))
+    fspace = F.FunctionSpace(mesh, F.H1Field, F.Lagrange)
+    u = F.ScalarFunction(fspace, "u")
+    assert len(u) == 1 and u.names() == ["u"]
+    u = F.VectorFunction(fspace, "u")
+    assert len(u) == 2 and u.names() == ["u_x", "u_y"]
+    u = F.TensorFunction(fspace, "u")
+    assert len(u) == 9 and u.names() == ["u_xx", "u_yy", "u_zz", "u_yz", "u_xz", "u_xy", "u_zy", "u_zx", "u_yx"]
+    u = F.TensorFunction(fspace, "u", use_spatial_dimension=True)
+    assert len(u) == 4 and u.names() == ["u_xx", "u_yy", "u_xy", "u_yx"]
+    u = F.SymmetricTensorFunction(fspace, "u")
+    assert len(u) == 6 and u.names() == ["u_xx", "u_yy", "u_zz", "u_yz", "u_xz", "u_xy"]
+    u = F.SymmetricTensorFunction(fspace, "u", use_spatial_dimension=True)
+    assert len(u) == 3 and u.names() == ["u_xx", "u_yy", "u_xy"]
+    g = F.GeneralFunction(F.VectorFunction(fspace, "u"), F.ScalarFunction(fspace, "t"))
+    assert len(g) == 3 and g.names() == ["u_x", "u_y", "t"]
+    dof1 = F.DofManager(F.VectorFunction(fspace, "u"))
+    assert dof1.size() == (2, 16641) and len(dof1) == 2 * 16641 and F.create_field(dof1).shape == (2, 16641)
+    # ICs
+    dof = F.DofManager(F.VectorFunction(fspace, "displ"))
+    f3 = lambda X: 3.0
+    ic = F.InitialCondition("my_var", f3, block_name="my_block")
+    assert (ic.block_name, ic.nset_name, ic.sset_name, ic.func, ic.var_name) == ("my_block", None, None, f3, "my_var")
+    for kw, nodes in (({"block_name": "block_1"}, np.arange(1, 16642)),
+                      ({"nodeset_name": "nset_1"}, mesh.nodeset_nodes.get("nset_1")),
+                      ({"sideset_name": "sset_1"}, mesh.sideset_nodes["sset_1"])):
+        if nodes is None:
+            continue
+        ics = F.InitialConditions(mesh, dof, [F.InitialCondition("displ_x", f3, **kw)])
+        U = F.create_field(dof)
+        F.update_ic_values(ics, mesh.nodal_coords)
+        assert np.all(ics.ic_caches[0]["vals"] == 3.0)
+        F.update_field_ics(U, ics)
+        assert np.all(U[0, np.asarray(nodes) - 1] == 3.0) and np.all(U[1] == 0.0)
