@@ -427,3 +427,34 @@ def test_reference_function_dof_and_ic_tests_restated():
         assert np.all(ics.ic_caches[0]["vals"] == 3.0)
         F.update_field_ics(U, ics)
         assert np.all(U[0, np.asarray(nodes) - 1] == 3.0) and np.all(U[1] == 0.0)
+
+
+def test_reference_field_tests_restated():
+    """test/TestFields.jl:1-98: Connectivity block views / per-element connectivity with the reference's 1-based offsets,
+    and H1Field indexing (flat column-major `field[n]`, dual `field[d, n]`), fill and similar."""
+    conns_in = [np.array([[1, 5, 9], [2, 6, 10], [3, 7, 11], [4, 8, 12]]),
+                np.array([[13, 16, 19, 22, 25], [14, 17, 20, 23, 26], [15, 18, 21, 24, 27]])]
+    conn = F.Connectivity(conns_in)
+    b1, b2 = F.connectivity(conn, 1), F.connectivity(conn, 2)
+    assert b1.shape == (4, 3) and b2.shape == (3, 5)
+    elem = lambda nnpe, e, off: conn.data[off - 1 + (e - 1) * nnpe: off - 1 + e * nnpe].tolist()   # Fields.jl:183-188
+    assert conn.offsets == [1, 13]
+    assert [elem(4, e, 1) for e in (1, 2, 3)] == [[1, 2, 3, 4], [5, 6, 7, 8], [9, 10, 11, 12]]
+    assert [elem(3, e, 13) for e in (1, 2, 3, 4, 5)] == [[13, 14, 15], [16, 17, 18], [19, 20, 21], [22, 23, 24], [25, 26, 27]]
+    rng = np.random.default_rng(1)
+    data = rng.random((2, 20))
+    field = F.H1Field(data)
+    assert field.dtype == data.dtype and field.ndim == 2 and field.shape == data.shape
+    assert F.num_fields(field) == 2 and F.num_entities(field) == 20
+    assert np.array_equal(field.data_flat, data.reshape(-1, order="F"))            # field[n] == data[n] (column-major)
+    assert all(field[d, n] == data[d, n] for n in range(20) for d in range(2))
+    data2 = rng.random((2, 20))
+    for n in range(20):
+        for d in range(2):
+            field[d, n] = data2[d, n]
+    assert np.array_equal(np.asarray(field), data2) and np.array_equal(field.data_flat, data2.reshape(-1, order="F"))
+    field.fill(3.9)
+    assert np.all(field == 3.9)
+    new = F.H1Field(np.empty_like(field))
+    new[...] = field
+    assert type(new) is type(field) and np.all(new == field)
