@@ -54,8 +54,27 @@ def sidesets(mesh):
 
 
 def num_fields(x):
-    """num_fields(field | function | dof)"""
+    """num_fields(field | function | dof | physics)"""
+    if isinstance(x, AbstractPhysics):
+        return x.NF
     return x.num_fields() if hasattr(x, "num_fields") else (x.nf if hasattr(x, "nf") else x.shape[0])
+
+
+def num_properties(physics):
+    """num_properties(::AbstractPhysics{NF, NP, NS}) (src/Physics.jl:20-30)"""
+    return physics.NP
+
+
+def num_states(physics):
+    return physics.NS
+
+
+def create_properties(physics):
+    return physics.create_properties()
+
+
+def create_initial_state(physics):
+    return physics.create_initial_state()
 
 
 def num_entities(field):

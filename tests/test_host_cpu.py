@@ -458,3 +458,18 @@ def test_reference_field_tests_restated():
     new = F.H1Field(np.empty_like(field))
     new[...] = field
     assert type(new) is type(field) and np.all(new == field)
+
+
+def test_reference_physics_test_restated():
+    """test/TestPhysics.jl:1-8: num_fields / num_properties / num_states of an AbstractPhysics{1, 2, 3}; and the shipped
+    physics' parameter counts (TestPoissonCommon.jl:4, TestMechanicsCommon.jl:3, TestMechanicsWithState.jl:15)."""
+    class MyPhysics(F.AbstractPhysics):
+        NF, NP, NS = 1, 2, 3
+    ph = MyPhysics()
+    assert (F.num_fields(ph), F.num_properties(ph), F.num_states(ph)) == (1, 2, 3)
+    assert len(F.create_initial_state(ph)) == 3
+    assert (F.num_fields(F.Poisson(None)), F.num_properties(F.Poisson(None)), F.num_states(F.Poisson(None))) == (1, 0, 0)
+    mech = F.Mechanics(F.ThreeDimensional())
+    assert F.num_fields(mech) == 3 and F.num_states(mech) == 0 and len(F.create_properties(mech)) == F.num_properties(mech) == 3
+    j2 = F.J2Plasticity(F.ThreeDimensional())
+    assert F.num_states(j2) == 7 and len(F.create_initial_state(j2)) == 7
