@@ -56,6 +56,9 @@ static const double* stage_in(fecb200_handle* h, const double* src, double* stag
     return staging;
   }
   FEC_CUDA(cudaMemcpyAsync(staging, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  // "every call is complete on return" (fecb200.h): a pageable source is staged by the driver before the call
+  // returns, a page-locked one is read by DMA later -- the caller may update Uu in place right after this call
+  if (is_pinned_host_ptr(src)) FEC_CUDA(cudaStreamSynchronize(h->stream));
   return staging;
 }
 // main stream waits for pending H2D copies right before their first consumer
@@ -130,14 +133,23 @@ static double* nz_for_kind(fecb200_handle* h, int kind, bool alloc) {
 
 static void ensure_cg(fecb200_handle* h) {
   const int64_t n = len_Uu(h);
-  if ((int64_t)h->d_cg_r.n < n) { h->d_cg_r.alloc(n); h->d_cg_p.alloc(n); h->d_cg_Ap.alloc(n); h->d_cg_x.alloc(n); }
+  if ((int64_t)h->d_cg_r.n < n) {
+    h->d_cg_r.alloc(n); h->d_cg_p.alloc(n); h->d_cg_Ap.alloc(n); h->d_cg_x.alloc(n);
+    h->d_cg_Ap.zero(h->stream);  // ghost rows of K p are never written on a partitioned handle
+  }
 }
 
 // operator application for CG: y = K x (assembled) or the matrix-free action at the current U
-static void apply_operator(fecb200_handle* h, bool matrix_free, const double* x, double* y) {
+// Partitioned handles (fecb200_comm_init): x is made consistent first (owner -> ghost copies, PVector consistent!,
+// ext/PartitionedArraysExt.jl:449-459); the assembled operator then needs no further exchange (every owned row is
+// complete), the matrix-free one sums the ghost contributions of the action into their owners (:469-481).
+static void apply_operator(fecb200_handle* h, bool matrix_free, double* x, double* y) {
+  const bool dist = comm_active(h) && h->n_neighbors > 0;
+  if (dist) comm_halo_update_unknowns(h, x);
   if (!matrix_free) {
     spmv(h, h->d_nz_stiff.p, x, y);
   } else {
+    FEC_REQUIRE(!(dist && h->peer_enabled && h->peer_field == FECB200_FIELD_ACTION) , "matrix-free CG over the peer-memory action halo is not wired; use the NCCL halo");
     FEC_CUDA(cudaMemsetAsync(h->d_Av.p, 0, h->ndof * sizeof(double), h->stream));
     k_update_field(h, h->d_V.p, x, false);
     for (auto& b : h->blocks) {
@@ -145,6 +157,7 @@ static void apply_operator(fecb200_handle* h, bool matrix_free, const double* x,
       VecLaunch a{h->d_U.p, h->d_V.p, h->d_Av.p, MODE_ACTION_STIFFNESS};
       launch_vector(h, b, a);
     }
+    if (dist) comm_halo_sum_field(h, h->d_Av.p);
     k_hvp_accessor(h, x, y);
   }
 }
@@ -152,27 +165,33 @@ static void apply_operator(fecb200_handle* h, bool matrix_free, const double* x,
 static void cg_impl(fecb200_handle* h, const double* b_dev, double* x_dev, double atol, double rtol, int64_t itmax,
                     bool matrix_free, int64_t* iters_out, double* rnorm_out) {
   // Krylov.jl cg with x0 = 0: r = b, p = r; stop when ||r|| <= atol + rtol ||r0||
+  // Partitioned handles: vectors keep the rank-local Uu layout (owned entries first, then ghosts); dots run over the
+  // OWNED prefix and are summed over the ranks (dot() all-reduces when a communicator is attached), so every rank
+  // takes the same branches and the iteration count equals the serial solve's.
   const int64_t n = len_Uu(h);
+  const int64_t nred = owned_len(h);
   ensure_cg(h);
   double* r = h->d_cg_r.p; double* p = h->d_cg_p.p; double* Ap = h->d_cg_Ap.p;
   FEC_CUDA(cudaMemsetAsync(x_dev, 0, n * sizeof(double), h->stream));
   FEC_CUDA(cudaMemcpyAsync(r, b_dev, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   FEC_CUDA(cudaMemcpyAsync(p, b_dev, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  double gamma = dot(h, r, r, n);
+  inputs_consumed(h);  // b may live in the H2D staging buffer (fecb200_cg_solve): free for the next async copy
+  double gamma = dot(h, r, r, nred);
   const double rn0 = std::sqrt(gamma);
   const double tol = atol + rtol * rn0;
   int64_t it = 0;
   while (rn0 > 0 && std::sqrt(gamma) > tol && it < itmax) {
     apply_operator(h, matrix_free, p, Ap);
-    const double pAp = dot(h, p, Ap, n);
+    const double pAp = dot(h, p, Ap, nred);
     const double alpha = gamma / pAp;
     axpy(h, alpha, p, x_dev, n);
     axpy(h, -alpha, Ap, r, n);
-    const double gnew = dot(h, r, r, n);
+    const double gnew = dot(h, r, r, nred);
     xpay(h, r, gnew / gamma, p, n);  // p = r + beta p
     gamma = gnew;
     ++it;
   }
+  if (comm_active(h) && h->n_neighbors > 0) comm_halo_update_unknowns(h, x_dev);  // ghost entries of the solution
   if (iters_out) *iters_out = it;
   if (rnorm_out) *rnorm_out = std::sqrt(gamma);
 }
@@ -311,6 +330,7 @@ int fecb200_destroy(fecb200_handle* h) {
     cudaStream_t s = h->own_stream ? h->stream : nullptr;
     cudaStreamSynchronize(h->stream);
     for (void* pp : h->peer_opened) cudaIpcCloseMemHandle(pp);
+    comm_release(h);
     if (h->s_h2d) { cudaStreamSynchronize(h->s_h2d); cudaStreamDestroy(h->s_h2d); }
     if (h->s_d2h) { cudaStreamSynchronize(h->s_d2h); cudaStreamDestroy(h->s_d2h); }
     for (cudaEvent_t ev : {h->ev_h2d, h->ev_in_consumed, h->ev_prod, h->ev_d2h}) if (ev) cudaEventDestroy(ev);
@@ -735,7 +755,42 @@ int fecb200_hvp(fecb200_handle* h, const double* v, double* out) {
   join_inputs(h);
   if (!dev) wait_out_free(h);
   k_hvp_accessor(h, vd, target);
+  inputs_consumed(h);
   if (!dev) copy_out(h, out, target, len_Uu(h));
+  FEC_API_END
+}
+
+int fecb200_update_field(fecb200_handle* h, const double* Uu) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && Uu, "null argument");
+  FEC_CUDA(cudaSetDevice(h->device));
+  const double* u = stage_in(h, Uu, h->d_Uu.p, len_Uu(h));
+  join_inputs(h);
+  k_update_field(h, h->d_U.p, u, true);
+  inputs_consumed(h);
+  FEC_API_END
+}
+
+int fecb200_matrix_multiply(fecb200_handle* h, int32_t kind, const double* x, double* y) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && x && y, "null argument");
+  FEC_CUDA(cudaSetDevice(h->device));
+  double* nz = adjusted_values(h, kind);
+  const int64_t n = len_Uu(h);
+  ensure_cg(h);
+  const double* xd = stage_in(h, x, h->d_Vu.p, n);
+  join_inputs(h);
+  const bool dev = is_device_ptr(y);
+  double* yd = dev ? y : h->d_cg_Ap.p;
+  if (comm_active(h) && h->n_neighbors > 0) {   // ghost entries of x from their owners (on a private copy: x is const)
+    FEC_CUDA(cudaMemcpyAsync(h->d_cg_p.p, xd, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    comm_halo_update_unknowns(h, h->d_cg_p.p);
+    xd = h->d_cg_p.p;
+  }
+  if (!dev || h->n_owned_nodes < h->nn) FEC_CUDA(cudaMemsetAsync(yd, 0, n * sizeof(double), h->stream));  // rows that are not stored
+  spmv(h, nz, xd, yd);
+  inputs_consumed(h);
+  if (!dev) copy_out(h, y, yd, n);
   FEC_API_END
 }
 
@@ -771,6 +826,7 @@ int fecb200_cg_solve(fecb200_handle* h, const double* b, double* x, double atol,
   if (rtol < 0) rtol = std::sqrt(2.220446049250313e-16);
   if (itmax <= 0) itmax = 2 * n;
   if (!matrix_free) adjusted_values(h, FECB200_STIFFNESS);
+  join_inputs(h);  // async mode: the H2D of b runs on the copy stream; the main stream must not read it early
   cg_impl(h, bd, xd, atol, rtol, itmax, matrix_free != 0, iters_out, rnorm_out);
   if (!dev) copy_out(h, x, xd, n);
   FEC_API_END
@@ -782,6 +838,8 @@ int fecb200_newton_solve(fecb200_handle* h, double* Uu, int32_t max_iters, doubl
   FEC_REQUIRE(h && Uu, "null argument");
   FEC_CUDA(cudaSetDevice(h->device));
   const int64_t n = len_Uu(h);
+  const int64_t nred = owned_len(h);
+  const bool dist = comm_active(h) && h->n_neighbors > 0;
   ensure_cg(h);
   const bool dev = is_device_ptr(Uu);
   double* u = h->d_Uu.p;
@@ -795,6 +853,13 @@ int fecb200_newton_solve(fecb200_handle* h, double* Uu, int32_t max_iters, doubl
   int it = 0;
   double* Rb = h->d_out.p;   // residual(asm)
   double* dU = h->d_cg_x.p;
+  if (dist) {
+    comm_halo_update_unknowns(h, u);   // consistent ghost entries of the initial guess
+    if (h->peer_enabled && h->peer_field == FECB200_FIELD_RESIDUAL) {
+      FEC_CUDA(cudaMemsetAsync(h->d_R.p, 0, h->ndof * sizeof(double), h->stream));
+      comm_barrier(h);
+    }
+  }
   for (it = 1; it <= max_iters; ++it) {
     // solve!(IterativeLinearSolver) (Solvers.jl:128-153)
     if (matrix_free) {
@@ -805,14 +870,22 @@ int fecb200_newton_solve(fecb200_handle* h, double* Uu, int32_t max_iters, doubl
     }
     add_source_loads(h, h->d_R.p);    // assemble_vector_source!      (Solvers.jl:135)
     add_neumann_loads(h, h->d_R.p);   // assemble_vector_neumann_bc!  (Solvers.jl:136)
+    if (dist) {                       // ghost -> owner sum of the residual (PartitionedArraysExt.jl:469-481)
+      if (h->peer_enabled && h->peer_field == FECB200_FIELD_RESIDUAL) comm_barrier(h);
+      else comm_halo_sum_field(h, h->d_R.p);
+    }
     k_residual_accessor(h, Rb);
+    if (dist && h->peer_enabled && h->peer_field == FECB200_FIELD_RESIDUAL) {
+      FEC_CUDA(cudaMemsetAsync(h->d_R.p, 0, h->ndof * sizeof(double), h->stream));
+      comm_barrier(h);                // every rank re-zeroed its residual before anyone scatters again
+    }
     if (!matrix_free) adjusted_values(h, FECB200_STIFFNESS);
     int64_t cgit = 0;
     cg_impl(h, Rb, dU, eps, eps, 2 * n, matrix_free != 0, &cgit, nullptr);
     cg_total += cgit;
     axpy(h, -1.0, dU, u, n);  // Uu += -solution
-    const double ndU = std::sqrt(dot(h, dU, dU, n));
-    nR = std::sqrt(dot(h, Rb, Rb, n));
+    const double ndU = std::sqrt(dot(h, dU, dU, nred));
+    nR = std::sqrt(dot(h, Rb, Rb, nred));
     if (it == 1) R0 = nR;
     const double rel = R0 > 0.0 ? nR / R0 : nR;
     if (ndU < tol || nR < tol || rel < tol) break;
@@ -931,10 +1004,17 @@ static void peer_detach_impl(fecb200_handle* h) {
 }
 
 int fecb200_peer_attach(fecb200_handle* h, int32_t which, int32_t n_peers, const void* handles64,
-                        const int32_t* ghost_peer, const int64_t* ghost_node, int64_t n_ghosts) {
+                        const int64_t* peer_n_nodes, const int32_t* ghost_peer, const int64_t* ghost_node, int64_t n_ghosts) {
   FEC_API_BEGIN
-  FEC_REQUIRE(h && (n_peers == 0 || handles64), "null argument");
+  FEC_REQUIRE(h && (n_peers == 0 || (handles64 && peer_n_nodes)), "null argument");
   FEC_REQUIRE(n_peers >= 0 && n_peers <= kMaxPeers, "too many peers");
+  // validate BEFORE any handle is opened: the kernels write to base[peer] + ghost_node * NF + d in another GPU's memory
+  for (int64_t g = 0; g < n_ghosts; ++g) {
+    FEC_REQUIRE(ghost_peer[g] >= -1 && ghost_peer[g] < n_peers, "ghost_peer out of range");
+    if (ghost_peer[g] >= 0)
+      FEC_REQUIRE(ghost_node[g] >= 0 && ghost_node[g] < peer_n_nodes[ghost_peer[g]] && ghost_node[g] < (int64_t)INT32_MAX,
+                  "ghost_node out of range for its owner (stale or mismatched exchange list)");
+  }
   FEC_REQUIRE(n_ghosts == h->nn - h->n_owned_nodes, "ghost arrays must cover every ghost node (call partition_setup first)");
   FEC_REQUIRE(which == FECB200_FIELD_RESIDUAL || which == FECB200_FIELD_ACTION, "peer scatter targets the residual or action field");
   FEC_CUDA(cudaSetDevice(h->device));
@@ -951,7 +1031,6 @@ int fecb200_peer_attach(fecb200_handle* h, int32_t which, int32_t n_peers, const
   }
   std::vector<int32_t> gp(ghost_peer, ghost_peer + n_ghosts), gn(n_ghosts);
   for (int64_t g = 0; g < n_ghosts; ++g) {
-    FEC_REQUIRE(gp[g] >= -1 && gp[g] < n_peers, "ghost_peer out of range");
     gn[g] = gp[g] >= 0 ? (int32_t)ghost_node[g] : 0;
   }
   h->d_ghost_peer.upload(gp, h->stream);

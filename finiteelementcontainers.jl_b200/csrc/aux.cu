@@ -50,21 +50,29 @@ __global__ void k_zero_indexed(double* f, const int32_t* idx, int64_t n) {
   if (i < n) f[idx[i]] = 0.0;
 }
 
+// _update_for_assembly! (Parameters.jl:404-425) as ONE launch: thread i handles Dirichlet entry i,
+// unknown i - n_bc or periodic pair i - n_bc - n_u.  The three index sets are disjoint (DofManagers.jl:261-284) and a
+// periodic side-a dof is always an unknown (checked in build_dof_structures), so U[b] = Uu[unknown(a)] + val needs no
+// ordering against the other two segments.
+__global__ void k_update_field_fused(double* f, const double* Uu, const int32_t* bc_dofs, const double* bc_vals, int64_t n_bc,
+                                     const int32_t* ud, int64_t n_u, int condensed, const int32_t* pa, const int32_t* pb,
+                                     const double* pvals, const int32_t* d2u, int64_t n_per) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n_bc) { f[bc_dofs[i]] = bc_vals[i]; return; }
+  i -= n_bc;
+  if (i < n_u) { const int32_t g = ud[i]; f[g] = condensed ? Uu[g] : Uu[i]; return; }
+  i -= n_u;
+  if (i < n_per) f[pb[i]] = Uu[d2u[pa[i]]] + pvals[i];
+}
+
 void k_update_field(fecb200_handle* h, double* field, const double* Uu, bool with_bcs) {
-  cudaStream_t s = h->stream;
-  if (with_bcs && h->n_bc) {
-    k_set_indexed<<<grid_for(h->n_bc), 256, 0, s>>>(field, h->d_bc_dofs.p, h->d_bc_vals.p, h->n_bc);
-    h->launches++;
-  }
-  if (h->n_unknowns) {
-    k_scatter_unknowns<<<grid_for(h->n_unknowns), 256, 0, s>>>(field, h->d_unknown_dofs.p, Uu, h->n_unknowns,
-                                                               h->opts.condensed);
-    h->launches++;
-  }
-  if (with_bcs && h->n_per) {
-    k_periodic<<<grid_for(h->n_per), 256, 0, s>>>(field, h->d_per_a.p, h->d_per_b.p, h->d_per_vals.p, h->n_per);
-    h->launches++;
-  }
+  const int64_t n_bc = with_bcs ? h->n_bc : 0, n_per = with_bcs ? h->n_per : 0;
+  const int64_t n = n_bc + h->n_unknowns + n_per;
+  if (!n) return;
+  k_update_field_fused<<<grid_for(n), 256, 0, h->stream>>>(field, Uu, h->d_bc_dofs.p, h->d_bc_vals.p, n_bc, h->d_unknown_dofs.p,
+                                                          h->n_unknowns, h->opts.condensed, h->d_per_a.p, h->d_per_b.p,
+                                                          h->d_per_vals.p, h->d_d2u.p, n_per);
+  h->launches++;
   FEC_CUDA(cudaGetLastError());
 }
 
@@ -200,6 +208,7 @@ double dot(fecb200_handle* h, const double* a, const double* b, int64_t n) {
   FEC_CUDA(cudaMemsetAsync(h->d_red.p, 0, sizeof(double), h->stream));
   const int grid = (int)std::min<int64_t>(148 * 8, (n + 255) / 256);
   if (n) { k_dot<<<grid, 256, 0, h->stream>>>(a, b, n, h->d_red.p); h->launches++; }
+  if (comm_active(h)) comm_allreduce_sum(h, h->d_red.p, 1);   // partitioned handles pass their OWNED length (owned_len)
   return read_scalar(h);
 }
 

@@ -276,7 +276,12 @@ struct fecb200_handle {
   std::vector<int32_t> neighbor_ranks;
   std::vector<int64_t> send_ptr, recv_ptr;
   fec::DevBuf<int32_t> d_send_nodes, d_recv_nodes;
-  fec::DevBuf<double> d_sendbuf;
+  fec::DevBuf<double> d_sendbuf, d_recvbuf;
+
+  // collective plane (comm.cu): NCCL communicator of this rank, created by fecb200_comm_init
+  void* comm = nullptr;
+  int comm_rank = 0, comm_nranks = 1;
+  fec::DevBuf<float> d_bar;
 
   // opt-in asynchronous host copies (fecb200_set_async): H2D / D2H run on their own streams, ordered with events
   bool async_copies = false;
@@ -360,6 +365,16 @@ void fill_indexed(fecb200_handle* h, double* field, const int32_t* idx, double v
 void halo_pack(fecb200_handle* h, const double* field, double* buf);
 void halo_unpack_add(fecb200_handle* h, double* field, const double* buf);
 
+// comm.cu
+bool comm_active(const fecb200_handle* h);
+void comm_allreduce_sum(fecb200_handle* h, double* dev, int n);
+void comm_barrier(fecb200_handle* h);
+void comm_halo_sum_field(fecb200_handle* h, double* field);
+void comm_halo_update_field(fecb200_handle* h, double* field);
+void comm_halo_update_unknowns(fecb200_handle* h, double* v);
+int64_t owned_len(const fecb200_handle* h);
+void comm_release(fecb200_handle* h);
+
 // loads.cu
 void add_neumann_loads(fecb200_handle* h, double* field);   // field += int_Gamma N g      (WeaklyEnforcedBCs.jl:61-83)
 void add_source_loads(fecb200_handle* h, double* field);    // field += -int_Omega N b    (Source.jl:44-63)
@@ -369,6 +384,13 @@ inline bool is_device_ptr(const void* p) {
   cudaError_t e = cudaPointerGetAttributes(&a, p);
   if (e != cudaSuccess) { cudaGetLastError(); return false; }
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+inline bool is_pinned_host_ptr(const void* p) {
+  cudaPointerAttributes a{};
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
 }
 
 }  // namespace fec

@@ -20,7 +20,7 @@ from .assemblers import (SparseMatrixAssembler, Parameters, create_parameters, u
                          update_time, create_field, create_unknowns, assemble_vector, assemble_stiffness,
                          assemble_mass, assemble_vector_and_stiffness, assemble_matrix_action, assemble_matrix_free_action,
                          assemble_matrix_free_action_full, hvp, full_field, assemble_lumped_mass, assemble_diagonal, diagonal, assemble_scalar, scalar_values,
-                         assemble_vector_neumann_bc, assemble_vector_source)
+                         assemble_vector_neumann_bc, assemble_vector_source, matrix_multiply, update_field)
 from .solvers import DirectLinearSolver, IterativeLinearSolver, NewtonSolver, QuasiStaticIntegrator
 from .postprocessors import PostProcessor, write_times, write_field, close
 from .partition import (Partition, partition_mesh, structured_brick_partition, metis_partition_elements,

@@ -95,6 +95,8 @@ SIGNATURES = {
     "fecb200_assemble_action_full": (C.c_int, [Handle, C.c_int32, VP, VP]),
     "fecb200_hvp": (C.c_int, [Handle, VP, VP]),
     "fecb200_field_copy": (C.c_int, [Handle, C.c_int32, VP]),
+    "fecb200_update_field": (C.c_int, [Handle, VP]),
+    "fecb200_matrix_multiply": (C.c_int, [Handle, C.c_int32, VP, VP]),
     "fecb200_set_neumann_bc": (C.c_int, [Handle, C.c_int32, C.c_int64, C.c_int32, C.c_int32, c_i64p, c_f64p, c_f64p, c_f64p]),
     "fecb200_set_neumann_values": (C.c_int, [Handle, C.c_int32, VP]),
     "fecb200_clear_neumann_bcs": (C.c_int, [Handle]),
@@ -113,7 +115,17 @@ SIGNATURES = {
     "fecb200_halo_unpack_add": (C.c_int, [Handle, C.c_int32, VP]),
     "fecb200_halo_recv_size": (C.c_int, [Handle, c_i64p]),
     "fecb200_ipc_export": (C.c_int, [Handle, C.c_int32, C.c_void_p]),
-    "fecb200_peer_attach": (C.c_int, [Handle, C.c_int32, C.c_int32, C.c_void_p, c_i32p, c_i64p, C.c_int64]),
+    "fecb200_peer_attach": (C.c_int, [Handle, C.c_int32, C.c_int32, C.c_void_p, c_i64p, c_i32p, c_i64p, C.c_int64]),
+    "fecb200_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "fecb200_comm_init": (C.c_int, [Handle, C.c_int32, C.c_int32, C.c_void_p]),
+    "fecb200_comm_destroy": (C.c_int, [Handle]),
+    "fecb200_halo_sum": (C.c_int, [Handle, C.c_int32]),
+    "fecb200_halo_update": (C.c_int, [Handle, C.c_int32]),
+    "fecb200_halo_update_unknowns": (C.c_int, [Handle, VP]),
+    "fecb200_owned_length": (C.c_int, [Handle, c_i64p]),
+    "fecb200_comm_barrier": (C.c_int, [Handle]),
+    "fecb200_comm_allreduce_sum": (C.c_int, [Handle, c_f64p, C.c_int32]),
+    "fecb200_comm_peer_enable": (C.c_int, [Handle, C.c_int32]),
     "fecb200_peer_detach": (C.c_int, [Handle]),
     "fecb200_launch_count": (C.c_int, [Handle, c_i64p]),
     "fecb200_enable_timing": (C.c_int, [Handle, C.c_int32]),

@@ -245,12 +245,12 @@ def update_bc_values(p):
     check(lib.fecb200_set_dirichlet_values(p.asm._require(), dp, vp, len(d)))
     if getattr(p, "periodic_bcs", None) is not None and len(p.periodic_bcs):    # jump values U[b] = U[a] + val
         p.periodic_bcs.update_bc_values(p.coords, p.times.time_current)
-        # the library keeps one value per (de-duplicated, chain-resolved) pair in registration order and checks the count;
-        # all-zero jumps (the default inside the library) need no call
+        # the library keeps one value per (de-duplicated, chain-resolved) pair in registration order and checks the count.
+        # Always pushed, like the reference rewrites its cache at every update_bc_values!: a time-dependent jump that
+        # returns to exactly 0 must not leave a stale value on the device.
         pv = p.periodic_bcs.values()
-        if np.any(pv != 0.0):
-            v, vp = _lib.f64(pv)
-            check(lib.fecb200_set_periodic_values(p.asm._require(), vp, len(v)))
+        v, vp = _lib.f64(pv)
+        check(lib.fecb200_set_periodic_values(p.asm._require(), vp, len(v)))
     if p.neumann_bcs is not None and len(p.neumann_bcs):     # update_bc_values!(p.neumann_bcs, asm, X, t)
         p.neumann_bcs.update_bc_values(p.coords, p.times.time_current)
         for i, c in enumerate(p.neumann_bcs.bc_caches):
@@ -438,6 +438,19 @@ def _mass_accessor(asm):
         n = asm.sizes()[2]
         return sp.csc_matrix((n, n))
     return _sparse(asm, _lib.MASS)
+
+
+def matrix_multiply(asm, x, out=None, kind=_lib.STIFFNESS):
+    """stiffness(asm) * x (or mass(asm) * x with kind=MASS) on the device-resident values: the product the Krylov
+    solve forms (src/Solvers.jl:144), without copying the matrix to the host."""
+    out = np.empty(asm.sizes()[2]) if out is None else out
+    check(lib.fecb200_matrix_multiply(asm._require(), kind, _lib.ptr(x), _lib.ptr(out)))
+    return out
+
+
+def update_field(p, Uu):
+    """_update_for_assembly!(p, dof, Uu) (src/Parameters.jl:404-413): p.field <- BC values, unknowns, periodic copies"""
+    check(lib.fecb200_update_field(p.asm._require(), _lib.ptr(Uu)))
 
 
 def full_field(asm, which="residual"):

@@ -123,12 +123,38 @@ class Partition:
         check(lib.fecb200_halo_setup(h, len(nbrs), nbrs.ctypes.data_as(_lib.c_i32p), _lib.i64(sp)[1], _lib.i64(sn)[1],
                                      _lib.i64(rp)[1], _lib.i64(rn)[1]))
         self._nf = asm.dof.nf
+        self._asm_handle = h
         self._send_counts = [int(sp[i + 1] - sp[i]) * self._nf for i in range(len(nbrs))]
         self._recv_counts = [int(rp[i + 1] - rp[i]) * self._nf for i in range(len(nbrs))]
 
+    def comm_init(self, asm, unique_id=None):
+        """fecb200_comm_init: the library's own NCCL communicator for this handle.  The 128-byte ncclUniqueId of rank 0
+        is the one thing that travels out of band: `unique_id` (bytes, e.g. from MPI_Bcast / a file), or, when None,
+        a torch.distributed object broadcast.  After this, halo sums, barriers, the peer-memory set-up and the
+        distributed CG / Newton run inside the library -- torch.distributed is not in the data path."""
+        if unique_id is None:
+            import torch.distributed as dist
+            box = [None]
+            if self.rank == 0:
+                buf = C.create_string_buffer(128)
+                check(lib.fecb200_comm_unique_id(C.cast(buf, C.c_void_p)))
+                box[0] = bytes(buf.raw)
+            dist.broadcast_object_list(box, src=0)
+            unique_id = box[0]
+        assert len(unique_id) == 128
+        buf = C.create_string_buffer(unique_id, 128)
+        check(lib.fecb200_comm_init(asm._require(), self.rank, self.nparts, C.cast(buf, C.c_void_p)))
+        self._comm = True
+
     def enable_peer_scatter(self, asm):
         """Switch the residual halo to the fused NVLink path: kernels add ghost contributions directly into the
-        owner's residual through peer-mapped memory (CUDA IPC).  Needs an initialised NCCL process group."""
+        owner's residual through peer-mapped memory (CUDA IPC).  With the library communicator (comm_init) the whole
+        exchange of IPC handles and owner-local ghost ids happens inside libfecb200; the torch.distributed variant
+        below is kept for hosts that drive the halo themselves."""
+        if getattr(self, "_comm", False):
+            check(lib.fecb200_comm_peer_enable(asm._require(), _lib.FIELD_RESIDUAL))
+            self._peer = True
+            return
         import torch
         import torch.distributed as dist
         h = asm._require()
@@ -161,13 +187,22 @@ class Partition:
                 gnode[g] = theirs[off:off + ns] - 1
             off += ns
         hb = C.create_string_buffer(handles, max(64, len(handles)))
+        # node count of every peer's local mesh (range check of the ghost ids inside the library)
+        nn_t = torch.tensor([len(self.local_to_global)], dtype=torch.int64, device=dev)
+        all_nn = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(self.nparts)]
+        dist.all_gather(all_nn, nn_t)
+        peer_nn = np.array([int(all_nn[r].item()) for r in peers] or [0], dtype=np.int64)
         check(lib.fecb200_peer_attach(h, _lib.FIELD_RESIDUAL, len(peers), C.cast(hb, C.c_void_p),
-                                      gpeer.ctypes.data_as(_lib.c_i32p), gnode.ctypes.data_as(_lib.c_i64p), n_ghost))
+                                      peer_nn.ctypes.data_as(_lib.c_i64p), gpeer.ctypes.data_as(_lib.c_i32p),
+                                      gnode.ctypes.data_as(_lib.c_i64p), n_ghost))
         self._peer = True
         self._bar = torch.zeros(1, dtype=torch.float32, device=dev)
 
     def barrier_on_stream(self, stream=None):
         """stream-ordered cross-rank barrier (a 4-byte NCCL all-reduce): orders the peer scatter phases"""
+        if getattr(self, "_comm", False):
+            check(lib.fecb200_comm_barrier(self._asm_handle))   # on the handle's stream
+            return
         import torch
         import torch.distributed as dist
         ctx = torch.cuda.stream(stream) if stream is not None else _nullctx()
@@ -176,6 +211,10 @@ class Partition:
 
     def halo_sum_residual(self, asm, stream=None, field=_lib.FIELD_RESIDUAL):
         """ghost -> owner accumulation of the assembled residual (device pack, NCCL send/recv, device add)"""
+        if getattr(self, "_comm", False):
+            # library communicator: pack / grouped ncclSend+ncclRecv / add, or the closing barrier of the peer halo
+            check(lib.fecb200_halo_sum(asm._require(), field))
+            return
         import torch
         if getattr(self, "_peer", False):
             # fused path: the kernels already added the ghost rows into their owners; just wait for everyone

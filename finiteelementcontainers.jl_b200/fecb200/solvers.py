@@ -102,14 +102,27 @@ class QuasiStaticIntegrator:
         self.solution = None
         self.failed = False
 
-    def evolve(self, p):
+    def evolve(self, p, commit_state=True):
+        """evolve!(integrator, p) (QuasiStaticIntegrator.jl:16-34).  After the solve the reference pushes the converged
+        solution into p.field (`_update_for_assembly!`, :21-24); so does this.  The reference never advances
+        state_old; with `commit_state` (default, needed by any stateful law) the state is re-evaluated AT the converged
+        solution by one residual pass and then committed (state_old <- state_new); pass False for the reference's
+        behaviour."""
+        from .assemblers import assemble_vector, update_field
+        from .physics import residual
         asm = self.solver.linear_solver.assembler
         if self.solution is None:
             self.solution = np.zeros(asm.sizes()[2])
         update_time(p)
         update_bc_values(p)
         self.solver.solve(self.solution, p)
-        # _update_for_assembly!(p, dof, solution): the handle's field already holds the last iterate's
-        # BC-enforced field; state_old <- state_new at the end of the load step
-        check(lib.fecb200_state_swap(asm._require()))
+        stateful = any(ph.NS > 0 for ph in p.physics)
+        if commit_state and stateful:
+            assemble_vector(asm, residual, self.solution, p)   # field + state_new at the converged solution
+            check(lib.fecb200_state_swap(asm._require()))
+        else:
+            update_field(p, self.solution)
+        # the reference flags a step whose last Newton increment AND residual are both above tolerance (:27-31);
+        # the device loop only leaves early when one of its three tests passed, so "ran out of iterations" is that case
+        self.failed = bool(self.solver.iterations >= self.solver.max_iters and not self.solver.residual_norm < self.solver.tol)
         return self.solution

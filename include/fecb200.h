@@ -208,6 +208,16 @@ int fecb200_hvp(fecb200_handle* h, const double* v, double* out);
 
 /* copy of a full-length nodal field (p.field, residual_storage, stiffness_action_storage) */
 int fecb200_field_copy(fecb200_handle* h, int32_t which, double* out);
+/* _update_for_assembly!(p, dof, Uu) on its own (src/Parameters.jl:404-413): Dirichlet values, unknowns and periodic
+ * copies into p.field, one launch.  evolve! calls it after the solve so that the stored field is the converged,
+ * BC-enforced one (src/integrators/QuasiStaticIntegrator.jl:21-24).  Uu [host|device], length len_Uu. */
+int fecb200_update_field(fecb200_handle* h, const double* Uu);
+/* y = stiffness(asm) * x / mass(asm) * x on the assembled values (the product Krylov forms, src/Solvers.jl:144):
+ * device SpMV over the reference-ordered CSR, constraint adjustment applied first in condensed mode.  x, y
+ * [host|device], length len_Uu.  CSC handles hold K^T row-wise; the product is K x for the (symmetric) operators
+ * assembled here.  On a partitioned handle x's ghost entries are refreshed from their owners first and only owned
+ * rows of y are produced (ghost entries of y are 0). */
+int fecb200_matrix_multiply(fecb200_handle* h, int32_t kind, const double* x, double* y);
 
 /* ---- external loads of the residual: the two calls solve! makes right after
  * assemble_vector! (src/Solvers.jl:66-69, 133-137).  Neither zeroes the residual storage, both add to it
@@ -284,9 +294,40 @@ int fecb200_halo_recv_size(fecb200_handle* h, int64_t* n_doubles);
  * The host must order steps across ranks: every rank's field is zeroed before any rank scatters, and all ranks
  * finished scattering before an owner reads (two stream-ordered barriers per assembly). */
 int fecb200_ipc_export(fecb200_handle* h, int32_t which_field, void* handle64);
+/* peer_n_nodes[i] = node count of peer i's local mesh: every ghost_node is range-checked against its owner before
+ * any handle is opened (a stale exchange list must not turn into a stray write into another process). */
 int fecb200_peer_attach(fecb200_handle* h, int32_t which_field, int32_t n_peers, const void* handles64,
-                        const int32_t* ghost_peer, const int64_t* ghost_node, int64_t n_ghosts);
+                        const int64_t* peer_n_nodes, const int32_t* ghost_peer, const int64_t* ghost_node, int64_t n_ghosts);
 int fecb200_peer_detach(fecb200_handle* h);
+
+/* ---- collective plane: include/fecb200.h alone drives N GPUs, one process per GPU, NCCL over
+ * NVLink.  The host moves ONE thing out of band: rank 0's 128-byte ncclUniqueId (MPI_Bcast in the reference's
+ * setting, ext/PartitionedArraysExt.jl:15-37).  Everything below is stream-ordered on the handle's stream.
+ *   fecb200_comm_unique_id       ncclGetUniqueId (rank 0)
+ *   fecb200_comm_init            ncclCommInitRank for this handle's device; needs fecb200_halo_setup for the halo calls
+ *   fecb200_halo_sum             ghost -> owner sum of a nodal field = assembly of a PVector (:469-481): device pack,
+ *                                one grouped ncclSend/ncclRecv per neighbour, device add; with the peer-memory halo
+ *                                enabled for that field it is the closing barrier only
+ *   fecb200_halo_update          owner -> ghost copy of a nodal field = consistent! (:449-459)
+ *   fecb200_halo_update_unknowns the same for a device vector in the Uu layout (ghost unknowns follow the owned ones)
+ *   fecb200_owned_length         leading entries of a Uu-shaped vector that belong to owned nodes (own_values)
+ *   fecb200_comm_barrier         stream-ordered barrier (4-byte all-reduce): orders the two phases of the peer halo
+ *   fecb200_comm_allreduce_sum   sum of 1..4 host scalars over the ranks (distributed dots / norms, :522-540)
+ *   fecb200_comm_peer_enable     exchanges the IPC handles and the owner-local ghost ids over NCCL inside the library
+ *                                and attaches the peer-memory halo for that field (fecb200_peer_attach)
+ * With a communicator attached, fecb200_cg_solve / fecb200_newton_solve / fecb200_matrix_multiply run distributed:
+ * dots over owned entries + ncclAllReduce, ghost refresh before every operator application, ghost -> owner sum of the
+ * residual; iteration counts equal the serial solve's. */
+int fecb200_comm_unique_id(void* id128);
+int fecb200_comm_init(fecb200_handle* h, int32_t rank, int32_t nranks, const void* id128);
+int fecb200_comm_destroy(fecb200_handle* h);
+int fecb200_halo_sum(fecb200_handle* h, int32_t which_field);
+int fecb200_halo_update(fecb200_handle* h, int32_t which_field);
+int fecb200_halo_update_unknowns(fecb200_handle* h, double* Uu_dev);
+int fecb200_owned_length(fecb200_handle* h, int64_t* n);
+int fecb200_comm_barrier(fecb200_handle* h);
+int fecb200_comm_allreduce_sum(fecb200_handle* h, double* vals, int32_t n);
+int fecb200_comm_peer_enable(fecb200_handle* h, int32_t which_field);
 
 /* ---- instrumentation: kernels launched by this handle since creation (bench `gpu_launches`) */
 int fecb200_launch_count(fecb200_handle* h, int64_t* n);
