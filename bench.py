@@ -5,7 +5,9 @@
     python bench.py --impl reference --steps K --warmup W    (CPU port of the reference path)
 
 Workload (BASELINE.json config 3 / 5): neo-Hookean hex8, 3 dof/node, structured 192^3 elements PER GPU
-(weak scaling: 1 GPU 192^3, 2 GPUs 384x192x192, 4 GPUs 384x384x192, 8 GPUs 384^3), Float64.  One
+(weak scaling: 1 GPU 192^3, 2 GPUs 384x192x192, 4 GPUs 384x384x192, 8 GPUs 384^3), Float64.  N > 1: the global grid
+is partitioned with METIS (k-way on the dual graph of 8^3-element cells; --partition brick gives flat bricks), ghost
+residual contributions travel over NVLink, the collective plane (NCCL) lives inside libfecb200.  One
 "step" = what one Newton iteration asks of the path: assemble_vector!(residual) + residual(asm), then
 assemble_stiffness!(stiffness) into the CSR values.  value = elements assembled per second over the
 whole job (all ranks), inputs resident in HBM.  `e2e` is the same step driven through the C ABI with
@@ -39,13 +41,21 @@ BYTES_ACTION = 160.0
 # FP64 flops per element counted from the kernels' instruction mix
 FLOPS_RESIDUAL = 7.0e3
 FLOPS_TANGENT = 34.0e3      # fused k_mat2: thread-level (2 DFMA + DMUL + DADD) per element, ncu r01z (36.6e3 before the tangent was re-factored)
-BYTES_ZERO_FILL = 1954.0   # fill!(storage, 0) of the CSR values (Matrix.jl:39): inside the kernel when double-buffered
-# DRAM bytes per launch of the dominant kernel from the `ncu --set full` capture of this same command at 192^3:
-#   double-buffered (default)  profiles/r01zz_dram_compression.txt: dram__bytes_read.sum 8.68 GB + write 19.90 GB with the
-#                              compressible CSR value arrays (17.30 + 28.33 GB without, profiles/r01z_fused_kmat2_details.txt)
-#   --single-buffer            profiles/r01h_fused_kmat2_details.txt  read 16.80 GB + write 14.45 GB (memset separate)
-TRAFFIC_NCU_BYTES_PER_ELEMENT = {True: (8.68e9 + 19.90e9) / 7077888, False: (16.796e9 + 14.452e9) / 7077888}
+BYTES_ZERO_FILL = 1954.0   # fill!(storage, 0) of the CSR values (Matrix.jl:39): NOT algorithmic (SURVEY 8d counts every
+                           # output once); reported as `extra_bytes_per_element` when the kernel clears the idle buffer
 NEO_PROPS = np.array([1e3, 10.0e6, 1.0e6])
+
+
+def ncu_traffic(dbuf):
+    """DRAM bytes per launch of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum from the committed
+    `ncu --set full` capture of this command (profiles/traffic.json names the capture).  None when no capture of the
+    current kernel is on file -- never a stale constant."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p))
+    e = d.get("double_buffered" if dbuf else "single_buffer")
+    return (e.get("dram_bytes_per_launch"), e.get("source")) if e else (None, None)
 
 
 def load_peaks():
@@ -129,9 +139,41 @@ def grid_for(world):
     return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
 
 
-def build_problem(F, n, rank, world, matrix_free=False):
+METIS_CELL = 8   # METIS runs on the dual graph of 8^3-element cells (384^3 elements -> 48^3 cells)
+
+
+def make_partition(F, n, rank, world, how, cell=METIS_CELL):
+    """rank-local mesh + Partition of the (gx n) x (gy n) x (gz n) grid.  metis: METIS_PartGraphKway on the coarse-cell
+    dual graph (computed by rank 0, broadcast), every rank materialises only its own ragged piece."""
+    from fecb200.partition import metis_cell_partition, structured_brick_partition, structured_cell_partition
+    g = grid_for(world)
+    if how == "brick":
+        return structured_brick_partition(F, n, g, rank)
+    import torch
+    import torch.distributed as dist
+    cell = cell if n % cell == 0 else next(c for c in (8, 6, 4, 3, 2, 1) if n % c == 0)
+    cells = tuple(gi * n // cell for gi in g)
+    cp = torch.zeros(cells, dtype=torch.int16, device="cuda")
+    if rank == 0:
+        cp.copy_(torch.from_numpy(metis_cell_partition(cells, world).astype(np.int16)))
+    if dist.is_initialized() and world > 1:
+        dist.broadcast(cp, src=0)
+    lm, part = structured_cell_partition(F, tuple(gi * n for gi in g), cp.cpu().numpy(), cell, rank, h=1.0 / n)
+    part.cell = cell
+    return lm, part
+
+
+def raw_state(X, n, rng=None):
+    """raw-throughput state: u = 0.02 (sin 2 pi y, sin 2 pi z, sin 2 pi x) [+ U(-1e-3,1e-3) h]"""
+    U = 0.02 * np.stack([np.sin(2 * np.pi * X[1]), np.sin(2 * np.pi * X[2]), np.sin(2 * np.pi * X[0])])
+    if rng is not None:
+        U += rng.uniform(-1e-3, 1e-3, U.shape) / n
+    return U
+
+
+def build_problem(F, n, rank, world, matrix_free=False, partition="metis", noise=True, mesh_part=None):
     """Rank-local neo-Hookean problem.  N = 1: StructuredMesh('hex', (0,0,0), (1,1,1), (n+1,)*3) with the
-    BCs of BASELINE config 3.  N > 1: this rank's brick of the global grid (see fecb200.partition)."""
+    BCs of BASELINE config 3.  N > 1: this rank's piece of the global grid (see fecb200.partition)."""
     verbose = bool(os.environ.get("FECB200_VERBOSE"))
     tick = [time.time()]
 
@@ -139,12 +181,13 @@ def build_problem(F, n, rank, world, matrix_free=False):
         if verbose and rank == 0:
             print(f"[bench setup] {name:28s} {time.time() - tick[0]:.3f} s", file=sys.stderr, flush=True)
         tick[0] = time.time()
-    if world == 1:
+    if mesh_part is not None:
+        mesh, part = mesh_part
+    elif world == 1:
         mesh = F.StructuredMesh("hex", (0., 0., 0.), (1., 1., 1.), (n + 1, n + 1, n + 1))
         part = None
     else:
-        from fecb200.partition import structured_brick_partition
-        mesh, part = structured_brick_partition(F, n, grid_for(world), rank)
+        mesh, part = make_partition(F, n, rank, world, partition)
     lap("mesh")
     V = F.FunctionSpace(mesh, F.H1Field, F.Lagrange, q_type="GaussLegendre", q_degree=2)
     u = F.VectorFunction(V, "displ")
@@ -163,11 +206,8 @@ def build_problem(F, n, rank, world, matrix_free=False):
     if part is not None:
         part.attach(asm)
         lap("partition attach")
-    # raw-throughput state: u = 0.02 (sin 2 pi y, sin 2 pi z, sin 2 pi x) + U(-1e-3,1e-3) h
     X = np.asarray(mesh.nodal_coords)
-    rng = np.random.default_rng(42 + rank)
-    U = 0.02 * np.stack([np.sin(2 * np.pi * X[1]), np.sin(2 * np.pi * X[2]), np.sin(2 * np.pi * X[0])])
-    U += rng.uniform(-1e-3, 1e-3, U.shape) / n
+    U = raw_state(X, n, np.random.default_rng(42 + rank) if noise else None)
     Uu = np.ascontiguousarray(U.reshape(-1, order="F")[asm.dof.unknown_dofs - 1])
     lap("initial state")
     return mesh, asm, p, Uu, part
@@ -188,6 +228,111 @@ def bind_to_gpu_numa_node(index):
         pass
 
 
+def _rel(a, b):
+    import torch
+    d = float(torch.linalg.vector_norm(a - b))
+    s = float(torch.linalg.vector_norm(b))
+    return d / s if s > 0 else d
+
+
+def check_single(F, asm, p, dUu, stream):
+    """Self-check of the VERY problem that is timed (N = 1, full size): the assembled tangent applied on the device
+    against the matrix-free action, the fused kernel's residual against the stand-alone residual kernel, and a
+    checksum of the values.  (Parity against the oracle at size: tests/test_gpu_at_size.py.)"""
+    import torch
+    N = len(dUu)
+    with torch.cuda.stream(stream):
+        v = torch.rand(N, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(7))
+        one = torch.ones(N, dtype=torch.float64, device="cuda")
+        Rf, Rv, Kv, Av, K1 = (torch.empty(N, dtype=torch.float64, device="cuda") for _ in range(5))
+    stream.synchronize()
+    F.assemble_vector_and_stiffness(asm, F.residual, F.stiffness, dUu, p)
+    F.residual(asm, Rf)
+    F.matrix_multiply(asm, v, Kv)
+    F.matrix_multiply(asm, one, K1)
+    F.assemble_matrix_free_action(asm, F.stiffness_action, dUu, v, p)
+    F.hvp(asm, v, Av)
+    F.assemble_vector(asm, F.residual, dUu, p)
+    F.residual(asm, Rv)
+    stream.synchronize()
+    torch.cuda.synchronize()
+    e_kv, e_r = _rel(Kv, Av), _rel(Rf, Rv)
+    finite = bool(torch.isfinite(Kv).all() and torch.isfinite(Rf).all())
+    return {"Kv_vs_matrix_free_action": e_kv, "fused_R_vs_residual_kernel": e_r, "sum_nzval": float(K1.sum()),
+            "norm_R": float(torch.linalg.vector_norm(Rf)), "tol": 1e-11, "ok": bool(finite and e_kv < 1e-11 and e_r < 1e-11)}
+
+
+def check_partitioned(F, rank, world, partition, n_c=48):
+    """N > 1: the partitioned path (same partitioner, library communicator, fused peer-memory halo) against a SERIAL
+    handle on the same global mesh, small enough to fit one GPU (n_c^3 elements per rank; 96^3 global at N = 8), under
+    this very launch: owned residual rows, K v and the row sums K 1 on owned rows."""
+    import torch
+    import torch.distributed as dist
+    from fecb200 import _lib
+    from fecb200._lib import check, lib
+    g = grid_for(world)
+    # ---- partitioned
+    mesh, asm, p, Uu, part = build_problem(F, n_c, rank, world, partition=partition, noise=False)
+    part.comm_init(asm)
+    part.enable_peer_scatter(asm)
+    h = asm._require()
+    dUu = torch.from_numpy(Uu).cuda()
+    N = len(Uu)
+    tmp = torch.empty(N, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    F.residual(asm, tmp)                       # flush: every rank's residual field is zero ...
+    part.barrier_on_stream()                   # ... before anyone scatters
+    asm.set_matrix_double_buffer(True)
+    for _ in range(2):                         # second pass lands in kernel-cleared storage
+        F.assemble_vector_and_stiffness(asm, F.residual, F.stiffness, dUu, p)
+        part.halo_sum_residual(asm)
+        R_field = F.full_field(asm, "residual").reshape(-1, 3)[:part.n_owned_nodes].copy()
+        F.residual(asm, tmp)
+        part.barrier_on_stream()
+    # ---- serial, same global mesh, on this rank's GPU
+    E = tuple(gi * n_c for gi in g)
+    gmesh = F.StructuredMesh("hex", (0., 0., 0.), tuple(e / n_c for e in E), tuple(e + 1 for e in E))
+    _, gasm, gp, gUu, _ = build_problem(F, n_c, 0, 1, noise=False, mesh_part=(gmesh, None))
+    F.assemble_vector_and_stiffness(gasm, F.residual, F.stiffness, gUu, gp)
+    Rg = F.full_field(gasm, "residual").reshape(-1, 3)
+    l2g = part.local_to_global - 1
+    own = l2g[:part.n_owned_nodes]
+    e_R = float(np.abs(R_field - Rg[own]).max() / np.abs(Rg).max())
+    # K v on owned rows: local unknown -> global unknown through the dof ids
+    nown = C_int64_value(lib.fecb200_owned_length, h)
+    ud_l = asm.dof.unknown_dofs[:nown] - 1
+    gdof = 3 * l2g[ud_l // 3] + ud_l % 3
+    ug = gasm.dof.dof_to_unknown[gdof] - 1
+    assert (ug >= 0).all()
+    rng = np.random.default_rng(7)
+    vg = rng.uniform(0, 1, gasm.sizes()[2])
+    # local v: owned AND ghost entries from the global vector (the library refreshes ghosts anyway)
+    ud_all = asm.dof.unknown_dofs - 1
+    ug_all = gasm.dof.dof_to_unknown[3 * l2g[ud_all // 3] + ud_all % 3] - 1
+    errs = {}
+    for name, xg in (("Kv", vg), ("rowsum", np.ones_like(vg))):
+        yl = F.matrix_multiply(asm, np.ascontiguousarray(xg[ug_all]))[:nown]
+        yg = F.matrix_multiply(gasm, xg)
+        errs[name] = float(np.abs(yl - yg[ug]).max() / np.abs(yg).max())
+    gasm.close()
+    t = torch.tensor([e_R, errs["Kv"], errs["rowsum"]], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    torch.cuda.synchronize()
+    asm.close()
+    e_R, e_kv, e_rs = (float(x) for x in t.tolist())
+    return {"against": f"serial assembly of the same {E[0]}x{E[1]}x{E[2]} mesh on every rank's own GPU", "partition": partition,
+            "owned_R_vs_serial": e_R, "Kv_owned_rows_vs_serial": e_kv, "rowsum_owned_rows_vs_serial": e_rs, "tol": 1e-11,
+            "ok": bool(max(e_R, e_kv, e_rs) < 1e-11)}
+
+
+def C_int64_value(fn, h):
+    import ctypes as C
+    from fecb200._lib import check
+    v = C.c_int64()
+    check(fn(h, C.byref(v)))
+    return v.value
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -206,7 +351,7 @@ def run_gpu(args):
 
     n = args.n
     t0 = time.time()
-    mesh, asm, p, Uu_h, part = build_problem(F, n, rank, world)
+    mesh, asm, p, Uu_h, part = build_problem(F, n, rank, world, partition=args.partition)
     setup_s = time.time() - t0
     ne_local = mesh.element_conns["block_1"].shape[1] if part is None else part.n_owned_elements
     h = asm._require()
@@ -226,15 +371,17 @@ def run_gpu(args):
         # under the element kernel) instead of running a stand-alone fill!(storage, 0) pass every step
         asm.set_matrix_double_buffer(True)
     peer = part is not None and not args.nccl_halo
-    if peer:
-        # fused halo: ghost-node REDs go straight into the owner's residual over NVLink peer memory
-        with torch.cuda.stream(stream):
+    if part is not None:
+        # the library's own NCCL communicator (fecb200_comm_init): torch.distributed only carries the 128-byte id
+        part.comm_init(asm)
+        if peer:
+            # fused halo: ghost-node REDs go straight into the owner's residual over NVLink peer memory
             part.enable_peer_scatter(asm)
         stream.synchronize()
 
     def halo():
         if part is not None:
-            part.halo_sum_residual(asm, stream)   # peer mode: a stream-ordered barrier; else pack / NCCL / unpack
+            part.halo_sum_residual(asm, stream)   # peer mode: a stream-ordered barrier; else pack / ncclSend+Recv / add
 
     def pre():
         if peer:
@@ -282,6 +429,8 @@ def run_gpu(args):
             ms = float(t.item())
         return ms
 
+    if peer:
+        F.residual(asm, dR)            # flush: every rank's residual field is zero before the first scatter
     for _ in range(max(args.warmup, 3)):
         step_device()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -316,6 +465,30 @@ def run_gpu(args):
     check(lib.fecb200_set_async(h, 0))
     e2e_value = ne_total * args.steps / (ms_e2e * 1e-3)
 
+    # ---- partition statistics (N > 1): imbalance, neighbours, ghost fraction -- gathered over the ranks
+    pstats = None
+    if part is not None:
+        mine = torch.tensor([part.n_owned_elements, getattr(part, "n_halo_elements", 0), part.n_owned_nodes,
+                             len(part.local_to_global) - part.n_owned_nodes, len(part.neighbors),
+                             sum(len(v) for v in part.send.values())], device="cuda", dtype=torch.float64)
+        allp = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allp, mine)
+        A = torch.stack(allp).cpu().numpy()
+        pstats = {"owned_elements_max_over_mean": round(float(A[:, 0].max() / A[:, 0].mean()), 4),
+                  "owned_elements_per_rank": [int(x) for x in A[:, 0]],
+                  "halo_elements_per_rank": [int(x) for x in A[:, 1]],
+                  "neighbours_per_rank": [int(x) for x in A[:, 4]],
+                  "ghost_node_fraction_max": round(float((A[:, 3] / (A[:, 2] + A[:, 3])).max()), 5),
+                  "residual_halo_nodes_per_rank": [int(x) for x in A[:, 5]]}
+
+    # ---- correctness of what was just timed
+    if args.no_check:
+        chk = None
+    elif world == 1:
+        chk = check_single(F, asm, p, dUu, stream)
+    else:
+        chk = check_partitioned(F, rank, world, args.partition)
+
     out = None
     if rank == 0:
         hbm, peak_src, peaks = load_peaks()
@@ -325,7 +498,7 @@ def run_gpu(args):
                 fn()
             return timed(fn, reps) / reps if world == 1 else None
 
-        roof, ops = {}, {}
+        roof, ops, cfgs = {}, {}, None
         if world == 1:
             Vu = torch.rand(N, dtype=torch.float64, device="cuda")
             t_unf = op_ms(step_unfused)
@@ -339,23 +512,20 @@ def run_gpu(args):
             t_act = op_ms(lambda: F.assemble_matrix_free_action(asm, F.stiffness_action, dUu, Vu, p))
             # dominant kernel alone: events recorded by the library around the element kernel launch
             check(lib.fecb200_enable_timing(h, 1))
-            kms = []
             import ctypes as C
-            for _ in range(5):
-                F.assemble_vector_and_stiffness(asm, F.residual, F.stiffness, dUu, p)
-                f = C.c_float()
-                check(lib.fecb200_last_kernel_ms(h, C.byref(f)))
-                kms.append(f.value)
-            kres = []
-            for _ in range(5):
-                F.assemble_vector(asm, F.residual, dUu, p)
-                f = C.c_float()
-                check(lib.fecb200_last_kernel_ms(h, C.byref(f)))
-                kres.append(f.value)
+
+            def kernel_ms(fn):
+                xs = []
+                for _ in range(6):
+                    fn()
+                    f = C.c_float()
+                    check(lib.fecb200_last_kernel_ms(h, C.byref(f)))
+                    xs.append(f.value)
+                return float(np.mean(xs[1:]))
+            k_tan = kernel_ms(lambda: F.assemble_vector_and_stiffness(asm, F.residual, F.stiffness, dUu, p))
+            k_res = kernel_ms(lambda: F.assemble_vector(asm, F.residual, dUu, p))
+            k_act = kernel_ms(lambda: F.assemble_matrix_free_action(asm, F.stiffness_action, dUu, Vu, p))
             check(lib.fecb200_enable_timing(h, 0))
-            k_tan, k_res = float(np.mean(kms[1:])), float(np.mean(kres[1:]))
-            bytes_el = BYTES_FUSED + (BYTES_ZERO_FILL if dbuf else 0.0)
-            ach = bytes_el * ne_local / (k_tan * 1e-3) / 1e9
             # FP64 roof measured here with cuBLAS DGEMM (MEASURED_PEAKS.json has no FP64 entry)
             a = torch.randn(6144, 6144, dtype=torch.float64, device="cuda")
             torch.mm(a, a)
@@ -364,21 +534,24 @@ def run_gpu(args):
             e0.record(); torch.mm(a, a); torch.mm(a, a); e1.record(); torch.cuda.synchronize()
             fp64_peak = 2 * 2 * 6144 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
             del a
-            roof = {"bound": "hbm", "kernel": "k_mat2<hex8,NF=3,neo-Hookean,WITH_R> (fused residual + tangent -> CSR" + (" + zero-fill of the idle value array)" if dbuf else ")"), "achieved": round(ach, 1),
-                    "peak": hbm, "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / hbm, 4), "traffic": round(TRAFFIC_NCU_BYTES_PER_ELEMENT[dbuf] * ne_local),
-                    "traffic_note": ("dram read+write bytes per launch, ncu (profiles/r01zz_dram_compression.txt): 1.0x algorithmic with the compressible CSR value arrays (zeros of the clear and of the first RED read stay compressed in HBM); 1.6x without"
-                                     if dbuf else "dram read+write bytes per launch, ncu --set full (profiles/r01h_fused_kmat2_details.txt); 2.1x algorithmic: memset write-back + RED read-modify-write of the CSR values"),
-                    "algorithmic_bytes_per_element": bytes_el, "kernel_ms": round(k_tan, 4),
-                    "binding_resource": "on-chip, not HBM: l1tex LSU data-pipe wavefronts 74 % of peak (shared-memory operand / staging traffic + REDs), FP64 pipe 52 % busy, DRAM side alone 12.3 ms of the 16.0 (ncu profiles/r01z_fused_kmat2_details.txt, knock-out sweep profiles/r01u_ko_sweep.txt; DESIGN.md section 5)",
-                    "fp64": {"flops_per_element": FLOPS_TANGENT,
-                             "achieved_tflops": round(FLOPS_TANGENT * ne_local / (k_tan * 1e-3) / 1e12, 2),
-                             "peak_tflops_dgemm_measured": round(fp64_peak, 1),
-                             "frac": round(FLOPS_TANGENT * ne_local / (k_tan * 1e-3) / 1e12 / fp64_peak, 4)},
-                    "residual_kernel": {"kernel_ms": round(k_res, 4),
-                                        "achieved_GBs": round(BYTES_RESIDUAL * ne_local / (k_res * 1e-3) / 1e9, 1),
-                                        "frac_hbm": round(BYTES_RESIDUAL * ne_local / (k_res * 1e-3) / 1e9 / hbm, 4),
-                                        "achieved_tflops": round(FLOPS_RESIDUAL * ne_local / (k_res * 1e-3) / 1e12, 2),
-                                        "frac_fp64": round(FLOPS_RESIDUAL * ne_local / (k_res * 1e-3) / 1e12 / fp64_peak, 4)}}
+            # compulsory bytes, every output counted once.  fused = conn 64 + X 24 + U 24 + CSR values 1954 + R 24
+            ach = BYTES_FUSED * ne_local / (k_tan * 1e-3) / 1e9
+            tf = FLOPS_TANGENT * ne_local / (k_tan * 1e-3) / 1e12
+            traffic, traffic_src = ncu_traffic(dbuf)
+            roof = {"bound": "hbm", "binding_roof": "fp64" if tf / fp64_peak > ach / hbm else "hbm",
+                    "kernel": "fused residual + tangent -> CSR (" + os.environ.get("FECB200_MAT_KERNEL", "default") + ")",
+                    "achieved": round(ach, 1), "peak": hbm, "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / hbm, 4),
+                    "algorithmic_bytes_per_element": BYTES_FUSED,
+                    "extra_bytes_per_element": BYTES_ZERO_FILL if dbuf else 0.0,
+                    "extra_bytes_note": "in-kernel clear of the idle CSR value array (fill!(storage, 0), Matrix.jl:39); not algorithmic" if dbuf else None,
+                    "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": round(k_tan, 4),
+                    "fp64_flops_per_element": FLOPS_TANGENT, "fp64_achieved_tflops": round(tf, 2),
+                    "fp64_peak_tflops_dgemm_measured": round(fp64_peak, 1), "fp64_frac": round(tf / fp64_peak, 4),
+                    "residual_kernel_ms": round(k_res, 4),
+                    "residual_frac_hbm": round(BYTES_RESIDUAL * ne_local / (k_res * 1e-3) / 1e9 / hbm, 4),
+                    "residual_frac_fp64": round(FLOPS_RESIDUAL * ne_local / (k_res * 1e-3) / 1e12 / fp64_peak, 4),
+                    "action_kernel_ms": round(k_act, 4),
+                    "action_frac_hbm": round(BYTES_ACTION * ne_local / (k_act * 1e-3) / 1e9 / hbm, 4)}
             ops = {"residual_elements_per_s": round(ne_local / (t_res * 1e-3), 1),
                    "tangent_elements_per_s": round(ne_local / (t_tan * 1e-3), 1),
                    "action_elements_per_s": round(ne_local / (t_act * 1e-3), 1),
@@ -387,6 +560,11 @@ def run_gpu(args):
             if t_sb is not None:
                 ops["single_buffer_step_ms"] = round(t_sb, 4)   # same step with cudaMemset of the CSR values instead
         cpu = cpu_baseline(args.cpu_n) if (world == 1 and not args.no_cpu) else None
+        par = "single GPU"
+        if world > 1:
+            par = (("METIS k-way on the dual graph of %d^3-element cells" % getattr(part, "cell", METIS_CELL)) if args.partition == "metis"
+                   else "structured bricks") + f" x{world}, owned/ghost nodes, halo-element block for local Jacobian rows, residual halo = " + \
+                  ("fused peer-memory REDs over NVLink + 2 library NCCL barriers" if peer else "library NCCL send/recv")
         out = {
             "metric": "assembled elements/s (residual + Jacobian), neo-Hookean hex8 FP64",
             "value": round(value, 1), "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -395,14 +573,16 @@ def run_gpu(args):
             "config": {"workload": f"neohookean_hex8_{n}^3_per_gpu residual+tangent(CSR) per Newton iteration",
                        "elements_per_gpu": int(ne_local), "elements_total": int(ne_total), "dofs_per_gpu": int(len(asm.dof)),
                        "csr_nnz_per_gpu": int(asm.pattern()[2].shape[0]) if args.report_nnz else None,
-                       "parallelism": (f"domain decomposition x{world}, halo = " + ("fused peer-memory REDs over NVLink" if peer else "NCCL send/recv")) if world > 1 else "single GPU",
+                       "parallelism": par, "partition": pstats,
                        "l2": "inputs and outputs larger than L2 (CSR values 13.8 GB at 192^3); no flush needed",
                        "csr_values": "double-buffered, idle buffer cleared inside the element kernel" if dbuf else "single buffer + memset per step",
                        "setup_s": round(setup_s, 1)},
             "e2e": {"value": round(e2e_value, 1), "unit": "elements/s", "ms_per_step": round(ms_e2e / args.steps, 4),
-                    "h2d_bytes_per_step": int(N * 8), "d2h_bytes_per_step": int(N * 8)},
+                    "h2d_bytes_per_step": int(N * 8), "d2h_bytes_per_step": int(N * 8),
+                    "pcie_GBs_per_rank": round(2 * N * 8 / (ms_e2e / args.steps * 1e-3) / 1e9, 1)},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "check": chk,
         }
         if roof:
             out["roofline"] = roof
@@ -410,11 +590,22 @@ def run_gpu(args):
             out["ops"] = ops
         if cpu:
             out["cpu_baseline"] = cpu
+    if world > 1:
+        dist.barrier()
+    asm.close()
+    if rank == 0 and world == 1 and not args.no_configs:
+        # BASELINE configs 2 and 4 (kernel timings with their own roofline fractions), same process, after the main run
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_configs
+            out["configs"] = [bench_configs.poisson(128), bench_configs.j2(64)]
+        except Exception as e:  # never lose the headline line to a side measurement
+            out["configs"] = {"error": repr(e)}
+    if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    asm.close()
     return out
 
 
@@ -457,8 +648,10 @@ def cpu_baseline(n):
         reps += 1
     dt = (time.perf_counter() - t0) / reps
     return {"value": round(ne / dt, 1), "unit": "elements/s", "cores": nthreads, "kind": "port",
-            "sample": f"neo-Hookean hex8 {n}^3 ({ne} elements): residual + COO tangent + sparse!, {reps} reps, "
-                      "C/OpenMP port of the reference CPU path (Julia is not installable here)"}
+            "sample": f"neo-Hookean hex8 {n}^3 ({ne} elements, NOT the 192^3 of the GPU arm: the reference's COO bookkeeping "
+                      f"does not fit a host there, BASELINE.md section 4): residual + COO tangent + sparse!, {reps} reps, reported per "
+                      "element; C/OpenMP port of the reference CPU path with analytic tangents (faster than the Julia AD path; "
+                      "Julia is not installable here)"}
 
 
 def run_reference(args):
@@ -477,7 +670,8 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     v = ne * args.steps / dt
-    sample = f"neo-Hookean hex8 {n}^3 ({ne} elements) per step: residual + COO tangent + sparse!"
+    sample = (f"neo-Hookean hex8 {n}^3 ({ne} elements) per step, not the GPU arm's 192^3 per GPU (the reference's COO arrays do not "
+              "fit a host there; per-element rate reported): residual + COO tangent + sparse!, C/OpenMP port, all host threads")
     print(json.dumps({
         "impl": "reference", "metric": "assembled elements/s (residual + Jacobian), neo-Hookean hex8 FP64",
         "value": round(v, 1), "unit": "elements/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -497,7 +691,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", dest="n", type=int, default=int(os.environ.get("FECB200_BENCH_N", 192)), help="elements per axis per GPU")
-    ap.add_argument("--cpu-n", type=int, default=48, help="elements per axis of the bounded CPU sample")
+    ap.add_argument("--cpu-n", type=int, default=64, help="elements per axis of the bounded CPU sample (BASELINE.md section 4: 64^3)")
+    ap.add_argument("--partition", default="metis", choices=["metis", "brick"], help="N > 1: METIS k-way on the coarse-cell dual graph (BASELINE config 5) or flat bricks")
+    ap.add_argument("--no-check", action="store_true", help="skip the correctness block")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE config 2 / 4 kernel timings")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--nccl-halo", action="store_true", help="N > 1: pack / NCCL send-recv / unpack instead of the fused peer-memory scatter")
     ap.add_argument("--report-nnz", action="store_true")

@@ -1,8 +1,6 @@
 // dispatch_hex8.cu -- HEX8 instantiations of the element kernels (3-D, 8 nodes).
 // Hot configurations (BASELINE.json configs 2, 3, 5): Poisson NF=1 and neo-Hookean NF=3 with 8-point rules.
 #include "kernel_mat2.cuh"
-#include "kernel_mat2c.cuh"
-#include "kernel_mat2w.cuh"
 #include "kernel_mat_scalar.cuh"
 
 // Warps per k_mat2 CTA.  The warps of a CTA start together and walk the phases (FP64-bound G/K, RED-bound S) in
@@ -38,6 +36,14 @@
 #endif
 #ifndef FEC_MAT2W_REG
 #define FEC_MAT2W_REG 128
+#endif
+// the two measured-slower variants live outside the product tree (tools/variants/, evidence in profiles/r01s_*, r01y_*);
+// they are compiled only by tools/build_variants.sh
+#if FEC_MAT2C
+#include "../../tools/variants/kernel_mat2c.cuh"
+#endif
+#if FEC_MAT2W
+#include "../../tools/variants/kernel_mat2w.cuh"
 #endif
 #include <cstdlib>
 

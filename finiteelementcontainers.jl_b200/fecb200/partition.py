@@ -404,3 +404,145 @@ def structured_brick_partition(F, n, grid, rank):
     part = Partition(rank, P, l2g + 1, l2o, n_owned, int(inside.sum()), int(np.prod(g * n)), int(np.prod(Ng)), send, recv,
                      bool((~inside).any()))
     return lm, part
+
+
+# --------------------------------------------------------------------------------------------------
+# METIS partition of the structured weak-scaling grid (BASELINE config 5) without the global mesh:
+# METIS k-way runs on the dual graph of COARSE cells (c^3 elements each; 384^3 elements -> 48^3 cells),
+# every rank then materialises only its own ragged piece.
+# --------------------------------------------------------------------------------------------------
+def metis_cell_partition(cells, nparts):
+    """METIS_PartGraphKway (ext/MetisExt.jl:6-14 partitions the same way, on the DOF graph) on the face-adjacency
+    graph of a cx x cy x cz grid of cells.  Returns part ids shaped (cx, cy, cz), 0-based."""
+    cx, cy, cz = (int(v) for v in cells)
+    nv = cx * cy * cz
+    ids = np.arange(nv, dtype=np.int64).reshape(cx, cy, cz)
+    src, dst = [], []
+    for ax in range(3):
+        lo = [slice(None)] * 3
+        hi = [slice(None)] * 3
+        lo[ax], hi[ax] = slice(0, -1), slice(1, None)
+        a, b = ids[tuple(lo)].reshape(-1), ids[tuple(hi)].reshape(-1)
+        src += [a, b]
+        dst += [b, a]
+    src, dst = np.concatenate(src), np.concatenate(dst)
+    order = np.lexsort((dst, src))
+    src, dst = src[order], dst[order]
+    xadj = np.zeros(nv + 1, dtype=np.int64)
+    np.add.at(xadj, src + 1, 1)
+    part = metis_partition_graph(np.cumsum(xadj), dst, nparts)
+    return part.reshape(cx, cy, cz)
+
+
+def _dilate_to_nodes(emask):
+    """element mask (ex, ey, ez) -> mask of the nodes those elements touch (ex+1, ey+1, ez+1)"""
+    out = np.zeros(tuple(s + 1 for s in emask.shape), dtype=bool)
+    for dx in (0, 1):
+        for dy in (0, 1):
+            for dz in (0, 1):
+                out[dx:dx + emask.shape[0], dy:dy + emask.shape[1], dz:dz + emask.shape[2]] |= emask
+    return out
+
+
+def structured_cell_partition(F, nel, cell_part, c, rank, h=None):
+    """Rank-local hex8 mesh + Partition of the structured grid of nel = (Ex, Ey, Ez) elements whose c^3-element
+    cells are assigned to ranks by `cell_part` (shape nel // c).  Same numbering and ownership rules as
+    partition_mesh (global node id x fastest; node owner = lowest rank among the touching elements' owners), but only
+    this rank's bounding box is ever materialised."""
+    Ex, Ey, Ez = (int(v) for v in nel)
+    cell_part = np.asarray(cell_part)
+    assert cell_part.shape == (Ex // c, Ey // c, Ez // c) and Ex % c == Ey % c == Ez % c == 0
+    P = int(cell_part.max()) + 1
+    h = 1.0 / min(Ex, Ey, Ez) if h is None else h
+    mine = np.argwhere(cell_part == rank)
+    assert len(mine), f"rank {rank} owns no cell"
+    # element box = my cells + TWO elements of margin on every side (clipped to the domain): halo elements sit in the
+    # first layer, and the owner of THEIR nodes depends on the second
+    elo = np.maximum(mine.min(axis=0) * c - 2, 0)
+    ehi = np.minimum((mine.max(axis=0) + 1) * c + 2, [Ex, Ey, Ez])           # exclusive
+    bx, by, bz = (ehi - elo).tolist()
+    BIG = np.int16(P)
+    # owner of every element of the box (int16), from the cell map
+    ix, iy, iz = (np.arange(elo[a], ehi[a]) // c for a in range(3))
+    eown = cell_part[np.ix_(ix, iy, iz)].astype(np.int16)
+    # node owner = min over the (up to 8) touching elements; elements outside the DOMAIN do not exist, elements outside
+    # the BOX only matter for nodes on the box boundary, which are never local (the margin guarantees it)
+    nown = np.full((bx + 1, by + 1, bz + 1), BIG, dtype=np.int16)
+    for dx in (0, 1):
+        for dy in (0, 1):
+            for dz in (0, 1):
+                v = nown[dx:dx + bx, dy:dy + by, dz:dz + bz]
+                np.minimum(v, eown, out=v)
+    e_mine = eown == rank
+    n_touched = _dilate_to_nodes(e_mine)                 # nodes of my elements (owned or ghost)
+    n_owned = n_touched & (nown == rank)
+    # halo elements: not mine, touching one of my owned nodes
+    touch = np.zeros((bx, by, bz), dtype=bool)
+    for dx in (0, 1):
+        for dy in (0, 1):
+            for dz in (0, 1):
+                touch |= n_owned[dx:dx + bx, dy:dy + by, dz:dz + bz]
+    e_halo = touch & ~e_mine
+    n_local = n_touched | _dilate_to_nodes(e_halo)
+    n_ghost = n_local & ~n_owned
+    # box-boundary sanity: a local node on the low/high face of the box must be on the domain boundary there
+    for a, (lo_, hi_, E_) in enumerate(zip(elo, ehi, (Ex, Ey, Ez))):
+        sl_lo = [slice(None)] * 3; sl_lo[a] = 0
+        sl_hi = [slice(None)] * 3; sl_hi[a] = -1
+        assert lo_ == 0 or not n_owned[tuple(sl_lo)].any()
+        assert hi_ == E_ or not n_owned[tuple(sl_hi)].any()
+    # local numbering: owned nodes by ascending global id, then ghosts by ascending global id.  Arrays are indexed
+    # [x][y][z]; global id = x + Nx (y + Ny z), so sort keys come from a transposed (z, y, x) walk.
+    Nx, Ny, Nz = Ex + 1, Ey + 1, Ez + 1
+
+    def ordered(mask):
+        kz, ky, kx = np.nonzero(mask.transpose(2, 1, 0))   # ascending (z, y, x) == ascending global id
+        return kx, ky, kz
+
+    ox, oy, oz = ordered(n_owned)
+    gx, gy, gz = ordered(n_ghost)
+    lx, ly, lz = np.concatenate([ox, gx]), np.concatenate([oy, gy]), np.concatenate([oz, gz])
+    n_own = len(ox)
+    box2loc = np.full((bx + 1, by + 1, bz + 1), -1, dtype=np.int32)
+    box2loc[lx, ly, lz] = np.arange(len(lx), dtype=np.int32)
+    GX, GY, GZ = lx + elo[0], ly + elo[1], lz + elo[2]
+    l2g = (GX + Nx * (GY + Ny * GZ)).astype(np.int64)
+    l2o = nown[lx, ly, lz].astype(np.int64)
+
+    def conn_of(emask):
+        ex, ey, ez = np.nonzero(emask)
+        c8 = [box2loc[ex, ey, ez], box2loc[ex + 1, ey, ez], box2loc[ex + 1, ey + 1, ez], box2loc[ex, ey + 1, ez],
+              box2loc[ex, ey, ez + 1], box2loc[ex + 1, ey, ez + 1], box2loc[ex + 1, ey + 1, ez + 1], box2loc[ex, ey + 1, ez + 1]]
+        out = np.stack(c8).astype(np.int64) + 1
+        assert out.min() >= 1
+        return out
+
+    lm = _LocalMesh()
+    lm.nodal_coords = H1Field(np.stack([GX * h, GY * h, GZ * h]).astype(float))
+    has_halo = bool(e_halo.any())
+    lm.element_block_names = ["owned"] + (["halo"] if has_halo else [])
+    lm.element_types = {b: "HEX8" for b in lm.element_block_names}
+    lm.element_conns = {"owned": conn_of(e_mine)}
+    if has_halo:
+        lm.element_conns["halo"] = conn_of(e_halo)
+    loc = np.arange(1, len(l2g) + 1)
+    lm.nodeset_nodes = {"bottom": loc[GY == 0], "top": loc[GY == Ny - 1], "left": loc[GX == 0], "right": loc[GX == Nx - 1],
+                        "back": loc[GZ == 0], "front": loc[GZ == Nz - 1]}
+    lm.sideset_nodes = dict(lm.nodeset_nodes)
+    # halo lists, both sides sorted by global id (= local order inside the owned and the ghost range)
+    send, recv = {}, {}
+    res_ghost = n_touched & ~n_owned                       # ghosts my OWNED elements add to
+    gl = box2loc[ordered(res_ghost)].astype(np.int64)
+    go = l2o[gl]
+    for r in np.unique(go):
+        send[int(r)] = gl[go == r] + 1
+    for r in np.unique(eown):
+        r = int(r)
+        if r == rank:
+            continue
+        hit = _dilate_to_nodes(eown == r) & n_owned        # my owned nodes that rank r's elements touch
+        if hit.any():
+            recv[r] = box2loc[ordered(hit)].astype(np.int64) + 1
+    part = Partition(rank, P, l2g + 1, l2o, n_own, int(e_mine.sum()), Ex * Ey * Ez, Nx * Ny * Nz, send, recv, has_halo)
+    part.n_halo_elements = int(e_halo.sum())
+    return lm, part

@@ -1,5 +1,6 @@
-"""Multi-GPU check (needs >= 2 visible GPUs, skipped otherwise): the fused peer-memory halo (ghost-node REDs
-into the owner's residual over NVLink) against the NCCL pack / send-recv / unpack halo, under torchrun."""
+"""Multi-GPU checks (need >= 2 visible GPUs, skipped otherwise).  The partitioned path -- METIS or brick partition, the
+library's own NCCL communicator, NCCL halo and fused peer-memory halo, distributed CG / Newton -- against a SERIAL
+assembly / solve of the same global mesh (tests/run_comm_check.py: plain processes + ctypes, no torch.distributed)."""
 import os
 import subprocess
 import sys
@@ -31,3 +32,16 @@ def test_partitioned_loads_match_serial():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "OK" in out.stdout and "FAIL" not in out.stdout, out.stdout[-2000:]
+
+
+@pytest.mark.parametrize("how", ["metis", "brick"])
+def test_library_collective_plane_matches_serial(how):
+    """fecb200_comm_init / halo_sum / halo_update / comm_peer_enable + distributed CG and Newton on 2 ranks, every
+    number against the serial handle; Newton iteration counts equal (north_star)."""
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "run_comm_check.py"), "2", "16", how]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "OK" in out.stdout and "FAIL" not in out.stdout, out.stdout[-3000:]

@@ -64,3 +64,30 @@ def test_c_port_matches_numpy_oracle(phys, el, nf):
     rowptr, colval, nzr = ws.csr(colptr, rowval, nz)
     rrowptr, rcolval, rnzr = O.csc_to_csr(rcolptr, rrowval, rnz, n)
     assert np.array_equal(rowptr, rrowptr) and np.array_equal(colval, rcolval) and _rel(nzr, rnzr) < 1e-13
+
+
+def test_at_size_helper_matches_numpy_assembler():
+    """util_parity.c_oracle_reference (C oracle + vectorised _update_dofs!, used by tests/test_gpu_at_size.py at 48^3)
+    against the numpy OracleAssembler on a small mesh: unknown residual, rowptr / colval bit-exact, values."""
+    import fecb200 as F
+    from util_parity import c_oracle_reference, perturb
+    n = 5
+    mesh = perturb(F.StructuredMesh("hex", (0, 0, 0), (1, 1, 1), (n + 1, n + 2, n + 1)), 0.1 / n)
+    props = np.array([1e3, 10e6, 1e6])
+    X = np.asarray(mesh.nodal_coords)
+    nn = X.shape[1]
+    bot, top = mesh.nodeset_nodes["bottom"], mesh.nodeset_nodes["top"]
+    dd = np.concatenate([3 * (bot - 1) + 1, 3 * (bot - 1) + 2, 3 * (bot - 1) + 3, 3 * (top - 1) + 2])
+    vals = np.concatenate([np.zeros(3 * len(bot)), np.full(len(top), 0.01)])
+    blk = O.Block(mesh.element_conns["block_1"], O.ref_fe_tables("HEX8", "gauss2"), O.NeoHookean(3), props=props)
+    oasm = O.OracleAssembler(X, [blk], 3, condensed=False, matrix_type="csr")
+    oasm.update_dofs(dd)
+    order = np.argsort(dd, kind="stable")
+    oasm.bc_vals[:] = vals[order]
+    Uu = 1e-3 * np.random.default_rng(0).standard_normal(oasm.n)
+    oasm.assemble_vector(Uu)
+    oasm.assemble_stiffness(Uu)
+    rowptr, colval, nz = oasm.stiffness()
+    ref = c_oracle_reference(mesh, "neo", props, dd, vals, Uu, nthreads=2)
+    assert np.array_equal(ref["rowptr"], rowptr) and np.array_equal(ref["colval"], colval)
+    assert _rel(ref["nz"], nz) < 1e-13 and _rel(ref["R"], oasm.residual()) < 1e-13

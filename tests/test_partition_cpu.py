@@ -12,7 +12,8 @@ import torch.multiprocessing as mp
 
 import fec_oracle as O
 import fecb200 as F
-from fecb200.partition import exchange, partition_mesh, structured_brick_partition, metis_partition_elements, metis_partition_graph
+from fecb200.partition import (exchange, partition_mesh, structured_brick_partition, metis_partition_elements, metis_partition_graph,
+                               metis_cell_partition, structured_cell_partition)
 
 PROPS = np.array([1e3, 10e6, 1e6])
 
@@ -216,3 +217,38 @@ def test_metis_partition_of_the_sparsity_pattern():
     rng = np.random.default_rng(0)
     rnd = rng.integers(0, 4, n)
     assert cut < 0.25 * np.count_nonzero(rnd[rows] != rnd[rowval - 1])
+
+
+@pytest.mark.parametrize("nel,c,P", [((8, 8, 4), 2, 4), ((12, 6, 6), 3, 3), ((8, 8, 8), 2, 8)])
+def test_metis_cell_partition_matches_general_builder(nel, c, P):
+    """BASELINE config 5 builder: METIS on the coarse-cell graph + rank-local materialisation == partition_mesh on
+    the global mesh with the same element owners (numbering, ownership, halo block, send / recv lists)."""
+    Ex, Ey, Ez = nel
+    cells = (Ex // c, Ey // c, Ez // c)
+    cp = metis_cell_partition(cells, P)
+    counts = np.bincount(cp.reshape(-1), minlength=P)
+    assert counts.min() > 0 and counts.max() <= 1.35 * counts.mean() + 1
+    h = 1.0 / min(nel)
+    gmesh = F.StructuredMesh("hex", (0, 0, 0), (Ex * h, Ey * h, Ez * h), (Ex + 1, Ey + 1, Ez + 1))
+    ex, ey, ez = np.meshgrid(np.arange(Ex), np.arange(Ey), np.arange(Ez), indexing="ij")   # StructuredMesh element order
+    epart = cp[ex // c, ey // c, ez // c].reshape(-1)
+    for rank in range(P):
+        lm_b, pb = structured_cell_partition(F, nel, cp, c, rank)
+        lm_g, pg = partition_mesh(gmesh, epart, P, rank)
+        assert pb.n_owned_nodes == pg.n_owned_nodes and pb.n_owned_elements == pg.n_owned_elements
+        assert np.array_equal(pb.local_to_global, pg.local_to_global)
+        assert np.array_equal(pb.local_to_owner, pg.local_to_owner)
+        assert pb.neighbors == pg.neighbors
+        for r in pb.neighbors:
+            for a, b in ((pb.send, pg.send), (pb.recv, pg.recv)):
+                ga = pb.local_to_global[a[r] - 1] if r in a else np.zeros(0, dtype=np.int64)
+                gb = pg.local_to_global[b[r] - 1] if r in b else np.zeros(0, dtype=np.int64)
+                assert np.array_equal(ga, gb)
+
+        def gl(lm, p, blk):
+            return {tuple(sorted(p.local_to_global[cc - 1])) for cc in lm.element_conns[blk].T} if blk in lm.element_conns else set()
+        assert gl(lm_b, pb, "owned") == gl(lm_g, pg, "owned") and gl(lm_b, pb, "halo") == gl(lm_g, pg, "halo")
+        assert np.allclose(np.asarray(lm_b.nodal_coords), np.asarray(lm_g.nodal_coords))
+        for name in ("bottom", "top", "left", "right", "back", "front"):
+            assert np.array_equal(np.sort(pb.local_to_global[lm_b.nodeset_nodes[name] - 1]),
+                                  np.sort(pg.local_to_global[lm_g.nodeset_nodes[name] - 1]))

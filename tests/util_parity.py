@@ -73,3 +73,41 @@ def perturb(mesh, amp, seed=1234):
     X = np.asarray(mesh.nodal_coords)
     X += rng.uniform(-amp, amp, X.shape)
     return mesh
+
+
+# ---- the same comparison AT SIZE: the C/OpenMP restatement (oracle/fec_oracle_c.c) does 48^3 neo-Hookean in about a
+# second, the numpy oracle does not.  _update_dofs! (SparsityPatterns.jl:160-231) is applied vectorised here.
+def c_oracle_reference(mesh, phys_name, props, dirichlet_dofs_1based, bc_vals, Uu, *, source_func=None, nthreads=None):
+    """Residual (unknown entries), CSR rowptr / colval / nzval of the NON-condensed assembler, through the C oracle.
+    Single-block meshes, no periodic BCs.  Returns dict(R, rowptr, colval, nz, U_full)."""
+    import fec_oracle_clib as OC
+    bname = mesh.element_block_names[0]
+    et = mesh.element_types[bname]
+    conn = np.asarray(mesh.element_conns[bname])
+    X = np.asarray(mesh.nodal_coords)
+    nd, nn = X.shape
+    nf = 1 if phys_name == "poisson" else nd
+    tabs = O.ref_fe_tables(et, _RULES[et])
+    nthreads = nthreads or OC.max_threads()
+    dof = O.update_dofs(nf, nn, np.unique(np.asarray(dirichlet_dofs_1based, dtype=np.int64)))
+    U = np.zeros(nf * nn)
+    U[np.asarray(dirichlet_dofs_1based, dtype=np.int64) - 1] = bc_vals
+    U[dof["unknown_dofs"] - 1] = Uu
+    fq = None
+    if phys_name == "poisson" and source_func is not None:
+        x_el = np.transpose(X[:, conn - 1], (2, 1, 0))                      # (NE, NNPE, ND)
+        fq = np.stack([source_func(np.einsum("a,eai->ei", tabs[0][q], x_el)) for q in range(len(tabs[2]))], axis=1)
+    cp = OC.CProblem(conn, X, tabs, phys_name, nf, props if props is not None else (), source_q=fq)
+    R = cp.assemble_vector(U, nthreads=nthreads)
+    coo = cp.assemble_matrix_coo(U, 2, nthreads=nthreads)
+    Is, Js = cp.pattern()
+    d2u = dof["dof_to_unknown"]
+    ri, rj = d2u[Is - 1], d2u[Js - 1]
+    keep = (ri > 0) & (rj > 0)
+    slots = np.nonzero(keep)[0].astype(np.int64) + 1
+    ri, rj = np.ascontiguousarray(ri[keep]), np.ascontiguousarray(rj[keep])
+    n = len(dof["unknown_dofs"])
+    ws = OC.SparseWorkspace(len(ri), n)
+    colptr, rowval, nz = ws.sparse_csc(ri, rj, slots, coo)
+    rowptr, colval, nzr = ws.csr(colptr, rowval, nz)
+    return dict(R=R[dof["unknown_dofs"] - 1], rowptr=rowptr, colval=colval, nz=nzr, U_full=U, dof=dof, cp=cp, n=n)

@@ -20,7 +20,7 @@
 //     27 LDS (18 of them LDS.128) per 132 DFMA.
 //   * no FMA is duplicated by the split: tb[b] = A9 g[b] is computed for the thread's own 4 columns only.
 #pragma once
-#include "kernel_mat2.cuh"
+#include "../../finiteelementcontainers.jl_b200/csrc/kernel_mat2.cuh"
 
 namespace fec {
 
