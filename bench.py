@@ -163,15 +163,19 @@ def make_partition(F, n, rank, world, how, cell=METIS_CELL):
     return lm, part
 
 
-def raw_state(X, n, rng=None):
-    """raw-throughput state: u = 0.02 (sin 2 pi y, sin 2 pi z, sin 2 pi x) [+ U(-1e-3,1e-3) h]"""
+def raw_state(X, n, rng=None, H=1.0):
+    """raw-throughput state: u = 0.02 (sin 2 pi y, sin 2 pi z, sin 2 pi x) [+ U(-1e-3,1e-3) h], times
+    4 y (1 - y) / H^2 so that it MEETS the Dirichlet data on the bottom / top faces: without the taper the fixed faces
+    (u = 0) sit one element away from |u| = 0.02, the boundary layer of elements is sheared to det F <= 0 and its
+    1/J terms dominate (and ill-condition) every norm -- round 1's state did that."""
+    taper = 4.0 * (X[1] / H) * (1.0 - X[1] / H)
     U = 0.02 * np.stack([np.sin(2 * np.pi * X[1]), np.sin(2 * np.pi * X[2]), np.sin(2 * np.pi * X[0])])
     if rng is not None:
         U += rng.uniform(-1e-3, 1e-3, U.shape) / n
-    return U
+    return U * taper
 
 
-def build_problem(F, n, rank, world, matrix_free=False, partition="metis", noise=True, mesh_part=None):
+def build_problem(F, n, rank, world, matrix_free=False, partition="metis", noise=True, mesh_part=None, height=None):
     """Rank-local neo-Hookean problem.  N = 1: StructuredMesh('hex', (0,0,0), (1,1,1), (n+1,)*3) with the
     BCs of BASELINE config 3.  N > 1: this rank's piece of the global grid (see fecb200.partition)."""
     verbose = bool(os.environ.get("FECB200_VERBOSE"))
@@ -207,7 +211,8 @@ def build_problem(F, n, rank, world, matrix_free=False, partition="metis", noise
         part.attach(asm)
         lap("partition attach")
     X = np.asarray(mesh.nodal_coords)
-    U = raw_state(X, n, np.random.default_rng(42 + rank) if noise else None)
+    H = float(grid_for(world)[1]) if height is None else float(height)      # y-extent of the GLOBAL grid (element size 1/n)
+    U = raw_state(X, n, np.random.default_rng(42 + rank) if noise else None, H)
     Uu = np.ascontiguousarray(U.reshape(-1, order="F")[asm.dof.unknown_dofs - 1])
     lap("initial state")
     return mesh, asm, p, Uu, part
@@ -292,7 +297,7 @@ def check_partitioned(F, rank, world, partition, n_c=48):
     # ---- serial, same global mesh, on this rank's GPU
     E = tuple(gi * n_c for gi in g)
     gmesh = F.StructuredMesh("hex", (0., 0., 0.), tuple(e / n_c for e in E), tuple(e + 1 for e in E))
-    _, gasm, gp, gUu, _ = build_problem(F, n_c, 0, 1, noise=False, mesh_part=(gmesh, None))
+    _, gasm, gp, gUu, _ = build_problem(F, n_c, 0, 1, noise=False, mesh_part=(gmesh, None), height=g[1])
     F.assemble_vector_and_stiffness(gasm, F.residual, F.stiffness, gUu, gp)
     Rg = F.full_field(gasm, "residual").reshape(-1, 3)
     l2g = part.local_to_global - 1

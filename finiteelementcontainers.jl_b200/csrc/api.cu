@@ -448,8 +448,8 @@ int fecb200_set_dirichlet_values(fecb200_handle* h, const int64_t* dofs, const d
 int fecb200_set_periodic_values(fecb200_handle* h, const double* vals, int64_t n) {
   FEC_API_BEGIN
   FEC_REQUIRE(h, "null handle");
-  FEC_REQUIRE(n == h->n_per, "periodic value count does not match the resolved periodic pairs");
-  std::vector<double> pv(n, 0.0);
+  FEC_REQUIRE(!vals || n == h->n_per, "periodic value count does not match the resolved periodic pairs");
+  std::vector<double> pv(h->n_per, 0.0);   // NULL = all jumps zero, whatever n says
   if (vals) pv.assign(vals, vals + n);
   h->d_per_vals.upload(pv, h->stream);
   FEC_API_END

@@ -246,11 +246,14 @@ def update_bc_values(p):
     if getattr(p, "periodic_bcs", None) is not None and len(p.periodic_bcs):    # jump values U[b] = U[a] + val
         p.periodic_bcs.update_bc_values(p.coords, p.times.time_current)
         # the library keeps one value per (de-duplicated, chain-resolved) pair in registration order and checks the count.
-        # Always pushed, like the reference rewrites its cache at every update_bc_values!: a time-dependent jump that
-        # returns to exactly 0 must not leave a stale value on the device.
+        # Pushed at EVERY update, like the reference rewrites its cache at every update_bc_values!: a time-dependent
+        # jump that returns to exactly 0 must not leave a stale value on the device (NULL = all zero).
         pv = p.periodic_bcs.values()
-        v, vp = _lib.f64(pv)
-        check(lib.fecb200_set_periodic_values(p.asm._require(), vp, len(v)))
+        if np.any(pv != 0.0):
+            v, vp = _lib.f64(pv)
+            check(lib.fecb200_set_periodic_values(p.asm._require(), vp, len(v)))
+        else:
+            check(lib.fecb200_set_periodic_values(p.asm._require(), None, 0))
     if p.neumann_bcs is not None and len(p.neumann_bcs):     # update_bc_values!(p.neumann_bcs, asm, X, t)
         p.neumann_bcs.update_bc_values(p.coords, p.times.time_current)
         for i, c in enumerate(p.neumann_bcs.bc_caches):

@@ -136,7 +136,7 @@ int fecb200_pattern_copy(fecb200_handle* h, int64_t* ptr, int64_t* idx);
 /* Dirichlet values: U[dofs[i]] = vals[i] before every assemble (update_field_dirichlet_bcs!,
  * src/bcs/DirichletBCs.jl:411-418; values come from update_bc_values!, Parameters.jl:358). */
 int fecb200_set_dirichlet_values(fecb200_handle* h, const int64_t* dofs, const double* vals, int64_t n);
-/* periodic offsets: U[b] = U[a] + val (src/bcs/PeriodicBCs.jl:253-262); NULL = zeros */
+/* periodic offsets: U[b] = U[a] + val (src/bcs/PeriodicBCs.jl:253-262), one per resolved pair; NULL = all zero (n ignored) */
 int fecb200_set_periodic_values(fecb200_handle* h, const double* vals, int64_t n);
 int fecb200_set_time(fecb200_handle* h, double t, double dt);
 /* Poisson source f(X_q, t) pre-evaluated at quadrature points on the host (the closure

@@ -49,6 +49,8 @@ def test_neohookean_48_fused_double_buffered_vs_c_oracle(F):
     rng = np.random.default_rng(42)
     U = 0.02 * np.stack([np.sin(2 * np.pi * X[1]), np.sin(2 * np.pi * X[2]), np.sin(2 * np.pi * X[0])])
     U += rng.uniform(-1e-3, 1e-3, U.shape) / n
+    U *= 4 * X[1] * (1 - X[1])          # meets u = 0 on the bottom face; the top face is pulled by 0.01 through the BC
+    U[1] += 0.01 * X[1]
     Uu = np.ascontiguousarray(U.reshape(-1, order="F")[asm.dof.unknown_dofs - 1])
     ref = c_oracle_reference(mesh, "neo", props, p.dirichlet_bcs.dofs, p.dirichlet_bcs.vals, Uu)
     assert np.array_equal(asm.dof.unknown_dofs, ref["dof"]["unknown_dofs"])
