@@ -153,9 +153,9 @@ def make_partition(F, n, rank, world, how, cell=METIS_CELL):
     import torch.distributed as dist
     cell = cell if n % cell == 0 else next(c for c in (8, 6, 4, 3, 2, 1) if n % c == 0)
     cells = tuple(gi * n // cell for gi in g)
-    cp = torch.zeros(cells, dtype=torch.int16, device="cuda")
+    cp = torch.zeros(cells, dtype=torch.int32, device="cuda")
     if rank == 0:
-        cp.copy_(torch.from_numpy(metis_cell_partition(cells, world).astype(np.int16)))
+        cp.copy_(torch.from_numpy(metis_cell_partition(cells, world).astype(np.int32)))
     if dist.is_initialized() and world > 1:
         dist.broadcast(cp, src=0)
     lm, part = structured_cell_partition(F, tuple(gi * n for gi in g), cp.cpu().numpy(), cell, rank, h=1.0 / n)

@@ -42,6 +42,18 @@ def _problem(F, mesh, device, part=None):
 
 
 def worker(rank, world, n, how, q_id, q_out):
+    try:
+        _worker(rank, world, n, how, q_id, q_out)
+    except BaseException:   # a rank that dies silently leaves the others blocked in NCCL: report and let the parent kill them
+        import traceback
+        q_out.put((rank, {"error": traceback.format_exc()}))
+
+
+def _say(rank, msg):
+    print(f"[rank {rank}] {msg}", file=sys.stderr, flush=True)
+
+
+def _worker(rank, world, n, how, q_id, q_out):
     import torch
     torch.cuda.set_device(rank)
     import fecb200 as F
@@ -69,6 +81,7 @@ def worker(rank, world, n, how, q_id, q_out):
     else:
         uid = q_id.get(timeout=120)
     part.comm_init(asm, unique_id=uid)
+    _say(rank, "communicator up")
     # ---- serial twin on this rank's GPU
     gmesh = F.StructuredMesh("hex", (0., 0., 0.), tuple(e / n for e in E), tuple(e + 1 for e in E))
     gasm, gp, gUu = _problem(F, gmesh, rank)
@@ -85,12 +98,14 @@ def worker(rank, world, n, how, q_id, q_out):
     ug = ug_all[:nown]
     rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
+    _say(rank, "serial twin assembled")
     # 1. NCCL halo (pack / grouped send-recv / add inside the library)
     F.assemble_vector_and_stiffness(asm, F.residual, F.stiffness, Uu, p)
     check(lib.fecb200_halo_sum(h, _lib.FIELD_RESIDUAL))
     R = F.full_field(asm, "residual").reshape(-1, 3)[:part.n_owned_nodes]
     res["R_nccl_halo_vs_serial"] = rel(R, Rg[own])
     res["residual_accessor_vs_serial"] = rel(F.residual(asm)[:nown], F.residual(gasm)[ug])
+    _say(rank, "1 done")
     # 2. owned Jacobian rows: K v and K 1 through the distributed SpMV (ghost refresh inside)
     vg = np.random.default_rng(7).uniform(0, 1, gasm.sizes()[2])
     for name, xg in (("Kv", vg), ("rowsum", np.ones_like(vg))):
@@ -98,11 +113,13 @@ def worker(rank, world, n, how, q_id, q_out):
         xl[nown:] = -123.0        # ghost entries deliberately wrong: the library must refresh them from their owners
         yl = F.matrix_multiply(asm, xl)[:nown]
         res[name + "_vs_serial"] = rel(yl, F.matrix_multiply(gasm, xg)[ug])
+    _say(rank, "2 done")
     # 3. owner -> ghost update of a nodal field
     F.update_field(p, Uu)
     check(lib.fecb200_halo_update(h, _lib.FIELD_U))
     F.update_field(gp, gUu)
     res["halo_update_U"] = rel(F.full_field(asm, "u").reshape(-1, 3), F.full_field(gasm, "u").reshape(-1, 3)[l2g])
+    _say(rank, "3 done")
     # 4. fused peer-memory halo (IPC handles + ghost ids exchanged over NCCL inside the library)
     part.enable_peer_scatter(asm)
     F.residual(asm)                                   # flush: R is zero on every rank ...
@@ -117,6 +134,7 @@ def worker(rank, world, n, how, q_id, q_out):
         res[f"R_peer_halo_vs_serial_{it}"] = rel(R, Rg[own])
         F.residual(asm)
         check(lib.fecb200_comm_barrier(h))
+    _say(rank, "4 done")
     # 5. distributed CG on the assembled tangent: same iterates as the serial solve
     bg = np.random.default_rng(3).uniform(-1, 1, gasm.sizes()[2])
     xs, its_s, _ = F.IterativeLinearSolver(gasm, "cg").solve(bg)
@@ -124,6 +142,7 @@ def worker(rank, world, n, how, q_id, q_out):
     xl, its_l, _ = F.IterativeLinearSolver(asm, "cg").solve(bl)
     res["cg_iterations"] = (int(its_l), int(its_s))
     res["cg_solution_vs_serial"] = rel(xl, xs[ug_all])       # ghost entries included: refreshed at the end of the solve
+    _say(rank, f"5 done {res['cg_iterations']}")
     # 6. distributed Newton load step (peer halo on): iteration counts equal the serial solve's
     for pp in (p, gp):
         F.update_time(pp); F.update_bc_values(pp)
@@ -149,16 +168,28 @@ def main():
     procs = [ctx.Process(target=worker, args=(r, world, n, how, q_id, q_out)) for r in range(world)]
     for pr in procs:
         pr.start()
-    results = {}
+    results, failed = {}, False
     try:
         for _ in range(world):
-            r, res = q_out.get(timeout=900)
+            r, res = q_out.get(timeout=int(os.environ.get("COMM_CHECK_TIMEOUT", 240)))
             results[r] = res
+            if "error" in res:
+                failed = True
+                break
+    except Exception as e:   # queue.Empty: a rank is stuck
+        print("comm check: no result within the time limit:", repr(e), flush=True)
+        failed = True
     finally:
         for pr in procs:
-            pr.join(timeout=60)
+            pr.join(timeout=1 if failed else 60)
             if pr.is_alive():
                 pr.kill()
+    if failed:
+        for r, res in results.items():
+            if "error" in res:
+                print(f"rank {r} raised:\n{res['error']}", flush=True)
+        print(f"comm check ({world} ranks, {how}): FAIL", flush=True)
+        sys.exit(1)
     ok = len(results) == world
     for r in sorted(results):
         res = results[r]

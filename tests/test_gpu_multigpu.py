@@ -42,6 +42,6 @@ def test_library_collective_plane_matches_serial(how):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     cmd = [sys.executable, os.path.join(ROOT, "tests", "run_comm_check.py"), "2", "16", how]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=400)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "OK" in out.stdout and "FAIL" not in out.stdout, out.stdout[-3000:]
