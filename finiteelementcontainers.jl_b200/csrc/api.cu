@@ -853,12 +853,12 @@ int fecb200_newton_solve(fecb200_handle* h, double* Uu, int32_t max_iters, doubl
   int it = 0;
   double* Rb = h->d_out.p;   // residual(asm)
   double* dU = h->d_cg_x.p;
-  if (dist) {
-    comm_halo_update_unknowns(h, u);   // consistent ghost entries of the initial guess
-    if (h->peer_enabled && h->peer_field == FECB200_FIELD_RESIDUAL) {
-      FEC_CUDA(cudaMemsetAsync(h->d_R.p, 0, h->ndof * sizeof(double), h->stream));
-      comm_barrier(h);
-    }
+  const bool peer_R = h->peer_enabled && h->peer_field == FECB200_FIELD_RESIDUAL;
+  FEC_REQUIRE(!peer_R || comm_active(h), "Newton over the peer-memory halo needs the library communicator (fecb200_comm_init)");
+  if (dist) comm_halo_update_unknowns(h, u);   // consistent ghost entries of the initial guess
+  if (peer_R) {
+    FEC_CUDA(cudaMemsetAsync(h->d_R.p, 0, h->ndof * sizeof(double), h->stream));
+    comm_barrier(h);
   }
   for (it = 1; it <= max_iters; ++it) {
     // solve!(IterativeLinearSolver) (Solvers.jl:128-153)
@@ -870,12 +870,11 @@ int fecb200_newton_solve(fecb200_handle* h, double* Uu, int32_t max_iters, doubl
     }
     add_source_loads(h, h->d_R.p);    // assemble_vector_source!      (Solvers.jl:135)
     add_neumann_loads(h, h->d_R.p);   // assemble_vector_neumann_bc!  (Solvers.jl:136)
-    if (dist) {                       // ghost -> owner sum of the residual (PartitionedArraysExt.jl:469-481)
-      if (h->peer_enabled && h->peer_field == FECB200_FIELD_RESIDUAL) comm_barrier(h);
-      else comm_halo_sum_field(h, h->d_R.p);
-    }
+    // ghost -> owner sum of the residual (PartitionedArraysExt.jl:469-481)
+    if (peer_R) comm_barrier(h);      // fused halo: the kernels already added the ghost rows; wait for every rank
+    else if (dist) comm_halo_sum_field(h, h->d_R.p);
     k_residual_accessor(h, Rb);
-    if (dist && h->peer_enabled && h->peer_field == FECB200_FIELD_RESIDUAL) {
+    if (peer_R) {                     // zero-after-read protocol of the peer halo (assemble_* does not clear R then)
       FEC_CUDA(cudaMemsetAsync(h->d_R.p, 0, h->ndof * sizeof(double), h->stream));
       comm_barrier(h);                // every rank re-zeroed its residual before anyone scatters again
     }
