@@ -147,8 +147,11 @@ def make_partition(F, n, rank, world, how, cell=METIS_CELL):
     dual graph (computed by rank 0, broadcast), every rank materialises only its own ragged piece."""
     from fecb200.partition import metis_cell_partition, structured_brick_partition, structured_cell_partition
     g = grid_for(world)
-    if how == "brick":
-        return structured_brick_partition(F, n, g, rank)
+    if how == "brick":   # the same builder with one n^3 cell per rank: rank = px + gx (py + gy pz)
+        ix, iy, iz = np.meshgrid(np.arange(g[0]), np.arange(g[1]), np.arange(g[2]), indexing="ij")
+        lm, part = structured_cell_partition(F, tuple(gi * n for gi in g), ix + g[0] * (iy + g[1] * iz), n, rank, h=1.0 / n)
+        part.cell = n
+        return lm, part
     import torch
     import torch.distributed as dist
     cell = cell if n % cell == 0 else next(c for c in (8, 6, 4, 3, 2, 1) if n % c == 0)

@@ -96,25 +96,38 @@ __global__ void k_unpack_set_nodes(double* f, const int32_t* nodes, const double
 
 void ensure_bufs(fecb200_handle* h) {
   const size_t ns = std::max<size_t>(1, h->d_send_nodes.n * h->nf), nr = std::max<size_t>(1, h->d_recv_nodes.n * h->nf);
-  const size_t n = std::max(ns, nr);  // each buffer serves both directions (halo_sum and halo_update)
+  const size_t ng = std::max(h->d_g_own_nodes.n, h->d_g_ghost_nodes.n) * h->nf;
+  const size_t n = std::max(std::max(ns, nr), ng);  // each buffer serves both directions (halo_sum and halo_update)
   if (h->d_sendbuf.n < n) h->d_sendbuf.alloc(n);
   if (h->d_recvbuf.n < n) h->d_recvbuf.alloc(n);
 }
 
-// one grouped point-to-point exchange with every neighbour.  reverse = false: ghosts -> owners (send lists out, recv
-// lists in); reverse = true: owners -> ghosts.
-void exchange(fecb200_handle* h, const double* out, double* in, bool reverse) {
+// one grouped point-to-point exchange with every neighbour: segment i of `out` goes to ranks[i], segment i of `in`
+// comes from it (segments in nodes, NF doubles per node)
+void exchange(fecb200_handle* h, const std::vector<int32_t>& ranks, const std::vector<int64_t>& optr,
+              const std::vector<int64_t>& iptr, const double* out, double* in) {
   Nccl& N = nccl();
   ncclComm_t c = comm_of(h);
-  const std::vector<int64_t>& optr = reverse ? h->recv_ptr : h->send_ptr;
-  const std::vector<int64_t>& iptr = reverse ? h->send_ptr : h->recv_ptr;
   FEC_NCCL(N.GroupStart());
-  for (int i = 0; i < h->n_neighbors; ++i) {
+  for (size_t i = 0; i < ranks.size(); ++i) {
     const int64_t no = (optr[i + 1] - optr[i]) * h->nf, ni = (iptr[i + 1] - iptr[i]) * h->nf;
-    if (no) FEC_NCCL(N.Send(out + optr[i] * h->nf, (size_t)no, ncclFloat64, h->neighbor_ranks[i], c, h->stream));
-    if (ni) FEC_NCCL(N.Recv(in + iptr[i] * h->nf, (size_t)ni, ncclFloat64, h->neighbor_ranks[i], c, h->stream));
+    if (no) FEC_NCCL(N.Send(out + optr[i] * h->nf, (size_t)no, ncclFloat64, ranks[i], c, h->stream));
+    if (ni) FEC_NCCL(N.Recv(in + iptr[i] * h->nf, (size_t)ni, ncclFloat64, ranks[i], c, h->stream));
   }
   FEC_NCCL(N.GroupEnd());
+}
+// the lists of the owner -> ghost update: fecb200_ghost_setup's (every ghost) or, without them, the residual halo
+// lists reversed (only the ghosts that owned elements touch)
+struct UpdateLists {
+  const std::vector<int32_t>* ranks; const std::vector<int64_t>* own_ptr; const std::vector<int64_t>* ghost_ptr;
+  const int32_t* own_nodes; const int32_t* ghost_nodes; int64_t n_own, n_ghost;
+};
+UpdateLists update_lists(fecb200_handle* h) {
+  if (h->ghost_lists)
+    return {&h->g_ranks, &h->g_own_ptr, &h->g_ghost_ptr, h->d_g_own_nodes.p, h->d_g_ghost_nodes.p,
+            (int64_t)h->d_g_own_nodes.n, (int64_t)h->d_g_ghost_nodes.n};
+  return {&h->neighbor_ranks, &h->recv_ptr, &h->send_ptr, h->d_recv_nodes.p, h->d_send_nodes.p,
+          (int64_t)h->d_recv_nodes.n, (int64_t)h->d_send_nodes.n};
 }
 }  // namespace
 
@@ -134,27 +147,29 @@ void comm_barrier(fecb200_handle* h) {
 void comm_halo_sum_field(fecb200_handle* h, double* field) {
   ensure_bufs(h);
   halo_pack(h, field, h->d_sendbuf.p);
-  exchange(h, h->d_sendbuf.p, h->d_recvbuf.p, false);
+  exchange(h, h->neighbor_ranks, h->send_ptr, h->recv_ptr, h->d_sendbuf.p, h->d_recvbuf.p);
   halo_unpack_add(h, field, h->d_recvbuf.p);
 }
 
 // owner -> ghost copy of a full-length nodal field
 void comm_halo_update_field(fecb200_handle* h, double* field) {
   ensure_bufs(h);
-  const int64_t no = (int64_t)h->d_recv_nodes.n, ni = (int64_t)h->d_send_nodes.n;
-  if (no) { k_pack_nodes<<<grid_for(no * h->nf), 256, 0, h->stream>>>(field, h->d_recv_nodes.p, h->d_sendbuf.p, no, h->nf); h->launches++; }
-  exchange(h, h->d_sendbuf.p, h->d_recvbuf.p, true);
-  if (ni) { k_unpack_set_nodes<<<grid_for(ni * h->nf), 256, 0, h->stream>>>(field, h->d_send_nodes.p, h->d_recvbuf.p, ni, h->nf); h->launches++; }
+  const UpdateLists L = update_lists(h);
+  const int64_t no = L.n_own, ni = L.n_ghost;
+  if (no) { k_pack_nodes<<<grid_for(no * h->nf), 256, 0, h->stream>>>(field, L.own_nodes, h->d_sendbuf.p, no, h->nf); h->launches++; }
+  exchange(h, *L.ranks, *L.own_ptr, *L.ghost_ptr, h->d_sendbuf.p, h->d_recvbuf.p);
+  if (ni) { k_unpack_set_nodes<<<grid_for(ni * h->nf), 256, 0, h->stream>>>(field, L.ghost_nodes, h->d_recvbuf.p, ni, h->nf); h->launches++; }
   FEC_CUDA(cudaGetLastError());
 }
 
 // owner -> ghost copy of an unknown-indexed vector (the Uu layout): what consistent!(x) does before K * x
 void comm_halo_update_unknowns(fecb200_handle* h, double* v) {
   ensure_bufs(h);
-  const int64_t no = (int64_t)h->d_recv_nodes.n, ni = (int64_t)h->d_send_nodes.n;
-  if (no) { k_pack_unknowns<<<grid_for(no * h->nf), 256, 0, h->stream>>>(v, h->d_recv_nodes.p, h->d_d2u.p, h->d_sendbuf.p, no, h->nf); h->launches++; }
-  exchange(h, h->d_sendbuf.p, h->d_recvbuf.p, true);
-  if (ni) { k_unpack_set_unknowns<<<grid_for(ni * h->nf), 256, 0, h->stream>>>(v, h->d_send_nodes.p, h->d_d2u.p, h->d_recvbuf.p, ni, h->nf); h->launches++; }
+  const UpdateLists L = update_lists(h);
+  const int64_t no = L.n_own, ni = L.n_ghost;
+  if (no) { k_pack_unknowns<<<grid_for(no * h->nf), 256, 0, h->stream>>>(v, L.own_nodes, h->d_d2u.p, h->d_sendbuf.p, no, h->nf); h->launches++; }
+  exchange(h, *L.ranks, *L.own_ptr, *L.ghost_ptr, h->d_sendbuf.p, h->d_recvbuf.p);
+  if (ni) { k_unpack_set_unknowns<<<grid_for(ni * h->nf), 256, 0, h->stream>>>(v, L.ghost_nodes, h->d_d2u.p, h->d_recvbuf.p, ni, h->nf); h->launches++; }
   FEC_CUDA(cudaGetLastError());
 }
 
@@ -254,6 +269,29 @@ static double* comm_field(fecb200_handle* h, int which) {
     case FECB200_FIELD_V: return h->d_V.p;
     default: throw Error("fecb200: bad field selector");
   }
+}
+
+int fecb200_ghost_setup(fecb200_handle* h, int32_t n_neighbors, const int32_t* ranks, const int64_t* own_ptr,
+                        const int64_t* own_nodes, const int64_t* ghost_ptr, const int64_t* ghost_nodes) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && n_neighbors >= 0 && (n_neighbors == 0 || (ranks && own_ptr && ghost_ptr)), "bad argument");
+  FEC_CUDA(cudaSetDevice(h->device));
+  h->g_ranks.assign(ranks, ranks + n_neighbors);
+  h->g_own_ptr.assign(own_ptr, own_ptr + n_neighbors + 1);
+  h->g_ghost_ptr.assign(ghost_ptr, ghost_ptr + n_neighbors + 1);
+  std::vector<int32_t> on(h->g_own_ptr.back()), gn(h->g_ghost_ptr.back());
+  for (size_t i = 0; i < on.size(); ++i) {
+    FEC_REQUIRE(own_nodes[i] >= 1 && own_nodes[i] <= h->n_owned_nodes, "ghost_setup: own list holds a node this rank does not own");
+    on[i] = (int32_t)(own_nodes[i] - 1);
+  }
+  for (size_t i = 0; i < gn.size(); ++i) {
+    FEC_REQUIRE(ghost_nodes[i] > h->n_owned_nodes && ghost_nodes[i] <= h->nn, "ghost_setup: ghost list holds an owned node");
+    gn[i] = (int32_t)(ghost_nodes[i] - 1);
+  }
+  h->d_g_own_nodes.upload(on, h->stream);
+  h->d_g_ghost_nodes.upload(gn, h->stream);
+  h->ghost_lists = true;
+  FEC_API_END
 }
 
 int fecb200_halo_sum(fecb200_handle* h, int32_t which) {

@@ -277,6 +277,12 @@ struct fecb200_handle {
   std::vector<int64_t> send_ptr, recv_ptr;
   fec::DevBuf<int32_t> d_send_nodes, d_recv_nodes;
   fec::DevBuf<double> d_sendbuf, d_recvbuf;
+  // owner -> ghost update lists (fecb200_ghost_setup): EVERY ghost node, including the far nodes of halo elements that
+  // no owned element touches (they are columns of owned Jacobian rows, but never receive residual contributions)
+  bool ghost_lists = false;
+  std::vector<int32_t> g_ranks;
+  std::vector<int64_t> g_own_ptr, g_ghost_ptr;
+  fec::DevBuf<int32_t> d_g_own_nodes, d_g_ghost_nodes;
 
   // collective plane (comm.cu): NCCL communicator of this rank, created by fecb200_comm_init
   void* comm = nullptr;

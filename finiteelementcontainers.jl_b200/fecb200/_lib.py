@@ -107,6 +107,7 @@ SIGNATURES = {
                                    c_i64p, c_f64p]),
     "fecb200_newton_solve": (C.c_int, [Handle, VP, C.c_int32, C.c_double, C.c_int32, c_i32p, c_i64p, c_f64p]),
     "fecb200_halo_setup": (C.c_int, [Handle, C.c_int32, c_i32p, c_i64p, c_i64p, c_i64p, c_i64p]),
+    "fecb200_ghost_setup": (C.c_int, [Handle, C.c_int32, c_i32p, c_i64p, c_i64p, c_i64p, c_i64p]),
     "fecb200_metis_part_mesh_dual": (C.c_int, [C.c_int64, C.c_int64, c_i64p, c_i64p, C.c_int64, C.c_int64, c_i64p, c_i64p]),
     "fecb200_metis_part_graph": (C.c_int, [C.c_int64, c_i64p, c_i64p, C.c_int64, c_i64p]),
     "fecb200_partition_setup": (C.c_int, [Handle, C.c_int64, c_i32p]),

@@ -86,7 +86,7 @@ class Partition:
     """Rank-local decomposition data + halo exchange."""
 
     def __init__(self, rank, nparts, local_to_global, local_to_owner, n_owned_nodes, n_owned_elements,
-                 n_global_elements, n_global_nodes, send, recv, has_halo_block):
+                 n_global_elements, n_global_nodes, send, recv, has_halo_block, own_ghosted=None):
         self.rank, self.nparts = rank, nparts
         self.local_to_global = np.asarray(local_to_global, dtype=np.int64)   # 1-based global node ids
         self.local_to_owner = np.asarray(local_to_owner, dtype=np.int64)     # 0-based owner rank per local node
@@ -99,6 +99,15 @@ class Partition:
         self.recv = {int(r): np.asarray(v, dtype=np.int64) for r, v in sorted(recv.items()) if len(v)}
         self.neighbors = sorted(set(self.send) | set(self.recv))
         self.has_halo_block = has_halo_block
+        # owner -> ghost update (consistent!): EVERY ghost node by owner, and (own_ghosted) my owned nodes every other
+        # rank holds as ghosts -- a superset of the residual lists: the far nodes of halo elements are Jacobian columns
+        # but never receive residual contributions.  Both sorted by global id.
+        l2g, l2o = self.local_to_global, self.local_to_owner
+        gh = np.arange(self.n_owned_nodes, len(l2g))
+        self.ghost_by_owner = {int(r): gh[l2o[gh] == r][np.argsort(l2g[gh[l2o[gh] == r]], kind="stable")] + 1
+                               for r in np.unique(l2o[gh])} if len(gh) else {}
+        self.own_ghosted = None if own_ghosted is None else \
+            {int(r): np.asarray(v, dtype=np.int64) for r, v in sorted(own_ghosted.items()) if len(v)}
         self._sendbuf = self._recvbuf = None
         self._nf = None
 
@@ -122,6 +131,20 @@ class Partition:
         rn = np.concatenate(rn) if rn else np.zeros(0, dtype=np.int64)
         check(lib.fecb200_halo_setup(h, len(nbrs), nbrs.ctypes.data_as(_lib.c_i32p), _lib.i64(sp)[1], _lib.i64(sn)[1],
                                      _lib.i64(rp)[1], _lib.i64(rn)[1]))
+        if self.own_ghosted is not None:
+            gr = sorted(set(self.own_ghosted) | set(self.ghost_by_owner))
+            op = np.zeros(len(gr) + 1, dtype=np.int64)
+            gp = np.zeros(len(gr) + 1, dtype=np.int64)
+            on, gn = [], []
+            for i, r in enumerate(gr):
+                a, b = self.own_ghosted.get(r, np.zeros(0, dtype=np.int64)), self.ghost_by_owner.get(r, np.zeros(0, dtype=np.int64))
+                on.append(a); gn.append(b)
+                op[i + 1], gp[i + 1] = op[i] + len(a), gp[i] + len(b)
+            on = np.concatenate(on) if on else np.zeros(0, dtype=np.int64)
+            gn = np.concatenate(gn) if gn else np.zeros(0, dtype=np.int64)
+            gra = np.array(gr, dtype=np.int32)
+            check(lib.fecb200_ghost_setup(h, len(gr), gra.ctypes.data_as(_lib.c_i32p), _lib.i64(op)[1], _lib.i64(on)[1],
+                                          _lib.i64(gp)[1], _lib.i64(gn)[1]))
         self._nf = asm.dof.nf
         self._asm_handle = h
         self._send_counts = [int(sp[i + 1] - sp[i]) * self._nf for i in range(len(nbrs))]
@@ -314,8 +337,23 @@ def partition_mesh(mesh, epart, nparts, rank):
 
     lm.nodeset_nodes = restrict(mesh.nodeset_nodes)
     lm.sideset_nodes = restrict(mesh.sideset_nodes)
+    own_ghosted = {}
+    for r in range(nparts):       # rank r's local node set = nodes of its owned + halo elements; my owned nodes in it
+        if r == rank:
+            continue
+        er = epart == r
+        if not er.any():
+            continue
+        own_r = owner == r
+        loc_r = np.zeros(nn, dtype=bool)
+        loc_r[conn[:, er].reshape(-1)] = True
+        halo_r = own_r[conn].any(axis=0) & ~er
+        loc_r[conn[:, halo_r].reshape(-1)] = True
+        hit = np.nonzero(loc_r & own_mask)[0]          # ascending global id
+        if len(hit):
+            own_ghosted[r] = g2l[hit] + 1
     part = Partition(rank, nparts, l2g + 1, owner[l2g], len(owned_nodes), len(mine_e), conn.shape[1], nn, send, recv,
-                     bool(len(halo_e)))
+                     bool(len(halo_e)), own_ghosted)
     part.owned_elements, part.halo_elements = mine_e, halo_e
     return lm, part
 
@@ -543,6 +581,24 @@ def structured_cell_partition(F, nel, cell_part, c, rank, h=None):
         hit = _dilate_to_nodes(eown == r) & n_owned        # my owned nodes that rank r's elements touch
         if hit.any():
             recv[r] = box2loc[ordered(hit)].astype(np.int64) + 1
-    part = Partition(rank, P, l2g + 1, l2o, n_own, int(e_mine.sum()), Ex * Ey * Ez, Nx * Ny * Nz, send, recv, has_halo)
+    # owner -> ghost update lists: my owned nodes inside rank r's local node set (its elements + ITS halo elements)
+    own_ghosted = {}
+    for r in np.unique(eown):
+        r = int(r)
+        if r == rank:
+            continue
+        e_r = eown == r
+        touch_r = np.zeros((bx, by, bz), dtype=bool)
+        n_r = nown == r
+        for dx in (0, 1):
+            for dy in (0, 1):
+                for dz in (0, 1):
+                    touch_r |= n_r[dx:dx + bx, dy:dy + by, dz:dz + bz]
+        loc_r = _dilate_to_nodes(e_r | (touch_r & ~e_r))
+        hit = loc_r & n_owned
+        if hit.any():
+            own_ghosted[r] = box2loc[ordered(hit)].astype(np.int64) + 1
+    part = Partition(rank, P, l2g + 1, l2o, n_own, int(e_mine.sum()), Ex * Ey * Ez, Nx * Ny * Nz, send, recv, has_halo,
+                     own_ghosted)
     part.n_halo_elements = int(e_halo.sum())
     return lm, part

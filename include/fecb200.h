@@ -277,6 +277,13 @@ int fecb200_partition_setup(fecb200_handle* h, int64_t n_owned_nodes, const int3
 int fecb200_halo_setup(fecb200_handle* h, int32_t n_neighbors, const int32_t* neighbor_ranks,
                        const int64_t* send_ptr, const int64_t* send_nodes,  /* ghosts I hold -> owner   */
                        const int64_t* recv_ptr, const int64_t* recv_nodes); /* my owned, ghosted by nbr */
+/* Lists of the owner -> ghost update (consistent!, ext/PartitionedArraysExt.jl:449-459), per neighbour rank: my OWNED
+ * nodes that the neighbour holds as ghosts, and my ghosts it owns -- EVERY ghost, including the far nodes of halo
+ * elements (columns of owned Jacobian rows that no owned element touches, hence absent from the residual lists
+ * above).  Both sides list a pair's nodes in the same (global-id) order.  Without this call halo_update falls back
+ * to the residual lists reversed. */
+int fecb200_ghost_setup(fecb200_handle* h, int32_t n_neighbors, const int32_t* neighbor_ranks,
+                        const int64_t* own_ptr, const int64_t* own_nodes, const int64_t* ghost_ptr, const int64_t* ghost_nodes);
 /* pack field values (NF per node) of the send nodes into the caller's device buffer (halo_send_size doubles) */
 int fecb200_halo_pack(fecb200_handle* h, int32_t which_field, double* sendbuf_dev);
 int fecb200_halo_send_size(fecb200_handle* h, int64_t* n_doubles);

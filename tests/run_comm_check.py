@@ -64,7 +64,8 @@ def _worker(rank, world, n, how, q_id, q_out):
     g = GRID[world]
     E = tuple(gi * n for gi in g)
     if how == "brick":
-        lm, part = structured_brick_partition(F, n, g, rank)
+        ix, iy, iz = np.meshgrid(np.arange(g[0]), np.arange(g[1]), np.arange(g[2]), indexing="ij")
+        lm, part = structured_cell_partition(F, E, ix + g[0] * (iy + g[1] * iz), n, rank, h=1.0 / n)
     else:
         c = 4
         cp = metis_cell_partition(tuple(e // c for e in E), world)     # deterministic: every rank computes the same map

@@ -134,6 +134,10 @@ def test_partition_invariants_four_parts():
             a = p.local_to_global[p.send[s] - 1] if s in p.send else np.zeros(0, dtype=np.int64)
             b = ps.local_to_global[ps.recv[r] - 1] if r in ps.recv else np.zeros(0, dtype=np.int64)
             assert np.array_equal(a, b)
+            # consistent!: r's ghosts owned by s == s's owned nodes that r holds, same order (global id)
+            a = p.local_to_global[p.ghost_by_owner[s] - 1] if s in p.ghost_by_owner else np.zeros(0, dtype=np.int64)
+            b = ps.local_to_global[ps.own_ghosted[r] - 1] if r in ps.own_ghosted else np.zeros(0, dtype=np.int64)
+            assert np.array_equal(a, b)
 
 
 def test_brick_partition_matches_general_builder():
@@ -249,6 +253,11 @@ def test_metis_cell_partition_matches_general_builder(nel, c, P):
             return {tuple(sorted(p.local_to_global[cc - 1])) for cc in lm.element_conns[blk].T} if blk in lm.element_conns else set()
         assert gl(lm_b, pb, "owned") == gl(lm_g, pg, "owned") and gl(lm_b, pb, "halo") == gl(lm_g, pg, "halo")
         assert np.allclose(np.asarray(lm_b.nodal_coords), np.asarray(lm_g.nodal_coords))
+        # owner -> ghost update lists (every ghost, incl. the far nodes of halo elements): same in both builders
+        assert set(pb.own_ghosted) == set(pg.own_ghosted) and set(pb.ghost_by_owner) == set(pg.ghost_by_owner)
+        for r in pb.own_ghosted:
+            assert np.array_equal(pb.own_ghosted[r], pg.own_ghosted[r])
+        assert sum(len(v) for v in pb.ghost_by_owner.values()) == len(pb.local_to_global) - pb.n_owned_nodes
         for name in ("bottom", "top", "left", "right", "back", "front"):
             assert np.array_equal(np.sort(pb.local_to_global[lm_b.nodeset_nodes[name] - 1]),
                                   np.sort(pg.local_to_global[lm_g.nodeset_nodes[name] - 1]))
