@@ -1,7 +1,6 @@
 // dispatch_hex8.cu -- HEX8 instantiations of the element kernels (3-D, 8 nodes).
 // Hot configurations (BASELINE.json configs 2, 3, 5): Poisson NF=1 and neo-Hookean NF=3 with 8-point rules.
 #include "kernel_mat2.cuh"
-#include "kernel_mat3.cuh"
 #include "kernel_mat_scalar.cuh"
 
 // Warps per k_mat2 CTA.  The warps of a CTA start together and walk the phases (FP64-bound G/K, RED-bound S) in
@@ -46,6 +45,12 @@
 #if FEC_MAT2W
 #include "../../tools/variants/kernel_mat2w.cuh"
 #endif
+#ifndef FEC_MAT3
+#define FEC_MAT3 0
+#endif
+#if FEC_MAT3   // warp-specialised persistent variant (4 producer + 4 consumer warps, mbarrier ring): 22.2 vs 16.0 ms
+#include "../../tools/variants/kernel_mat3.cuh"
+#endif
 #include <cstdlib>
 
 namespace fec {
@@ -65,9 +70,9 @@ static void mat8(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
 #elif FEC_MAT2C
     run_mat2c<3, 8, NF, 8, Phys, FEC_MAT2C_EPC, FEC_MAT2C_MINB>(h, b, a);
 #else
-    // FECB200_MAT_KERNEL=mat3: the warp-specialised persistent kernel (kernel_mat3.cuh); default: k_mat2
-    static const bool use3 = [] { const char* e = getenv("FECB200_MAT_KERNEL"); return e && std::string(e) == "mat3"; }();
-    if constexpr (NF == 3) { if (use3) { run_mat3<3, 8, NF, 8, Phys>(h, b, a); return; } }
+#if FEC_MAT3
+    if constexpr (NF == 3) { run_mat3<3, 8, NF, 8, Phys>(h, b, a); return; }
+#endif
     run_mat2<3, 8, NF, 8, Phys, FEC_MAT2_WARPS>(h, b, a);
 #endif
   }

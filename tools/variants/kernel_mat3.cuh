@@ -20,10 +20,18 @@
 // one consumer warp, and a slot is refilled only after its consumer released it, so plain phase parities are safe.
 // A bounded spin turns a protocol error into a trap instead of a hang.
 //
+// MEASURED (round 2, B200, 192^3, profiles/r02_kmat3_prof.txt): correct (all parity tests), but 22.2 ms against 16.0 ms for
+// k_mat2 (31.7 ms with the in-kernel zero-fill, whose bulk stores stall the issuing producer lane).  Per consumer warp
+// phase K takes 9.9 k cycles per 5-element batch -- the same as in k_mat2: ONE warp in K reaches only ~55 % of its
+// scheduler's FP64 pipe (3 dependent DFMAs per accumulator, ptxas has no registers left to interleave chains), and with
+// one 255-register consumer per scheduler nobody fills the gaps; in k_mat2 the second general-purpose warp does.  The
+// register file (64 K) holds 8 such warps and no more, so specialisation cannot add K-capable warps.  Kept here
+// (compiled only with -DFEC_MAT3=1, see tools/build_variants.sh) as the record of that experiment.
+//
 // The CTA also clears its share of the idle CSR value buffer (TMA bulk stores from a zero page), a few pages per
 // producer pass, so the stores drain under the whole kernel instead of in one burst.
 #pragma once
-#include "kernel_mat2.cuh"
+#include "../../finiteelementcontainers.jl_b200/csrc/kernel_mat2.cuh"
 
 namespace fec {
 
@@ -39,7 +47,8 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+// returns the cycles spent waiting (only meaningful with -DFEC_MAT3_PROF; the compiler drops it otherwise)
+__device__ __forceinline__ long long mbar_wait(uint64_t* bar, unsigned parity) {
   const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
   unsigned done = 0;
   const long long t0 = clock64();
@@ -49,7 +58,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
     if (done) break;
     if (clock64() - t0 > 20000000000ll) __trap();   // ~10 s: a protocol error must not hang the device
   }
+  return clock64() - t0;
 }
+#ifdef FEC_MAT3_PROF
+__device__ unsigned long long g_prof[8];   // [0] producer wait, [1] producer total, [2] consumer wait, [3] consumer total, [4] K, [5] S
+#define FEC_PROF(...) __VA_ARGS__
+#else
+#define FEC_PROF(...)
+#endif
 }  // namespace mat3
 
 template <int ND, int NNPE, int NQT>
@@ -109,9 +125,10 @@ __global__ void __launch_bounds__(mat3::kWarps * 32, 1) k_mat3(const __grid_cons
       zf_pos = beg + warp * share;
       zf_end = zf_pos + share < end ? zf_pos + share : end;
     }
+    FEC_PROF(long long t_wait = 0; const long long t_start = clock64();)
     for (int pb = warp; pb < n_pb; pb += kProducers) {
       const int sp = pb % kNPB, use = pb / kNPB;
-      if (use > 0) mbar_wait(&empty_pb[sp], (use - 1) & 1);
+      if (use > 0) { FEC_PROF(t_wait +=) mbar_wait(&empty_pb[sp], (use - 1) & 1); }
       const int64_t i = (int64_t)pb * kPB + elw;        // element index inside the CTA's chunk
       const int64_t e = e_begin + i;
       const bool active = i < n_el;
@@ -225,6 +242,7 @@ __global__ void __launch_bounds__(mat3::kWarps * 32, 1) k_mat3(const __grid_cons
         }
       }
     }
+    FEC_PROF(if (lane == 0) { atomicAdd(&g_prof[0], (unsigned long long)t_wait); atomicAdd(&g_prof[1], (unsigned long long)(clock64() - t_start)); })
     if (lane == 0 && p.zf.p != nullptr) {
       // whatever is left of the share (short chunks), then keep the zero page alive until the stores have read it
       const unsigned zs = (unsigned)__cvta_generic_to_shared(zero_page);
@@ -258,10 +276,12 @@ __global__ void __launch_bounds__(mat3::kWarps * 32, 1) k_mat3(const __grid_cons
         const int i = d1 * ND + j1, j = d2 * ND + j2;
         aidx[j1][j2] = NNPE * ND + (i <= j ? i * NDF - (i * (i - 1)) / 2 + (j - i) : j * NDF - (j * (j - 1)) / 2 + (i - j));
       }
+    FEC_PROF(long long t_wait = 0, t_k = 0, t_s = 0; const long long t_start = clock64();)
 #pragma unroll 1
     for (int cb = cw; cb < n_cb; cb += kConsumers) {
       const int sc = cb % kNCB, use = cb / kNCB;
-      mbar_wait(&full_cb[sc], use & 1);
+      FEC_PROF(t_wait +=) mbar_wait(&full_cb[sc], use & 1);
+      FEC_PROF(const long long tk0 = clock64();)
       const int64_t i0 = (int64_t)cb * kCB;
       const int nel = (int)((n_el - i0) < kCB ? (n_el - i0) : kCB);
       double* wsm = ring + (size_t)(i0 % kRing) * L::ELSM;
@@ -322,6 +342,7 @@ __global__ void __launch_bounds__(mat3::kWarps * 32, 1) k_mat3(const __grid_cons
         }
       }
       __syncwarp();   // every thread of the warp is done reading the slots (re-used as the K_el stage)
+      FEC_PROF(const long long ts0 = clock64(); t_k += ts0 - tk0;)
       // ---- phase S1: stage K_el (row = dof of the row node, column = (local node, dof)); see k_mat2
       if (active) {
 #pragma unroll
@@ -374,11 +395,13 @@ __global__ void __launch_bounds__(mat3::kWarps * 32, 1) k_mat3(const __grid_cons
         }
       }
       __syncwarp();   // all reads of the batch's slots are done: hand them back
+      FEC_PROF(t_s += clock64() - ts0;)
       if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < kCB; ++k) mbar_arrive(&empty_pb[((i0 + k) / kPB) % kNPB]);
       }
     }
+    FEC_PROF(if (lane == 0) { atomicAdd(&g_prof[2], (unsigned long long)t_wait); atomicAdd(&g_prof[3], (unsigned long long)(clock64() - t_start)); atomicAdd(&g_prof[4], (unsigned long long)t_k); atomicAdd(&g_prof[5], (unsigned long long)t_s); })
   }
 }
 
@@ -420,6 +443,17 @@ void run_mat3_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   FEC_CUDA(cudaGetLastError());
   timing_end(h);
   h->launches++;
+#ifdef FEC_MAT3_PROF
+  {
+    unsigned long long v[8], z[8] = {0};
+    FEC_CUDA(cudaStreamSynchronize(h->stream));
+    FEC_CUDA(cudaMemcpyFromSymbol(v, mat3::g_prof, sizeof v));
+    FEC_CUDA(cudaMemcpyToSymbol(mat3::g_prof, z, sizeof z));
+    const double np = (double)grid * mat3::kProducers, nc = (double)grid * mat3::kConsumers;
+    fprintf(stderr, "[k_mat3 prof] per warp, Mcycles: producer wait %.2f of %.2f | consumer wait %.2f of %.2f (K %.2f, S %.2f)\n",
+            v[0] / np / 1e6, v[1] / np / 1e6, v[2] / nc / 1e6, v[3] / nc / 1e6, v[4] / nc / 1e6, v[5] / nc / 1e6);
+  }
+#endif
 }
 
 template <int ND, int NNPE, int NF, int NQT, class Phys>
