@@ -209,6 +209,14 @@ struct SurfaceLoad {
   DevBuf<double> vals;    // [NF, nqs, nsides] = Matrix{SVector{NF}}(nqs, nsides)
 };
 
+// One RobinBCContainer (src/bcs/RobinBCs.jl:29-48): side-set geometry like a Neumann BC plus the flux law at the
+// surface quadrature points in affine form  vals(q, e) = g0(q, e) + D(q, e) u_q  (dvalsdu = D).
+struct RobinLoad {
+  SurfaceLoad geo;        // nodes, tables (vals unused)
+  DevBuf<double> g0;      // [NF, nqs, nsides]
+  DevBuf<double> D;       // [NF, NF, nqs, nsides]: D[di + NF*dj] = d vals_di / d u_dj  (column-major SMatrix{NF,NF})
+};
+
 }  // namespace fec
 
 struct fecb200_handle {
@@ -259,6 +267,7 @@ struct fecb200_handle {
   // external loads (loads.cu): U-independent, so they are integrated once per value update into a cached nodal
   // vector and every assemble_vector_neumann_bc! / assemble_vector_source! is one streaming add
   std::vector<fec::SurfaceLoad> surface_loads;
+  std::vector<fec::RobinLoad> robin_loads;
   fec::DevBuf<double> d_F_neumann, d_F_source;
   bool neumann_dirty = false, source_dirty = false;
   bool has_neumann() const { return !surface_loads.empty(); }

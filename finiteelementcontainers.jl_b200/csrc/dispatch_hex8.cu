@@ -97,6 +97,7 @@ void launch_vector_hex8(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
     case FECB200_PHYS_NEOHOOKEAN: FEC_REQUIRE(h->nf == 3, "mechanics needs NF = ND"); vec8<PhysNeoHookean<3>, 3, kMinB3>(h, b, a); break;
     case FECB200_PHYS_NEOHOOKEAN_AS_WRITTEN: FEC_REQUIRE(h->nf == 3, "mechanics needs NF = ND"); vec8<PhysNeoHookeanAsWritten<3>, 3, kMinB3>(h, b, a); break;
     case FECB200_PHYS_J2_PLASTICITY: FEC_REQUIRE(h->nf == 3, "mechanics needs NF = ND"); vec8<PhysJ2<3>, 3, kMinB3>(h, b, a); break;
+    case FECB200_PHYS_TEST_NONSYMMETRIC: FEC_REQUIRE(h->nf == 3, "mechanics needs NF = ND"); vec8<PhysNonSymmetricTest<3>, 3, kMinB3>(h, b, a); break;
     default: throw Error("fecb200: unsupported physics for HEX8");
   }
 }
@@ -114,6 +115,7 @@ void launch_matrix_hex8(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
     case FECB200_PHYS_NEOHOOKEAN: mat8<PhysNeoHookean<3>, 3, 16>(h, b, a); break;
     case FECB200_PHYS_NEOHOOKEAN_AS_WRITTEN: mat8<PhysNeoHookeanAsWritten<3>, 3, 16>(h, b, a); break;
     case FECB200_PHYS_J2_PLASTICITY: mat8<PhysJ2<3>, 3, 16>(h, b, a); break;
+    case FECB200_PHYS_TEST_NONSYMMETRIC: run_mat<3, 8, 3, 8, PhysNonSymmetricTest<3>, 16>(h, b, a); break;   // k_mat honours the transposed convention
     default: throw Error("fecb200: unsupported physics for HEX8");
   }
 }

@@ -19,6 +19,10 @@ static void vec2d(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
       FEC_REQUIRE(h->nf == 2, "plane-strain mechanics needs NF = 2");
       run_vec_modes<2, NNPE, 2, 0, PhysNeoHookean<2>, kTE, kMinB1>(h, b, a);
       break;
+    case FECB200_PHYS_TEST_NONSYMMETRIC:
+      FEC_REQUIRE(h->nf == 2, "plane-strain mechanics needs NF = 2");
+      run_vec_modes<2, NNPE, 2, 0, PhysNonSymmetricTest<2>, kTE, kMinB1>(h, b, a);
+      break;
     default: throw Error("fecb200: unsupported physics for QUAD4/TRI3");
   }
 }
@@ -36,6 +40,10 @@ static void mat2d(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
     case FECB200_PHYS_NEOHOOKEAN:
       FEC_REQUIRE(h->nf == 2, "plane-strain mechanics needs NF = 2");
       run_mat<2, NNPE, 2, 0, PhysNeoHookean<2>, 32>(h, b, a);
+      break;
+    case FECB200_PHYS_TEST_NONSYMMETRIC:
+      FEC_REQUIRE(h->nf == 2, "plane-strain mechanics needs NF = 2");
+      run_mat<2, NNPE, 2, 0, PhysNonSymmetricTest<2>, 32>(h, b, a);
       break;
     default: throw Error("fecb200: unsupported physics for QUAD4/TRI3");
   }

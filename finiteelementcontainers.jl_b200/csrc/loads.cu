@@ -88,6 +88,111 @@ __global__ void __launch_bounds__(128) k_surface_load(int64_t nsides, int nnps, 
     for (int d = 0; d < nf; ++d) scatter_add(peer, out, (int64_t)node[a], nf, d, r[a][d]);
 }
 
+// ---- Robin BCs (src/assemblers/WeaklyEnforcedBCs.jl:17-32, 85-180; src/bcs/RobinBCs.jl:72-86).  The flux law
+// func(X_q, t, u_q) is a user closure in the reference (differentiated with ForwardDiff); it cannot cross the ABI, so
+// the host hands over its affine form at the surface quadrature points: vals = g0 + D u_q, dvalsdu = D.
+// One thread per side; JxW as in k_surface_load.
+__device__ __forceinline__ double surface_jxw(const double (*x)[3], const double* dN, const double* w, int q, int nnps, int nd) {
+  const int ns = nd - 1;
+  double t[2][3] = {{0, 0, 0}, {0, 0, 0}};
+  for (int a = 0; a < nnps; ++a)
+    for (int k = 0; k < ns; ++k)
+      for (int i = 0; i < nd; ++i) t[k][i] = fma(x[a][i], dN[((size_t)q * nnps + a) * ns + k], t[k][i]);
+  double jac;
+  if (nd == 2) {
+    jac = sqrt(t[0][0] * t[0][0] + t[0][1] * t[0][1]);
+  } else {
+    const double c0 = t[0][1] * t[1][2] - t[0][2] * t[1][1], c1 = t[0][2] * t[1][0] - t[0][0] * t[1][2],
+                 c2 = t[0][0] * t[1][1] - t[0][1] * t[1][0];
+    jac = sqrt(c0 * c0 + c1 * c1 + c2 * c2);
+  }
+  return jac * w[q];
+}
+
+// assemble_vector_robin_bc!: R[(n,d)] += sum_q JxW N_n (g0_d + sum_c D_dc u_c(q)),  u(q) = sum_a N_a U_a  (RobinBCs.jl:80-83)
+__global__ void __launch_bounds__(128) k_robin_vector(int64_t nsides, int nnps, int nqs, int nd, int nf, const int32_t* nodes,
+                                                      const double* tab, const double* g0, const double* D, const double* X,
+                                                      const double* U, double* out) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= nsides) return;
+  const double* N = tab;
+  const double* dN = tab + (size_t)nqs * nnps;
+  const double* w = dN + (size_t)nqs * nnps * (nd - 1);
+  double x[kMaxLoadNodes][3], u[kMaxLoadNodes][3], r[kMaxLoadNodes][3];
+  int32_t node[kMaxLoadNodes];
+  for (int a = 0; a < nnps; ++a) {
+    node[a] = nodes[e * nnps + a];
+    for (int j = 0; j < 3; ++j) {
+      x[a][j] = j < nd ? X[(size_t)node[a] * nd + j] : 0.0;
+      u[a][j] = j < nf ? U[(size_t)node[a] * nf + j] : 0.0;
+      r[a][j] = 0.0;
+    }
+  }
+  for (int q = 0; q < nqs; ++q) {
+    const double JxW = surface_jxw(x, dN, w, q, nnps, nd);
+    double uq[3] = {0, 0, 0}, g[3];
+    for (int a = 0; a < nnps; ++a)
+      for (int c = 0; c < nf; ++c) uq[c] = fma(N[(size_t)q * nnps + a], u[a][c], uq[c]);
+    const double* g0q = g0 + ((size_t)e * nqs + q) * nf;
+    const double* Dq = D + ((size_t)e * nqs + q) * nf * nf;
+    for (int d = 0; d < nf; ++d) {
+      g[d] = g0q[d];
+      for (int c = 0; c < nf; ++c) g[d] = fma(Dq[d + nf * c], uq[c], g[d]);
+    }
+    for (int a = 0; a < nnps; ++a) {
+      const double s = JxW * N[(size_t)q * nnps + a];
+      for (int d = 0; d < nf; ++d) r[a][d] = fma(s, g[d], r[a][d]);
+    }
+  }
+  for (int a = 0; a < nnps; ++a)
+    for (int d = 0; d < nf; ++d) atomicAdd(&out[(size_t)node[a] * nf + d], r[a][d]);
+}
+
+// assemble_matrix_robin_bc!: K_el[(i,di),(j,dj)] = sum_q JxW N_i N_j D[di,dj] over the side's nodes, added into the
+// element's COO slots (_assemble_element_add!, :155-165), i.e. with the transposed labelling of the pattern
+// (SparsityPatterns.jl:76-83): stored entry (row dof(j,dj), col dof(i,di)) += K_el[(i,di),(j,dj)].  Here: straight into
+// the CSR / CSC values.  `csc` swaps the roles once more (values of K^T are stored row-wise).
+__global__ void __launch_bounds__(128) k_robin_matrix(int64_t nsides, int nnps, int nqs, int nd, int nf, const int32_t* nodes,
+                                                      const double* tab, const double* D, const double* X, double* nz,
+                                                      const int32_t* adjptr, const int32_t* adj, const uint16_t* coloff,
+                                                      const uint8_t* freemask, const int64_t* rowstart, int csc) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= nsides) return;
+  const double* N = tab;
+  const double* dN = tab + (size_t)nqs * nnps;
+  const double* w = dN + (size_t)nqs * nnps * (nd - 1);
+  double x[kMaxLoadNodes][3];
+  int32_t node[kMaxLoadNodes];
+  for (int a = 0; a < nnps; ++a) {
+    node[a] = nodes[e * nnps + a];
+    for (int j = 0; j < 3; ++j) x[a][j] = j < nd ? X[(size_t)node[a] * nd + j] : 0.0;
+  }
+  for (int i = 0; i < nnps; ++i)
+    for (int j = 0; j < nnps; ++j) {
+      double kij[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // [di + nf*dj]
+      for (int q = 0; q < nqs; ++q) {
+        const double s = surface_jxw(x, dN, w, q, nnps, nd) * N[(size_t)q * nnps + i] * N[(size_t)q * nnps + j];
+        const double* Dq = D + ((size_t)e * nqs + q) * nf * nf;
+        for (int k = 0; k < nf * nf; ++k) kij[k] = fma(s, Dq[k], kij[k]);
+      }
+      // stored (row, col) = (dof(j,dj), dof(i,di)) in CSR; CSC stores the transpose row-wise -> (dof(i,di), dof(j,dj))
+      const int rn = csc ? node[i] : node[j], cn = csc ? node[j] : node[i];
+      const int32_t* row = adj + adjptr[rn];
+      const int len = adjptr[rn + 1] - adjptr[rn];
+      int pos = 0;
+      while (pos < len && row[pos] != cn) ++pos;
+      if (pos == len) continue;
+      const unsigned cmask = freemask[cn];
+      for (int di = 0; di < nf; ++di)
+        for (int dj = 0; dj < nf; ++dj) {
+          const int rd = csc ? di : dj, cd = csc ? dj : di;
+          const int64_t rs = rowstart[(int64_t)rn * nf + rd];
+          if (rs < 0 || !(cmask & (1u << cd))) continue;
+          atomicAdd(&nz[rs + coloff[adjptr[rn] + pos] + __popc(cmask & ((1u << cd) - 1u))], kij[di + nf * dj]);
+        }
+    }
+}
+
 __global__ void k_add_field(double* __restrict__ dst, const double* __restrict__ src, int64_t n) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) dst[i] += src[i];
@@ -246,6 +351,93 @@ int fecb200_set_source_values(fecb200_handle* h, int32_t block, const double* va
   if (!vals) { FEC_CUDA(cudaStreamSynchronize(h->stream)); b.d_body_force.release(); }
   else upload_doubles(h, b.d_body_force, vals, (size_t)b.ne * b.nq * h->nf);
   h->source_dirty = true;
+  FEC_API_END
+}
+
+int fecb200_set_robin_bc(fecb200_handle* h, int32_t id, int64_t nsides, int32_t nnps, int32_t nqs, const int64_t* side_nodes,
+                         const double* Ns, const double* dNs, const double* ws) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && id >= 0 && id <= (int)h->robin_loads.size(), "Robin BC ids are 0, 1, 2, ... in order");
+  FEC_REQUIRE(nsides >= 0 && nnps >= 1 && nnps <= kMaxLoadNodes && nqs >= 1, "bad side-set shape");
+  FEC_REQUIRE(nsides == 0 || (side_nodes && Ns && dNs && ws), "null argument");
+  FEC_REQUIRE(h->n_owned_nodes == h->nn, "Robin BCs are not supported on a partitioned handle");
+  FEC_CUDA(cudaSetDevice(h->device));
+  if (id == (int)h->robin_loads.size()) h->robin_loads.emplace_back();
+  SurfaceLoad& s = h->robin_loads[id].geo;
+  s.nsides = nsides; s.nnps = nnps; s.nqs = nqs;
+  std::vector<int32_t> nodes((size_t)nsides * nnps);
+  for (size_t i = 0; i < nodes.size(); ++i) {
+    FEC_REQUIRE(side_nodes[i] >= 1 && side_nodes[i] <= h->nn, "side node id out of range");
+    nodes[i] = (int32_t)(side_nodes[i] - 1);
+  }
+  s.nodes.upload(nodes, h->stream);
+  std::vector<double> t;
+  if (nsides) {
+    t.insert(t.end(), Ns, Ns + (size_t)nqs * nnps);
+    t.insert(t.end(), dNs, dNs + (size_t)nqs * nnps * (h->nd - 1));
+    t.insert(t.end(), ws, ws + nqs);
+  }
+  s.tab.upload(t, h->stream);
+  h->robin_loads[id].g0.release();
+  h->robin_loads[id].D.release();
+  FEC_API_END
+}
+
+int fecb200_set_robin_values(fecb200_handle* h, int32_t id, const double* g0, const double* dvalsdu) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && id >= 0 && id < (int)h->robin_loads.size(), "unknown Robin BC id");
+  FEC_CUDA(cudaSetDevice(h->device));
+  RobinLoad& r = h->robin_loads[id];
+  FEC_REQUIRE((g0 && dvalsdu) || !r.geo.nsides, "null argument");
+  upload_doubles(h, r.g0, g0, (size_t)r.geo.nsides * r.geo.nqs * h->nf);
+  upload_doubles(h, r.D, dvalsdu, (size_t)r.geo.nsides * r.geo.nqs * h->nf * h->nf);
+  FEC_API_END
+}
+
+int fecb200_clear_robin_bcs(fecb200_handle* h) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h, "null handle");
+  FEC_CUDA(cudaSetDevice(h->device));
+  FEC_CUDA(cudaStreamSynchronize(h->stream));
+  h->robin_loads.clear();
+  FEC_API_END
+}
+
+int fecb200_assemble_vector_robin_bc(fecb200_handle* h) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h, "null handle");
+  FEC_CUDA(cudaSetDevice(h->device));
+  for (auto& r : h->robin_loads) {
+    const SurfaceLoad& s = r.geo;
+    if (!s.nsides) continue;
+    FEC_REQUIRE(r.g0.p && r.D.p, "Robin BC values were never set (fecb200_set_robin_values)");
+    k_robin_vector<<<grid_for(s.nsides), 128, 0, h->stream>>>(s.nsides, s.nnps, s.nqs, h->nd, h->nf, s.nodes.p, s.tab.p, r.g0.p, r.D.p,
+                                                             h->d_X.p, h->d_U.p, h->d_R.p);
+    FEC_CUDA(cudaGetLastError());
+    h->launches++;
+  }
+  FEC_API_END
+}
+
+int fecb200_assemble_matrix_robin_bc(fecb200_handle* h) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h, "null handle");
+  FEC_CUDA(cudaSetDevice(h->device));
+  FEC_REQUIRE(!h->opts.matrix_free, "assemble_matrix_robin_bc! called on a matrix-free SparseMatrixAssembler");
+  ensure_matrix_structure(h);
+  FEC_REQUIRE(h->matrix_ready && h->d_nz_stiff.p, "assemble_stiffness! must run before assemble_matrix_robin_bc!");
+  FEC_REQUIRE(!h->stiff_adjusted, "assemble_matrix_robin_bc! must run before stiffness(asm) applies the constraint adjustment");
+  FEC_REQUIRE(h->per_b.empty(), "Robin BCs together with periodic BCs are not supported in matrix assembly");
+  for (auto& r : h->robin_loads) {
+    const SurfaceLoad& s = r.geo;
+    if (!s.nsides) continue;
+    FEC_REQUIRE(r.D.p, "Robin BC values were never set (fecb200_set_robin_values)");
+    k_robin_matrix<<<grid_for(s.nsides), 128, 0, h->stream>>>(s.nsides, s.nnps, s.nqs, h->nd, h->nf, s.nodes.p, s.tab.p, r.D.p, h->d_X.p,
+                                                             h->d_nz_stiff.p, h->d_adjptr.p, h->d_adj.p, h->d_coloff.p,
+                                                             h->d_freemask.p, h->d_rowstart.p, h->opts.matrix_type == FECB200_CSC);
+    FEC_CUDA(cudaGetLastError());
+    h->launches++;
+  }
   FEC_API_END
 }
 

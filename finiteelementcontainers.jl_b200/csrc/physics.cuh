@@ -429,7 +429,47 @@ struct J2Impl {
   }
 };
 
+// -------------------------------------------------------------------------------------------
+// TEST physics with a NON-symmetric tangent (A_ijkl != A_klij): linear elasticity plus beta * delta_ij T_kl with a
+// fixed non-symmetric T.  Not a material model: it exists so that the transposed COO labelling of the reference's
+// pattern (Assemblers.jl:109-124 vs SparsityPatterns.jl:76-83) is observable in a parity test -- every
+// shipped law has a symmetric tangent, for which the convention is invisible.  props = (rho, K, G, beta).
+// -------------------------------------------------------------------------------------------
+struct NonSymmetricTestImpl {
+  static constexpr int NS = 0;
+  static constexpr bool kScalesTangent = true;
+  static constexpr bool kHasEnergy = false;
+  struct Pre { double K, G, beta; };
+  FEC_DEV static double T(int k, int l) {
+    return (k == 0 && l == 1) ? 1.0 : (k == 1 && l == 2) ? 2.0 : (k == 2 && l == 0) ? 3.0 : (k == 1 && l == 0) ? -0.5 : (k == l ? 0.25 * (k + 1) : 0.0);
+  }
+  FEC_DEV static void stress(const double (&g)[3][3], const double* props, const double*, double*, double (&P)[3][3]) {
+    LinearElasticImpl::stress(g, props, nullptr, nullptr, P);
+    double tg = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int l = 0; l < 3; ++l) tg = fma(T(k, l), g[k][l], tg);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) P[i][i] = fma(props[3], tg, P[i][i]);
+  }
+  FEC_DEV static void dstress(const double (&)[3][3], const double (&v)[3][3], const double* props, const double*,
+                              double (&D)[3][3]) {
+    stress(v, props, nullptr, nullptr, D);
+  }
+  FEC_DEV static void prepare(const double (&)[3][3], const double* props, const double*, Pre& p) {
+    p.K = props[1]; p.G = props[2]; p.beta = props[3];
+  }
+  FEC_DEV static void scale_tangent(Pre& p, const double s) { p.K *= s; p.G *= s; p.beta *= s; }
+  FEC_DEV static double A(const Pre& p, int i, int j, int k, int l) {
+    const double dij = (i == j), dkl = (k == l), dik = (i == k), djl = (j == l), dil = (i == l), djk = (j == k);
+    return (p.K - 2.0 * p.G / 3.0) * dij * dkl + p.G * (dik * djl + dil * djk) + p.beta * dij * T(k, l);
+  }
+  FEC_DEV static double energy(const double (&)[3][3], const double*, const double*) { return 0.0; }
+};
+
 template <int ND> using PhysLinearElastic = PhysMech3<ND, LinearElasticImpl>;
+template <int ND> using PhysNonSymmetricTest = PhysMech3<ND, NonSymmetricTestImpl>;
 template <int ND> using PhysNeoHookean = PhysMech3<ND, NeoHookeanImpl<false>>;
 template <int ND> using PhysNeoHookeanAsWritten = PhysMech3<ND, NeoHookeanImpl<true>>;
 template <int ND> using PhysJ2 = PhysMech3<ND, J2Impl>;

@@ -12,15 +12,16 @@ from .function_spaces import (FunctionSpace, Lagrange, ScalarFunction, VectorFun
                               SymmetricTensorFunction, GeneralFunction, DofManager, update_field_unknowns,
                               extract_field_unknowns, update_field_dirichlet_bcs)
 from .bcs import (DirichletBC, DirichletBCs, InitialCondition, InitialConditions, NeumannBC, NeumannBCs, PeriodicBC,
-                  PeriodicBCs, Source, Sources, TimeStepper)
-from .physics import (AbstractPhysics, Poisson, Mechanics, NeoHookean, J2Plasticity, ThreeDimensional, PlaneStrain,
+                  PeriodicBCs, RobinBC, RobinBCs, Source, Sources, TimeStepper)
+from .physics import (AbstractPhysics, Poisson, Mechanics, NeoHookean, J2Plasticity, NonSymmetricTestPhysics, ThreeDimensional, PlaneStrain,
                       residual, residual_b, stiffness, stiffness_b, mass, mass_b, stiffness_action,
                       stiffness_action_b, mass_action, mass_action_b, lumped_mass, energy)
 from .assemblers import (SparseMatrixAssembler, Parameters, create_parameters, update_dofs, update_bc_values,
                          update_time, create_field, create_unknowns, assemble_vector, assemble_stiffness,
                          assemble_mass, assemble_vector_and_stiffness, assemble_matrix_action, assemble_matrix_free_action,
                          assemble_matrix_free_action_full, hvp, full_field, assemble_lumped_mass, assemble_diagonal, diagonal, assemble_scalar, scalar_values,
-                         assemble_vector_neumann_bc, assemble_vector_source, matrix_multiply, update_field)
+                         assemble_vector_neumann_bc, assemble_vector_source, assemble_vector_robin_bc, assemble_matrix_robin_bc,
+                         matrix_multiply, update_field)
 from .solvers import DirectLinearSolver, IterativeLinearSolver, NewtonSolver, QuasiStaticIntegrator
 from .postprocessors import PostProcessor, write_times, write_field, close
 from .partition import (Partition, partition_mesh, structured_brick_partition, metis_partition_elements,

@@ -30,6 +30,7 @@ lib = C.CDLL(LIB_PATH)
 # element / physics / kind enums (keep in sync with include/fecb200.h)
 QUAD4, TRI3, HEX8, TET4, TET10 = 1, 2, 3, 4, 5
 PHYS_POISSON, PHYS_LINEAR_ELASTIC, PHYS_NEOHOOKEAN, PHYS_NEOHOOKEAN_AS_WRITTEN, PHYS_J2_PLASTICITY = 1, 2, 3, 4, 5
+PHYS_TEST_NONSYMMETRIC = 6
 RESIDUAL, STIFFNESS, MASS = 1, 2, 3
 LUMPED_MASS, DIAGONAL_STIFFNESS, DIAGONAL_MASS = 4, 5, 6
 ENERGY = 7   # host-side token only (fecb200_assemble_scalar has no kind argument)
@@ -101,6 +102,11 @@ SIGNATURES = {
     "fecb200_set_neumann_values": (C.c_int, [Handle, C.c_int32, VP]),
     "fecb200_clear_neumann_bcs": (C.c_int, [Handle]),
     "fecb200_assemble_vector_neumann_bc": (C.c_int, [Handle]),
+    "fecb200_set_robin_bc": (C.c_int, [Handle, C.c_int32, C.c_int64, C.c_int32, C.c_int32, c_i64p, c_f64p, c_f64p, c_f64p]),
+    "fecb200_set_robin_values": (C.c_int, [Handle, C.c_int32, VP, VP]),
+    "fecb200_clear_robin_bcs": (C.c_int, [Handle]),
+    "fecb200_assemble_vector_robin_bc": (C.c_int, [Handle]),
+    "fecb200_assemble_matrix_robin_bc": (C.c_int, [Handle]),
     "fecb200_set_source_values": (C.c_int, [Handle, C.c_int32, VP]),
     "fecb200_assemble_vector_source": (C.c_int, [Handle]),
     "fecb200_cg_solve": (C.c_int, [Handle, VP, VP, C.c_double, C.c_double, C.c_int64, C.c_int32,

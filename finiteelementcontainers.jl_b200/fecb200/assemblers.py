@@ -18,7 +18,7 @@ import scipy.sparse as sp
 
 from . import _lib
 from ._lib import FECError, check, lib
-from .bcs import DirichletBCs, NeumannBCs, PeriodicBCs, Sources, TimeStepper
+from .bcs import DirichletBCs, NeumannBCs, PeriodicBCs, RobinBCs, Sources, TimeStepper
 from .fields import H1Field
 from .function_spaces import AbstractFunction, DofManager
 from .physics import AbstractPhysics, Poisson, kind_of
@@ -133,11 +133,13 @@ class Parameters:
     """The slice of Parameters (src/Parameters.jl:37-73) the hot path touches; device-resident
     fields live inside the handle (`p |> cuda`)."""
 
-    def __init__(self, mesh, asm, physics, props, dirichlet_bcs, times, neumann_bcs=None, sources=None, periodic_bcs=None):
+    def __init__(self, mesh, asm, physics, props, dirichlet_bcs, times, neumann_bcs=None, sources=None, periodic_bcs=None,
+                 robin_bcs=None):
         self.mesh, self.asm = mesh, asm
         self.physics, self.properties = physics, props
         self.dirichlet_bcs = dirichlet_bcs
         self.neumann_bcs, self.sources = neumann_bcs, sources
+        self.robin_bcs = robin_bcs
         self.periodic_bcs = periodic_bcs
         self.times = times
         self.coords = mesh.nodal_coords
@@ -171,7 +173,7 @@ def _per_block(x, nb, kind):
 
 
 def create_parameters(mesh, asm, physics, props=None, *, dirichlet_bcs=(), neumann_bcs=(), sources=(), periodic_bcs=(),
-                      times=None):
+                      robin_bcs=(), times=None):
     """create_parameters(mesh, asm, physics, props; dirichlet_bcs, neumann_bcs, sources, times)  (src/Parameters.jl:288-302):
     builds the device handle (the `|> cuda` step), the BC containers, and calls update_dofs!."""
     fspace = asm.dof.var.fspace
@@ -196,13 +198,19 @@ def create_parameters(mesh, asm, physics, props=None, *, dirichlet_bcs=(), neuma
     nbcs = NeumannBCs(mesh, asm.dof, list(neumann_bcs))
     srcs = Sources(mesh, asm.dof, list(sources))
     pbcs = PeriodicBCs(mesh, asm.dof, list(periodic_bcs))
-    p = Parameters(mesh, asm, physics_list, props_list, dbcs, times, nbcs, srcs, pbcs)
+    rbcs = RobinBCs(mesh, asm.dof, list(robin_bcs))
+    p = Parameters(mesh, asm, physics_list, props_list, dbcs, times, nbcs, srcs, pbcs, rbcs)
     update_dofs(asm, dbcs, periodic=pbcs.periodic_dofs())      # update_dofs!(asm, dbcs, pbcs) (Parameters.jl:118-125)
     for i, c in enumerate(nbcs.bc_caches):   # the side sets' geometry is uploaded once (`p |> cuda`)
         sn, snp = _lib.i64(c["side_nodes"].reshape(-1, order="F"))
         Ns, Nsp = _lib.f64(c["Ns"]); dNs, dNsp = _lib.f64(c["dNs"]); ws, wsp = _lib.f64(c["ws"])
         check(lib.fecb200_set_neumann_bc(asm._require(), i, c["side_nodes"].shape[1], c["side_nodes"].shape[0], len(ws),
                                          snp, Nsp, dNsp, wsp))
+    for i, c in enumerate(rbcs.bc_caches):
+        sn, snp = _lib.i64(c["side_nodes"].reshape(-1, order="F"))
+        Ns, Nsp = _lib.f64(c["Ns"]); dNs, dNsp = _lib.f64(c["dNs"]); ws, wsp = _lib.f64(c["ws"])
+        check(lib.fecb200_set_robin_bc(asm._require(), i, c["side_nodes"].shape[1], c["side_nodes"].shape[0], len(ws),
+                                       snp, Nsp, dNsp, wsp))
     update_bc_values(p)
     _upload_sources(p)
     return p
@@ -259,6 +267,12 @@ def update_bc_values(p):
         for i, c in enumerate(p.neumann_bcs.bc_caches):
             v = np.ascontiguousarray(c["vals"].reshape(-1, order="F"))
             check(lib.fecb200_set_neumann_values(p.asm._require(), i, _lib.ptr(v)))
+    if getattr(p, "robin_bcs", None) is not None and len(p.robin_bcs):   # update_bc_values!(p.robin_bcs, ...) (Solvers.jl:74)
+        p.robin_bcs.update_bc_values(p.coords, p.times.time_current)
+        for i, c in enumerate(p.robin_bcs.bc_caches):
+            g0 = np.ascontiguousarray(c["g0"].reshape(-1, order="F"))
+            D = np.ascontiguousarray(c["dvalsdu"].reshape(-1, order="F"))
+            check(lib.fecb200_set_robin_values(p.asm._require(), i, _lib.ptr(g0), _lib.ptr(D)))
     if p.sources is not None and len(p.sources):             # _update_source_values! (Sources.jl:55-66)
         p.sources.update_source_values(p.asm.dof.var.fspace, p.times.time_current)
         for b, vals in zip(p.sources.blocks, p.sources.vals):
@@ -296,6 +310,17 @@ def assemble_vector_neumann_bc(asm, Uu, p):
     p.neumann_bcs to the residual storage (no zeroing).  The loads do not depend on Uu; the library integrates them
     once per update_bc_values! and adds the cached vector."""
     check(lib.fecb200_assemble_vector_neumann_bc(asm._require()))
+
+
+def assemble_vector_robin_bc(asm, Uu, p):
+    """assemble_vector_robin_bc!(asm, Uu, p) (src/assemblers/WeaklyEnforcedBCs.jl:20-32): adds the Robin flux at the
+    CURRENT p.field to the residual storage (no _update_for_assembly!, like the reference)"""
+    check(lib.fecb200_assemble_vector_robin_bc(asm._require()))
+
+
+def assemble_matrix_robin_bc(asm, Uu, p):
+    """assemble_matrix_robin_bc!(asm, Uu, p) (:88-116): adds the Robin tangent to the assembled stiffness values"""
+    check(lib.fecb200_assemble_matrix_robin_bc(asm._require()))
 
 
 def assemble_vector_source(asm, Uu, p):

@@ -134,6 +134,47 @@ class NeumannBCs:
             c["vals"] = np.asfortranarray(v.reshape(Xq.shape[0], Xq.shape[1], self.nf).transpose(2, 1, 0))
 
 
+class RobinBC:
+    """RobinBC(var_name, func, sset_name)  (src/bcs/RobinBCs.jl:7-20).  `func(X, t, u)` returns the flux vector (NF
+    components) as a function of the field value at the surface point; called vectorised: X (n, ND), u (n, NF),
+    result (n, NF).  The device path needs the law in AFFINE form g0(X, t) + D(X, t) u (the reference differentiates
+    the closure with ForwardDiff, :72-75; a closure cannot cross the C ABI): g0 and D are recovered from func at u = 0
+    and u = e_c, and a law that is not affine in u is rejected loudly."""
+
+    def __init__(self, var_name, func, sset_name):
+        self.var_name, self.func, self.sset_name = var_name, func, sset_name
+
+
+class RobinBCs(NeumannBCs):
+    """RobinBCs(mesh, dof, robin_bcs) (src/bcs/RobinBCs.jl:88-131): the Neumann side-set caches plus
+    `g0[NF, nqs, nsides]`, `dvalsdu[NF, NF, nqs, nsides]` (vals = g0 + dvalsdu u_q is formed on the device)."""
+
+    def update_bc_values(self, X, t):
+        X = np.asarray(X)
+        rng = np.random.default_rng(0)
+        for func, c in zip(self.bc_funcs, self.bc_caches):
+            ns = c["side_nodes"].shape[1]
+            nq = len(c["ws"])
+            c["g0"] = np.zeros((self.nf, nq, ns), order="F")
+            c["dvalsdu"] = np.zeros((self.nf, self.nf, nq, ns), order="F")
+            if ns == 0:
+                continue
+            xs = X[:, c["side_nodes"] - 1]
+            Xq = np.einsum("qa,dae->eqd", c["Ns"], xs).reshape(ns * nq, -1)      # (nsides*nqs, ND), q fastest
+            n = Xq.shape[0]
+            ev = lambda u: _as_values(func(Xq, t, u), n, self.nf)
+            g0 = ev(np.zeros((n, self.nf)))
+            D = np.zeros((n, self.nf, self.nf))
+            for cdof in range(self.nf):
+                u = np.zeros((n, self.nf)); u[:, cdof] = 1.0
+                D[:, :, cdof] = ev(u) - g0
+            ut = rng.standard_normal((n, self.nf))
+            if not np.allclose(ev(ut), g0 + np.einsum("ndc,nc->nd", D, ut), rtol=1e-10, atol=1e-12 * (1 + np.abs(g0).max())):
+                raise ValueError("RobinBC: the flux law is not affine in u; only g0(X,t) + D(X,t) u is supported on the device path")
+            c["g0"] = np.asfortranarray(g0.reshape(ns, nq, self.nf).transpose(2, 1, 0))
+            c["dvalsdu"] = np.asfortranarray(D.reshape(ns, nq, self.nf, self.nf).transpose(2, 3, 1, 0))
+
+
 class Source:
     """Source(var_name, func, block_name)  (src/bcs/Sources.jl:17-27): body force density b(X, t) (all NF components)
     on one element block; the assembler adds -int N b dOmega to the residual (:1-5)."""

@@ -77,6 +77,17 @@ class NeoHookean(_MechanicsBase):
         return np.array([1e3, 10.0e6, 1.0e6])
 
 
+class NonSymmetricTestPhysics(_MechanicsBase):
+    """TEST law (not in the reference): linear elasticity + beta * delta_ij T_kl, a tangent without major symmetry, so
+    that the transposed COO labelling of the reference's pattern is visible in a parity test.
+    props = (rho, K, G, beta)."""
+    NP, NS = 4, 0
+    physics_id = _lib.PHYS_TEST_NONSYMMETRIC
+
+    def create_properties(self):
+        return np.array([1e3, 10.0e6, 1.0e6, 3.0e6])
+
+
 class J2Plasticity(_MechanicsBase):
     """Stateful mechanics: AbstractPhysics{3,5,7} (hooks: test/mechanics_with_state/
     TestMechanicsWithState.jl:15-67); props = (rho, K, G, sigma_y, H), 7 states per qp."""

@@ -34,7 +34,7 @@ class IterativeLinearSolver:
 class DirectLinearSolver:
     """DirectLinearSolver(asm) + solve!(solver, Uu, p) (src/Solvers.jl:37-86): residual (+ source + Neumann loads) and
     stiffness assembled on the device, the sparse direct solve of K x = R on the host -- exactly where the reference does it ("currently doesn't
-    work on GPU", Solvers.jl:81; Robin terms are out of scope).  Uu is updated in place."""
+    work on GPU", Solvers.jl:81; incl. the Robin vector / matrix terms, Solvers.jl:73-76).  Uu is updated in place."""
 
     def __init__(self, assembler):
         if assembler.matrix_free:
@@ -52,6 +52,9 @@ class DirectLinearSolver:
         A.assemble_vector_source(asm, Uu, p)
         A.assemble_vector_neumann_bc(asm, Uu, p)
         A.assemble_stiffness(asm, stiffness, Uu, p)
+        if getattr(p, "robin_bcs", None) is not None and len(p.robin_bcs):     # Solvers.jl:73-76
+            A.assemble_vector_robin_bc(asm, Uu, p)
+            A.assemble_matrix_robin_bc(asm, Uu, p)
         R = A._residual_accessor(asm)
         K = A._stiffness_accessor(asm)
         self.dUu = -spla.spsolve(K.tocsc(), R)

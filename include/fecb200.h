@@ -43,7 +43,10 @@ enum {
   FECB200_PHYS_LINEAR_ELASTIC = 2,     /* test/mechanics/TestMechanicsCommon.jl:3-236  props (rho,K,G) */
   FECB200_PHYS_NEOHOOKEAN = 3,         /* TestMechanicsLargeDeformation.jl:17-27, stress-free U(J)  */
   FECB200_PHYS_NEOHOOKEAN_AS_WRITTEN = 4, /* the script's U(J) verbatim               */
-  FECB200_PHYS_J2_PLASTICITY = 5       /* NS=7 state, props (rho,K,G,sigma_y,H); hooks only in the reference */
+  FECB200_PHYS_J2_PLASTICITY = 5,      /* NS=7 state, props (rho,K,G,sigma_y,H); hooks only in the reference */
+  FECB200_PHYS_TEST_NONSYMMETRIC = 6   /* TEST law, props (rho,K,G,beta): linear elasticity + beta d_ij T_kl, a tangent WITHOUT
+                                          major symmetry, so that the transposed COO labelling of the pattern
+                                          (Assemblers.jl:109-124 vs SparsityPatterns.jl:76-83) shows in a parity test */
 };
 
 /* which element-level function is assembled: the `f` argument of assemble_vector! etc.
@@ -237,6 +240,24 @@ int fecb200_set_neumann_bc(fecb200_handle* h, int32_t id, int64_t nsides, int32_
 int fecb200_set_neumann_values(fecb200_handle* h, int32_t id, const double* vals);
 int fecb200_clear_neumann_bcs(fecb200_handle* h);
 int fecb200_assemble_vector_neumann_bc(fecb200_handle* h);
+/* Robin BCs = RobinBCContainer (src/bcs/RobinBCs.jl:29-86): same side-set geometry as a Neumann BC; the flux law
+ * func(X_q, t, u_q) of the reference is a closure differentiated with ForwardDiff (:72-75) and cannot cross the ABI, so
+ * the host hands over its AFFINE form at the surface quadrature points (update_bc_values!, :77-86):
+ *   g0       [NF, nqs, nsides]      vals(q, e)    = g0 + dvalsdu * u_q,   u_q = sum_a Ns[q][a] U_a
+ *   dvalsdu  [NF, NF, nqs, nsides]  dvalsdu(q, e) = d func / d u          (column-major SMatrix{NF,NF} per point)
+ * (the reference's own Robin regression, test/poisson/TestPoisson.jl:106-127, is of this form: a(x) - alpha u).
+ * fecb200_assemble_vector_robin_bc = assemble_vector_robin_bc! (src/assemblers/WeaklyEnforcedBCs.jl:20-32, 61-83):
+ *   R[(n,d)] += sum_q JxW_s Ns[q][n] vals_d(q, e)  at the CURRENT p.field (no _update_for_assembly!, like the reference).
+ * fecb200_assemble_matrix_robin_bc = assemble_matrix_robin_bc! (:88-180): K_el = sum_q JxW_s Ns_i Ns_j dvalsdu[di,dj]
+ *   added to the assembled stiffness values with the pattern's (transposed) COO labelling; call it after
+ *   fecb200_assemble_matrix(STIFFNESS) and before fecb200_matrix_values, as solve!(::DirectLinearSolver) does
+ *   (src/Solvers.jl:73-79).  Not available on partitioned handles. */
+int fecb200_set_robin_bc(fecb200_handle* h, int32_t id, int64_t nsides, int32_t nnps, int32_t nqs,
+                         const int64_t* side_nodes, const double* Ns, const double* dNs, const double* ws);
+int fecb200_set_robin_values(fecb200_handle* h, int32_t id, const double* g0, const double* dvalsdu);
+int fecb200_clear_robin_bcs(fecb200_handle* h);
+int fecb200_assemble_vector_robin_bc(fecb200_handle* h);
+int fecb200_assemble_matrix_robin_bc(fecb200_handle* h);
 /* Body forces = SourceContainer.vals (src/bcs/Sources.jl:38-66): vals [NF, NQ, NE] of one block, element order of
  * the block's conn; NULL removes the block's source  [host|device].
  * assemble_vector_source! (src/assemblers/Source.jl:10-64): R[(n,d)] += - sum_q JxW(q) N[q][n] vals[d,q,e]. */

@@ -412,6 +412,52 @@ def assemble_vector_neumann_bc(R, snodes, tables, vals, X, nf):
     return R
 
 
+def robin_update_bc_values(snodes, tables, X, U, func, dfuncdu, t=0.0):
+    """_update_bc_values! of the Robin container (src/bcs/RobinBCs.jl:77-86): u_q = u_el * interps.N at every surface
+    point, vals[q, e] = func(X_q, t, u_q), dvalsdu[q, e] = dfuncdu(X_q, t, u_q) (ForwardDiff.jacobian in the reference,
+    :72-75; an explicit callable here).  U (NF, NN).  Returns vals (NF, nqs, nsides), dvalsdu (NF, NF, nqs, nsides)."""
+    Ns = tables[0]
+    nf = U.shape[0]
+    Xq = surface_quadrature_points(snodes, tables, X)                   # (nqs, nsides, ND)
+    u_s = np.transpose(U[:, snodes - 1], (2, 1, 0))                     # (nsides, nnps, NF)
+    uq = np.einsum("qa,eac->qec", Ns, u_s)                              # (nqs, nsides, NF)
+    nq, ne = Xq.shape[0], Xq.shape[1]
+    vals = np.zeros((nf, nq, ne))
+    dvals = np.zeros((nf, nf, nq, ne))
+    for q in range(nq):
+        for e in range(ne):
+            vals[:, q, e] = np.asarray(func(Xq[q, e], t, uq[q, e]), dtype=float).reshape(nf)
+            dvals[:, :, q, e] = np.asarray(dfuncdu(Xq[q, e], t, uq[q, e]), dtype=float).reshape(nf, nf)
+    return vals, dvals
+
+
+def assemble_matrix_robin_bc(storage, conn, elements, snodes, tables, dvals, X, nf):
+    """_assemble_block_matrix_weakly_enforced_bc! (src/assemblers/WeaklyEnforcedBCs.jl:118-153): per side
+    K_el = sum_q _expand_face_block(Nvec, JxW, dval, node_to_face_idx) (:167-180), added to the COO storage of the parent
+    element, column-major, at (el_id - 1) * NDOF^2 (:155-165).  conn (NNPE, NE) of the block, elements block-local
+    1-based, snodes (nnps, nsides), dvals (NF, NF, nqs, nsides).  `storage` is the block view of the COO values."""
+    Ns, dNs, ws = tables
+    nnpe = conn.shape[0]
+    ndofs = nf * nnpe
+    x_s = np.transpose(X[:, snodes - 1], (2, 1, 0))
+    jxw = np.stack([surface_jxw(dNs[q], ws[q], x_s) for q in range(len(ws))])      # (nqs, nsides)
+    for e, el in enumerate(elements):
+        c = conn[:, el - 1]
+        face_idx = [int(np.nonzero(snodes[:, e] == n)[0][0]) + 1 if n in snodes[:, e] else 0 for n in c]   # node_to_face_idx
+        K_el = np.zeros((ndofs, ndofs))
+        for q in range(len(ws)):
+            for row in range(ndofs):
+                ni, di = row // nf, row % nf
+                for col in range(ndofs):
+                    nj, dj = col // nf, col % nf
+                    ii, jj = face_idx[ni], face_idx[nj]
+                    if ii and jj:
+                        K_el[row, col] += jxw[q, e] * Ns[q, ii - 1] * Ns[q, jj - 1] * dvals[di, dj, q, e]
+        s0 = (el - 1) * ndofs * ndofs
+        storage[s0:s0 + ndofs * ndofs] += K_el.reshape(-1, order="F")      # K_el.data[i], column-major
+    return storage
+
+
 def cell_quadrature_points(block, X):
     """X_q of every (q, e): (NQ, NE, ND)   (_update_source_values!, Sources.jl:55-66)"""
     return np.einsum("qa,eai->qei", block.N, _gather(X, block.conn))
@@ -735,6 +781,22 @@ class NeoHookean(_Mechanics):
                     np.einsum("ik,jl->ijkl", I, I)[None]
                     - (2.0 / 3.0) * np.einsum("eij,ekl->eijkl", H, F)
                     + (I1 / 3.0)[:, None, None, None, None] * HxH))
+        return P, A
+
+
+class NonSymmetricTest(_Mechanics):
+    """TEST law, not in the reference: linear elasticity + beta * delta_ij T_kl (T fixed, non-symmetric), i.e. a
+    tangent with A_ijkl != A_klij.  Every law the reference ships has a symmetric tangent, for which the transposed COO
+    labelling of its pattern (Assemblers.jl:109-124 vs SparsityPatterns.jl:76-83) cannot be seen; with this one the
+    assembled matrix is the TRANSPOSE of dR/dU, exactly what the reference's loops produce.  props = (rho, K, G, beta)."""
+    T = np.array([[0.25, 1.0, 0.0], [-0.5, 0.5, 2.0], [3.0, 0.0, 0.75]])
+
+    def stress_tangent(self, gu, props, so, sn, need_A=True):
+        P, A = LinearElastic.stress_tangent(self, gu, props, so, sn, need_A)
+        beta, I = props[3], np.eye(3)
+        P = P + beta * np.einsum("kl,ekl->e", self.T, gu)[:, None, None] * I
+        if need_A:
+            A = A + beta * np.einsum("ij,kl->ijkl", I, self.T)[None]
         return P, A
 
 

@@ -902,3 +902,131 @@ def test_direct_linear_solver_reproduces_the_gold_and_the_neumann_answer(F):
     F.QuasiStaticIntegrator(s2).evolve(p2)
     assert np.abs(p2.field.data_flat - np.asarray(m2.nodal_coords)[0]).max() < 1e-9
     asm2.close()
+
+
+# ---- Robin BCs (src/assemblers/WeaklyEnforcedBCs.jl:17-32, 85-180; src/bcs/RobinBCs.jl:72-86) ----
+@pytest.mark.parametrize("case", ["poisson_quad4_csr", "poisson_quad4_csc", "linear_hex8_csr", "linear_hex8_csc", "poisson_tri3_csr"])
+def test_robin_bc_vector_and_matrix_vs_oracle(F, case):
+    """assemble_vector_robin_bc! / assemble_matrix_robin_bc! against the oracle's restatement of the reference loops.
+    The hex8 case uses a NON-symmetric dvalsdu, so the transposed COO labelling of the pattern is visible."""
+    el, mt = case.split("_")[1], case.split("_")[2]
+    rng = np.random.default_rng(5)
+    if el == "hex8":
+        mesh = perturb(F.StructuredMesh("hex", (0, 0, 0), (1, 1, 1), (5, 4, 6)), 0.03)
+        phys, props, nf, sset, fixed = "linear", np.array([1e3, 10e6, 1e6]), 3, "top", "bottom"
+        Dm = np.array([[2.0, 0.7, -0.3], [0.1, 1.5, 0.4], [-0.6, 0.2, 3.0]])
+        g0 = lambda X: np.stack([np.sin(X[:, 0]), X[:, 1] * X[:, 2], 1.0 + X[:, 0]], axis=1)
+    else:
+        mesh = perturb(F.StructuredMesh("quad" if el == "quad4" else "tri", (0, 0), (1, 1), (7, 6)), 0.02)
+        phys, props, nf, sset, fixed = "poisson", None, 1, "right", "left"
+        Dm = np.array([[1.3]])
+        g0 = lambda X: (0.5 + np.sin(3 * X[:, 1]))[:, None]
+    V = F.FunctionSpace(mesh, F.H1Field, F.Lagrange, q_type="GaussLegendre", q_degree=2)
+    u = F.ScalarFunction(V, "u") if nf == 1 else F.VectorFunction(V, "displ")
+    asm = F.SparseMatrixAssembler(u, sparse_matrix_type=mt, use_condensed=False)
+    dbcs = [F.DirichletBC(c, lambda X, t: np.full(X.shape[0], 0.01), nodeset_name=fixed) for c in u.names()]
+    func = lambda X, t, uu: g0(X) + uu @ Dm.T
+    rbcs = [F.RobinBC(u.names()[0], func, sset)]
+    p = F.create_parameters(mesh, asm, product_physics(F, phys, mesh.num_dimensions()), props, dirichlet_bcs=dbcs, robin_bcs=rbcs)
+    N = asm.sizes()[2]
+    Uu = 0.05 * rng.standard_normal(N)
+    F.assemble_vector(asm, F.residual, Uu, p)
+    F.assemble_vector_robin_bc(asm, Uu, p)
+    R = F.residual(asm).copy()
+    F.assemble_stiffness(asm, F.stiffness, Uu, p)
+    F.assemble_matrix_robin_bc(asm, Uu, p)
+    K = F.stiffness(asm)
+    # ---- oracle twin
+    bname = mesh.element_block_names[0]
+    et = mesh.element_types[bname]
+    from util_parity import _ORACLE_PHYS, _RULES
+    blk = O.Block(mesh.element_conns[bname], O.ref_fe_tables(et, _RULES[et]), _ORACLE_PHYS[phys](None, mesh.num_dimensions()),
+                  props=props if props is not None else ())
+    X = np.asarray(mesh.nodal_coords)
+    oasm = O.OracleAssembler(X, [blk], nf, condensed=False, matrix_type=mt)
+    oasm.update_dofs(p.dirichlet_bcs.dirichlet_dofs())
+    oasm.bc_vals[:] = 0.01
+    snodes = np.asarray(mesh.sideset_side_nodes[sset])
+    stabs = O.surface_tables(et, "gauss2")
+    oasm.assemble_vector(Uu)
+    vals, dvals = O.robin_update_bc_values(snodes, stabs, X, oasm._U(), lambda x, t, uu: g0(x[None, :])[0] + Dm @ uu,
+                                           lambda x, t, uu: Dm)
+    O.assemble_vector_neumann_bc(oasm.residual_storage, snodes, stabs, vals, X, nf)
+    oasm.assemble_stiffness(Uu)
+    O.assemble_matrix_robin_bc(oasm.stiffness_storage, mesh.element_conns[bname], np.asarray(mesh.sideset_elems[sset]), snodes,
+                               stabs, dvals, X, nf)
+    assert rel_err(R, oasm.residual()) < RTOL
+    _check_pattern_and_values(F, asm, oasm, K)
+    # the Robin term really is in there (and, for hex8, non-symmetric)
+    F.assemble_stiffness(asm, F.stiffness, Uu, p)
+    K0 = F.stiffness(asm)
+    assert abs(K - K0).max() > 1e-3
+    if el == "hex8":
+        assert abs((K - K0) - (K - K0).T).max() > 1e-3
+    asm.close()
+
+
+def test_robin_known_answer(F):
+    """-lap u = f on the unit square, u = exp(x) sin(pi y), Robin data du/dn + alpha u = r on all four sides (the set-up of
+    the reference's disabled regression, test/poisson/TestPoisson.jl:106-127, with the sign the assembler's convention
+    asks for: the flux handed over is g = -du/dn = alpha u - r, cf. TestLaplace.jl:438-440).  Direct solve as in
+    solve!(::DirectLinearSolver) (src/Solvers.jl:64-86); second-order convergence to the exact solution."""
+    alpha = 1.0
+    uex = lambda X: np.exp(X[:, 0]) * np.sin(np.pi * X[:, 1])
+    src = lambda X, t: (np.pi ** 2 - 1.0) * uex(X)
+    dudn = {"left": lambda X: -uex(X), "right": lambda X: uex(X),
+            "bottom": lambda X: -np.pi * np.exp(X[:, 0]) * np.cos(np.pi * X[:, 1]),
+            "top": lambda X: np.pi * np.exp(X[:, 0]) * np.cos(np.pi * X[:, 1])}
+    errs = []
+    for n in (16, 32):
+        mesh = F.StructuredMesh("quad", (0, 0), (1, 1), (n + 1, n + 1))
+        V = F.FunctionSpace(mesh, F.H1Field, F.Lagrange)
+        u = F.ScalarFunction(V, "u")
+        asm = F.SparseMatrixAssembler(u, sparse_matrix_type="csc", use_condensed=False)
+        rbcs = [F.RobinBC("u", (lambda X, t, uu, s=s: alpha * uu - (dudn[s](X) + alpha * uex(X))[:, None]), s)
+                for s in ("left", "right", "bottom", "top")]
+        p = F.create_parameters(mesh, asm, F.Poisson(src), None, dirichlet_bcs=[], robin_bcs=rbcs)
+        solver = F.NewtonSolver(F.DirectLinearSolver(asm))
+        F.QuasiStaticIntegrator(solver).evolve(p)
+        U = np.asarray(p.field).reshape(-1)
+        errs.append(np.abs(U - uex(np.asarray(mesh.nodal_coords).T)).max())
+        asm.close()
+    assert errs[1] < 2e-3 and errs[0] / errs[1] > 3.0, errs
+
+
+@pytest.mark.parametrize("el", ["hex", "quad"])
+@pytest.mark.parametrize("matrix_type", ["csr", "csc"])
+@pytest.mark.parametrize("condensed", [False, True])
+def test_nonsymmetric_tangent_shows_the_transposed_coo_convention(F, el, matrix_type, condensed):
+    """SURVEY a-7 / B2: the reference writes K_el column-major into COO slots labelled (i outer, j inner), i.e. the
+    assembled matrix holds K_el TRANSPOSED (Assemblers.jl:109-124 vs SparsityPatterns.jl:76-83).  Invisible for the
+    shipped (symmetric) laws; the test law has A_ijkl != A_klij.  Values and pattern must match the oracle's literal
+    restatement, the matrix must NOT be symmetric, and K^T v must equal the (true) element-wise action."""
+    if el == "hex":
+        mesh = perturb(F.StructuredMesh("hex", (0, 0, 0), (1, 1, 1), (5, 4, 4)), 0.03)
+        fixed = mesh.nodeset_nodes["bottom"]
+    else:
+        mesh = perturb(F.StructuredMesh("quad", (0, 0), (1, 1), (7, 6)), 0.02)
+        fixed = mesh.nodeset_nodes["left"]
+    props = np.array([1e3, 10e6, 1e6, 3e6])
+    asm, p, oasm = build_pair(F, mesh, "nonsym", props, condensed=condensed, matrix_type=matrix_type,
+                              bc_nodes_1based=fixed, bc_value=0.01)
+    rng = np.random.default_rng(12)
+    N = asm.sizes()[2]
+    Uu, Vu = 0.01 * rng.standard_normal(N), rng.random(N)
+    F.assemble_vector(asm, F.residual, Uu, p)
+    oasm.assemble_vector(Uu)
+    assert rel_err(F.residual(asm), oasm.residual()) < RTOL
+    F.assemble_stiffness(asm, F.stiffness, Uu, p)
+    K = F.stiffness(asm)
+    oasm.assemble_stiffness(Uu)
+    _check_pattern_and_values(F, asm, oasm, K)
+    assert abs(K - K.T).max() > 1e-3 * abs(K).max()
+    F.assemble_matrix_action(asm, F.stiffness, Uu, Vu, p)
+    Kv = F.hvp(asm, Vu).copy()
+    oasm.assemble_matrix_action(Uu, Vu)
+    assert rel_err(Kv, oasm.hvp(Vu)) < RTOL
+    if not condensed:
+        assert rel_err(K.T @ Vu, Kv) < 1e-11          # stored matrix = (dR/dU)^T
+        assert rel_err(K @ Vu, Kv) > 1e-3
+    asm.close()

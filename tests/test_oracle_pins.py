@@ -407,3 +407,63 @@ def test_surface_loads_are_linear_and_rotation_invariant():
     Q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
     ones = np.ones((3, 4, sn.shape[1]))
     assert np.allclose(R(ones, X).reshape(-1, 3).sum(axis=0), R(ones, Q @ X).reshape(-1, 3).sum(axis=0), rtol=1e-12)
+
+
+def test_robin_restatement_known_answer_and_tangent():
+    """The oracle's Robin restatement (robin_update_bc_values / assemble_matrix_robin_bc, following
+    src/bcs/RobinBCs.jl:77-86 and src/assemblers/WeaklyEnforcedBCs.jl:118-180) pinned two ways, since the reference's
+    own Robin regression is disabled (test/poisson/TestPoisson.jl:51): (i) the matrix term is the derivative of the
+    vector term with respect to U under the pattern's transposed labelling; (ii) a manufactured Poisson solution with
+    Robin data on all four sides converges at second order (direct solve as in src/Solvers.jl:64-86)."""
+    import scipy.sparse.linalg as spla
+    uex = lambda X: np.exp(X[:, 0]) * np.sin(np.pi * X[:, 1])
+    dudn = {"left": lambda X: -uex(X), "right": lambda X: uex(X),
+            "bottom": lambda X: -np.pi * np.exp(X[:, 0]) * np.cos(np.pi * X[:, 1]),
+            "top": lambda X: np.pi * np.exp(X[:, 0]) * np.cos(np.pi * X[:, 1])}
+    alpha, errs = 1.0, []
+    stabs = O.surface_tables("QUAD4", "gauss2")
+    for n in (8, 16):
+        m = O.structured_mesh("quad", (0., 0.), (1., 1.), (n + 1, n + 1))
+        X, conn = m["coords"], m["conn"]
+        ss = O.structured_sidesets("quad", (n + 1, n + 1))
+        src = lambda Xq: (np.pi ** 2 - 1.0) * uex(Xq)
+        blk = O.Block(conn, O.ref_fe_tables("QUAD4", "gauss2"), O.Poisson(src))
+        oasm = O.OracleAssembler(X, [blk], 1, condensed=False, matrix_type="csc")
+        Uu = np.zeros(oasm.n)
+
+        def assemble(Uu):
+            oasm.assemble_vector(Uu)
+            oasm.assemble_stiffness(Uu)
+            for name, (els, sides) in ss.items():
+                sn = O.side_nodes("QUAD4", conn, els, sides)
+                f = lambda x, t, u, name=name: alpha * u - (dudn[name](x[None, :]) + alpha * uex(x[None, :]))
+                vals, dvals = O.robin_update_bc_values(sn, stabs, X, oasm._U(), f, lambda x, t, u: np.array([[alpha]]))
+                O.assemble_vector_neumann_bc(oasm.residual_storage, sn, stabs, vals, X, 1)
+                O.assemble_matrix_robin_bc(oasm.stiffness_storage, conn, els, sn, stabs, dvals, X, 1)
+            return oasm.residual().copy(), oasm.stiffness_scipy().tocsc()
+        R0, K = assemble(Uu)
+        if n == 8:   # (i) K = dR/dU: the problem is linear, so R(U) - R(0) == K U exactly
+            Ut = np.random.default_rng(0).standard_normal(oasm.n)
+            R1, _ = assemble(Ut)
+            assert np.abs((R1 - R0) - K @ Ut).max() < 1e-11 * np.abs(R1).max()
+        U = -spla.spsolve(K, R0)
+        errs.append(np.abs(U - uex(X.T)).max())
+    assert errs[1] < 5e-3 and errs[0] / errs[1] > 3.0, errs
+    # non-symmetric dvalsdu on a hex8 face: the matrix term lands TRANSPOSED, like every element matrix of the reference
+    m = O.structured_mesh("hex", (0., 0., 0.), (1., 1., 1.), (3, 3, 3))
+    X, conn = m["coords"], m["conn"]
+    els, sides = O.structured_sidesets("hex", (3, 3, 3))["top"]
+    sn = O.side_nodes("HEX8", conn, els, sides)
+    Dm = np.array([[2.0, 0.7, -0.3], [0.1, 1.5, 0.4], [-0.6, 0.2, 3.0]])
+    U = np.random.default_rng(1).standard_normal((3, X.shape[1]))
+    st = O.surface_tables("HEX8", "gauss2")
+    vals, dvals = O.robin_update_bc_values(sn, st, X, U, lambda x, t, u: Dm @ u, lambda x, t, u: Dm)
+    R = O.assemble_vector_neumann_bc(np.zeros(3 * X.shape[1]), sn, st, vals, X, 3)
+    coo = O.assemble_matrix_robin_bc(np.zeros(conn.shape[1] * 24 * 24), conn, els, sn, st, dvals, X, 3)
+    pat = O.matrix_pattern([conn], 3)
+    colptr, rowval, nz = O.sparse_csc(pat["Is"], pat["Js"], coo, 3 * X.shape[1])
+    import scipy.sparse as sp
+    Kr = sp.csc_matrix((nz, rowval - 1, colptr - 1), shape=(3 * X.shape[1],) * 2)
+    Uf = U.reshape(-1, order="F")
+    assert np.abs(Kr.T @ Uf - R).max() < 1e-12 * np.abs(R).max()       # stored matrix = (dR/dU)^T  (SURVEY B2)
+    assert np.abs(Kr @ Uf - R).max() > 1e-3 * np.abs(R).max()

@@ -22,6 +22,7 @@ _ORACLE_PHYS = {
     "neo": lambda f, nd: O.NeoHookean(nd, "standard"),
     "neo_as_written": lambda f, nd: O.NeoHookean(nd, "as_written"),
     "j2": lambda f, nd: O.J2Plasticity(nd),
+    "nonsym": lambda f, nd: O.NonSymmetricTest(nd),
 }
 _RULES = {"QUAD4": "gauss2", "HEX8": "gauss2", "TRI3": "tri3", "TETRA4": "tet4", "TETRA10": "tet4"}
 
@@ -34,6 +35,7 @@ def product_physics(F, name, nd, func=None):
         "neo": lambda: F.NeoHookean(form),
         "neo_as_written": lambda: F.NeoHookean(form, variant="as_written"),
         "j2": lambda: F.J2Plasticity(form),
+        "nonsym": lambda: F.NonSymmetricTestPhysics(form),
     }[name]()
 
 
