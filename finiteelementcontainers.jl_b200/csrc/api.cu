@@ -267,7 +267,7 @@ int fecb200_create(const fecb200_mesh_desc* mesh, const fecb200_opts* opts, fecb
   FEC_REQUIRE(mesh->nnodes > 0 && mesh->nnodes * (int64_t)mesh->nf < (int64_t)INT32_MAX, "bad node count");
   FEC_REQUIRE(opts->matrix_type == FECB200_CSC || opts->matrix_type == FECB200_CSR,
               "Unsupported sparse matrix type. Only csc and csr are supported.");
-  FEC_CUDA(cudaSetDevice(opts->device));
+  { PhaseTimer _t("cuda context"); FEC_CUDA(cudaSetDevice(opts->device)); FEC_CUDA(cudaFree(nullptr)); }
   std::unique_ptr<fecb200_handle> h(new fecb200_handle());
   h->device = opts->device;
   h->opts = *opts;
@@ -294,11 +294,18 @@ int fecb200_create(const fecb200_mesh_desc* mesh, const fecb200_opts* opts, fecb
     b.dN.assign(d.dN, d.dN + (size_t)d.nq * d.nnpe * mesh->ndim);
     b.w.assign(d.w, d.w + d.nq);
     if (d.nprops) b.props.assign(d.props, d.props + d.nprops);
-    b.conn0.resize((size_t)d.nelem * d.nnpe);
-    for (size_t i = 0; i < b.conn0.size(); ++i) {
-      const int64_t n = d.conn[i];
-      FEC_REQUIRE(n >= 1 && n <= mesh->nnodes, "connectivity entry out of range (expects 1-based node ids)");
-      b.conn0[i] = (int32_t)(n - 1);
+    {
+      PhaseTimer _t("connectivity narrow + check");
+      b.conn0.resize((size_t)d.nelem * d.nnpe);
+      bool ok = true;
+      const int64_t nc = (int64_t)b.conn0.size(), nnodes = mesh->nnodes;
+#pragma omp parallel for schedule(static) reduction(&& : ok)
+      for (int64_t i = 0; i < nc; ++i) {
+        const int64_t n = d.conn[i];
+        ok = ok && n >= 1 && n <= nnodes;
+        b.conn0[i] = (int32_t)(n - 1);
+      }
+      FEC_REQUIRE(ok, "connectivity entry out of range (expects 1-based node ids)");
     }
     build_block_tiles(h.get(), b, mesh->coords);
     if (b.nstate) {
@@ -307,8 +314,10 @@ int fecb200_create(const fecb200_mesh_desc* mesh, const fecb200_opts* opts, fecb
     }
   }
   {
-    std::vector<double> X(mesh->coords, mesh->coords + (size_t)h->nn * h->nd);
-    h->d_X.upload(X, h->stream);
+    PhaseTimer _t("coords upload + field alloc");
+    h->d_X.alloc((size_t)h->nn * h->nd);
+    FEC_CUDA(cudaMemcpyAsync(h->d_X.p, mesh->coords, (size_t)h->nn * h->nd * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    FEC_CUDA(cudaStreamSynchronize(h->stream));
   }
   h->d_U.alloc(h->ndof); h->d_U.zero(h->stream);
   h->d_V.alloc(h->ndof); h->d_V.zero(h->stream);
