@@ -29,7 +29,7 @@ if VARIANT:
     OBJ = os.path.join(HERE, "build", VARIANT)
     LIB = os.path.join(LIBDIR, f"libfecb200_{VARIANT}.so")
 
-SOURCES = ["api.cu", "aux.cu", "plan.cu", "loads.cu", "vmm.cu", "comm.cu", "dispatch_hex8.cu", "dispatch_quad_tri.cu", "dispatch_tet.cu"]
+SOURCES = ["api.cu", "aux.cu", "plan.cu", "plan_gpu.cu", "loads.cu", "vmm.cu", "comm.cu", "dispatch_hex8.cu", "dispatch_quad_tri.cu", "dispatch_tet.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", "kernel_mat2.cuh", "kernel_mat_scalar.cuh", "physics.cuh", os.path.join("..", "..", "include", "fecb200.h")]
 
 

@@ -278,6 +278,12 @@ int fecb200_create(const fecb200_mesh_desc* mesh, const fecb200_opts* opts, fecb
   FEC_CUDA(cudaEventCreate(&h->ev1));
   const int te = opts->tile_elems > 0 ? opts->tile_elems : kTE;
   FEC_REQUIRE(te == kTE, "tile_elems does not match the tile size this build was compiled for");
+  {
+    PhaseTimer _t("coords upload");   // first: the device tile builder bins element centroids
+    h->d_X.alloc((size_t)h->nn * h->nd);
+    FEC_CUDA(cudaMemcpyAsync(h->d_X.p, mesh->coords, (size_t)h->nn * h->nd * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    FEC_CUDA(cudaStreamSynchronize(h->stream));
+  }
   h->blocks.resize(mesh->nblocks);
   for (int bi = 0; bi < mesh->nblocks; ++bi) {
     const fecb200_block_desc& d = mesh->blocks[bi];
@@ -312,12 +318,6 @@ int fecb200_create(const fecb200_mesh_desc* mesh, const fecb200_opts* opts, fecb
       b.d_state_old.alloc((size_t)b.nstate * b.nq * b.ne); b.d_state_old.zero(h->stream);
       b.d_state_new.alloc((size_t)b.nstate * b.nq * b.ne); b.d_state_new.zero(h->stream);
     }
-  }
-  {
-    PhaseTimer _t("coords upload + field alloc");
-    h->d_X.alloc((size_t)h->nn * h->nd);
-    FEC_CUDA(cudaMemcpyAsync(h->d_X.p, mesh->coords, (size_t)h->nn * h->nd * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    FEC_CUDA(cudaStreamSynchronize(h->stream));
   }
   h->d_U.alloc(h->ndof); h->d_U.zero(h->stream);
   h->d_V.alloc(h->ndof); h->d_V.zero(h->stream);

@@ -249,6 +249,7 @@ struct fecb200_handle {
   // node adjacency and the (block-compressed) CSR structure
   std::vector<int32_t> adjptr, adj;  // host
   fec::DevBuf<int32_t> d_adjptr, d_adj;
+  bool host_structure_valid = true;  // host copies of adjacency / row starts match the device (plan_gpu.cu fetches them lazily)
   bool matrix_ready = false;
   bool adj_folded = false;           // the node adjacency was built on the periodic-folded connectivity
   bool matrix_dirty = false;         // DOF maps changed since the CSR structure was built (built lazily after create)
@@ -319,6 +320,13 @@ namespace fec {
 // CSR value buffers: nnz values + the trash region of the branch-free RED streams (4096 hashed row starts, each
 // followed by up to one row of column offsets), even length (16-byte units)
 inline size_t nz_alloc_len(const fecb200_handle* h) { return ((size_t)h->nnz + 4096 + (size_t)h->max_rowlen + 8 + 1) & ~(size_t)1; }
+
+// plan_gpu.cu: the same builders on the device (default; FECB200_HOST_PLAN=1 keeps the OpenMP versions of plan.cu)
+bool use_gpu_plan();
+void build_block_tiles_gpu(fecb200_handle* h, BlockPlan& b);
+void build_adjacency_gpu(fecb200_handle* h);
+void build_matrix_offsets_gpu(fecb200_handle* h);
+void ensure_host_structure(fecb200_handle* h);
 
 // plan.cu
 void build_block_tiles(fecb200_handle* h, BlockPlan& b, const double* coords);

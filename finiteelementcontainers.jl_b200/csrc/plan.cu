@@ -74,6 +74,7 @@ static inline uint64_t spread2(uint32_t v) {
 // ~NE^(1/ND) cells per axis, so structured meshes -- StructuredMesh.jl enumerates ez fastest,
 // nodes x fastest -- fall into exact bricks: 256 elements = 8x8x4) and cut into tiles of `te`.
 void build_block_tiles(fecb200_handle* h, BlockPlan& b, const double* coords) {
+  if (use_gpu_plan()) { build_block_tiles_gpu(h, b); return; }
   PhaseTimer _pt("build_block_tiles");
   const int nd = h->nd, nnpe = b.nnpe, nf = h->nf;
   const int64_t ne = b.ne;
@@ -197,6 +198,7 @@ static inline const std::vector<int32_t>& scatter_conn(const BlockPlan& b) { ret
 // Row n lists, ascending, every node sharing an element with n (all blocks).  With periodic BCs the scatter
 // connectivity has side-b nodes replaced by their side-a node (dof_to_unknown_index, DofManagers.jl:188-201).
 void build_adjacency(fecb200_handle* h) {
+  if (use_gpu_plan()) { build_adjacency_gpu(h); return; }
   PhaseTimer _pt("build_adjacency");
   const int64_t nn = h->nn;
   // node -> (block, element) incidence via counting sort
@@ -469,6 +471,19 @@ void build_matrix_structure(fecb200_handle* h) {
   FEC_REQUIRE(h->per_b.empty() || h->opts.condensed == 0,
               "Currently not supported periodic bcs in condensed mode");  // SparseMatrixAssembler.jl:251
   fold_periodic_nodes(h);
+  if (use_gpu_plan()) {
+    build_matrix_offsets_gpu(h);
+    h->d_nz_stiff.alloc_compressible(nz_alloc_len(h), h->device);
+    h->d_nz_stiff.zero(h->stream);
+    h->d_nz_stiff_alt.release();
+    h->alt_clean = false;
+    if (h->double_buffer) { h->d_nz_stiff_alt.alloc_compressible(nz_alloc_len(h), h->device); h->d_nz_stiff_alt.zero(h->stream); h->alt_clean = true; }
+    h->d_nz_mass.release();
+    h->matrix_ready = true;
+    h->stiff_adjusted = h->mass_adjusted = false;
+    build_ecol(h);
+    return;
+  }
   const bool condensed = h->opts.condensed != 0;
   h->freemask_h.assign(nn, 0);
   std::vector<uint8_t> nfree(nn);
@@ -545,6 +560,7 @@ void build_matrix_structure(fecb200_handle* h) {
 void export_pattern(fecb200_handle* h, int64_t* ptr, int64_t* idx) {
   ensure_matrix_structure(h);
   FEC_REQUIRE(h->matrix_ready, "no matrix pattern (matrix_free assembler or update_dofs not called)");
+  ensure_host_structure(h);
   const int nf = h->nf;
   const int64_t nn = h->nn;
   const bool condensed = h->opts.condensed != 0;
