@@ -43,13 +43,24 @@ class AbstractMesh:
         offs = np.cumsum([0] + [self.element_conns[b].shape[1] for b in self.element_block_names])
         for name, (el, sd) in sets.items():
             el, sd = np.asarray(el, dtype=np.int64), np.asarray(sd, dtype=np.int64)
-            cols = []
-            for e, s in zip(el, sd):
-                b = int(np.searchsorted(offs, e - 1, side="right") - 1)
-                bn = self.element_block_names[b]
-                cols.append(self.element_conns[bn][list(_SIDE_NODES[self.element_types[bn]][s - 1]), e - 1 - offs[b]])
             self.sideset_elems[name], self.sideset_sides[name] = el, sd
-            self.sideset_side_nodes[name] = (np.stack(cols, axis=1) if cols else np.zeros((0, 0))).astype(np.int64)
+            if not len(el):
+                self.sideset_side_nodes[name] = np.zeros((0, 0), dtype=np.int64)
+                continue
+            # vectorised over the sides: one fancy-indexing gather per (block, side number) group
+            blk = np.searchsorted(offs, el - 1, side="right") - 1
+            out, nnps = None, None
+            for b in np.unique(blk):
+                bn = self.element_block_names[int(b)]
+                conn, tab = self.element_conns[bn], _SIDE_NODES[self.element_types[bn]]
+                for sn in np.unique(sd[blk == b]):
+                    sel = np.nonzero((blk == b) & (sd == sn))[0]
+                    loc = list(tab[int(sn) - 1])
+                    if out is None:
+                        nnps = len(loc)
+                        out = np.empty((nnps, len(el)), dtype=np.int64)
+                    out[:, sel] = conn[np.asarray(loc)[:, None], (el[sel] - 1 - offs[b])[None, :]]
+            self.sideset_side_nodes[name] = out
 
     def _sidesets_from_nodesets(self, nodesets, blocks=None):
         """every element side whose nodes all belong to the node set (meshes without side-set records);
@@ -179,13 +190,13 @@ class StructuredMesh(AbstractMesh):
         coords[1] = np.tile(np.repeat(ys, Nx), Nz)
         coords[2] = np.repeat(zs, Nx * Ny)
         Ex, Ey, Ez = Nx - 1, Ny - 1, Nz - 1
-        ez = np.tile(np.arange(1, Ez + 1), Ex * Ey)                 # ez inner
-        ey = np.tile(np.repeat(np.arange(1, Ey + 1), Ez), Ex)
-        ex = np.repeat(np.arange(1, Ex + 1), Ey * Ez)               # ex outer
         n = lambda i, j, k: i + Nx * (j - 1) + Nx * Ny * (k - 1)
-        conn = np.stack([n(ex, ey, ez), n(ex + 1, ey, ez), n(ex + 1, ey + 1, ez), n(ex, ey + 1, ez),
-                         n(ex, ey, ez + 1), n(ex + 1, ey, ez + 1), n(ex + 1, ey + 1, ez + 1),
-                         n(ex, ey + 1, ez + 1)]).astype(np.int64)
+        # elements ex outer / ey / ez inner (StructuredMesh.jl:113-127): first node of every element by broadcasting, the
+        # other seven are fixed offsets from it (Exodus ordering, :116-123)
+        n0 = (np.arange(1, Ex + 1, dtype=np.int64)[:, None, None] + Nx * np.arange(Ey, dtype=np.int64)[None, :, None]
+              + Nx * Ny * np.arange(Ez, dtype=np.int64)[None, None, :]).reshape(-1)
+        offs = np.array([0, 1, 1 + Nx, Nx, Nx * Ny, 1 + Nx * Ny, 1 + Nx + Nx * Ny, Nx + Nx * Ny], dtype=np.int64)
+        conn = n0[None, :] + offs[:, None]
         I, J, K = np.arange(1, Nx + 1), np.arange(1, Ny + 1), np.arange(1, Nz + 1)
 
         def face(f, A, B):  # [f(a, b) for a in A, b in B] |> vec   (a fastest)
