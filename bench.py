@@ -239,6 +239,32 @@ def bind_to_gpu_numa_node(index):
         pass
 
 
+def prefer_gpu_numa_memory(index):
+    """Best effort: make this process allocate (and therefore pin) host memory on the NUMA node the GPU hangs off
+    (set_mempolicy(MPOL_PREFERRED, node)); the pinned staging buffers of the e2e path are allocated afterwards.
+    Returns the node or None (no NUMA information, e.g. a virtualised host)."""
+    try:
+        import ctypes
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:      # 00000000:17:00.0 -> 0000:17:00.0
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        mask = (ctypes.c_ulong * 2)(0, 0)
+        mask[node // 64] = 1 << (node % 64)
+        libc = ctypes.CDLL(None, use_errno=True)
+        MPOL_PREFERRED, SYS_set_mempolicy = 1, 238
+        if libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), 129) != 0:
+            return None
+        return node
+    except Exception:
+        return None
+
+
 def _rel(a, b):
     import torch
     d = float(torch.linalg.vector_norm(a - b))
@@ -353,8 +379,10 @@ def run_gpu(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
+    numa_node = None
     if world > 1:
         bind_to_gpu_numa_node(local)   # pinned staging buffers of the e2e path land next to this rank's GPU
+        numa_node = prefer_gpu_numa_memory(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import fecb200 as F
     from fecb200 import _lib
@@ -592,7 +620,9 @@ def run_gpu(args):
                        "setup_note": "mesh = host mesh generation (numpy), create_parameters = the library set-up (device-side tile / adjacency / CSR-offset build, host DOF maps) + first-use CUDA module load, initial state = the benchmark's synthetic displacement field"},
             "e2e": {"value": round(e2e_value, 1), "unit": "elements/s", "ms_per_step": round(ms_e2e / args.steps, 4),
                     "h2d_bytes_per_step": int(N * 8), "d2h_bytes_per_step": int(N * 8),
-                    "pcie_GBs_per_rank": round(2 * N * 8 / (ms_e2e / args.steps * 1e-3) / 1e9, 1)},
+                    "pcie_GBs_per_rank": round(2 * N * 8 / (ms_e2e / args.steps * 1e-3) / 1e9, 1),
+                    "pcie_GBs_all_ranks": round(world * 2 * N * 8 / (ms_e2e / args.steps * 1e-3) / 1e9, 1),
+                    "host_numa_node_rank0": numa_node, "host_cpus_visible": len(os.sched_getaffinity(0))},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "check": chk,

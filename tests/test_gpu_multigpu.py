@@ -34,6 +34,17 @@ def test_partitioned_loads_match_serial():
     assert "OK" in out.stdout and "FAIL" not in out.stdout, out.stdout[-2000:]
 
 
+def test_library_collective_plane_eight_ranks():
+    """the same check on an 8-way METIS split (edge / corner nodes ghosted by several ranks); needs 8 GPUs"""
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 8:
+        pytest.skip("needs eight GPUs")
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "run_comm_check.py"), "8", "8", "metis"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=400)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "OK" in out.stdout and "FAIL" not in out.stdout, out.stdout[-3000:]
+
+
 @pytest.mark.parametrize("how", ["metis", "brick"])
 def test_library_collective_plane_matches_serial(how):
     """fecb200_comm_init / halo_sum / halo_update / comm_peer_enable + distributed CG and Newton on 2 ranks, every
