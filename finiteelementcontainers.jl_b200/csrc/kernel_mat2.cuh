@@ -40,6 +40,8 @@ struct Mat2Params {
   int32_t ne, nq;
   int32_t ko;                // knock-out mask of the phase-cost experiment (only read when built with -DFEC_MAT2_KO)
   ZeroFill zf;               // in-kernel clear of the idle CSR value buffer (common.cuh)
+  double wc[5];              // Walsh path: c^n / 64, n = 0..4 (c = |xi| of the 2-point rule per axis, read off the tables)
+  double wr[3];              //             c^n / 8,  n = 0..2 (fused residual)
   double props[kMaxProps];
   Tables<ND, NNPE, NQT> tab;
 };
@@ -56,14 +58,18 @@ __host__ __device__ constexpr int sym_index(int i, int j) {  // packed upper tri
   return i * N - (i * (i - 1)) / 2 + (j - i);
 }
 
-template <int ND, int NNPE, int NF, int NQ, bool WITH_R>
+template <int ND, int NNPE, int NF, int NQ, bool WITH_R, bool WALSH = false>
 struct Mat2Layout {
   static constexpr int NP = NF * (NF + 1) / 2;
   static constexpr int EPW = 32 / NP;
   static constexpr int NDF = NF * ND;
   static constexpr int ASZ = NDF * (NDF + 1) / 2;
-  static constexpr int OFF_P = NNPE * ND + ASZ;         // JxW * P (only when the residual is fused)
-  static constexpr int SLOT_RAW = OFF_P + (WITH_R ? NDF : 0); // dN_X + packed JxW*A [+ JxW*P]
+  // classic slot: dN_X [NNPE*ND] + packed JxW*A [ASZ] [+ JxW*P].  Walsh slot: J^-1 [ND*ND] + JxW*A as NP pair blocks of
+  // ND*ND (block t = (d1,d2) at OFF_A + t*ND*ND, overwritten in place by the pair thread with J^-1 A J^-T) [+ JxW*P];
+  // pair stride 9 and element stride == NP (mod 16) keep the lanes (element, pair) on distinct 8-byte banks.
+  static constexpr int OFF_A = WALSH ? ND * ND : NNPE * ND;
+  static constexpr int OFF_P = OFF_A + (WALSH ? NP * ND * ND : ASZ);   // JxW * P (only when the residual is fused)
+  static constexpr int SLOT_RAW = OFF_P + (WITH_R ? NDF : 0);
 #ifndef FEC_MAT2_NOPAD
   // bank spreading (8-byte banks, 16 per wavefront): slot stride == 1 and element stride == NP (mod 16) put the
   // EPW*NP lanes that store / load "the same field of different (element, quadrature point)" on distinct banks
@@ -108,10 +114,59 @@ __device__ __forceinline__ void red_add_f64_pred(double* addr, double v, bool ok
                : "memory");
 }
 
-template <int ND, int NNPE, int NF, int NQT, class Phys, int WARPS, bool WITH_R>
+// ---- Walsh form of phase K for trilinear hexahedra with a symmetric 2-point rule per axis (tools/walsh/derive.py).
+// With nodes a and points q labelled by their sign triples s_a, sigma_q in {+-1}^3,
+//   dN_a/dxi_k (q) = 1/8 sum_{S subset of the other two axes} c^|S| s_a^({k} u S) sigma_q^S        (monomials of signs),
+// so the pair block M[a][b] = sum_q sum_{k1,k2} dN[q][a][k1] B_q[k1][k2] dN[q][b][k2], B_q = J^-1 (JxW A9) J^-T, is
+//   M[a][b] = sum_{alpha,beta} s_a^alpha s_b^beta Mh[alpha][beta],
+//   Mh[alpha][beta] = c^(|alpha|+|beta|-2)/64 sum_{k1 in alpha, k2 in beta} Bh_{(alpha\k1) xor (beta\k2)}[k1][k2],
+//   Bh_m = sum_q sigma_q^m B_q                                                     (Walsh transform over the 8 points).
+// Per pair thread: 432 (B) + 216 (transform over q) + 144 (Mh) + 330 (synthesis; Mh[0][.] = Mh[.][0] = 0) = 1122 FP64
+// instructions instead of the 2112 of the quadrature loop, and 49 instead of 64 accumulators.  Sign index i: bit k set
+// <=> +1 on axis k.  kNodeOfSign is the Exodus HEX8 numbering; the host checks the tables against the formula
+// (walsh_tables_ok) and takes the classic loop when they differ.
+__device__ __host__ constexpr int walsh_node_of_sign(int i) {
+  constexpr int t[8] = {0, 1, 3, 2, 4, 5, 7, 6};
+  return t[i];
+}
+// in-place 8-point transform over sign bits: (lo, hi) -> (lo + hi, hi - lo): v[m] = sum_i s_i^m v[i]
+FEC_DEV void walsh_fwd8(double (&v)[8]) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (!(i & (1 << k))) {
+        const double lo = v[i], hi = v[i | (1 << k)];
+        v[i] = hi + lo;
+        v[i | (1 << k)] = hi - lo;
+      }
+}
+// in-place synthesis v[i] = sum_alpha s_i^alpha v[alpha] with v[0] == 0 on entry (its value is ignored)
+FEC_DEV void walsh_syn8_z(double (&v)[8]) {
+  v[0] = -v[1];                                   // (0 - v1, 0 + v1)
+#pragma unroll
+  for (int i = 2; i < 8; i += 2) {
+    const double lo = v[i], hi = v[i + 1];
+    v[i] = lo - hi;
+    v[i + 1] = lo + hi;
+  }
+#pragma unroll
+  for (int k = 1; k < 3; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (!(i & (1 << k))) {
+        const double lo = v[i], hi = v[i | (1 << k)];
+        v[i] = lo - hi;
+        v[i | (1 << k)] = lo + hi;
+      }
+}
+__host__ __device__ constexpr int popc3(int m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1); }
+
+template <int ND, int NNPE, int NF, int NQT, class Phys, int WARPS, bool WITH_R, bool WALSH = false>
 __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat2Params<ND, NNPE, NQT> p) {
   static_assert(NQT > 0, "k_mat2 is compiled for fixed quadrature rules");
-  using L = Mat2Layout<ND, NNPE, NF, NQT, WITH_R>;
+  static_assert(!WALSH || (ND == 3 && NNPE == 8 && NF == 3 && NQT == 8), "the Walsh form is the HEX8 / 2x2x2 case");
+  using L = Mat2Layout<ND, NNPE, NF, NQT, WITH_R, WALSH>;
   constexpr int NP = L::NP, EPW = L::EPW, NDF = L::NDF, SLOT = L::SLOT, NROW = L::NROW, RS = L::RSTRIDE;
   constexpr int NS = Phys::NS;
   extern __shared__ __align__(16) double smem[];
@@ -177,20 +232,47 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
       const double JxW = invert<ND>(J, Ji) * p.tab.w[q];
       double* slot = esm + (size_t)q * SLOT;
       double gu[NF][ND];
+      if constexpr (WALSH) {
+        // publish J^-1 only; grad u = (sum_a u_a (x) dN_a/dxi) J^-1
+        double H[NF][ND];
 #pragma unroll
-      for (int d = 0; d < NF; ++d)
+        for (int d = 0; d < NF; ++d)
 #pragma unroll
-        for (int k = 0; k < ND; ++k) gu[d][k] = 0.0;
+          for (int k = 0; k < ND; ++k) {
+            double s = 0.0;
 #pragma unroll
-      for (int a = 0; a < NNPE; ++a) {
+            for (int a = 0; a < NNPE; ++a) s = fma(u[a][d], p.tab.dN[q][a][k], s);
+            H[d][k] = s;
+          }
 #pragma unroll
-        for (int k = 0; k < ND; ++k) {
-          double s = 0.0;
+        for (int k = 0; k < ND; ++k)
 #pragma unroll
-          for (int j = 0; j < ND; ++j) s = fma(p.tab.dN[q][a][j], Ji[j][k], s);
-          slot[a * ND + k] = s;
+          for (int j = 0; j < ND; ++j) slot[k * ND + j] = Ji[k][j];
 #pragma unroll
-          for (int d = 0; d < NF; ++d) gu[d][k] = fma(u[a][d], s, gu[d][k]);
+        for (int d = 0; d < NF; ++d)
+#pragma unroll
+          for (int j = 0; j < ND; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < ND; ++k) s = fma(H[d][k], Ji[k][j], s);
+            gu[d][j] = s;
+          }
+      } else {
+#pragma unroll
+        for (int d = 0; d < NF; ++d)
+#pragma unroll
+          for (int k = 0; k < ND; ++k) gu[d][k] = 0.0;
+#pragma unroll
+        for (int a = 0; a < NNPE; ++a) {
+#pragma unroll
+          for (int k = 0; k < ND; ++k) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < ND; ++j) s = fma(p.tab.dN[q][a][j], Ji[j][k], s);
+            slot[a * ND + k] = s;
+#pragma unroll
+            for (int d = 0; d < NF; ++d) gu[d][k] = fma(u[a][d], s, gu[d][k]);
+          }
         }
       }
       double so[NS > 0 ? NS : 1];
@@ -200,10 +282,24 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
       }
       double A[NDF][NDF];
       Phys::tangent_scaled(gu, p.props, so, JxW, A);   // JxW * A (folded into the law's coefficients where possible)
+      if constexpr (WALSH) {
+        int tb = 0;
 #pragma unroll
-      for (int i = 0; i < NDF; ++i)
+        for (int i = 0; i < NF; ++i)
 #pragma unroll
-        for (int j = i; j < NDF; ++j) slot[NNPE * ND + sym_index<NDF>(i, j)] = A[i][j];
+          for (int j = i; j < NF; ++j) {
+#pragma unroll
+            for (int j1 = 0; j1 < ND; ++j1)
+#pragma unroll
+              for (int j2 = 0; j2 < ND; ++j2) slot[L::OFF_A + tb * ND * ND + j1 * ND + j2] = A[i * ND + j1][j * ND + j2];
+            ++tb;
+          }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NDF; ++i)
+#pragma unroll
+          for (int j = i; j < NDF; ++j) slot[NNPE * ND + sym_index<NDF>(i, j)] = A[i][j];
+      }
       if constexpr (WITH_R) {
         // fused residual: P at the same state (the compiler shares the kinematics with the tangent above)
         double P[NF][ND], bsrc[NF], sn[NS > 0 ? NS : 1];
@@ -230,7 +326,109 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
   double rr[WITH_R ? NNPE : 1];  // fused residual rows (a, d1) of the diagonal-pair threads (d1 == d2)
 #pragma unroll
   for (int a = 0; a < (WITH_R ? NNPE : 1); ++a) rr[a] = 0.0;
-  if (active && !FEC_KO(8)) {
+  if constexpr (WALSH) {
+    if (active && !FEC_KO(8)) {
+      const int blk = L::OFF_A + t * ND * ND;
+      // pass 1: this pair's block of every point goes to reference coordinates, in place: B = J^-1 A9 J^-T
+      double Ph[WITH_R ? NQT : 1][ND];
+#pragma unroll
+      for (int q = 0; q < NQT; ++q) {
+        double* slot = esm + (size_t)q * SLOT;
+        double Ji[ND][ND], A9[ND][ND], T[ND][ND];
+#pragma unroll
+        for (int k = 0; k < ND; ++k)
+#pragma unroll
+          for (int j = 0; j < ND; ++j) Ji[k][j] = slot[k * ND + j];
+#pragma unroll
+        for (int j1 = 0; j1 < ND; ++j1)
+#pragma unroll
+          for (int j2 = 0; j2 < ND; ++j2) A9[j1][j2] = slot[blk + j1 * ND + j2];
+#pragma unroll
+        for (int j1 = 0; j1 < ND; ++j1)
+#pragma unroll
+          for (int k2 = 0; k2 < ND; ++k2) {
+            double s = A9[j1][0] * Ji[k2][0];
+#pragma unroll
+            for (int j2 = 1; j2 < ND; ++j2) s = fma(A9[j1][j2], Ji[k2][j2], s);
+            T[j1][k2] = s;
+          }
+#pragma unroll
+        for (int k1 = 0; k1 < ND; ++k1)
+#pragma unroll
+          for (int k2 = 0; k2 < ND; ++k2) {
+            double s = Ji[k1][0] * T[0][k2];
+#pragma unroll
+            for (int j1 = 1; j1 < ND; ++j1) s = fma(Ji[k1][j1], T[j1][k2], s);
+            slot[blk + k1 * ND + k2] = s;
+          }
+        if constexpr (WITH_R) {
+          if (d1 == d2) {  // (JxW P)[d1][.] pulled back the same way: Ph[k] = sum_j J^-1[k][j] P[d1][j]
+            double Pd[ND];
+#pragma unroll
+            for (int k = 0; k < ND; ++k) Pd[k] = slot[L::OFF_P + d1 * ND + k];
+#pragma unroll
+            for (int k = 0; k < ND; ++k) {
+              double s = Ji[k][0] * Pd[0];
+#pragma unroll
+              for (int j = 1; j < ND; ++j) s = fma(Ji[k][j], Pd[j], s);
+              Ph[q][k] = s;
+            }
+          }
+        }
+      }
+      // pass 2: Walsh transform over the points, entry by entry, and accumulation of the 7 x 7 spectrum Mh
+#pragma unroll
+      for (int k1 = 0; k1 < ND; ++k1)
+#pragma unroll
+        for (int k2 = 0; k2 < ND; ++k2) {
+          double bq[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) bq[q] = esm[(size_t)q * SLOT + blk + k1 * ND + k2];
+          walsh_fwd8(bq);
+#pragma unroll
+          for (int s1 = 0; s1 < 8; ++s1)
+#pragma unroll
+            for (int s2 = 0; s2 < 8; ++s2)
+              if (!(s1 & (1 << k1)) && !(s2 & (1 << k2))) {
+                const int al = s1 | (1 << k1), be = s2 | (1 << k2);
+                M[al][be] = fma(p.wc[popc3(s1) + popc3(s2)], bq[s1 ^ s2], M[al][be]);
+              }
+        }
+      // synthesis over beta (rows alpha = 1..7), then over alpha (all columns): M[ia][ib] in sign indices
+#pragma unroll
+      for (int al = 1; al < 8; ++al) walsh_syn8_z(M[al]);
+#pragma unroll
+      for (int ib = 0; ib < 8; ++ib) {
+        double col[8];
+#pragma unroll
+        for (int al = 0; al < 8; ++al) col[al] = M[al][ib];
+        walsh_syn8_z(col);
+#pragma unroll
+        for (int ia = 0; ia < 8; ++ia) M[ia][ib] = col[ia];
+      }
+      if constexpr (WITH_R) {
+        if (d1 == d2) {  // rr[a] = sum_q sum_k dN[q][a][k] Ph_q[k] = sum_alpha s_a^alpha rh[alpha]
+          double rh[8];
+#pragma unroll
+          for (int al = 0; al < 8; ++al) rh[al] = 0.0;
+#pragma unroll
+          for (int k = 0; k < ND; ++k) {
+            double pq[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) pq[q] = Ph[q][k];
+            walsh_fwd8(pq);
+#pragma unroll
+            for (int s1 = 0; s1 < 8; ++s1)
+              if (!(s1 & (1 << k))) rh[s1 | (1 << k)] = fma(p.wr[popc3(s1)], pq[s1], rh[s1 | (1 << k)]);
+          }
+          walsh_syn8_z(rh);
+#pragma unroll
+          for (int ia = 0; ia < 8; ++ia) rr[ia] = rh[ia];
+        }
+      }
+    }
+  }
+  if (!WALSH && active && !FEC_KO(8)) {
     // packed indices of this thread's ND x ND block (d1 <= d2 so (d1,j1) <= (d2,j2) unless d1 == d2 and j1 > j2)
     int aidx[ND][ND];
 #pragma unroll
@@ -296,15 +494,17 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
     for (int a = 0; a < NNPE; ++a) {
 #pragma unroll
       for (int b = 0; b < NNPE; ++b) {
-        // entry (row dof (a,d1), col dof (b,d2)) and its mirror (row (b,d2), col (a,d1))
-        esm[(a * NF + d1) * RS + b * NF + d2] = M[a][b];
-        if (d1 != d2) esm[(b * NF + d2) * RS + a * NF + d1] = M[a][b];
+        // entry (row dof (a,d1), col dof (b,d2)) and its mirror (row (b,d2), col (a,d1)); the Walsh form holds M in
+        // sign indices
+        const int na = WALSH ? walsh_node_of_sign(a) : a, nb = WALSH ? walsh_node_of_sign(b) : b;
+        esm[(na * NF + d1) * RS + nb * NF + d2] = M[a][b];
+        if (d1 != d2) esm[(nb * NF + d2) * RS + na * NF + d1] = M[a][b];
       }
     }
     if constexpr (WITH_R) {
       if (d1 == d2) {
 #pragma unroll
-        for (int a = 0; a < NNPE; ++a) esm[L::R_OFF + a * NF + d1] = rr[a];  // residual row, laid out like the columns
+        for (int a = 0; a < NNPE; ++a) esm[L::R_OFF + (WALSH ? walsh_node_of_sign(a) : a) * NF + d1] = rr[a];  // residual row, laid out like the columns
       }
     }
   }
@@ -384,9 +584,32 @@ __global__ void k_build_emeta(const int32_t* conn, const int32_t* gconn, const u
                               const uint8_t* freemask, const int64_t* rowstart, unsigned char* emeta, int nnpe, int nf,
                               int rec, int64_t ne, int64_t nnz, int trash_rows);
 
-template <int ND, int NNPE, int NF, int NQT, class Phys, int WARPS, bool WITH_R>
-void run_mat2_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
-  using L = Mat2Layout<ND, NNPE, NF, NQT, WITH_R>;
+// True when the block's dN table is the trilinear HEX8 table on a symmetric 2-point rule per axis, with the node and
+// point numbering the Walsh form of k_mat2 is compiled for (nodes: Exodus order, points: x fastest); *c = |xi|.
+// Weights are free (they are folded into JxW).  Anything else takes the classic quadrature loop.
+inline bool walsh_tables_ok(const BlockPlan& b, double* c_out) {
+  if (b.nq != 8 || b.dN.size() != 8u * 8u * 3u) return false;
+  auto sgn = [](int i, int k) { return ((i >> k) & 1) ? 1.0 : -1.0; };
+  int sign_of_node[8];
+  for (int i = 0; i < 8; ++i) sign_of_node[walsh_node_of_sign(i)] = i;
+  const double d000 = std::fabs(b.dN[0]);              // point 0 = (-,-,-), node 0 = (-,-,-): (1 + c)^2 / 8
+  const double c = std::sqrt(8.0 * d000) - 1.0;
+  if (!(c > 0.0 && c <= 1.0)) return false;
+  for (int q = 0; q < 8; ++q)
+    for (int a = 0; a < 8; ++a)
+      for (int k = 0; k < 3; ++k) {
+        double v = sgn(sign_of_node[a], k) / 8.0;
+        for (int kp = 0; kp < 3; ++kp)
+          if (kp != k) v *= 1.0 + c * sgn(sign_of_node[a], kp) * sgn(q, kp);
+        if (std::fabs(v - b.dN[((size_t)q * 8 + a) * 3 + k]) > 1e-14) return false;
+      }
+  *c_out = c;
+  return true;
+}
+
+template <int ND, int NNPE, int NF, int NQT, class Phys, int WARPS, bool WITH_R, bool WALSH = false>
+void run_mat2_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a, double walsh_c = 0.0) {
+  using L = Mat2Layout<ND, NNPE, NF, NQT, WITH_R, WALSH>;
   auto pp = std::make_unique<Mat2Params<ND, NNPE, NQT>>();
   auto& p = *pp;
   p.X = h->d_X.p; p.U = a.U; p.nz = a.nz;
@@ -400,6 +623,8 @@ void run_mat2_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   p.ne = (int32_t)b.ne; p.nq = b.nq; p.nnz = h->nnz;
   for (int i = 0; i < kMaxProps; ++i) p.props[i] = i < (int)b.props.size() ? b.props[i] : 0.0;
   fill_tables<ND, NNPE, NQT>(b, p.tab);
+  for (int n = 0; n < 5; ++n) p.wc[n] = std::pow(walsh_c, n) / 64.0;
+  for (int n = 0; n < 3; ++n) p.wr[n] = std::pow(walsh_c, n) / 8.0;
 #ifdef FEC_MAT2_KO
   p.ko = getenv("FECB200_KO") ? atoi(getenv("FECB200_KO")) : 0;
 #endif
@@ -409,7 +634,7 @@ void run_mat2_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   p.zf = make_zero_fill(a, grid);
   timing_begin(h);
   // K_el is symmetric here, so CSR and CSC storage receive the same values through the same addressing
-  auto kern = k_mat2<ND, NNPE, NF, NQT, Phys, WARPS, WITH_R>;
+  auto kern = k_mat2<ND, NNPE, NF, NQT, Phys, WARPS, WITH_R, WALSH>;
   FEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, WARPS * 32, smem, h->stream>>>(p);
   FEC_CUDA(cudaGetLastError());
@@ -419,6 +644,14 @@ void run_mat2_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
 
 template <int ND, int NNPE, int NF, int NQT, class Phys, int WARPS>
 void run_mat2(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
+  if constexpr (ND == 3 && NNPE == 8 && NF == 3 && NQT == 8) {
+    double c = 0.0;
+    if (!getenv("FECB200_MAT2_CLASSIC") && walsh_tables_ok(b, &c)) {
+      if (a.R) run_mat2_t<ND, NNPE, NF, NQT, Phys, WARPS, true, true>(h, b, a, c);
+      else run_mat2_t<ND, NNPE, NF, NQT, Phys, WARPS, false, true>(h, b, a, c);
+      return;
+    }
+  }
   if (a.R) run_mat2_t<ND, NNPE, NF, NQT, Phys, WARPS, true>(h, b, a);
   else run_mat2_t<ND, NNPE, NF, NQT, Phys, WARPS, false>(h, b, a);
 }
