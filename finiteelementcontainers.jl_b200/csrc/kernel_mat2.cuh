@@ -58,7 +58,7 @@ __host__ __device__ constexpr int sym_index(int i, int j) {  // packed upper tri
   return i * N - (i * (i - 1)) / 2 + (j - i);
 }
 
-template <int ND, int NNPE, int NF, int NQ, bool WITH_R, bool WALSH = false>
+template <int ND, int NNPE, int NF, int NQ, bool WITH_R, bool WALSH = false, bool REF = false>
 struct Mat2Layout {
   static constexpr int NP = NF * (NF + 1) / 2;
   static constexpr int EPW = 32 / NP;
@@ -67,7 +67,9 @@ struct Mat2Layout {
   // classic slot: dN_X [NNPE*ND] + packed JxW*A [ASZ] [+ JxW*P].  Walsh slot: J^-1 [ND*ND] + JxW*A as NP pair blocks of
   // ND*ND (block t = (d1,d2) at OFF_A + t*ND*ND, overwritten in place by the pair thread with J^-1 A J^-T) [+ JxW*P];
   // pair stride 9 and element stride == NP (mod 16) keep the lanes (element, pair) on distinct 8-byte banks.
-  static constexpr int OFF_A = WALSH ? ND * ND : NNPE * ND;
+  // REF (laws that deliver the tangent in reference coordinates, Phys::kRefTangent): no J^-1, the blocks and P arrive
+  // pulled back.
+  static constexpr int OFF_A = WALSH ? (REF ? 0 : ND * ND) : NNPE * ND;
   static constexpr int OFF_P = OFF_A + (WALSH ? NP * ND * ND : ASZ);   // JxW * P (only when the residual is fused)
   static constexpr int SLOT_RAW = OFF_P + (WITH_R ? NDF : 0);
 #ifndef FEC_MAT2_NOPAD
@@ -166,7 +168,8 @@ template <int ND, int NNPE, int NF, int NQT, class Phys, int WARPS, bool WITH_R,
 __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat2Params<ND, NNPE, NQT> p) {
   static_assert(NQT > 0, "k_mat2 is compiled for fixed quadrature rules");
   static_assert(!WALSH || (ND == 3 && NNPE == 8 && NF == 3 && NQT == 8), "the Walsh form is the HEX8 / 2x2x2 case");
-  using L = Mat2Layout<ND, NNPE, NF, NQT, WITH_R, WALSH>;
+  constexpr bool REF = WALSH && Phys::kRefTangent;
+  using L = Mat2Layout<ND, NNPE, NF, NQT, WITH_R, WALSH, REF>;
   constexpr int NP = L::NP, EPW = L::EPW, NDF = L::NDF, SLOT = L::SLOT, NROW = L::NROW, RS = L::RSTRIDE;
   constexpr int NS = Phys::NS;
   extern __shared__ __align__(16) double smem[];
@@ -244,10 +247,12 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
             for (int a = 0; a < NNPE; ++a) s = fma(u[a][d], p.tab.dN[q][a][k], s);
             H[d][k] = s;
           }
+        if constexpr (!REF) {
 #pragma unroll
-        for (int k = 0; k < ND; ++k)
+          for (int k = 0; k < ND; ++k)
 #pragma unroll
-          for (int j = 0; j < ND; ++j) slot[k * ND + j] = Ji[k][j];
+            for (int j = 0; j < ND; ++j) slot[k * ND + j] = Ji[k][j];
+        }
 #pragma unroll
         for (int d = 0; d < NF; ++d)
 #pragma unroll
@@ -281,7 +286,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
         for (int s = 0; s < NS; ++s) so[s] = p.state_old[((size_t)s * p.nq + q) * p.ne + e];
       }
       double A[NDF][NDF];
-      Phys::tangent_scaled(gu, p.props, so, JxW, A);   // JxW * A (folded into the law's coefficients where possible)
+      if constexpr (REF) Phys::tangent_scaled_ref(gu, Ji, p.props, so, JxW, A);   // JxW * J^-1 A J^-T
+      else Phys::tangent_scaled(gu, p.props, so, JxW, A);   // JxW * A (folded into the law's coefficients where possible)
       if constexpr (WALSH) {
         int tb = 0;
 #pragma unroll
@@ -307,7 +313,16 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
 #pragma unroll
         for (int d = 0; d < NF; ++d)
 #pragma unroll
-          for (int k = 0; k < ND; ++k) slot[L::OFF_P + d * ND + k] = P[d][k] * JxW;
+          for (int k = 0; k < ND; ++k) {
+            if constexpr (REF) {   // pulled back: sum_j J^-1[k][j] P[d][j]
+              double s = Ji[k][0] * P[d][0];
+#pragma unroll
+              for (int j = 1; j < ND; ++j) s = fma(Ji[k][j], P[d][j], s);
+              slot[L::OFF_P + d * ND + k] = s * JxW;
+            } else {
+              slot[L::OFF_P + d * ND + k] = P[d][k] * JxW;
+            }
+          }
         if constexpr (NS > 0) {
 #pragma unroll
           for (int s = 0; s < NS; ++s) p.state_new[((size_t)s * p.nq + q) * p.ne + e] = sn[s];
@@ -331,8 +346,18 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
       const int blk = L::OFF_A + t * ND * ND;
       // pass 1: this pair's block of every point goes to reference coordinates, in place: B = J^-1 A9 J^-T
       double Ph[WITH_R ? NQT : 1][ND];
+      if constexpr (REF) {
+        if constexpr (WITH_R) {
+          if (d1 == d2) {
 #pragma unroll
-      for (int q = 0; q < NQT; ++q) {
+            for (int q = 0; q < NQT; ++q)
+#pragma unroll
+              for (int k = 0; k < ND; ++k) Ph[q][k] = esm[(size_t)q * SLOT + L::OFF_P + d1 * ND + k];
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < (REF ? 0 : NQT); ++q) {
         double* slot = esm + (size_t)q * SLOT;
         double Ji[ND][ND], A9[ND][ND], T[ND][ND];
 #pragma unroll
@@ -609,7 +634,7 @@ inline bool walsh_tables_ok(const BlockPlan& b, double* c_out) {
 
 template <int ND, int NNPE, int NF, int NQT, class Phys, int WARPS, bool WITH_R, bool WALSH = false>
 void run_mat2_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a, double walsh_c = 0.0) {
-  using L = Mat2Layout<ND, NNPE, NF, NQT, WITH_R, WALSH>;
+  using L = Mat2Layout<ND, NNPE, NF, NQT, WITH_R, WALSH, WALSH && Phys::kRefTangent>;
   auto pp = std::make_unique<Mat2Params<ND, NNPE, NQT>>();
   auto& p = *pp;
   p.X = h->d_X.p; p.U = a.U; p.nz = a.nz;

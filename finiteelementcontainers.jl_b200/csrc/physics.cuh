@@ -165,6 +165,30 @@ struct PhysMech3 {
             A[i * ND + j][k * ND + l] = Impl::kScalesTangent ? a : a * scale;
           }
   }
+  // The same tangent pulled back to reference gradients, Ahat[(i,k1)][(k,k2)] = sum_{J,L} Ji[k1][J] A_iJkL Ji[k2][L]
+  // (Ji = inverse element Jacobian), for laws that can build it at the cost of A itself (Impl::kRefTangent): the Walsh
+  // form of k_mat2 consumes it directly and skips its per-pair transform.
+  static constexpr bool kRefTangent = (ND == 3) && Impl::kRefTangent;
+  FEC_DEV static void tangent_scaled_ref(const double (&gu)[ND][ND], const double (&Ji)[ND][ND], const double* props,
+                                         const double* so, const double scale, double (&A)[ND * ND][ND * ND]) {
+    if constexpr (kRefTangent) {
+      typename Impl::Pre pre;
+      Impl::prepare(gu, props, so, pre);
+      Impl::to_reference(pre, Ji);
+      if constexpr (Impl::kScalesTangent) Impl::scale_tangent(pre, scale);
+#pragma unroll
+      for (int i = 0; i < ND; ++i)
+#pragma unroll
+        for (int j = 0; j < ND; ++j)
+#pragma unroll
+          for (int k = 0; k < ND; ++k)
+#pragma unroll
+            for (int l = 0; l < ND; ++l) {
+              const double a = Impl::A_ref(pre, i, j, k, l);
+              A[i * ND + j][k * ND + l] = Impl::kScalesTangent ? a : a * scale;
+            }
+    }
+  }
 };
 
 // -------------------------------------------------------------------------------------------
@@ -175,7 +199,8 @@ struct LinearElasticImpl {
   static constexpr int NS = 0;
   static constexpr bool kScalesTangent = true;    // A is linear in (K, G): a scale factor goes into the two moduli
   static constexpr bool kHasEnergy = true;
-  struct Pre { double K, G; };
+  static constexpr bool kRefTangent = true;
+  struct Pre { double K, G, Ji[3][3], C[3][3]; };
   // psi = 1/2 K tr(eps)^2 + G dev(eps):dev(eps)   (TestMechanicsCommon.jl:14-20)
   FEC_DEV static double energy(const double (&g)[3][3], const double* props, const double*) {
     const double K = props[1], G = props[2];
@@ -210,6 +235,23 @@ struct LinearElasticImpl {
     const double dij = (i == j), dkl = (k == l), dik = (i == k), djl = (j == l), dil = (i == l), djk = (j == k);
     return (p.K - 2.0 * p.G / 3.0) * dij * dkl + p.G * (dik * djl + dil * djk);
   }
+  // pulled back: lam Ji[k1][i] Ji[k2][k] + G (d_ik (Ji Ji^T)[k1][k2] + Ji[k2][i] Ji[k1][k])
+  FEC_DEV static void to_reference(Pre& p, const double (&Ji)[3][3]) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        p.Ji[a][b] = Ji[a][b];
+        double s = Ji[a][0] * Ji[b][0];
+        s = fma(Ji[a][1], Ji[b][1], s);
+        p.C[a][b] = fma(Ji[a][2], Ji[b][2], s);
+      }
+  }
+  FEC_DEV static double A_ref(const Pre& p, int i, int k1, int k, int k2) {
+    double a = (p.K - 2.0 * p.G / 3.0) * p.Ji[k1][i] * p.Ji[k2][k];
+    a = fma(p.G * p.Ji[k2][i], p.Ji[k1][k], a);
+    return (i == k) ? fma(p.G, p.C[k1][k2], a) : a;
+  }
 };
 
 // -------------------------------------------------------------------------------------------
@@ -227,7 +269,8 @@ struct NeoHookeanImpl {
   static constexpr int NS = 0;
   static constexpr bool kHasEnergy = true;
   // Hs, Hg, Hb: the three coefficient-scaled copies of H / F the tangent is built from (see A below)
-  struct Pre { double F[3][3], H[3][3], Hs[3][3], Hg[3][3], Hb[3][3], J, I1, m, c, cpJ, G, gm; };
+  static constexpr bool kRefTangent = true;
+  struct Pre { double F[3][3], H[3][3], Hs[3][3], Hg[3][3], Hb[3][3], C[3][3], J, I1, m, c, cpJ, G, gm; };
   // psi = 1/2 K U(J) + 1/2 G (J^-2/3 tr(F F^T) - 3)   (TestMechanicsLargeDeformation.jl:17-27; U: see prepare)
   FEC_DEV static double energy(const double (&g)[3][3], const double* props, const double*) {
     Pre p;
@@ -332,6 +375,35 @@ struct NeoHookeanImpl {
     a = fma(p.Hb[i][l], p.H[k][j], a);
     return (i == k && j == l) ? a + p.gm : a;
   }
+  // pulled back to reference gradients: every factor X_iJ of A becomes (X Ji^T)[i][k]; d_JL becomes (Ji Ji^T)[k1][k2].
+  // Call between prepare and scale_tangent (Hs, Hg, Hb are linear in H and F).
+  FEC_DEV static void to_reference(Pre& p, const double (&Ji)[3][3]) {
+    double Ht[3][3], Ft[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double h = p.H[i][0] * Ji[k][0], f = p.F[i][0] * Ji[k][0];
+#pragma unroll
+        for (int j = 1; j < 3; ++j) { h = fma(p.H[i][j], Ji[k][j], h); f = fma(p.F[i][j], Ji[k][j], f); }
+        Ht[i][k] = h; Ft[i][k] = f;
+      }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        p.H[i][k] = Ht[i][k]; p.F[i][k] = Ft[i][k];
+        double s = Ji[i][0] * Ji[k][0];
+        s = fma(Ji[i][1], Ji[k][1], s);
+        p.C[i][k] = fma(Ji[i][2], Ji[k][2], s);
+      }
+  }
+  FEC_DEV static double A_ref(const Pre& p, int i, int k1, int k, int k2) {
+    double a = p.Hs[i][k1] * p.H[k][k2];
+    a = fma(p.Hg[i][k1], p.F[k][k2], a);
+    a = fma(p.Hb[i][k2], p.H[k][k1], a);
+    return (i == k) ? fma(p.gm, p.C[k1][k2], a) : a;
+  }
 };
 
 // -------------------------------------------------------------------------------------------
@@ -344,6 +416,7 @@ struct NeoHookeanImpl {
 struct J2Impl {
   static constexpr int NS = 7;
   static constexpr bool kScalesTangent = false;
+  static constexpr bool kRefTangent = false;  // general A: the Walsh kernel pulls the pair blocks back itself
   static constexpr bool kHasEnergy = false;  // no energy is defined for the (oracle-defined) J2 law
   struct Pre { double K, G, theta, thbar, n[3][3]; };
   struct RM { double tr, s[3][3], n[3][3], dg, q; bool yld; };
@@ -437,6 +510,7 @@ struct J2Impl {
 // -------------------------------------------------------------------------------------------
 struct NonSymmetricTestImpl {
   static constexpr int NS = 0;
+  static constexpr bool kRefTangent = false;
   static constexpr bool kScalesTangent = true;
   static constexpr bool kHasEnergy = false;
   struct Pre { double K, G, beta; };
