@@ -61,7 +61,14 @@ __host__ __device__ constexpr int sym_index(int i, int j) {  // packed upper tri
 template <int ND, int NNPE, int NF, int NQ, bool WITH_R, bool WALSH = false, bool REF = false>
 struct Mat2Layout {
   static constexpr int NP = NF * (NF + 1) / 2;
-  static constexpr int EPW = 32 / NP;
+  // threads per element.  Classic: one per component pair.  Walsh (FEC_MAT2_TPE, default 8): phase K is cheap enough
+  // that phase G dominates, so an element gets one thread per QUADRATURE POINT (phase G is one full round of 32
+  // (element, point) tasks instead of 30 + 10) and phase K / S1 run on NP of them.
+#ifndef FEC_MAT2_TPE
+#define FEC_MAT2_TPE 8
+#endif
+  static constexpr int TPE = (WALSH && FEC_MAT2_TPE > NP) ? FEC_MAT2_TPE : NP;
+  static constexpr int EPW = 32 / TPE;
   static constexpr int NDF = NF * ND;
   static constexpr int ASZ = NDF * (NDF + 1) / 2;
   // classic slot: dN_X [NNPE*ND] + packed JxW*A [ASZ] [+ JxW*P].  Walsh slot: J^-1 [ND*ND] + JxW*A as NP pair blocks of
@@ -83,7 +90,15 @@ struct Mat2Layout {
   // row stride of the staged K_el: a bank simulation of the S1 stores (lane = (element, pair), 8-byte banks) gives
   // 384 wavefronts per warp for stride 24 against 512 for 25 with NROW = 24; the S2 loads are conflict-free either way
   static constexpr int RSTRIDE = (NROW % 16 == 8) ? NROW : NROW + 1;
-  static constexpr int KSZ = NROW * RSTRIDE;
+  // staging passes: the Walsh form stages and scatters K_el in two halves of rows (nodes 0..3, then 4..7) so that the
+  // element's shared memory is bounded by the quadrature-point slots (520 doubles) instead of the 600 of a full K_el +
+  // residual row: 568 doubles per element = 12 warps per SM with 4 elements per warp
+#ifndef FEC_MAT2_HALF
+#define FEC_MAT2_HALF 1
+#endif
+  static constexpr int NH = (WALSH && FEC_MAT2_HALF && NNPE % 2 == 0) ? 2 : 1;
+  static constexpr int HROWS = NROW / NH;
+  static constexpr int KSZ = HROWS * RSTRIDE;
   static constexpr int R_OFF = KSZ;                     // staged fused-residual row (NROW doubles) behind K_el
   static constexpr int BODY = (NQ * SLOT > KSZ + NROW) ? NQ * SLOT : KSZ + NROW;
   // per-element scatter record (global, contiguous; copied verbatim into shared memory with cp.async):
@@ -99,7 +114,7 @@ struct Mat2Layout {
   static constexpr int META = REC / 8;
   static constexpr int BODY16 = ((BODY + 1) / 2) * 2;   // keep the record 16-byte aligned in shared memory
 #ifndef FEC_MAT2_NOPAD
-  static constexpr int ELSM = BODY16 + META + ((NP + 16 - (BODY16 + META) % 16) % 16);
+  static constexpr int ELSM = BODY16 + META + ((TPE + 16 - (BODY16 + META) % 16) % 16);
 #else
   static constexpr int ELSM = BODY16 + META;
 #endif
@@ -164,8 +179,13 @@ FEC_DEV void walsh_syn8_z(double (&v)[8]) {
 }
 __host__ __device__ constexpr int popc3(int m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1); }
 
+// CTAs per SM the Walsh form is compiled for (register cap 65536 / (FEC_MAT2_MINB * WARPS * 32)); the classic loop needs
+// all 255
+#ifndef FEC_MAT2_MINB
+#define FEC_MAT2_MINB 6
+#endif
 template <int ND, int NNPE, int NF, int NQT, class Phys, int WARPS, bool WITH_R, bool WALSH = false>
-__global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat2Params<ND, NNPE, NQT> p) {
+__global__ void __launch_bounds__(WARPS * 32, WALSH ? FEC_MAT2_MINB : 1) k_mat2(const __grid_constant__ Mat2Params<ND, NNPE, NQT> p) {
   static_assert(NQT > 0, "k_mat2 is compiled for fixed quadrature rules");
   static_assert(!WALSH || (ND == 3 && NNPE == 8 && NF == 3 && NQT == 8), "the Walsh form is the HEX8 / 2x2x2 case");
   constexpr bool REF = WALSH && Phys::kRefTangent;
@@ -174,11 +194,13 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
   constexpr int NS = Phys::NS;
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int elw = lane / NP, t = lane % NP;
+  constexpr int TPE = L::TPE;
+  const int elw = lane / TPE, t = lane % TPE;
   const bool lane_valid = elw < EPW;
   const int e0 = (blockIdx.x * WARPS + warp) * EPW;      // first element of this warp
   const int e = e0 + elw;
   const bool active = lane_valid && e < p.ne;
+  const bool pair_active = active && t < NP;   // threads that own a component pair in phases K and S1
   double* wsm = smem + (size_t)warp * EPW * L::ELSM;
   double* esm = wsm + (size_t)(lane_valid ? elw : 0) * L::ELSM;
   // component pair of this thread: enumerate d1 <= d2
@@ -220,7 +242,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
   }
   if (!FEC_KO(32)) zero_fill_begin(p.zf, zero_page);   // queued while the gathers above are in flight (0.13 ms better than up front)
   if (active && !FEC_KO(16)) {
-    for (int q = t; q < NQT; q += NP) {
+    for (int q = t; q < NQT; q += TPE) {
       double J[ND][ND];
 #pragma unroll
       for (int i = 0; i < ND; ++i)
@@ -342,20 +364,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
 #pragma unroll
   for (int a = 0; a < (WITH_R ? NNPE : 1); ++a) rr[a] = 0.0;
   if constexpr (WALSH) {
-    if (active && !FEC_KO(8)) {
+    if (pair_active && !FEC_KO(8)) {
       const int blk = L::OFF_A + t * ND * ND;
       // pass 1: this pair's block of every point goes to reference coordinates, in place: B = J^-1 A9 J^-T
-      double Ph[WITH_R ? NQT : 1][ND];
-      if constexpr (REF) {
-        if constexpr (WITH_R) {
-          if (d1 == d2) {
-#pragma unroll
-            for (int q = 0; q < NQT; ++q)
-#pragma unroll
-              for (int k = 0; k < ND; ++k) Ph[q][k] = esm[(size_t)q * SLOT + L::OFF_P + d1 * ND + k];
-          }
-        }
-      }
+      double Ph[(WITH_R && !REF) ? NQT : 1][ND];   // !REF: pulled-back flux rows of the diagonal-pair threads
 #pragma unroll
       for (int q = 0; q < (REF ? 0 : NQT); ++q) {
         double* slot = esm + (size_t)q * SLOT;
@@ -401,6 +413,30 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
           }
         }
       }
+      // fused residual first (before the spectrum is live): one flux component at a time
+      if constexpr (WITH_R) {
+        if (d1 == d2) {  // rr[a] = sum_q sum_k dN[q][a][k] Ph_q[k] = sum_alpha s_a^alpha rh[alpha]
+          double rh[8];
+#pragma unroll
+          for (int al = 0; al < 8; ++al) rh[al] = 0.0;
+#pragma unroll
+          for (int k = 0; k < ND; ++k) {
+            double pq[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if constexpr (REF) pq[q] = esm[(size_t)q * SLOT + L::OFF_P + d1 * ND + k];   // published pulled back
+              else pq[q] = Ph[q][k];
+            }
+            walsh_fwd8(pq);
+#pragma unroll
+            for (int s1 = 0; s1 < 8; ++s1)
+              if (!(s1 & (1 << k))) rh[s1 | (1 << k)] = fma(p.wr[popc3(s1)], pq[s1], rh[s1 | (1 << k)]);
+          }
+          walsh_syn8_z(rh);
+#pragma unroll
+          for (int ia = 0; ia < 8; ++ia) rr[ia] = rh[ia];
+        }
+      }
       // pass 2: Walsh transform over the points, entry by entry, and accumulation of the 7 x 7 spectrum Mh
 #pragma unroll
       for (int k1 = 0; k1 < ND; ++k1)
@@ -430,26 +466,6 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
         walsh_syn8_z(col);
 #pragma unroll
         for (int ia = 0; ia < 8; ++ia) M[ia][ib] = col[ia];
-      }
-      if constexpr (WITH_R) {
-        if (d1 == d2) {  // rr[a] = sum_q sum_k dN[q][a][k] Ph_q[k] = sum_alpha s_a^alpha rh[alpha]
-          double rh[8];
-#pragma unroll
-          for (int al = 0; al < 8; ++al) rh[al] = 0.0;
-#pragma unroll
-          for (int k = 0; k < ND; ++k) {
-            double pq[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) pq[q] = Ph[q][k];
-            walsh_fwd8(pq);
-#pragma unroll
-            for (int s1 = 0; s1 < 8; ++s1)
-              if (!(s1 & (1 << k))) rh[s1 | (1 << k)] = fma(p.wr[popc3(s1)], pq[s1], rh[s1 | (1 << k)]);
-          }
-          walsh_syn8_z(rh);
-#pragma unroll
-          for (int ia = 0; ia < 8; ++ia) rr[ia] = rh[ia];
-        }
       }
     }
   }
@@ -510,84 +526,92 @@ __global__ void __launch_bounds__(WARPS * 32) k_mat2(const __grid_constant__ Mat
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncwarp();  // every thread of the warp is done reading the slots (re-used as the K_el stage); records landed
 
-  // ---- phase S1: stage K_el.  Storage row = dof of the ROW node, storage column = (local column node, dof).
+  // ---- phases S1 + S2, once per staging pass (L::NH = 1: whole K_el; 2: rows of nodes 0..3, then of nodes 4..7).
+  // S1: stage K_el.  Storage row = dof of the ROW node, storage column = (local column node, dof).
   // K_el is symmetric, so the reference's transposed COO convention and the CSR/CSC distinction do
   // not change the values.  (Sorting the columns by global node id was measured to make no difference: the RED
   // coalescer merges a warp's lanes into sectors whatever their order, so all offsets here are static.)
-  if (active && !FEC_KO(4)) {
+  // S2: REDs.  Lane = one storage column (local node k, dof dc) of the element; the warp walks the rows, so one RED
+  // instruction covers one CSR row segment of the element: NROW consecutive-ish slots.  All shared-memory reads of an
+  // element are issued before its REDs so their latencies overlap.  The RED stream has no per-entry tests: rows that
+  // are not stored (Dirichlet dofs, ghost rows) carry a row offset inside a 4096-slot hashed trash region behind the
+  // matrix, written by k_build_emeta.
+  constexpr int NH = L::NH, HROWS = L::HROWS, HNODES = NNPE / NH;
 #pragma unroll
-    for (int a = 0; a < NNPE; ++a) {
+  for (int hp = 0; hp < NH; ++hp) {
+    if (hp > 0) __syncwarp();   // the previous pass has been read back
+    if (pair_active && !FEC_KO(4)) {
 #pragma unroll
-      for (int b = 0; b < NNPE; ++b) {
-        // entry (row dof (a,d1), col dof (b,d2)) and its mirror (row (b,d2), col (a,d1)); the Walsh form holds M in
-        // sign indices
-        const int na = WALSH ? walsh_node_of_sign(a) : a, nb = WALSH ? walsh_node_of_sign(b) : b;
-        esm[(na * NF + d1) * RS + nb * NF + d2] = M[a][b];
-        if (d1 != d2) esm[(nb * NF + d2) * RS + na * NF + d1] = M[a][b];
-      }
-    }
-    if constexpr (WITH_R) {
-      if (d1 == d2) {
+      for (int a = 0; a < NNPE; ++a) {
 #pragma unroll
-        for (int a = 0; a < NNPE; ++a) esm[L::R_OFF + (WALSH ? walsh_node_of_sign(a) : a) * NF + d1] = rr[a];  // residual row, laid out like the columns
-      }
-    }
-  }
-  __syncwarp();
-
-  // ---- phase S2: REDs.  Lane = one storage column (local node k, dof dc) of the element; the warp walks
-  // the NROW rows, so one RED instruction covers one CSR row segment of the element: NROW consecutive-ish slots.
-  // All shared-memory reads of an element are issued before its REDs so their latencies overlap (registers are
-  // free here: M is dead).  The RED stream has no per-entry tests: rows that are not stored (Dirichlet dofs, ghost
-  // rows) carry a row offset inside a 4096-slot hashed trash region behind the matrix, written by k_build_emeta.
-  if (lane < NROW && !FEC_KO(2 | 4)) {
-    const int nel = (p.ne - e0) < EPW ? (p.ne - e0) : EPW;
-    const int k = lane / NF, dc = lane - k * NF;
-    for (int el = 0; el < nel; ++el) {
-      const double* ks = wsm + (size_t)el * L::ELSM;
-      const unsigned char* rec = reinterpret_cast<const unsigned char*>(ks + L::BODY16);
-      const uint32_t* rs = reinterpret_cast<const uint32_t*>(rec);
-      const uint16_t* ec = reinterpret_cast<const uint16_t*>(rec + L::OFF_EC);
-      const unsigned mask = rec[L::OFF_MK + k];
-      if (mask & (1u << dc)) {  // eliminated column (Dirichlet dof, rare): the lane sits this element out
-        const int rank = __popc(mask & ((1u << dc) - 1u));
-        uint32_t r0[NROW];
-        double val[NROW];
-        uint32_t off[NNPE];
-#pragma unroll
-        for (int b = 0; b < NNPE; ++b) off[b] = ec[b * NNPE + k] + rank;
-        if constexpr (NROW % 4 == 0) {  // the row offsets are 16-byte aligned in the record: broadcast LDS.128
-          const uint4* rs4 = reinterpret_cast<const uint4*>(rec);
-#pragma unroll
-          for (int i = 0; i < NROW / 4; ++i) {
-            const uint4 v = rs4[i];
-            r0[4 * i] = v.x; r0[4 * i + 1] = v.y; r0[4 * i + 2] = v.z; r0[4 * i + 3] = v.w;
-          }
-        } else {
-#pragma unroll
-          for (int row = 0; row < NROW; ++row) r0[row] = rs[row];
+        for (int b = 0; b < NNPE; ++b) {
+          // entry (row dof (a,d1), col dof (b,d2)) and its mirror (row (b,d2), col (a,d1)); the Walsh form holds M in
+          // sign indices
+          const int na = WALSH ? walsh_node_of_sign(a) : a, nb = WALSH ? walsh_node_of_sign(b) : b;
+          if (na / HNODES == hp) esm[((na - hp * HNODES) * NF + d1) * RS + nb * NF + d2] = M[a][b];
+          if (nb / HNODES == hp && d1 != d2) esm[((nb - hp * HNODES) * NF + d2) * RS + na * NF + d1] = M[a][b];
         }
-#pragma unroll
-        for (int row = 0; row < NROW; ++row) val[row] = ks[row * RS + lane];
-        if (!FEC_KO(1)) {
-#pragma unroll
-          for (int row = 0; row < NROW; ++row)  // rows that are not stored point into the trash region (k_build_emeta)
-            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p.nz + (r0[row] + off[row / NF])), "d"(val[row]));
-        }
-#ifdef FEC_MAT2_KO
-        else {  // keep the loads alive
-          double sacc = 0.0;
-#pragma unroll
-          for (int row = 0; row < NROW; ++row) sacc += val[row] + (double)(r0[row] + off[row / NF]);
-          if (sacc == 1.234567e300) p.nz[0] = sacc;
-        }
-#endif
       }
       if constexpr (WITH_R) {
-        // fused residual: lane (k, dc) adds the staged entry into R[node_k, dc] -- 3 consecutive doubles per node
-        // (ghost nodes go to their owner over NVLink, see scatter_add)
-        const uint32_t n = reinterpret_cast<const uint32_t*>(rec + L::OFF_ND)[k];
-        scatter_add(p.peer, p.R, (int64_t)n, NF, dc, ks[L::R_OFF + lane]);
+        if (hp == 0 && d1 == d2) {
+#pragma unroll
+          for (int a = 0; a < NNPE; ++a) esm[L::R_OFF + (WALSH ? walsh_node_of_sign(a) : a) * NF + d1] = rr[a];  // residual row, laid out like the columns
+        }
+      }
+    }
+    __syncwarp();
+
+    if (lane < NROW && !FEC_KO(2 | 4)) {
+      const int nel = (p.ne - e0) < EPW ? (p.ne - e0) : EPW;
+      const int k = lane / NF, dc = lane - k * NF;
+      for (int el = 0; el < nel; ++el) {
+        const double* ks = wsm + (size_t)el * L::ELSM;
+        const unsigned char* rec = reinterpret_cast<const unsigned char*>(ks + L::BODY16);
+        const uint32_t* rs = reinterpret_cast<const uint32_t*>(rec) + hp * HROWS;
+        const uint16_t* ec = reinterpret_cast<const uint16_t*>(rec + L::OFF_EC) + hp * HNODES * NNPE;
+        const unsigned mask = rec[L::OFF_MK + k];
+        if (mask & (1u << dc)) {  // eliminated column (Dirichlet dof, rare): the lane sits this element out
+          const int rank = __popc(mask & ((1u << dc) - 1u));
+          uint32_t r0[HROWS];
+          double val[HROWS];
+          uint32_t off[HNODES];
+#pragma unroll
+          for (int b = 0; b < HNODES; ++b) off[b] = ec[b * NNPE + k] + rank;
+          if constexpr (HROWS % 4 == 0) {  // the row offsets are 16-byte aligned in the record: broadcast LDS.128
+            const uint4* rs4 = reinterpret_cast<const uint4*>(rs);
+#pragma unroll
+            for (int i = 0; i < HROWS / 4; ++i) {
+              const uint4 v = rs4[i];
+              r0[4 * i] = v.x; r0[4 * i + 1] = v.y; r0[4 * i + 2] = v.z; r0[4 * i + 3] = v.w;
+            }
+          } else {
+#pragma unroll
+            for (int row = 0; row < HROWS; ++row) r0[row] = rs[row];
+          }
+#pragma unroll
+          for (int row = 0; row < HROWS; ++row) val[row] = ks[row * RS + lane];
+          if (!FEC_KO(1)) {
+#pragma unroll
+            for (int row = 0; row < HROWS; ++row)  // rows that are not stored point into the trash region (k_build_emeta)
+              asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p.nz + (r0[row] + off[row / NF])), "d"(val[row]));
+          }
+#ifdef FEC_MAT2_KO
+          else {  // keep the loads alive
+            double sacc = 0.0;
+#pragma unroll
+            for (int row = 0; row < HROWS; ++row) sacc += val[row] + (double)(r0[row] + off[row / NF]);
+            if (sacc == 1.234567e300) p.nz[0] = sacc;
+          }
+#endif
+        }
+        if constexpr (WITH_R) {
+          // fused residual: lane (k, dc) adds the staged entry into R[node_k, dc] -- 3 consecutive doubles per node
+          // (ghost nodes go to their owner over NVLink, see scatter_add)
+          if (hp == 0) {
+            const uint32_t n = reinterpret_cast<const uint32_t*>(rec + L::OFF_ND)[k];
+            scatter_add(p.peer, p.R, (int64_t)n, NF, dc, ks[L::R_OFF + lane]);
+          }
+        }
       }
     }
   }
