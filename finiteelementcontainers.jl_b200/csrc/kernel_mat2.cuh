@@ -89,7 +89,14 @@ struct Mat2Layout {
   static constexpr int NROW = NNPE * NF;
   // row stride of the staged K_el: a bank simulation of the S1 stores (lane = (element, pair), 8-byte banks) gives
   // 384 wavefronts per warp for stride 24 against 512 for 25 with NROW = 24; the S2 loads are conflict-free either way
-  static constexpr int RSTRIDE = (NROW % 16 == 8) ? NROW : NROW + 1;
+#ifndef FEC_MAT2_RS
+#define FEC_MAT2_RS 34
+#endif
+  // Walsh form, 8 threads per element: lanes (element, pair (d1,d2)) store K_el[(a,d1)][(b,d2)] at row (a,d1), column
+  // (b,d2); with row stride == 2 and element stride == 8 (mod 16) the 12 pair lanes of a half-warp hit the banks
+  // {0,1,2,3,4,6} + 8 * (element & 1) and the mirror stores {2,4,5} + 8 * (element & 1): conflict-free, 2 wavefronts per
+  // STS instead of 6 with stride 24 (the slack is free: the element's shared memory is bounded by the point slots)
+  static constexpr int RSTRIDE = (WALSH && TPE == 8) ? FEC_MAT2_RS : ((NROW % 16 == 8) ? NROW : NROW + 1);
   // staging passes: the Walsh form stages and scatters K_el in two halves of rows (nodes 0..3, then 4..7) so that the
   // element's shared memory is bounded by the quadrature-point slots (520 doubles) instead of the 600 of a full K_el +
   // residual row: 568 doubles per element = 12 warps per SM with 4 elements per warp
@@ -592,8 +599,12 @@ __global__ void __launch_bounds__(WARPS * 32, WALSH ? FEC_MAT2_MINB : 1) k_mat2(
           for (int row = 0; row < HROWS; ++row) val[row] = ks[row * RS + lane];
           if (!FEC_KO(1)) {
 #pragma unroll
-            for (int row = 0; row < HROWS; ++row)  // rows that are not stored point into the trash region (k_build_emeta)
+            for (int row = 0; row < HROWS; ++row) {  // rows that are not stored point into the trash region (k_build_emeta)
+#ifdef FEC_MAT2_KO
+              if (FEC_KO(64) && row % 3 == 2) continue;   // a third of the RED sectors gone: what would merging buy?
+#endif
               asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p.nz + (r0[row] + off[row / NF])), "d"(val[row]));
+            }
           }
 #ifdef FEC_MAT2_KO
           else {  // keep the loads alive
