@@ -40,7 +40,8 @@ BYTES_FUSED = 2090.0       # tangent + R 24 (conn/X/U shared with the residual)
 BYTES_ACTION = 160.0
 # FP64 flops per element counted from the kernels' instruction mix
 FLOPS_RESIDUAL = 7.0e3
-FLOPS_TANGENT = 34.0e3      # fused k_mat2: thread-level (2 DFMA + DMUL + DADD) per element, ncu r01z (36.6e3 before the tangent was re-factored)
+FLOPS_TANGENT = 14.0e3      # fused k_mat2, Walsh form: thread-level (2 DFMA + DMUL + DADD) per element = 2*4500 + 1600 + 3430, ncu r02i
+FLOPS_TANGENT_QLOOP = 34.0e3  # the same element matrix by the plain quadrature loop (k_mat2 before the Walsh form, ncu r01z)
 BYTES_ZERO_FILL = 1954.0   # fill!(storage, 0) of the CSR values (Matrix.jl:39): NOT algorithmic (SURVEY 8d counts every
                            # output once); reported as `extra_bytes_per_element` when the kernel clears the idle buffer
 NEO_PROPS = np.array([1e3, 10.0e6, 1.0e6])
@@ -56,6 +57,16 @@ def ncu_traffic(dbuf):
     d = json.load(open(p))
     e = d.get("double_buffered" if dbuf else "single_buffer")
     return (e.get("dram_bytes_per_launch"), e.get("source")) if e else (None, None)
+
+
+def ncu_onchip(dbuf):
+    """On-chip pipe utilisation of the dominant kernel from the same committed capture (the kernel is bound by the
+    L1/TEX LSU data pipe, not by DRAM or the FP64 pipe): {'lsu_data_pipe_pct', 'fp64_pipe_pct', ...} or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    e = json.load(open(p)).get("double_buffered" if dbuf else "single_buffer")
+    return e.get("onchip") if e else None
 
 
 def load_peaks():
@@ -577,14 +588,19 @@ def run_gpu(args):
             ach = BYTES_FUSED * ne_local / (k_tan * 1e-3) / 1e9
             tf = FLOPS_TANGENT * ne_local / (k_tan * 1e-3) / 1e12
             traffic, traffic_src = ncu_traffic(dbuf)
-            roof = {"bound": "hbm", "binding_roof": "fp64" if tf / fp64_peak > ach / hbm else "hbm",
+            onchip = ncu_onchip(dbuf)
+            roof = {"bound": "hbm",
+                    "binding_roof": ("l1tex_lsu_data_pipe" if onchip and onchip.get("lsu_data_pipe_pct", 0) > 100 * max(tf / fp64_peak, ach / hbm)
+                                     else "fp64" if tf / fp64_peak > ach / hbm else "hbm"),
+                    "onchip_ncu": onchip,
                     "kernel": "fused residual + tangent -> CSR (" + os.environ.get("FECB200_MAT_KERNEL", "default") + ")",
                     "achieved": round(ach, 1), "peak": hbm, "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / hbm, 4),
                     "algorithmic_bytes_per_element": BYTES_FUSED,
                     "extra_bytes_per_element": BYTES_ZERO_FILL if dbuf else 0.0,
                     "extra_bytes_note": "in-kernel clear of the idle CSR value array (fill!(storage, 0), Matrix.jl:39); not algorithmic" if dbuf else None,
                     "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": round(k_tan, 4),
-                    "fp64_flops_per_element": FLOPS_TANGENT, "fp64_achieved_tflops": round(tf, 2),
+                    "fp64_flops_per_element": FLOPS_TANGENT, "fp64_flops_per_element_quadrature_loop": FLOPS_TANGENT_QLOOP,
+                    "fp64_achieved_tflops": round(tf, 2),
                     "fp64_peak_tflops_dgemm_measured": round(fp64_peak, 1), "fp64_frac": round(tf / fp64_peak, 4),
                     "residual_kernel_ms": round(k_res, 4),
                     "residual_frac_hbm": round(BYTES_RESIDUAL * ne_local / (k_res * 1e-3) / 1e9 / hbm, 4),
