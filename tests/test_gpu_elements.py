@@ -47,7 +47,9 @@ CASES = [
     ("tet10", "linear", "GaussLegendre", 2, "tet4"),
     ("tet10", "neo", "GaussLegendre", 2, "tet4"),
     ("tet10", "poisson", "GaussLegendre", 2, "tet4"),
-    ("hex", "j2", "GaussLegendre", 2, "gauss2"),
+    ("hex", "j2", "GaussLegendre", 2, "gauss2"),                # Walsh form of k_mat2 with the generic per-pair pull-back
+    ("hex", "neo", "GaussLobattoLegendre", 2, "gll2"),          # Walsh form with c = 1 (points on the vertices)
+    ("hex", "linear", "GaussLobattoLegendre", 2, "gll2"),
 ]
 
 
@@ -142,4 +144,42 @@ def test_error_behaviour(F):
     with pytest.raises(TypeError):
         F.assemble_vector(asm, lambda *a: 0, Uu, p)
     assert F.stiffness(asm).shape == (27, 27) and F.stiffness(asm).nnz == 0   # _zero_sparse_matrix (Assemblers.jl:393-400)
+    asm.close()
+
+
+@pytest.mark.parametrize("mode", ["classic_env", "permuted_points"])
+def test_k_mat2_walsh_fallbacks(F, mode, monkeypatch):
+    """The Walsh form of the HEX8 tangent kernel is taken only when the block's dN table is the trilinear table on a
+    symmetric 2-point rule in the numbering it is compiled for (walsh_tables_ok, kernel_mat2.cuh).  Forced off
+    (FECB200_MAT2_CLASSIC) and with a rule whose points come in another order the classic quadrature loop must run and
+    give the same answer as the oracle on the very same tables."""
+    from fecb200.reference_fe import ReferenceFE
+    rng = np.random.default_rng(5)
+    mesh = perturb(F.StructuredMesh("hex", (0, 0, 0), (1, 1, 1), (6, 5, 4)), 0.03)
+    props = np.array([1e3, 10e6, 1e6])
+    rfe = ReferenceFE("HEX8", "GaussLegendre", 2)
+    tabs = O.ref_fe_tables("HEX8", "gauss2")
+    if mode == "classic_env":
+        monkeypatch.setenv("FECB200_MAT2_CLASSIC", "1")
+    else:
+        perm = np.array([3, 0, 6, 1, 7, 2, 5, 4])
+        rfe.N, rfe.dN, rfe.w = (np.ascontiguousarray(rfe.N[perm]), np.ascontiguousarray(rfe.dN[perm]),
+                                np.ascontiguousarray(rfe.w[perm]))
+        tabs = tuple(np.ascontiguousarray(np.asarray(t)[perm]) for t in tabs)
+    V = F.FunctionSpace(mesh, F.H1Field, F.Lagrange, ref_fes=[rfe])
+    u = F.VectorFunction(V, "displ")
+    asm = F.SparseMatrixAssembler(u, sparse_matrix_type="csr")
+    dbcs = [F.DirichletBC(c, lambda X, t: np.full(X.shape[0], 0.01), nodeset_name="bottom") for c in u.names()]
+    p = F.create_parameters(mesh, asm, product_physics(F, "neo", 3, None), props, dirichlet_bcs=dbcs)
+    bname = mesh.element_block_names[0]
+    blk = O.Block(mesh.element_conns[bname], tabs, O.NeoHookean(3), props=props)
+    oasm = O.OracleAssembler(np.asarray(mesh.nodal_coords), [blk], 3, condensed=False, matrix_type="csr")
+    oasm.update_dofs(p.dirichlet_bcs.dirichlet_dofs())
+    oasm.bc_vals[:] = 0.01
+    Uu = 0.02 * rng.standard_normal(asm.sizes()[2])
+    F.assemble_vector_and_stiffness(asm, F.residual, F.stiffness, Uu, p)   # the fused kernel
+    oasm.assemble_vector(Uu)
+    oasm.assemble_stiffness(Uu)
+    assert rel_err(F.residual(asm), oasm.residual()) < RTOL
+    assert rel_err(F.stiffness(asm).data, oasm.stiffness()[2]) < RTOL
     asm.close()
