@@ -644,29 +644,6 @@ __global__ void k_build_emeta(const int32_t* conn, const int32_t* gconn, const u
                               const uint8_t* freemask, const int64_t* rowstart, unsigned char* emeta, int nnpe, int nf,
                               int rec, int64_t ne, int64_t nnz, int trash_rows);
 
-// True when the block's dN table is the trilinear HEX8 table on a symmetric 2-point rule per axis, with the node and
-// point numbering the Walsh form of k_mat2 is compiled for (nodes: Exodus order, points: x fastest); *c = |xi|.
-// Weights are free (they are folded into JxW).  Anything else takes the classic quadrature loop.
-inline bool walsh_tables_ok(const BlockPlan& b, double* c_out) {
-  if (b.nq != 8 || b.dN.size() != 8u * 8u * 3u) return false;
-  auto sgn = [](int i, int k) { return ((i >> k) & 1) ? 1.0 : -1.0; };
-  int sign_of_node[8];
-  for (int i = 0; i < 8; ++i) sign_of_node[walsh_node_of_sign(i)] = i;
-  const double d000 = std::fabs(b.dN[0]);              // point 0 = (-,-,-), node 0 = (-,-,-): (1 + c)^2 / 8
-  const double c = std::sqrt(8.0 * d000) - 1.0;
-  if (!(c > 0.0 && c <= 1.0)) return false;
-  for (int q = 0; q < 8; ++q)
-    for (int a = 0; a < 8; ++a)
-      for (int k = 0; k < 3; ++k) {
-        double v = sgn(sign_of_node[a], k) / 8.0;
-        for (int kp = 0; kp < 3; ++kp)
-          if (kp != k) v *= 1.0 + c * sgn(sign_of_node[a], kp) * sgn(q, kp);
-        if (std::fabs(v - b.dN[((size_t)q * 8 + a) * 3 + k]) > 1e-14) return false;
-      }
-  *c_out = c;
-  return true;
-}
-
 template <int ND, int NNPE, int NF, int NQT, class Phys, int WARPS, bool WITH_R, bool WALSH = false>
 void run_mat2_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a, double walsh_c = 0.0) {
   using L = Mat2Layout<ND, NNPE, NF, NQT, WITH_R, WALSH, WALSH && Phys::kRefTangent>;

@@ -27,6 +27,8 @@
 #include "common.cuh"
 #include "physics.cuh"
 #include <memory>
+#include <cmath>
+#include <cstdlib>
 
 namespace fec {
 
@@ -55,6 +57,7 @@ struct VecParams {
   PeerScatter peer;
   int32_t ne, nq;
   int32_t body_doubles, max_nodes;  // shared-memory layout: [node data | element-vector stage][node ids][inc_ptr][inc]
+  double wr[4];                     // Walsh path: c^n / 8, n = 0..3 (c = |xi| of the 2-point rule per axis)
   double props[kMaxProps];
   Tables<ND, NNPE, NQT> tab;
 };
@@ -229,7 +232,183 @@ FEC_DEV void vec_qp(const Tab& tab, const int q, const double (&x)[NNPE][ND], co
   }
 }
 
-template <int ND, int NNPE, int NF, int NQT, class Phys, int MODE, int TE, int MINB>
+// ------------------------------------------------------------------------------------------------
+// Walsh form of the HEX8 / 2x2x2 vector kernels (same identities as kernel_mat2.cuh).  With nodes and
+// points labelled by sign triples, dN_a/dxi_k (q) = 1/8 sum_{S subset of the other axes} c^|S| s_a^({k} u S) sigma_q^S, so
+//   J_q[i][k]     = sum_S sigma_q^S Xh[{k} u S][i],     Xh[alpha][i] = c^(|alpha|-1)/8 sum_a s_a^alpha x_a[i]   (once per element)
+//   (grad_xi u)_q = the same with Uh,
+//   r[a][d]       = sum_alpha s_a^alpha rh[alpha][d],   rh[alpha][d] = c^(|alpha|-1)/8 sum_q sum_{k in alpha} sigma_q^(alpha\k) Px_q[d][k]:
+// 3 add/sub per entry and point instead of 8 FMA for J and grad u, 36 add/sub instead of 72 FMA per point for the
+// scatter.  Sign index i: bit k set <=> +1 on axis k; nodes in Exodus order, points x fastest (checked on the host).
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int vw_node_of_sign(int i) {
+  constexpr int t[8] = {0, 1, 3, 2, 4, 5, 7, 6};
+  return t[i];
+}
+__host__ __device__ constexpr int vw_popc3(int m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1); }
+__host__ __device__ constexpr bool vw_sign(int q, int S) { return (vw_popc3((~q) & S) & 1) != 0; }   // sigma_q^S == -1 ?
+
+// f[a][c] (local node order) -> pre-scaled monomial coefficients fh[alpha][c], alpha = 1..7 (alpha = 0 is never needed)
+template <int NC>
+FEC_DEV void vw_analyse(const double (&f)[8][NC], const double* wr, double (&fh)[8][NC]) {
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = f[vw_node_of_sign(i)][c];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (!(i & (1 << k))) {
+          const double lo = v[i], hi = v[i | (1 << k)];
+          v[i] = hi + lo;
+          v[i | (1 << k)] = hi - lo;
+        }
+#pragma unroll
+    for (int al = 1; al < 8; ++al) fh[al][c] = v[al] * wr[vw_popc3(al) - 1];
+  }
+}
+// g[c][k] = sum_a f[a][c] dN[q][a][k] from the coefficients: 4 signed terms
+template <int NC, int Q>
+FEC_DEV void vw_gradient(const double (&fh)[8][NC], double (&g)[NC][3]) {
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double s = fh[1 << k][c];
+#pragma unroll
+      for (int S = 1; S < 8; ++S)
+        if (!(S & (1 << k))) s = vw_sign(Q, S) ? s - fh[S | (1 << k)][c] : s + fh[S | (1 << k)][c];
+      g[c][k] = s;
+    }
+}
+
+template <int NF, class Phys, int MODE, int Q, class Tab>
+FEC_DEV void vec_qp_walsh(const Tab& tab, const double (&Xh)[8][3], const double (&Uh)[8][NF], const double (&Vh)[8][NF],
+                          const double* props, const double fq, const double* so, double* sn, double (&rh)[8][NF],
+                          double (&sh)[8][NF]) {
+  constexpr int ND = 3;
+  double Jt[ND][ND], J[ND][ND], Ji[ND][ND];
+  vw_gradient<ND, Q>(Xh, Jt);   // Jt[i][k] = dx_i / dxi_k
+#pragma unroll
+  for (int i = 0; i < ND; ++i)
+#pragma unroll
+    for (int k = 0; k < ND; ++k) J[i][k] = Jt[i][k];
+  const double JxW = invert<ND>(J, Ji) * tab.w[Q];
+  double gx[NF][ND], gu[NF][ND];
+  vw_gradient<NF, Q>(Uh, gx);
+#pragma unroll
+  for (int d = 0; d < NF; ++d)
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < ND; ++j) s = fma(gx[d][j], Ji[j][k], s);
+      gu[d][k] = s;
+    }
+  double P[NF][ND], b[NF];
+  if constexpr (MODE == MODE_RESIDUAL) {
+    Phys::flux(gu, fq, props, so, sn, P, b);
+  } else {
+    double gvx[NF][ND], gv[NF][ND];
+    vw_gradient<NF, Q>(Vh, gvx);
+#pragma unroll
+    for (int d = 0; d < NF; ++d)
+#pragma unroll
+      for (int k = 0; k < ND; ++k) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < ND; ++j) s = fma(gvx[d][j], Ji[j][k], s);
+        gv[d][k] = s;
+      }
+    Phys::dflux(gu, gv, props, so, P);
+  }
+#pragma unroll
+  for (int d = 0; d < NF; ++d) {
+    double Px[ND];
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < ND; ++k) s = fma(P[d][k], Ji[j][k], s);
+      Px[j] = s * JxW;
+    }
+#pragma unroll
+    for (int al = 1; al < 8; ++al)
+#pragma unroll
+      for (int k = 0; k < ND; ++k)
+        if (al & (1 << k)) rh[al][d] = vw_sign(Q, al & ~(1 << k)) ? rh[al][d] - Px[k] : rh[al][d] + Px[k];
+    if constexpr (MODE == MODE_RESIDUAL && Phys::kHasSource) {   // N[q][a] JxW b[d]: N_a = 1/8 sum_S c^|S| s_a^S sigma_q^S
+      const double sb = JxW * b[d];
+#pragma unroll
+      for (int al = 0; al < 8; ++al) sh[al][d] = vw_sign(Q, al) ? sh[al][d] - sb : sh[al][d] + sb;
+    }
+  }
+}
+
+template <int NF, class Phys, int MODE, int Q, class Tab, class Params>
+FEC_DEV void vec_walsh_points(const Tab& tab, const Params& p, const int e, const double (&Xh)[8][3], const double (&Uh)[8][NF],
+                              const double (&Vh)[8][NF], double (&rh)[8][NF], double (&sh)[8][NF]) {
+  if constexpr (Q < 8) {
+    constexpr int NS = Phys::NS;
+    double so[NS > 0 ? NS : 1], sn[NS > 0 ? NS : 1];
+    if constexpr (NS > 0) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) so[s] = p.state_old[((size_t)s * p.nq + Q) * p.ne + e];
+    }
+    double fq = 0.0;
+    if constexpr (Phys::kHasSource && MODE == MODE_RESIDUAL) {
+      if (p.source) fq = p.source[(size_t)Q * p.ne + e];
+    }
+    vec_qp_walsh<NF, Phys, MODE, Q>(tab, Xh, Uh, Vh, p.props, fq, so, (NS > 0 && MODE == MODE_RESIDUAL) ? sn : nullptr, rh, sh);
+    if constexpr (NS > 0 && MODE == MODE_RESIDUAL) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) p.state_new[((size_t)s * p.nq + Q) * p.ne + e] = sn[s];
+    }
+    vec_walsh_points<NF, Phys, MODE, Q + 1>(tab, p, e, Xh, Uh, Vh, rh, sh);
+  }
+}
+
+// the whole element: r[a][d] (local node order) for MODE_RESIDUAL / MODE_ACTION_STIFFNESS
+template <int NF, class Phys, int MODE, class Params>
+FEC_DEV void vec_element_walsh(const Params& p, const int e, const double (&x)[8][3], const double (&u)[8][NF],
+                               const double (&v)[8][NF], double (&r)[8][NF]) {
+  double Xh[8][3], Uh[8][NF], Vh[8][NF], rh[8][NF], sh[8][NF];
+  vw_analyse<3>(x, p.wr, Xh);
+  vw_analyse<NF>(u, p.wr, Uh);
+  if constexpr (MODE == MODE_ACTION_STIFFNESS) vw_analyse<NF>(v, p.wr, Vh);
+#pragma unroll
+  for (int al = 0; al < 8; ++al)
+#pragma unroll
+    for (int d = 0; d < NF; ++d) { rh[al][d] = 0.0; sh[al][d] = 0.0; }
+  vec_walsh_points<NF, Phys, MODE, 0>(p.tab, p, e, Xh, Uh, Vh, rh, sh);
+#pragma unroll
+  for (int d = 0; d < NF; ++d) {
+    double w[8];
+    w[0] = 0.0;
+#pragma unroll
+    for (int al = 1; al < 8; ++al) w[al] = rh[al][d] * p.wr[vw_popc3(al) - 1];
+    if constexpr (MODE == MODE_RESIDUAL && Phys::kHasSource) {
+#pragma unroll
+      for (int al = 0; al < 8; ++al) w[al] = fma(sh[al][d], p.wr[vw_popc3(al)], w[al]);
+    }
+    // synthesis over the sign bits: out[i] = sum_alpha s_i^alpha w[alpha]
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (!(i & (1 << k))) {
+          const double lo = w[i], hi = w[i | (1 << k)];
+          w[i] = lo - hi;
+          w[i | (1 << k)] = lo + hi;
+        }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[vw_node_of_sign(i)][d] = w[i];
+  }
+}
+
+template <int ND, int NNPE, int NF, int NQT, class Phys, int MODE, int TE, int MINB, bool WALSH = false>
 __global__ void __launch_bounds__(TE, MINB) k_vec(const __grid_constant__ VecParams<ND, NNPE, NQT> p) {
   extern __shared__ double smem[];
   constexpr bool kNeedV = (MODE == MODE_ACTION_STIFFNESS || MODE == MODE_ACTION_MASS);
@@ -289,7 +468,9 @@ __global__ void __launch_bounds__(TE, MINB) k_vec(const __grid_constant__ VecPar
   for (int a = 0; a < NNPE; ++a)
 #pragma unroll
     for (int d = 0; d < NF; ++d) r[a][d] = 0.0;
-  if (active) {
+  if constexpr (WALSH) {
+    if (active) vec_element_walsh<NF, Phys, MODE>(p, e, x, u, v, r);
+  } else if (active) {
     auto body = [&](const int q) {
       double so[NS > 0 ? NS : 1], sn[NS > 0 ? NS : 1];
       if constexpr (NS > 0) {
@@ -650,8 +831,31 @@ inline void timing_end(fecb200_handle* h) {
   }
 }
 
-template <int ND, int NNPE, int NF, int NQT, class Phys, int MODE, int TE, int MINB>
-void run_vec(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
+// True when the block's dN table is the trilinear HEX8 table on a symmetric 2-point rule per axis, with the node and
+// point numbering the Walsh forms of k_mat2 and k_vec are compiled for (nodes: Exodus order, points: x fastest); *c = |xi|.
+// Weights are free (they are folded into JxW).  Anything else takes the classic quadrature loop.
+inline bool walsh_tables_ok(const BlockPlan& b, double* c_out) {
+  if (b.nq != 8 || b.dN.size() != 8u * 8u * 3u) return false;
+  auto sgn = [](int i, int k) { return ((i >> k) & 1) ? 1.0 : -1.0; };
+  int sign_of_node[8];
+  for (int i = 0; i < 8; ++i) sign_of_node[vw_node_of_sign(i)] = i;
+  const double d000 = std::fabs(b.dN[0]);              // point 0 = (-,-,-), node 0 = (-,-,-): (1 + c)^2 / 8
+  const double c = std::sqrt(8.0 * d000) - 1.0;
+  if (!(c > 0.0 && c <= 1.0)) return false;
+  for (int q = 0; q < 8; ++q)
+    for (int a = 0; a < 8; ++a)
+      for (int k = 0; k < 3; ++k) {
+        double v = sgn(sign_of_node[a], k) / 8.0;
+        for (int kp = 0; kp < 3; ++kp)
+          if (kp != k) v *= 1.0 + c * sgn(sign_of_node[a], kp) * sgn(q, kp);
+        if (std::fabs(v - b.dN[((size_t)q * 8 + a) * 3 + k]) > 1e-14) return false;
+      }
+  *c_out = c;
+  return true;
+}
+
+template <int ND, int NNPE, int NF, int NQT, class Phys, int MODE, int TE, int MINB, bool WALSH>
+void run_vec_t(fecb200_handle* h, BlockPlan& b, const VecLaunch& a, const double walsh_c) {
   FEC_REQUIRE(b.te == TE, "tile size does not match the compiled kernel");
   auto pp = std::make_unique<VecParams<ND, NNPE, NQT>>();  // large: keep off the stack
   auto& p = *pp;
@@ -664,6 +868,7 @@ void run_vec(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
   p.ne = (int32_t)b.ne; p.nq = b.nq;
   for (int i = 0; i < kMaxProps; ++i) p.props[i] = i < (int)b.props.size() ? b.props[i] : 0.0;
   fill_tables<ND, NNPE, NQT>(b, p.tab);
+  for (int n = 0; n < 4; ++n) p.wr[n] = std::pow(walsh_c, n) / 8.0;
   const int nfields = (MODE == MODE_ACTION_STIFFNESS || MODE == MODE_ACTION_MASS) ? 2 : 1;
   size_t sm_nodes = (size_t)b.max_tile_nodes * (ND + nfields * NF) * sizeof(double);
   size_t sm_stage = (size_t)NNPE * NF * TE * sizeof(double);
@@ -671,13 +876,30 @@ void run_vec(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
   p.body_doubles = (int32_t)(body / sizeof(double));
   p.max_nodes = b.max_tile_nodes;
   size_t smem = body + (size_t)(2 * b.max_tile_nodes + 1) * sizeof(int32_t) + (size_t)NNPE * TE * sizeof(uint16_t) + 8;
-  auto kern = k_vec<ND, NNPE, NF, NQT, Phys, MODE, TE, MINB>;
+  auto kern = k_vec<ND, NNPE, NF, NQT, Phys, MODE, TE, MINB, WALSH>;
   FEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   timing_begin(h);
   kern<<<b.ntiles, TE, smem, h->stream>>>(p);
   FEC_CUDA(cudaGetLastError());
   timing_end(h);
   h->launches++;
+}
+
+template <int ND, int NNPE, int NF, int NQT, class Phys, int MODE, int TE, int MINB>
+void run_vec(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
+  // Walsh form where it pays (B200, 192^3 / 128^3): mechanics residual 2.23 -> 1.82 ms.  The matrix-free action is register
+  // bound either way (3.16 ms both, more spills in the Walsh form) and the scalar kernels lose occupancy (Poisson residual
+  // 0.34 -> 0.45 ms at 184 instead of 144 registers), so those keep the quadrature loop; FECB200_VEC_WALSH_ALL=1 is the A/B switch.
+  constexpr bool kPays = (MODE == MODE_RESIDUAL && NF == 3);
+  if constexpr (ND == 3 && NNPE == 8 && NQT == 8 && (MODE == MODE_RESIDUAL || MODE == MODE_ACTION_STIFFNESS)) {
+    double c = 0.0;
+    if (!kPays && !getenv("FECB200_VEC_WALSH_ALL")) { run_vec_t<ND, NNPE, NF, NQT, Phys, MODE, TE, MINB, false>(h, b, a, 0.0); return; }
+    if (!getenv("FECB200_VEC_CLASSIC") && walsh_tables_ok(b, &c)) {
+      run_vec_t<ND, NNPE, NF, NQT, Phys, MODE, TE, MINB, true>(h, b, a, c);
+      return;
+    }
+  }
+  run_vec_t<ND, NNPE, NF, NQT, Phys, MODE, TE, MINB, false>(h, b, a, 0.0);
 }
 
 template <int ND, int NNPE, int NF, int NQT, class Phys>
