@@ -183,3 +183,36 @@ def test_k_mat2_walsh_fallbacks(F, mode, monkeypatch):
     assert rel_err(F.residual(asm), oasm.residual()) < RTOL
     assert rel_err(F.stiffness(asm).data, oasm.stiffness()[2]) < RTOL
     asm.close()
+
+
+@pytest.mark.parametrize("phys", ["poisson", "neo"])
+def test_k_vec_walsh_all_modes(F, phys, monkeypatch):
+    """The Walsh form of the vector kernel is the product path only for the mechanics residual (where it is faster);
+    FECB200_VEC_WALSH_ALL=1 routes the scalar residual (with its source term) and the matrix-free actions through it
+    too, so the whole restatement stays parity-tested."""
+    monkeypatch.setenv("FECB200_VEC_WALSH_ALL", "1")
+    rng = np.random.default_rng(11)
+    mesh = perturb(F.StructuredMesh("hex", (0, 0, 0), (1, 1, 1), (5, 6, 4)), 0.03)
+    nf = 1 if phys == "poisson" else 3
+    props = None if phys == "poisson" else np.array([1e3, 10e6, 1e6])
+    src = (lambda X: 1.0 + X[:, 0] * X[:, 1]) if phys == "poisson" else None
+    V = F.FunctionSpace(mesh, F.H1Field, F.Lagrange)
+    u = F.ScalarFunction(V, "u") if nf == 1 else F.VectorFunction(V, "displ")
+    asm = F.SparseMatrixAssembler(u, sparse_matrix_type="csr")
+    dbcs = [F.DirichletBC(c, lambda X, t: np.full(X.shape[0], 0.01), nodeset_name="bottom") for c in u.names()]
+    p = F.create_parameters(mesh, asm, product_physics(F, phys, 3, src), props, dirichlet_bcs=dbcs)
+    bname = mesh.element_block_names[0]
+    ophys = O.Poisson(src) if phys == "poisson" else O.NeoHookean(3)
+    blk = O.Block(mesh.element_conns[bname], O.ref_fe_tables("HEX8", "gauss2"), ophys, props=props if props is not None else ())
+    oasm = O.OracleAssembler(np.asarray(mesh.nodal_coords), [blk], nf, condensed=False, matrix_type="csr")
+    oasm.update_dofs(p.dirichlet_bcs.dirichlet_dofs())
+    oasm.bc_vals[:] = 0.01
+    N = asm.sizes()[2]
+    Uu, Vu = 0.02 * rng.standard_normal(N), rng.random(N)
+    F.assemble_vector(asm, F.residual, Uu, p)
+    oasm.assemble_vector(Uu)
+    assert rel_err(F.residual(asm), oasm.residual()) < RTOL
+    F.assemble_matrix_action(asm, F.stiffness, Uu, Vu, p)
+    oasm.assemble_matrix_action(Uu, Vu)
+    assert rel_err(F.hvp(asm, Vu), oasm.hvp(Vu)) < 1e-11
+    asm.close()
