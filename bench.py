@@ -39,7 +39,7 @@ BYTES_TANGENT = 2066.0     # conn 64 + X 24 + U 24 + CSR values 1954 (nnz/NE * 8
 BYTES_FUSED = 2090.0       # tangent + R 24 (conn/X/U shared with the residual)
 BYTES_ACTION = 160.0
 # FP64 flops per element counted from the kernels' instruction mix
-FLOPS_RESIDUAL = 7.0e3
+FLOPS_RESIDUAL = 4.5e3      # Walsh form of the HEX8 residual (estimate from instruction counts: 7.0e3 of the quadrature loop - 1728 FMA + ~1000 add/mul)
 FLOPS_TANGENT = 14.0e3      # fused k_mat2, Walsh form: thread-level (2 DFMA + DMUL + DADD) per element = 2*4500 + 1600 + 3430, ncu r02i
 FLOPS_TANGENT_QLOOP = 34.0e3  # the same element matrix by the plain quadrature loop (k_mat2 before the Walsh form, ncu r01z)
 BYTES_ZERO_FILL = 1954.0   # fill!(storage, 0) of the CSR values (Matrix.jl:39): NOT algorithmic (SURVEY 8d counts every
