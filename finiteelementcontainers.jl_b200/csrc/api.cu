@@ -299,6 +299,7 @@ int fecb200_create(const fecb200_mesh_desc* mesh, const fecb200_opts* opts, fecb
     b.N.assign(d.N, d.N + (size_t)d.nq * d.nnpe);
     b.dN.assign(d.dN, d.dN + (size_t)d.nq * d.nnpe * mesh->ndim);
     b.w.assign(d.w, d.w + d.nq);
+    detect_walsh(b);   // HEX8 tables of the trilinear / 2-point-rule kind take the Walsh form of the element kernels
     if (d.nprops) b.props.assign(d.props, d.props + d.nprops);
     {
       PhaseTimer _t("connectivity narrow + check");
@@ -1063,6 +1064,14 @@ int fecb200_launch_count(fecb200_handle* h, int64_t* n) {
   FEC_API_BEGIN
   FEC_REQUIRE(h && n, "null argument");
   *n = h->launches;
+  FEC_API_END
+}
+
+int fecb200_block_kernel_form(fecb200_handle* h, int32_t block, int32_t* form) {
+  FEC_API_BEGIN
+  FEC_REQUIRE(h && form, "null argument");
+  FEC_REQUIRE(block >= 0 && block < (int32_t)h->blocks.size(), "block index out of range");
+  *form = h->blocks[block].walsh ? 1 : 0;
   FEC_API_END
 }
 

@@ -123,9 +123,10 @@ void k_zero_bc_slots(fecb200_handle* h, double* field) {
 //   rows without testing); otherwise the 0xFFFFFFFF sentinel the scalar kernel tests for
 __global__ void k_build_emeta(const int32_t* conn, const int32_t* gconn, const uint8_t* epos, const int32_t* adjptr, const uint16_t* coloff,
                               const uint8_t* freemask, const int64_t* rowstart, unsigned char* emeta, int nnpe, int nf,
-                              int rec, int64_t ne, int64_t nnz, int trash_rows) {
+                              int rec, int64_t ne, int64_t nnz, int trash_rows, EmetaOrder ord) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= ne) return;
+  // record entry i describes local node ord.node[i]: identity, or the SIGN order of the Walsh form of k_mat2
   const int32_t* c = conn + e * nnpe;
   unsigned char* r = emeta + e * rec;
   uint32_t* rs = reinterpret_cast<uint32_t*>(r);
@@ -133,19 +134,21 @@ __global__ void k_build_emeta(const int32_t* conn, const int32_t* gconn, const u
   uint8_t* mk = r + nnpe * nf * 4 + nnpe * nnpe * 2;
   uint8_t* rk = mk + nnpe;   // reserved (identity): columns are indexed by local node
   uint32_t* nd = reinterpret_cast<uint32_t*>(rk + nnpe);
-  for (int a = 0; a < nnpe; ++a) {
-    rk[a] = (uint8_t)a;
-    mk[a] = freemask[c[a]];
-    nd[a] = (uint32_t)gconn[e * nnpe + a];   // fused residual: the node the element really gathers from
+  for (int i = 0; i < nnpe; ++i) {
+    const int a = ord.node[i];
+    rk[i] = (uint8_t)a;
+    mk[i] = freemask[c[a]];
+    nd[i] = (uint32_t)gconn[e * nnpe + a];   // fused residual: the node the element really gathers from
   }
-  for (int b = 0; b < nnpe; ++b) {
+  for (int i = 0; i < nnpe; ++i) {
+    const int b = ord.node[i];
     for (int d = 0; d < nf; ++d) {
       const int64_t v = rowstart[(int64_t)c[b] * nf + d];
-      const uint32_t dead = trash_rows ? (uint32_t)nnz + (uint32_t)(((uint32_t)e * 613u + (uint32_t)(b * nf + d) * 97u) & 4095u) : 0xFFFFFFFFu;
-      rs[b * nf + d] = v < 0 ? dead : (uint32_t)v;
+      const uint32_t dead = trash_rows ? (uint32_t)nnz + (uint32_t)(((uint32_t)e * 613u + (uint32_t)(i * nf + d) * 97u) & 4095u) : 0xFFFFFFFFu;
+      rs[i * nf + d] = v < 0 ? dead : (uint32_t)v;
     }
     const int base = adjptr[c[b]];
-    for (int a = 0; a < nnpe; ++a) ec[b * nnpe + a] = coloff[base + epos[(e * nnpe + b) * nnpe + a]];
+    for (int j = 0; j < nnpe; ++j) ec[i * nnpe + j] = coloff[base + epos[(e * nnpe + b) * nnpe + ord.node[j]]];
   }
 }
 
@@ -158,9 +161,13 @@ void build_ecol(fecb200_handle* h) {
     if (b.d_emeta.n != rec * b.ne) b.d_emeta.alloc(rec * b.ne);
     b.emeta_rec = rec;
     b.emeta_trash_rows = h->nf > 1;  // k_mat2 records (dead rows point into the trash region); else scalar-kernel records
+    // the Walsh form of k_mat2 keeps K_el in sign order: its records are written in that order (free at run time)
+    b.emeta_sign_order = b.walsh && b.elem_type == FECB200_HEX8 && h->nf == 3 && !getenv("FECB200_MAT2_CLASSIC");
+    EmetaOrder ord;
+    for (int i = 0; i < 16; ++i) ord.node[i] = (b.emeta_sign_order && i < 8) ? b.node_of_sign[i] : i;
     k_build_emeta<<<grid_for(b.ne), 256, 0, h->stream>>>(b.d_sconn_perm.p ? b.d_sconn_perm.p : b.d_conn_perm.p, b.d_conn_perm.p, b.d_epos.p, h->d_adjptr.p, h->d_coloff.p,
                                                          h->d_freemask.p, h->d_rowstart.p, b.d_emeta.p, b.nnpe, h->nf,
-                                                         (int)rec, b.ne, h->nnz, b.emeta_trash_rows ? 1 : 0);
+                                                         (int)rec, b.ne, h->nnz, b.emeta_trash_rows ? 1 : 0, ord);
     h->launches++;
   }
   FEC_CUDA(cudaGetLastError());

@@ -1,5 +1,6 @@
 // common.cuh -- internal declarations of libfecb200 (not part of the C ABI).
 #pragma once
+#include <cmath>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -142,6 +143,7 @@ __device__ __forceinline__ void scatter_add(const PeerScatter& ps, double* local
 // proxy) from a shared-memory zero page; they drain to HBM underneath the element kernel without touching the
 // LSU / L1 data pipe its REDs are bound by.
 struct ZeroFill { double* p; int64_t total16; int32_t chunk16; };
+struct EmetaOrder { int node[16]; };   // order of the per-element scatter record entries (k_build_emeta)
 #ifndef FEC_ZPAGE
 #define FEC_ZPAGE 1024
 #endif
@@ -178,6 +180,13 @@ struct BlockPlan {
   int elem_type = 0, nnpe = 0, nd = 0, nq = 0, physics = 0, nprops = 0, nstate = 0;
   int64_t ne = 0;
   std::vector<double> N, dN, w, props;
+  // Walsh form of the HEX8 kernels: set by detect_walsh() when the dN table is the trilinear one on a
+  // symmetric 2-point rule per axis, in ANY node / point numbering.  Sign index i: bit k set <=> +1 on axis k.
+  bool walsh = false;
+  double walsh_c = 0.0;                 // |xi| of the rule
+  int node_of_sign[8] = {0, 1, 2, 3, 4, 5, 6, 7};    // sign index -> local node
+  int point_of_sign[8] = {0, 1, 2, 3, 4, 5, 6, 7};   // sign index -> quadrature point
+  int sign_of_point[8] = {0, 1, 2, 3, 4, 5, 6, 7};   // quadrature point -> sign index
   std::vector<int32_t> conn0;  // [ne*nnpe] 0-based node ids, caller's element order
   std::vector<int32_t> sconn0; // scatter connectivity: periodic side-b nodes folded into side a (empty = conn0)
   // tiling (vector kernels): elements permuted into locality-ordered tiles of `te` elements
@@ -193,6 +202,7 @@ struct BlockPlan {
   DevBuf<unsigned char> d_emeta;  // [ne * emeta_rec] per-element scatter records of k_mat2 (kernel_mat2.cuh)
   size_t emeta_rec = 0;
   bool emeta_trash_rows = true;  // which flavour of scatter record d_emeta holds (k_build_emeta)
+  bool emeta_sign_order = false; // records written in the sign order of the Walsh form (node_of_sign) instead of local order
   DevBuf<double> d_state_old, d_state_new;  // [(s*nq+q)*ne + e_tile_order]
   DevBuf<double> d_source;                  // [q*ne + e_tile_order]
   DevBuf<double> d_scalar;                  // [q*ne + e_tile_order] assemble_scalar! storage (allocated on first use)
@@ -327,6 +337,49 @@ void build_block_tiles_gpu(fecb200_handle* h, BlockPlan& b);
 void build_adjacency_gpu(fecb200_handle* h);
 void build_matrix_offsets_gpu(fecb200_handle* h);
 void ensure_host_structure(fecb200_handle* h);
+
+// Recognises the trilinear HEX8 table on a symmetric 2-point rule per axis in any node / point numbering and fills the
+// block's sign maps: s_a^k = sign(sum_q dN[q][a][k]) (the sum is exactly s_a^k), c sigma_q^k' = sum_a s_a^k s_a^k' dN[q][a][k]
+// for k' != k.  Every entry is then checked against dN = s_a^k/8 prod_{k' != k} (1 + c s_a^k' sigma_q^k'); weights are free
+// (folded into JxW).  Anything else keeps the plain quadrature loop.
+inline void detect_walsh(BlockPlan& b) {
+  b.walsh = false;
+  if (b.elem_type != FECB200_HEX8 || b.nq != 8 || b.nnpe != 8 || b.dN.size() != 8u * 8u * 3u) return;
+  auto dn = [&](int q, int a, int k) { return b.dN[((size_t)q * 8 + a) * 3 + k]; };
+  int sa[8][3], sq[8][3];
+  for (int a = 0; a < 8; ++a)
+    for (int k = 0; k < 3; ++k) {
+      double s = 0.0;
+      for (int q = 0; q < 8; ++q) s += dn(q, a, k);
+      if (std::fabs(std::fabs(s) - 1.0) > 1e-12) return;
+      sa[a][k] = s > 0 ? 1 : -1;
+    }
+  double c = -1.0;
+  for (int q = 0; q < 8; ++q)
+    for (int kp = 0; kp < 3; ++kp) {
+      const int k = (kp + 1) % 3;
+      double s = 0.0;
+      for (int a = 0; a < 8; ++a) s += sa[a][k] * sa[a][kp] * dn(q, a, k);
+      if (c < 0.0) c = std::fabs(s);
+      if (std::fabs(std::fabs(s) - c) > 1e-12 || !(c > 1e-3 && c <= 1.0 + 1e-12)) return;
+      sq[q][kp] = s > 0 ? 1 : -1;
+    }
+  int nos[8], pos[8], seen_n = 0, seen_q = 0;
+  for (int a = 0; a < 8; ++a) { const int i = (sa[a][0] > 0) | ((sa[a][1] > 0) << 1) | ((sa[a][2] > 0) << 2); nos[i] = a; seen_n |= 1 << i; }
+  for (int q = 0; q < 8; ++q) { const int i = (sq[q][0] > 0) | ((sq[q][1] > 0) << 1) | ((sq[q][2] > 0) << 2); pos[i] = q; seen_q |= 1 << i; }
+  if (seen_n != 0xFF || seen_q != 0xFF) return;
+  for (int q = 0; q < 8; ++q)
+    for (int a = 0; a < 8; ++a)
+      for (int k = 0; k < 3; ++k) {
+        double v = sa[a][k] / 8.0;
+        for (int kp = 0; kp < 3; ++kp)
+          if (kp != k) v *= 1.0 + c * sa[a][kp] * sq[q][kp];
+        if (std::fabs(v - dn(q, a, k)) > 1e-13) return;
+      }
+  b.walsh = true;
+  b.walsh_c = c;
+  for (int i = 0; i < 8; ++i) { b.node_of_sign[i] = nos[i]; b.point_of_sign[i] = pos[i]; b.sign_of_point[pos[i]] = i; }
+}
 
 // plan.cu
 void build_block_tiles(fecb200_handle* h, BlockPlan& b, const double* coords);

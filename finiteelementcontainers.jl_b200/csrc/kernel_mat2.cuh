@@ -42,6 +42,7 @@ struct Mat2Params {
   ZeroFill zf;               // in-kernel clear of the idle CSR value buffer (common.cuh)
   double wc[5];              // Walsh path: c^n / 64, n = 0..4 (c = |xi| of the 2-point rule per axis, read off the tables)
   double wr[3];              //             c^n / 8,  n = 0..2 (fused residual)
+  int32_t qslot[8];          //             quadrature point -> sign index (the slot its thread publishes into)
   double props[kMaxProps];
   Tables<ND, NNPE, NQT> tab;
 };
@@ -147,12 +148,9 @@ __device__ __forceinline__ void red_add_f64_pred(double* addr, double v, bool ok
 //   Bh_m = sum_q sigma_q^m B_q                                                     (Walsh transform over the 8 points).
 // Per pair thread: 432 (B) + 216 (transform over q) + 144 (Mh) + 330 (synthesis; Mh[0][.] = Mh[.][0] = 0) = 1122 FP64
 // instructions instead of the 2112 of the quadrature loop, and 49 instead of 64 accumulators.  Sign index i: bit k set
-// <=> +1 on axis k.  kNodeOfSign is the Exodus HEX8 numbering; the host checks the tables against the formula
-// (walsh_tables_ok) and takes the classic loop when they differ.
-__device__ __host__ constexpr int walsh_node_of_sign(int i) {
-  constexpr int t[8] = {0, 1, 3, 2, 4, 5, 7, 6};
-  return t[i];
-}
+// <=> +1 on axis k.  Any node / point numbering works: the host reads the sign triples off the table (detect_walsh),
+// point q publishes into slot qslot[q], K_el is staged in SIGN order and the scatter records are written in that order
+// (k_build_emeta); tables of another kind take the classic loop.
 // in-place 8-point transform over sign bits: (lo, hi) -> (lo + hi, hi - lo): v[m] = sum_i s_i^m v[i]
 FEC_DEV void walsh_fwd8(double (&v)[8]) {
 #pragma unroll
@@ -262,7 +260,7 @@ __global__ void __launch_bounds__(WARPS * 32, WALSH ? FEC_MAT2_MINB : 1) k_mat2(
         }
       double Ji[ND][ND];
       const double JxW = invert<ND>(J, Ji) * p.tab.w[q];
-      double* slot = esm + (size_t)q * SLOT;
+      double* slot = esm + (size_t)(WALSH ? p.qslot[q] : q) * SLOT;
       double gu[NF][ND];
       if constexpr (WALSH) {
         // publish J^-1 only; grad u = (sum_a u_a (x) dN_a/dxi) J^-1
@@ -552,9 +550,9 @@ __global__ void __launch_bounds__(WARPS * 32, WALSH ? FEC_MAT2_MINB : 1) k_mat2(
       for (int a = 0; a < NNPE; ++a) {
 #pragma unroll
         for (int b = 0; b < NNPE; ++b) {
-          // entry (row dof (a,d1), col dof (b,d2)) and its mirror (row (b,d2), col (a,d1)); the Walsh form holds M in
-          // sign indices
-          const int na = WALSH ? walsh_node_of_sign(a) : a, nb = WALSH ? walsh_node_of_sign(b) : b;
+          // entry (row dof (a,d1), col dof (b,d2)) and its mirror (row (b,d2), col (a,d1)); the Walsh form holds M, stages
+          // K_el and reads its scatter records in sign order
+          const int na = a, nb = b;
           if (na / HNODES == hp) esm[((na - hp * HNODES) * NF + d1) * RS + nb * NF + d2] = M[a][b];
           if (nb / HNODES == hp && d1 != d2) esm[((nb - hp * HNODES) * NF + d2) * RS + na * NF + d1] = M[a][b];
         }
@@ -562,7 +560,7 @@ __global__ void __launch_bounds__(WARPS * 32, WALSH ? FEC_MAT2_MINB : 1) k_mat2(
       if constexpr (WITH_R) {
         if (hp == 0 && d1 == d2) {
 #pragma unroll
-          for (int a = 0; a < NNPE; ++a) esm[L::R_OFF + (WALSH ? walsh_node_of_sign(a) : a) * NF + d1] = rr[a];  // residual row, laid out like the columns
+          for (int a = 0; a < NNPE; ++a) esm[L::R_OFF + a * NF + d1] = rr[a];  // residual row, laid out like the columns
         }
       }
     }
@@ -642,7 +640,7 @@ __global__ void __launch_bounds__(WARPS * 32, WALSH ? FEC_MAT2_MINB : 1) k_mat2(
 // element -> CSR column-offset table, rebuilt whenever update_dofs changes the kept-dof masks
 __global__ void k_build_emeta(const int32_t* conn, const int32_t* gconn, const uint8_t* epos, const int32_t* adjptr, const uint16_t* coloff,
                               const uint8_t* freemask, const int64_t* rowstart, unsigned char* emeta, int nnpe, int nf,
-                              int rec, int64_t ne, int64_t nnz, int trash_rows);
+                              int rec, int64_t ne, int64_t nnz, int trash_rows, EmetaOrder ord);
 
 template <int ND, int NNPE, int NF, int NQT, class Phys, int WARPS, bool WITH_R, bool WALSH = false>
 void run_mat2_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a, double walsh_c = 0.0) {
@@ -662,6 +660,8 @@ void run_mat2_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a, double wals
   fill_tables<ND, NNPE, NQT>(b, p.tab);
   for (int n = 0; n < 5; ++n) p.wc[n] = std::pow(walsh_c, n) / 64.0;
   for (int n = 0; n < 3; ++n) p.wr[n] = std::pow(walsh_c, n) / 8.0;
+  for (int q = 0; q < 8; ++q) p.qslot[q] = WALSH ? b.sign_of_point[q] : q;
+  FEC_REQUIRE(b.emeta_sign_order == WALSH, "scatter records are not in the order this kernel stages K_el in");
 #ifdef FEC_MAT2_KO
   p.ko = getenv("FECB200_KO") ? atoi(getenv("FECB200_KO")) : 0;
 #endif
@@ -682,10 +682,9 @@ void run_mat2_t(fecb200_handle* h, BlockPlan& b, const MatLaunch& a, double wals
 template <int ND, int NNPE, int NF, int NQT, class Phys, int WARPS>
 void run_mat2(fecb200_handle* h, BlockPlan& b, const MatLaunch& a) {
   if constexpr (ND == 3 && NNPE == 8 && NF == 3 && NQT == 8) {
-    double c = 0.0;
-    if (!getenv("FECB200_MAT2_CLASSIC") && walsh_tables_ok(b, &c)) {
-      if (a.R) run_mat2_t<ND, NNPE, NF, NQT, Phys, WARPS, true, true>(h, b, a, c);
-      else run_mat2_t<ND, NNPE, NF, NQT, Phys, WARPS, false, true>(h, b, a, c);
+    if (b.emeta_sign_order) {   // decided with the records (build_ecol): Walsh tables and not FECB200_MAT2_CLASSIC
+      if (a.R) run_mat2_t<ND, NNPE, NF, NQT, Phys, WARPS, true, true>(h, b, a, b.walsh_c);
+      else run_mat2_t<ND, NNPE, NF, NQT, Phys, WARPS, false, true>(h, b, a, b.walsh_c);
       return;
     }
   }

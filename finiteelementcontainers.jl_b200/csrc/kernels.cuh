@@ -58,6 +58,7 @@ struct VecParams {
   int32_t ne, nq;
   int32_t body_doubles, max_nodes;  // shared-memory layout: [node data | element-vector stage][node ids][inc_ptr][inc]
   double wr[4];                     // Walsh path: c^n / 8, n = 0..3 (c = |xi| of the 2-point rule per axis)
+  int32_t nos[8], pos[8];           //             sign index -> local node / quadrature point (identity otherwise)
   double props[kMaxProps];
   Tables<ND, NNPE, NQT> tab;
 };
@@ -239,23 +240,20 @@ FEC_DEV void vec_qp(const Tab& tab, const int q, const double (&x)[NNPE][ND], co
 //   (grad_xi u)_q = the same with Uh,
 //   r[a][d]       = sum_alpha s_a^alpha rh[alpha][d],   rh[alpha][d] = c^(|alpha|-1)/8 sum_q sum_{k in alpha} sigma_q^(alpha\k) Px_q[d][k]:
 // 3 add/sub per entry and point instead of 8 FMA for J and grad u, 36 add/sub instead of 72 FMA per point for the
-// scatter.  Sign index i: bit k set <=> +1 on axis k; nodes in Exodus order, points x fastest (checked on the host).
+// scatter.  Sign index i: bit k set <=> +1 on axis k.  The kernel gathers the element fields in SIGN order (p.nos) and walks
+// the points in sign order (p.pos), so any node / point numbering of the table works (detect_walsh on the host).
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int vw_node_of_sign(int i) {
-  constexpr int t[8] = {0, 1, 3, 2, 4, 5, 7, 6};
-  return t[i];
-}
 __host__ __device__ constexpr int vw_popc3(int m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1); }
 __host__ __device__ constexpr bool vw_sign(int q, int S) { return (vw_popc3((~q) & S) & 1) != 0; }   // sigma_q^S == -1 ?
 
-// f[a][c] (local node order) -> pre-scaled monomial coefficients fh[alpha][c], alpha = 1..7 (alpha = 0 is never needed)
+// f[i][c] (sign order) -> pre-scaled monomial coefficients fh[alpha][c], alpha = 1..7 (alpha = 0 is never needed)
 template <int NC>
 FEC_DEV void vw_analyse(const double (&f)[8][NC], const double* wr, double (&fh)[8][NC]) {
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     double v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = f[vw_node_of_sign(i)][c];
+    for (int i = 0; i < 8; ++i) v[i] = f[i][c];
 #pragma unroll
     for (int k = 0; k < 3; ++k)
 #pragma unroll
@@ -284,8 +282,8 @@ FEC_DEV void vw_gradient(const double (&fh)[8][NC], double (&g)[NC][3]) {
     }
 }
 
-template <int NF, class Phys, int MODE, int Q, class Tab>
-FEC_DEV void vec_qp_walsh(const Tab& tab, const double (&Xh)[8][3], const double (&Uh)[8][NF], const double (&Vh)[8][NF],
+template <int NF, class Phys, int MODE, int Q>
+FEC_DEV void vec_qp_walsh(const double wq, const double (&Xh)[8][3], const double (&Uh)[8][NF], const double (&Vh)[8][NF],
                           const double* props, const double fq, const double* so, double* sn, double (&rh)[8][NF],
                           double (&sh)[8][NF]) {
   constexpr int ND = 3;
@@ -295,7 +293,7 @@ FEC_DEV void vec_qp_walsh(const Tab& tab, const double (&Xh)[8][3], const double
   for (int i = 0; i < ND; ++i)
 #pragma unroll
     for (int k = 0; k < ND; ++k) J[i][k] = Jt[i][k];
-  const double JxW = invert<ND>(J, Ji) * tab.w[Q];
+  const double JxW = invert<ND>(J, Ji) * wq;
   double gx[NF][ND], gu[NF][ND];
   vw_gradient<NF, Q>(Uh, gx);
 #pragma unroll
@@ -355,22 +353,22 @@ FEC_DEV void vec_walsh_points(const Tab& tab, const Params& p, const int e, cons
     double so[NS > 0 ? NS : 1], sn[NS > 0 ? NS : 1];
     if constexpr (NS > 0) {
 #pragma unroll
-      for (int s = 0; s < NS; ++s) so[s] = p.state_old[((size_t)s * p.nq + Q) * p.ne + e];
+      for (int s = 0; s < NS; ++s) so[s] = p.state_old[((size_t)s * p.nq + p.pos[Q]) * p.ne + e];
     }
     double fq = 0.0;
     if constexpr (Phys::kHasSource && MODE == MODE_RESIDUAL) {
-      if (p.source) fq = p.source[(size_t)Q * p.ne + e];
+      if (p.source) fq = p.source[(size_t)p.pos[Q] * p.ne + e];
     }
-    vec_qp_walsh<NF, Phys, MODE, Q>(tab, Xh, Uh, Vh, p.props, fq, so, (NS > 0 && MODE == MODE_RESIDUAL) ? sn : nullptr, rh, sh);
+    vec_qp_walsh<NF, Phys, MODE, Q>(tab.w[p.pos[Q]], Xh, Uh, Vh, p.props, fq, so, (NS > 0 && MODE == MODE_RESIDUAL) ? sn : nullptr, rh, sh);
     if constexpr (NS > 0 && MODE == MODE_RESIDUAL) {
 #pragma unroll
-      for (int s = 0; s < NS; ++s) p.state_new[((size_t)s * p.nq + Q) * p.ne + e] = sn[s];
+      for (int s = 0; s < NS; ++s) p.state_new[((size_t)s * p.nq + p.pos[Q]) * p.ne + e] = sn[s];
     }
     vec_walsh_points<NF, Phys, MODE, Q + 1>(tab, p, e, Xh, Uh, Vh, rh, sh);
   }
 }
 
-// the whole element: r[a][d] (local node order) for MODE_RESIDUAL / MODE_ACTION_STIFFNESS
+// the whole element, fields and result in SIGN order, for MODE_RESIDUAL / MODE_ACTION_STIFFNESS
 template <int NF, class Phys, int MODE, class Params>
 FEC_DEV void vec_element_walsh(const Params& p, const int e, const double (&x)[8][3], const double (&u)[8][NF],
                                const double (&v)[8][NF], double (&r)[8][NF]) {
@@ -404,7 +402,7 @@ FEC_DEV void vec_element_walsh(const Params& p, const int e, const double (&x)[8
           w[i | (1 << k)] = lo + hi;
         }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) r[vw_node_of_sign(i)][d] = w[i];
+    for (int i = 0; i < 8; ++i) r[i][d] = w[i];
   }
 }
 
@@ -451,7 +449,7 @@ __global__ void __launch_bounds__(TE, MINB) k_vec(const __grid_constant__ VecPar
   if (active) {
 #pragma unroll
     for (int a = 0; a < NNPE; ++a) {
-      const int l = p.lconn[((size_t)tile * NNPE + a) * TE + tid];
+      const int l = p.lconn[((size_t)tile * NNPE + (WALSH ? p.nos[a] : a)) * TE + tid];   // Walsh form: fields in sign order
 #pragma unroll
       for (int j = 0; j < ND; ++j) x[a][j] = sX[l * ND + j];
 #pragma unroll
@@ -501,7 +499,7 @@ __global__ void __launch_bounds__(TE, MINB) k_vec(const __grid_constant__ VecPar
 #pragma unroll
   for (int a = 0; a < NNPE; ++a)
 #pragma unroll
-    for (int d = 0; d < NF; ++d) sR[(a * NF + d) * TE + tid] = r[a][d];
+    for (int d = 0; d < NF; ++d) sR[((WALSH ? p.nos[a] : a) * NF + d) * TE + tid] = r[a][d];
   __syncthreads();
   for (int i = tid; i < nn; i += TE) {
     double acc[NF];
@@ -831,29 +829,6 @@ inline void timing_end(fecb200_handle* h) {
   }
 }
 
-// True when the block's dN table is the trilinear HEX8 table on a symmetric 2-point rule per axis, with the node and
-// point numbering the Walsh forms of k_mat2 and k_vec are compiled for (nodes: Exodus order, points: x fastest); *c = |xi|.
-// Weights are free (they are folded into JxW).  Anything else takes the classic quadrature loop.
-inline bool walsh_tables_ok(const BlockPlan& b, double* c_out) {
-  if (b.nq != 8 || b.dN.size() != 8u * 8u * 3u) return false;
-  auto sgn = [](int i, int k) { return ((i >> k) & 1) ? 1.0 : -1.0; };
-  int sign_of_node[8];
-  for (int i = 0; i < 8; ++i) sign_of_node[vw_node_of_sign(i)] = i;
-  const double d000 = std::fabs(b.dN[0]);              // point 0 = (-,-,-), node 0 = (-,-,-): (1 + c)^2 / 8
-  const double c = std::sqrt(8.0 * d000) - 1.0;
-  if (!(c > 0.0 && c <= 1.0)) return false;
-  for (int q = 0; q < 8; ++q)
-    for (int a = 0; a < 8; ++a)
-      for (int k = 0; k < 3; ++k) {
-        double v = sgn(sign_of_node[a], k) / 8.0;
-        for (int kp = 0; kp < 3; ++kp)
-          if (kp != k) v *= 1.0 + c * sgn(sign_of_node[a], kp) * sgn(q, kp);
-        if (std::fabs(v - b.dN[((size_t)q * 8 + a) * 3 + k]) > 1e-14) return false;
-      }
-  *c_out = c;
-  return true;
-}
-
 template <int ND, int NNPE, int NF, int NQT, class Phys, int MODE, int TE, int MINB, bool WALSH>
 void run_vec_t(fecb200_handle* h, BlockPlan& b, const VecLaunch& a, const double walsh_c) {
   FEC_REQUIRE(b.te == TE, "tile size does not match the compiled kernel");
@@ -869,6 +844,7 @@ void run_vec_t(fecb200_handle* h, BlockPlan& b, const VecLaunch& a, const double
   for (int i = 0; i < kMaxProps; ++i) p.props[i] = i < (int)b.props.size() ? b.props[i] : 0.0;
   fill_tables<ND, NNPE, NQT>(b, p.tab);
   for (int n = 0; n < 4; ++n) p.wr[n] = std::pow(walsh_c, n) / 8.0;
+  for (int i = 0; i < 8; ++i) { p.nos[i] = WALSH ? b.node_of_sign[i] : i; p.pos[i] = WALSH ? b.point_of_sign[i] : i; }
   const int nfields = (MODE == MODE_ACTION_STIFFNESS || MODE == MODE_ACTION_MASS) ? 2 : 1;
   size_t sm_nodes = (size_t)b.max_tile_nodes * (ND + nfields * NF) * sizeof(double);
   size_t sm_stage = (size_t)NNPE * NF * TE * sizeof(double);
@@ -892,10 +868,9 @@ void run_vec(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
   // 0.34 -> 0.45 ms at 184 instead of 144 registers), so those keep the quadrature loop; FECB200_VEC_WALSH_ALL=1 is the A/B switch.
   constexpr bool kPays = (MODE == MODE_RESIDUAL && NF == 3);
   if constexpr (ND == 3 && NNPE == 8 && NQT == 8 && (MODE == MODE_RESIDUAL || MODE == MODE_ACTION_STIFFNESS)) {
-    double c = 0.0;
     if (!kPays && !getenv("FECB200_VEC_WALSH_ALL")) { run_vec_t<ND, NNPE, NF, NQT, Phys, MODE, TE, MINB, false>(h, b, a, 0.0); return; }
-    if (!getenv("FECB200_VEC_CLASSIC") && walsh_tables_ok(b, &c)) {
-      run_vec_t<ND, NNPE, NF, NQT, Phys, MODE, TE, MINB, true>(h, b, a, c);
+    if (!getenv("FECB200_VEC_CLASSIC") && b.walsh) {
+      run_vec_t<ND, NNPE, NF, NQT, Phys, MODE, TE, MINB, true>(h, b, a, b.walsh_c);
       return;
     }
   }

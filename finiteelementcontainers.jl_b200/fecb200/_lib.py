@@ -135,6 +135,7 @@ SIGNATURES = {
     "fecb200_comm_peer_enable": (C.c_int, [Handle, C.c_int32]),
     "fecb200_peer_detach": (C.c_int, [Handle]),
     "fecb200_launch_count": (C.c_int, [Handle, c_i64p]),
+    "fecb200_block_kernel_form": (C.c_int, [Handle, C.c_int32, C.POINTER(C.c_int32)]),
     "fecb200_enable_timing": (C.c_int, [Handle, C.c_int32]),
     "fecb200_last_kernel_ms": (C.c_int, [Handle, C.POINTER(C.c_float)]),
 }

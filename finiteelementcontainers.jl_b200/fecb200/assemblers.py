@@ -128,6 +128,13 @@ class SparseMatrixAssembler:
         check(lib.fecb200_launch_count(self._require(), C.byref(n)))
         return n.value
 
+    def kernel_form(self, block=0):
+        """1 when the block's element kernels take the Walsh-Hadamard form (HEX8, trilinear table on a 2-point rule per
+        axis, any numbering), 0 for the plain quadrature loop."""
+        f = C.c_int32()
+        check(lib.fecb200_block_kernel_form(self._require(), block, C.byref(f)))
+        return f.value
+
 
 class Parameters:
     """The slice of Parameters (src/Parameters.jl:37-73) the hot path touches; device-resident

@@ -359,6 +359,10 @@ int fecb200_comm_peer_enable(fecb200_handle* h, int32_t which_field);
 
 /* ---- instrumentation: kernels launched by this handle since creation (bench `gpu_launches`) */
 int fecb200_launch_count(fecb200_handle* h, int64_t* n);
+/* which form of the element kernels block `block` (0-based) takes: 1 = the Walsh-Hadamard form (HEX8 blocks whose
+ * ReferenceFE table -- `ref_fe.cell_interps` of the block's FunctionSpace entry, src/FunctionSpaces.jl -- is the trilinear
+ * one on a symmetric 2-point rule per axis, in any node / point numbering), 0 = the plain quadrature loop. */
+int fecb200_block_kernel_form(fecb200_handle* h, int32_t block, int32_t* form);
 /* last kernel timing (ms) measured with CUDA events on the handle's stream around the dominant
  * element kernel of the last assemble_* call; enabled by fecb200_enable_timing(h, 1) */
 int fecb200_enable_timing(fecb200_handle* h, int32_t on);

@@ -147,20 +147,29 @@ def test_error_behaviour(F):
     asm.close()
 
 
-@pytest.mark.parametrize("mode", ["classic_env", "permuted_points"])
+@pytest.mark.parametrize("mode", ["classic_env", "permuted_points", "skewed_rule"])
 def test_k_mat2_walsh_fallbacks(F, mode, monkeypatch):
-    """The Walsh form of the HEX8 tangent kernel is taken only when the block's dN table is the trilinear table on a
-    symmetric 2-point rule in the numbering it is compiled for (walsh_tables_ok, kernel_mat2.cuh).  Forced off
-    (FECB200_MAT2_CLASSIC) and with a rule whose points come in another order the classic quadrature loop must run and
-    give the same answer as the oracle on the very same tables."""
+    """The Walsh form of the HEX8 kernels is taken only when the block's dN table is the trilinear table on a symmetric
+    2-point rule per axis (detect_walsh, common.cuh).  Forced off (FECB200_MAT2_CLASSIC / FECB200_VEC_CLASSIC) and with a
+    rule that is not of that kind (one point moved) the plain quadrature loop must run; a rule whose points merely come in
+    another order keeps the Walsh form.  Same answer as the oracle on the very same tables in every case."""
     from fecb200.reference_fe import ReferenceFE
     rng = np.random.default_rng(5)
     mesh = perturb(F.StructuredMesh("hex", (0, 0, 0), (1, 1, 1), (6, 5, 4)), 0.03)
     props = np.array([1e3, 10e6, 1e6])
     rfe = ReferenceFE("HEX8", "GaussLegendre", 2)
     tabs = O.ref_fe_tables("HEX8", "gauss2")
+    expect = 1
     if mode == "classic_env":
         monkeypatch.setenv("FECB200_MAT2_CLASSIC", "1")
+        monkeypatch.setenv("FECB200_VEC_CLASSIC", "1")
+    elif mode == "skewed_rule":   # 8 points, but not a tensor rule: point 5 sits elsewhere
+        from fecb200.reference_fe import _tensor_shape, _SIGNS
+        xi = np.array([[sx, sy, sz] for sz in (-1, 1) for sy in (-1, 1) for sx in (-1, 1)], dtype=float) / np.sqrt(3.0)
+        xi[5] = [0.3, -0.45, 0.6]
+        rfe.N, rfe.dN = (np.ascontiguousarray(t) for t in _tensor_shape(_SIGNS["HEX8"], xi))
+        tabs = (rfe.N, rfe.dN, rfe.w)
+        expect = 0
     else:
         perm = np.array([3, 0, 6, 1, 7, 2, 5, 4])
         rfe.N, rfe.dN, rfe.w = (np.ascontiguousarray(rfe.N[perm]), np.ascontiguousarray(rfe.dN[perm]),
@@ -177,6 +186,7 @@ def test_k_mat2_walsh_fallbacks(F, mode, monkeypatch):
     oasm.update_dofs(p.dirichlet_bcs.dirichlet_dofs())
     oasm.bc_vals[:] = 0.01
     Uu = 0.02 * rng.standard_normal(asm.sizes()[2])
+    assert asm.kernel_form(0) == expect   # a permuted rule is still of the Walsh kind; the env switches force the loop at launch
     F.assemble_vector_and_stiffness(asm, F.residual, F.stiffness, Uu, p)   # the fused kernel
     oasm.assemble_vector(Uu)
     oasm.assemble_stiffness(Uu)
@@ -215,4 +225,50 @@ def test_k_vec_walsh_all_modes(F, phys, monkeypatch):
     F.assemble_matrix_action(asm, F.stiffness, Uu, Vu, p)
     oasm.assemble_matrix_action(Uu, Vu)
     assert rel_err(F.hvp(asm, Vu), oasm.hvp(Vu)) < 1e-11
+    asm.close()
+
+
+@pytest.mark.parametrize("phys", ["neo", "j2"])
+def test_walsh_form_in_any_numbering(F, phys):
+    """The Walsh form reads the node / point sign triples off the block's own dN table (detect_walsh), so a host that
+    numbers the HEX8 nodes and the 8 quadrature points differently (ReferenceFiniteElements.jl is not vendored: its
+    ordering is unknown here) still gets the fast kernels -- and the same numbers as the oracle on the same tables."""
+    from fecb200.reference_fe import ReferenceFE
+    rng = np.random.default_rng(23)
+    mesh = perturb(F.StructuredMesh("hex", (0, 0, 0), (1, 1, 1), (6, 4, 5)), 0.03)
+    bname = mesh.element_block_names[0]
+    pn, pq = rng.permutation(8), rng.permutation(8)
+    mesh.element_conns[bname] = np.ascontiguousarray(np.asarray(mesh.element_conns[bname])[pn])   # local node a := old node pn[a]
+    rfe = ReferenceFE("HEX8", "GaussLegendre", 2)
+    rfe.N = np.ascontiguousarray(rfe.N[pq][:, pn])
+    rfe.dN = np.ascontiguousarray(rfe.dN[pq][:, pn, :])
+    rfe.w = np.ascontiguousarray(rfe.w[pq])
+    N0, dN0, w0 = O.ref_fe_tables("HEX8", "gauss2")
+    tabs = (np.ascontiguousarray(np.asarray(N0)[pq][:, pn]), np.ascontiguousarray(np.asarray(dN0)[pq][:, pn, :]),
+            np.ascontiguousarray(np.asarray(w0)[pq]))
+    props = np.array([1e3, 10e9, 1e9, 2e8, 1e8]) if phys == "j2" else np.array([1e3, 10e6, 1e6])
+    V = F.FunctionSpace(mesh, F.H1Field, F.Lagrange, ref_fes=[rfe])
+    u = F.VectorFunction(V, "displ")
+    asm = F.SparseMatrixAssembler(u, sparse_matrix_type="csr")
+    dbcs = [F.DirichletBC(c, lambda X, t: np.full(X.shape[0], 0.01), nodeset_name="bottom") for c in u.names()]
+    p = F.create_parameters(mesh, asm, product_physics(F, phys, 3, None), props, dirichlet_bcs=dbcs)
+    assert asm.kernel_form(0) == 1, "the permuted table should still be recognised"
+    ophys = O.J2Plasticity(3) if phys == "j2" else O.NeoHookean(3)
+    blk = O.Block(mesh.element_conns[bname], tabs, ophys, props=props)
+    oasm = O.OracleAssembler(np.asarray(mesh.nodal_coords), [blk], 3, condensed=False, matrix_type="csr")
+    oasm.update_dofs(p.dirichlet_bcs.dirichlet_dofs())
+    oasm.bc_vals[:] = 0.01
+    Uu = (0.15 if phys == "j2" else 0.02) * rng.standard_normal(asm.sizes()[2])
+    F.assemble_vector(asm, F.residual, Uu, p)                              # Walsh k_vec
+    oasm.assemble_vector(Uu)
+    assert rel_err(F.residual(asm), oasm.residual()) < RTOL
+    F.assemble_vector_and_stiffness(asm, F.residual, F.stiffness, Uu, p)   # Walsh k_mat2, fused
+    oasm.assemble_stiffness(Uu)
+    n, ptr, idx = asm.pattern()
+    optr, oidx, onz = oasm.stiffness()
+    assert np.array_equal(ptr, optr) and np.array_equal(idx, oidx)
+    assert rel_err(F.residual(asm), oasm.residual()) < RTOL
+    assert rel_err(F.stiffness(asm).data, onz) < RTOL
+    F.assemble_stiffness(asm, F.stiffness, Uu, p)                          # tangent only
+    assert rel_err(F.stiffness(asm).data, onz) < RTOL
     asm.close()
