@@ -412,4 +412,12 @@ function cg_solve!(x, asm::B200Assembler, b; atol = -1.0, rtol = -1.0, itmax = 0
   return its[], rn[]
 end
 
+# 1: the block's element kernels take the Walsh-Hadamard form (HEX8, trilinear table on a 2-point rule per axis, any
+# node / point numbering of the ReferenceFE tables handed over at construction), 0: the plain quadrature loop
+function block_kernel_form(asm::B200Assembler, block::Integer)
+  f = Ref{Int32}(0)
+  check(ccall((:fecb200_block_kernel_form, LIB), Cint, (Ptr{Cvoid}, Int32, Ref{Int32}), asm.handle, Int32(block - 1), f))
+  return Int(f[])
+end
+
 end # module
