@@ -27,6 +27,8 @@
 #include "common.cuh"
 #include "physics.cuh"
 #include <memory>
+#include <type_traits>
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 
@@ -267,23 +269,42 @@ FEC_DEV void vw_analyse(const double (&f)[8][NC], const double* wr, double (&fh)
     for (int al = 1; al < 8; ++al) fh[al][c] = v[al] * wr[vw_popc3(al) - 1];
   }
 }
+// where the coefficients of a field live: registers, or the thread's column of a shared-memory stash
+// (entry (alpha, c) at base[((alpha - 1) * NC + c) * STRIDE], STRIDE = threads per CTA: conflict-free)
+template <int NC>
+struct VwReg {
+  const double (&fh)[8][NC];
+  FEC_DEV double operator()(int al, int c) const { return fh[al][c]; }
+};
+template <int NC, int STRIDE>
+struct VwStash {
+  const double* base;
+  FEC_DEV double operator()(int al, int c) const { return base[((al - 1) * NC + c) * STRIDE]; }
+};
+template <int NC, int STRIDE>
+FEC_DEV void vw_stash(const double (&fh)[8][NC], double* base) {
+#pragma unroll
+  for (int al = 1; al < 8; ++al)
+#pragma unroll
+    for (int c = 0; c < NC; ++c) base[((al - 1) * NC + c) * STRIDE] = fh[al][c];
+}
 // g[c][k] = sum_a f[a][c] dN[q][a][k] from the coefficients: 4 signed terms
-template <int NC, int Q>
-FEC_DEV void vw_gradient(const double (&fh)[8][NC], double (&g)[NC][3]) {
+template <int NC, int Q, class Acc>
+FEC_DEV void vw_gradient(const Acc& fh, double (&g)[NC][3]) {
 #pragma unroll
   for (int c = 0; c < NC; ++c)
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      double s = fh[1 << k][c];
+      double s = fh(1 << k, c);
 #pragma unroll
       for (int S = 1; S < 8; ++S)
-        if (!(S & (1 << k))) s = vw_sign(Q, S) ? s - fh[S | (1 << k)][c] : s + fh[S | (1 << k)][c];
+        if (!(S & (1 << k))) s = vw_sign(Q, S) ? s - fh(S | (1 << k), c) : s + fh(S | (1 << k), c);
       g[c][k] = s;
     }
 }
 
-template <int NF, class Phys, int MODE, int Q>
-FEC_DEV void vec_qp_walsh(const double wq, const double (&Xh)[8][3], const double (&Uh)[8][NF], const double (&Vh)[8][NF],
+template <int NF, class Phys, int MODE, int Q, class AccX, class AccV>
+FEC_DEV void vec_qp_walsh(const double wq, const AccX& Xh, const double (&Uh_)[8][NF], const AccV& Vh,
                           const double* props, const double fq, const double* so, double* sn, double (&rh)[8][NF],
                           double (&sh)[8][NF]) {
   constexpr int ND = 3;
@@ -295,7 +316,7 @@ FEC_DEV void vec_qp_walsh(const double wq, const double (&Xh)[8][3], const doubl
     for (int k = 0; k < ND; ++k) J[i][k] = Jt[i][k];
   const double JxW = invert<ND>(J, Ji) * wq;
   double gx[NF][ND], gu[NF][ND];
-  vw_gradient<NF, Q>(Uh, gx);
+  vw_gradient<NF, Q>(VwReg<NF>{Uh_}, gx);
 #pragma unroll
   for (int d = 0; d < NF; ++d)
 #pragma unroll
@@ -345,10 +366,12 @@ FEC_DEV void vec_qp_walsh(const double wq, const double (&Xh)[8][3], const doubl
   }
 }
 
-template <int NF, class Phys, int MODE, int Q, class Tab, class Params>
-FEC_DEV void vec_walsh_points(const Tab& tab, const Params& p, const int e, const double (&Xh)[8][3], const double (&Uh)[8][NF],
-                              const double (&Vh)[8][NF], double (&rh)[8][NF], double (&sh)[8][NF]) {
+template <int NF, class Phys, int MODE, int Q, class Tab, class Params, class AccX, class AccV>
+FEC_DEV void vec_walsh_points(const Tab& tab, const Params& p, const int e, const AccX& Xh, const double (&Uh)[8][NF],
+                              const AccV& Vh, double (&rh)[8][NF], double (&sh)[8][NF]) {
   if constexpr (Q < 8) {
+    if constexpr (!std::is_same<AccX, VwReg<3>>::value)
+      asm volatile("" ::: "memory");   // keep the stash loads of later points from being hoisted (register pressure)
     constexpr int NS = Phys::NS;
     double so[NS > 0 ? NS : 1], sn[NS > 0 ? NS : 1];
     if constexpr (NS > 0) {
@@ -368,19 +391,36 @@ FEC_DEV void vec_walsh_points(const Tab& tab, const Params& p, const int e, cons
   }
 }
 
-// the whole element, fields and result in SIGN order, for MODE_RESIDUAL / MODE_ACTION_STIFFNESS
-template <int NF, class Phys, int MODE, class Params>
+// the whole element, fields and result in SIGN order, for MODE_RESIDUAL / MODE_ACTION_STIFFNESS.  STASH: the
+// coefficients of X and V wait in the thread's column of shared memory (the action kernel of NF = 3 holds four 21-entry
+// fields plus the constitutive temporaries: 432 B of spills otherwise); `stash` = 2 * 21 * TE doubles, this thread's column.
+template <int NF, class Phys, int MODE, bool STASH, int TE, class Params>
 FEC_DEV void vec_element_walsh(const Params& p, const int e, const double (&x)[8][3], const double (&u)[8][NF],
-                               const double (&v)[8][NF], double (&r)[8][NF]) {
-  double Xh[8][3], Uh[8][NF], Vh[8][NF], rh[8][NF], sh[8][NF];
-  vw_analyse<3>(x, p.wr, Xh);
+                               const double (&v)[8][NF], double (&r)[8][NF], double* stash) {
+  double Uh[8][NF], rh[8][NF], sh[8][NF];
   vw_analyse<NF>(u, p.wr, Uh);
-  if constexpr (MODE == MODE_ACTION_STIFFNESS) vw_analyse<NF>(v, p.wr, Vh);
 #pragma unroll
   for (int al = 0; al < 8; ++al)
 #pragma unroll
     for (int d = 0; d < NF; ++d) { rh[al][d] = 0.0; sh[al][d] = 0.0; }
-  vec_walsh_points<NF, Phys, MODE, 0>(p.tab, p, e, Xh, Uh, Vh, rh, sh);
+  if constexpr (STASH) {
+    {
+      double Xh[8][3];
+      vw_analyse<3>(x, p.wr, Xh);
+      vw_stash<3, TE>(Xh, stash);
+    }
+    {
+      double Vh[8][NF];
+      vw_analyse<NF>(v, p.wr, Vh);
+      vw_stash<NF, TE>(Vh, stash + 7 * 3 * TE);
+    }
+    vec_walsh_points<NF, Phys, MODE, 0>(p.tab, p, e, VwStash<3, TE>{stash}, Uh, VwStash<NF, TE>{stash + 7 * 3 * TE}, rh, sh);
+  } else {
+    double Xh[8][3], Vh[8][NF];
+    vw_analyse<3>(x, p.wr, Xh);
+    if constexpr (MODE == MODE_ACTION_STIFFNESS) vw_analyse<NF>(v, p.wr, Vh);
+    vec_walsh_points<NF, Phys, MODE, 0>(p.tab, p, e, VwReg<3>{Xh}, Uh, VwReg<NF>{Vh}, rh, sh);
+  }
 #pragma unroll
   for (int d = 0; d < NF; ++d) {
     double w[8];
@@ -467,7 +507,8 @@ __global__ void __launch_bounds__(TE, MINB) k_vec(const __grid_constant__ VecPar
 #pragma unroll
     for (int d = 0; d < NF; ++d) r[a][d] = 0.0;
   if constexpr (WALSH) {
-    if (active) vec_element_walsh<NF, Phys, MODE>(p, e, x, u, v, r);
+    constexpr bool kStash = (MODE == MODE_ACTION_STIFFNESS && NF == 3);
+    if (active) vec_element_walsh<NF, Phys, MODE, kStash, TE>(p, e, x, u, v, r, smem + tid);
   } else if (active) {
     auto body = [&](const int q) {
       double so[NS > 0 ? NS : 1], sn[NS > 0 ? NS : 1];
@@ -849,6 +890,7 @@ void run_vec_t(fecb200_handle* h, BlockPlan& b, const VecLaunch& a, const double
   size_t sm_nodes = (size_t)b.max_tile_nodes * (ND + nfields * NF) * sizeof(double);
   size_t sm_stage = (size_t)NNPE * NF * TE * sizeof(double);
   size_t body = sm_nodes > sm_stage ? sm_nodes : sm_stage;
+  if (WALSH && MODE == MODE_ACTION_STIFFNESS && NF == 3) body = std::max(body, (size_t)(7 * 3 + 7 * NF) * TE * sizeof(double));   // the coefficient stash
   p.body_doubles = (int32_t)(body / sizeof(double));
   p.max_nodes = b.max_tile_nodes;
   size_t smem = body + (size_t)(2 * b.max_tile_nodes + 1) * sizeof(int32_t) + (size_t)NNPE * TE * sizeof(uint16_t) + 8;
@@ -863,14 +905,16 @@ void run_vec_t(fecb200_handle* h, BlockPlan& b, const VecLaunch& a, const double
 
 template <int ND, int NNPE, int NF, int NQT, class Phys, int MODE, int TE, int MINB>
 void run_vec(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
-  // Walsh form where it pays (B200, 192^3 / 128^3): mechanics residual 2.23 -> 1.82 ms.  The matrix-free action is register
-  // bound either way (3.16 ms both, more spills in the Walsh form) and the scalar kernels lose occupancy (Poisson residual
-  // 0.34 -> 0.45 ms at 184 instead of 144 registers), so those keep the quadrature loop; FECB200_VEC_WALSH_ALL=1 is the A/B switch.
-  constexpr bool kPays = (MODE == MODE_RESIDUAL && NF == 3);
+  // Walsh form where it pays (B200, 192^3 / 128^3): mechanics residual 2.23 -> 1.82 ms; scalar residual 0.339 -> 0.324 ms and
+  // action 0.285 -> 0.257 ms once the kernel is capped at 168 registers (3 CTAs per SM; at 184 registers it LOSES, 0.45 ms).
+  // The mechanics action is register bound either way (3.16 ms both, more spills in the Walsh form) and keeps the quadrature
+  // loop; FECB200_VEC_WALSH_ALL=1 is the A/B switch.
+  constexpr bool kPays = NF == 3 || NF == 1;
+  constexpr int WMINB = (NF == 1) ? MINB + 1 : MINB;
   if constexpr (ND == 3 && NNPE == 8 && NQT == 8 && (MODE == MODE_RESIDUAL || MODE == MODE_ACTION_STIFFNESS)) {
     if (!kPays && !getenv("FECB200_VEC_WALSH_ALL")) { run_vec_t<ND, NNPE, NF, NQT, Phys, MODE, TE, MINB, false>(h, b, a, 0.0); return; }
     if (!getenv("FECB200_VEC_CLASSIC") && b.walsh) {
-      run_vec_t<ND, NNPE, NF, NQT, Phys, MODE, TE, MINB, true>(h, b, a, b.walsh_c);
+      run_vec_t<ND, NNPE, NF, NQT, Phys, MODE, TE, WMINB, true>(h, b, a, b.walsh_c);
       return;
     }
   }
