@@ -32,6 +32,12 @@
 #include <cmath>
 #include <cstdlib>
 
+// experiment switch: the Walsh residual kernel with its X / U coefficients in the shared-memory stash and 3 CTAs per SM
+// (154 registers, no spills): 1.88 ms against 1.84 ms with everything in registers at 2 CTAs per SM -- off
+#ifndef FEC_VEC_STASH_R
+#define FEC_VEC_STASH_R 0
+#endif
+
 namespace fec {
 
 template <int ND, int NNPE, int NQT>
@@ -303,8 +309,8 @@ FEC_DEV void vw_gradient(const Acc& fh, double (&g)[NC][3]) {
     }
 }
 
-template <int NF, class Phys, int MODE, int Q, class AccX, class AccV>
-FEC_DEV void vec_qp_walsh(const double wq, const AccX& Xh, const double (&Uh_)[8][NF], const AccV& Vh,
+template <int NF, class Phys, int MODE, int Q, class AccX, class AccU, class AccV>
+FEC_DEV void vec_qp_walsh(const double wq, const AccX& Xh, const AccU& Uh, const AccV& Vh,
                           const double* props, const double fq, const double* so, double* sn, double (&rh)[8][NF],
                           double (&sh)[8][NF]) {
   constexpr int ND = 3;
@@ -316,7 +322,7 @@ FEC_DEV void vec_qp_walsh(const double wq, const AccX& Xh, const double (&Uh_)[8
     for (int k = 0; k < ND; ++k) J[i][k] = Jt[i][k];
   const double JxW = invert<ND>(J, Ji) * wq;
   double gx[NF][ND], gu[NF][ND];
-  vw_gradient<NF, Q>(VwReg<NF>{Uh_}, gx);
+  vw_gradient<NF, Q>(Uh, gx);
 #pragma unroll
   for (int d = 0; d < NF; ++d)
 #pragma unroll
@@ -366,8 +372,8 @@ FEC_DEV void vec_qp_walsh(const double wq, const AccX& Xh, const double (&Uh_)[8
   }
 }
 
-template <int NF, class Phys, int MODE, int Q, class Tab, class Params, class AccX, class AccV>
-FEC_DEV void vec_walsh_points(const Tab& tab, const Params& p, const int e, const AccX& Xh, const double (&Uh)[8][NF],
+template <int NF, class Phys, int MODE, int Q, class Tab, class Params, class AccX, class AccU, class AccV>
+FEC_DEV void vec_walsh_points(const Tab& tab, const Params& p, const int e, const AccX& Xh, const AccU& Uh,
                               const AccV& Vh, double (&rh)[8][NF], double (&sh)[8][NF]) {
   if constexpr (Q < 8) {
     if constexpr (!std::is_same<AccX, VwReg<3>>::value)
@@ -397,8 +403,7 @@ FEC_DEV void vec_walsh_points(const Tab& tab, const Params& p, const int e, cons
 template <int NF, class Phys, int MODE, bool STASH, int TE, class Params>
 FEC_DEV void vec_element_walsh(const Params& p, const int e, const double (&x)[8][3], const double (&u)[8][NF],
                                const double (&v)[8][NF], double (&r)[8][NF], double* stash) {
-  double Uh[8][NF], rh[8][NF], sh[8][NF];
-  vw_analyse<NF>(u, p.wr, Uh);
+  double rh[8][NF], sh[8][NF];
 #pragma unroll
   for (int al = 0; al < 8; ++al)
 #pragma unroll
@@ -409,17 +414,30 @@ FEC_DEV void vec_element_walsh(const Params& p, const int e, const double (&x)[8
       vw_analyse<3>(x, p.wr, Xh);
       vw_stash<3, TE>(Xh, stash);
     }
-    {
-      double Vh[8][NF];
-      vw_analyse<NF>(v, p.wr, Vh);
-      vw_stash<NF, TE>(Vh, stash + 7 * 3 * TE);
+    double* st2 = stash + 7 * 3 * TE;
+    if constexpr (MODE == MODE_ACTION_STIFFNESS) {   // X and V in the stash, U in registers
+      double Uh[8][NF];
+      vw_analyse<NF>(u, p.wr, Uh);
+      {
+        double Vh[8][NF];
+        vw_analyse<NF>(v, p.wr, Vh);
+        vw_stash<NF, TE>(Vh, st2);
+      }
+      vec_walsh_points<NF, Phys, MODE, 0>(p.tab, p, e, VwStash<3, TE>{stash}, VwReg<NF>{Uh}, VwStash<NF, TE>{st2}, rh, sh);
+    } else {                                         // residual: X and U in the stash
+      {
+        double Uh[8][NF];
+        vw_analyse<NF>(u, p.wr, Uh);
+        vw_stash<NF, TE>(Uh, st2);
+      }
+      vec_walsh_points<NF, Phys, MODE, 0>(p.tab, p, e, VwStash<3, TE>{stash}, VwStash<NF, TE>{st2}, VwStash<NF, TE>{st2}, rh, sh);
     }
-    vec_walsh_points<NF, Phys, MODE, 0>(p.tab, p, e, VwStash<3, TE>{stash}, Uh, VwStash<NF, TE>{stash + 7 * 3 * TE}, rh, sh);
   } else {
-    double Xh[8][3], Vh[8][NF];
+    double Xh[8][3], Uh[8][NF], Vh[8][NF];
     vw_analyse<3>(x, p.wr, Xh);
+    vw_analyse<NF>(u, p.wr, Uh);
     if constexpr (MODE == MODE_ACTION_STIFFNESS) vw_analyse<NF>(v, p.wr, Vh);
-    vec_walsh_points<NF, Phys, MODE, 0>(p.tab, p, e, VwReg<3>{Xh}, Uh, VwReg<NF>{Vh}, rh, sh);
+    vec_walsh_points<NF, Phys, MODE, 0>(p.tab, p, e, VwReg<3>{Xh}, VwReg<NF>{Uh}, VwReg<NF>{Vh}, rh, sh);
   }
 #pragma unroll
   for (int d = 0; d < NF; ++d) {
@@ -507,7 +525,7 @@ __global__ void __launch_bounds__(TE, MINB) k_vec(const __grid_constant__ VecPar
 #pragma unroll
     for (int d = 0; d < NF; ++d) r[a][d] = 0.0;
   if constexpr (WALSH) {
-    constexpr bool kStash = (MODE == MODE_ACTION_STIFFNESS && NF == 3);
+    constexpr bool kStash = (NF == 3) && (MODE == MODE_ACTION_STIFFNESS || FEC_VEC_STASH_R);
     if (active) vec_element_walsh<NF, Phys, MODE, kStash, TE>(p, e, x, u, v, r, smem + tid);
   } else if (active) {
     auto body = [&](const int q) {
@@ -890,7 +908,7 @@ void run_vec_t(fecb200_handle* h, BlockPlan& b, const VecLaunch& a, const double
   size_t sm_nodes = (size_t)b.max_tile_nodes * (ND + nfields * NF) * sizeof(double);
   size_t sm_stage = (size_t)NNPE * NF * TE * sizeof(double);
   size_t body = sm_nodes > sm_stage ? sm_nodes : sm_stage;
-  if (WALSH && MODE == MODE_ACTION_STIFFNESS && NF == 3) body = std::max(body, (size_t)(7 * 3 + 7 * NF) * TE * sizeof(double));   // the coefficient stash
+  if (WALSH && NF == 3) body = std::max(body, (size_t)(7 * 3 + 7 * NF) * TE * sizeof(double));   // the coefficient stash
   p.body_doubles = (int32_t)(body / sizeof(double));
   p.max_nodes = b.max_tile_nodes;
   size_t smem = body + (size_t)(2 * b.max_tile_nodes + 1) * sizeof(int32_t) + (size_t)NNPE * TE * sizeof(uint16_t) + 8;
@@ -910,7 +928,7 @@ void run_vec(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
   // The mechanics action is register bound either way (3.16 ms both, more spills in the Walsh form) and keeps the quadrature
   // loop; FECB200_VEC_WALSH_ALL=1 is the A/B switch.
   constexpr bool kPays = NF == 3 || NF == 1;
-  constexpr int WMINB = (NF == 1) ? MINB + 1 : MINB;
+  constexpr int WMINB = (NF == 1 || (FEC_VEC_STASH_R && NF == 3 && MODE == MODE_RESIDUAL)) ? MINB + 1 : MINB;
   if constexpr (ND == 3 && NNPE == 8 && NQT == 8 && (MODE == MODE_RESIDUAL || MODE == MODE_ACTION_STIFFNESS)) {
     if (!kPays && !getenv("FECB200_VEC_WALSH_ALL")) { run_vec_t<ND, NNPE, NF, NQT, Phys, MODE, TE, MINB, false>(h, b, a, 0.0); return; }
     if (!getenv("FECB200_VEC_CLASSIC") && b.walsh) {
