@@ -9,8 +9,9 @@ is multilinear in the sign bits of q, a and b.  Hence
     Mh[alpha][beta] = sum_{k1,k2,m} W[alpha,beta,k1,k2,m] Bh_m[k1][k2]     (144 non-zero W)
     M[a][b] = sum_{alpha,beta} s_a^alpha s_b^beta Mh[alpha][beta]          (inverse Walsh over 6 sign bits, 384 add/sub)
 = 744 FP64 instructions per block after the 432 of B, against 2112 for the quadrature loop.
-This script computes W, checks the identity against the direct sum on random data and writes the generated
-accumulation code (csrc/kernel_mat2_walsh_gen.cuh)."""
+This script computes W and checks the identity against the direct sum on random data; the kernel (csrc/kernel_mat2.cuh)
+uses the closed form of W -- Mh[alpha][beta] += c^(|alpha|+|beta|-2)/64 Bh_{(alpha\\k1) xor (beta\\k2)}[k1][k2] for k1 in alpha,
+k2 in beta -- written as compile-time-unrolled loops, and tests/test_walsh_cpu.py restates those loops in numpy."""
 import itertools
 import sys
 
