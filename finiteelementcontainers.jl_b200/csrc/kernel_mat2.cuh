@@ -236,9 +236,21 @@ __global__ void __launch_bounds__(WARPS * 32, WALSH ? FEC_MAT2_MINB : 1) k_mat2(
   // ---- phase G: geometry + material tangent of the element's quadrature points, split over its threads
   double x[NNPE][ND], u[NNPE][NF];
   if (active && !FEC_KO(16)) {
+    int nid[NNPE];
+    if constexpr (NNPE % 4 == 0) {   // the element's connectivity row is 16-byte aligned: NNPE / 4 vector loads
+      const int4* c4 = reinterpret_cast<const int4*>(p.conn + (size_t)e * NNPE);
+#pragma unroll
+      for (int i = 0; i < NNPE / 4; ++i) {
+        const int4 v = c4[i];
+        nid[4 * i] = v.x; nid[4 * i + 1] = v.y; nid[4 * i + 2] = v.z; nid[4 * i + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int a = 0; a < NNPE; ++a) nid[a] = p.conn[(size_t)e * NNPE + a];
+    }
 #pragma unroll
     for (int a = 0; a < NNPE; ++a) {
-      const int n = p.conn[(size_t)e * NNPE + a];
+      const int n = nid[a];
 #pragma unroll
       for (int j = 0; j < ND; ++j) x[a][j] = p.X[(size_t)n * ND + j];
 #pragma unroll
