@@ -590,7 +590,7 @@ def run_gpu(args):
             traffic, traffic_src = ncu_traffic(dbuf)
             onchip = ncu_onchip(dbuf)
             roof = {"bound": "hbm",
-                    "binding_roof": ("l1tex_lsu_data_pipe" if onchip and onchip.get("lsu_data_pipe_pct", 0) > 100 * max(tf / fp64_peak, ach / hbm)
+                    "binding_roof": ("scatter: L2 RED-sector rate / L1-LSU data pipe (on chip)" if onchip and onchip.get("lsu_data_pipe_pct", 0) > 100 * max(tf / fp64_peak, ach / hbm)
                                      else "fp64" if tf / fp64_peak > ach / hbm else "hbm"),
                     "onchip_ncu": onchip,
                     "kernel": "fused residual + tangent -> CSR (" + os.environ.get("FECB200_MAT_KERNEL", "default") + ")",
