@@ -154,6 +154,7 @@ __global__ void k_build_emeta(const int32_t* conn, const int32_t* gconn, const u
 
 void build_ecol(fecb200_handle* h) {
   PhaseTimer _pt("build_ecol");
+  h->adjx_ok = false;   // the dof maps changed: the SpMV's packed column table is rebuilt on its next use
   if (!h->matrix_ready || (int64_t)nz_alloc_len(h) >= (int64_t)0xFFFFFFFFll) return;
   for (auto& b : h->blocks) {
     if (b.nnpe > 16) continue;
@@ -320,6 +321,83 @@ __global__ void k_spmv(const double* __restrict__ nz, const double* __restrict__
   }
 }
 
+// SpMV, second version.  The first one chains four dependent loads per entry (adjptr -> adj -> freemask / d2u -> x) and
+// walks a row in a run-time loop: 5.09 ms for the 13.8 GB of values at 192^3 (2.7 TB/s).  Here the column node's kept-dof
+// mask and the Uu index of its first kept dof (the others follow: unknowns are numbered in dof order) are packed into one
+// word per adjacency entry (d_adjx, rebuilt when the dof maps change), and the first three 32-lane steps of a row -- every
+// row of a trilinear mesh -- are unrolled so that all their loads are in flight together.
+__global__ void k_build_adjx(const int32_t* adj, const uint8_t* freemask, const int32_t* d2u, uint32_t* adjx, int nf, int64_t nadj) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= nadj) return;
+  const int m = adj[k];
+  const unsigned mask = freemask[m];
+  const int first = mask ? __ffs((int)mask) - 1 : 0;
+  const int32_t ub = mask ? d2u[(int64_t)m * nf + first] : 0;
+  adjx[k] = (mask << 29) | (uint32_t)(ub < 0 ? 0 : ub);
+}
+template <int NF>
+__global__ void __launch_bounds__(256) k_spmv2(const double* __restrict__ nz, const double* __restrict__ x, double* __restrict__ y,
+                                               const int32_t* __restrict__ adjptr, const uint32_t* __restrict__ adjx,
+                                               const uint16_t* __restrict__ coloff, const int64_t* __restrict__ rowstart,
+                                               const int32_t* __restrict__ d2u, int64_t nn) {
+  const int64_t n = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= nn) return;
+  const int k0 = adjptr[n], k1 = adjptr[n + 1];
+  int64_t rs[NF];
+  double acc[NF];
+#pragma unroll
+  for (int d = 0; d < NF; ++d) { rs[d] = rowstart[n * NF + d]; acc[d] = 0.0; }
+  const int npairs = (k1 - k0) * NF;
+  constexpr int UN = 3;
+  uint32_t ax[UN];
+  int co[UN], dd[UN];
+#pragma unroll
+  for (int it = 0; it < UN; ++it) {
+    const int i = lane + 32 * it;
+    const bool valid = i < npairs;
+    const int k = k0 + (valid ? i / NF : 0);
+    dd[it] = i % NF;
+    ax[it] = valid ? adjx[k] : 0u;
+    co[it] = valid ? (int)coloff[k] : 0;
+  }
+  double xv[UN];
+  int pos[UN];
+#pragma unroll
+  for (int it = 0; it < UN; ++it) {
+    const unsigned mask = ax[it] >> 29;
+    const bool keep = (mask >> dd[it]) & 1u;
+    const int r = __popc(mask & ((1u << dd[it]) - 1u));
+    pos[it] = keep ? co[it] + r : -1;
+    xv[it] = keep ? x[(ax[it] & 0x1FFFFFFFu) + r] : 0.0;
+  }
+#pragma unroll
+  for (int it = 0; it < UN; ++it)
+    if (pos[it] >= 0) {
+#pragma unroll
+      for (int d = 0; d < NF; ++d)
+        if (rs[d] >= 0) acc[d] = fma(nz[rs[d] + pos[it]], xv[it], acc[d]);
+    }
+  for (int i = lane + 32 * UN; i < npairs; i += 32) {   // longer rows (unstructured meshes, higher valence)
+    const int k = k0 + i / NF, d2 = i % NF;
+    const uint32_t a = adjx[k];
+    const unsigned mask = a >> 29;
+    if (!((mask >> d2) & 1u)) continue;
+    const int r = __popc(mask & ((1u << d2) - 1u));
+    const int ps = coloff[k] + r;
+    const double v = x[(a & 0x1FFFFFFFu) + r];
+#pragma unroll
+    for (int d = 0; d < NF; ++d)
+      if (rs[d] >= 0) acc[d] = fma(nz[rs[d] + ps], v, acc[d]);
+  }
+#pragma unroll
+  for (int d = 0; d < NF; ++d) {
+    double s = acc[d];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0 && rs[d] >= 0) y[d2u[n * NF + d]] = s;
+  }
+}
+
 // For CSC storage the same arrays hold K^T row-wise, i.e. y = K x needs the transposed product; the
 // operators assembled here are symmetric in structure, and CG is only used for symmetric K, so
 // the row-wise product is used for both (documented in DESIGN.md).
@@ -327,6 +405,25 @@ void spmv(fecb200_handle* h, const double* nz, const double* x, double* y) {
   const int64_t threads = h->nn * 32;
   const int grid = grid_for(threads);
   const int32_t* d2u = h->d_d2u.p;
+  if (h->nf <= 3 && h->n_unknowns < (int64_t)0x1FFFFFFF && !getenv("FECB200_SPMV1")) {
+    const int64_t nadj = (int64_t)h->d_adj.n;
+    if (!h->adjx_ok) {
+      if (h->d_adjx.n != (size_t)nadj) h->d_adjx.alloc((size_t)nadj);
+      k_build_adjx<<<grid_for(nadj), 256, 0, h->stream>>>(h->d_adj.p, h->d_freemask.p, d2u, h->d_adjx.p, h->nf, nadj);
+      h->adjx_ok = true;
+      h->launches++;
+    }
+#define SPMV2(NF_) k_spmv2<NF_><<<grid, 256, 0, h->stream>>>(nz, x, y, h->d_adjptr.p, h->d_adjx.p, h->d_coloff.p, h->d_rowstart.p, d2u, h->nn)
+    switch (h->nf) {
+      case 1: SPMV2(1); break;
+      case 2: SPMV2(2); break;
+      default: SPMV2(3); break;
+    }
+#undef SPMV2
+    h->launches++;
+    FEC_CUDA(cudaGetLastError());
+    return;
+  }
 #define SPMV(NF_)                                                                                       \
   k_spmv<NF_, false><<<grid, 256, 0, h->stream>>>(nz, x, y, h->d_adjptr.p, h->d_adj.p, h->d_freemask.p, \
                                                   h->d_coloff.p, h->d_rowstart.p, d2u, h->nn)

@@ -250,6 +250,8 @@ struct fecb200_handle {
   int64_t n_unknowns = 0;
   fec::DevBuf<int32_t> d_unknown_dofs;  // 0-based dof ids
   fec::DevBuf<int32_t> d_d2u;           // dof -> index into Uu (or -1)
+  fec::DevBuf<uint32_t> d_adjx;         // per adjacency entry: kept-dof mask << 29 | Uu index of the column node's first kept dof (SpMV)
+  bool adjx_ok = false;                 // d_adjx matches the current dof maps (reset by build_ecol)
   fec::DevBuf<double> d_constraint;     // 1.0 at Dirichlet dofs
   // Dirichlet / periodic values
   int64_t n_bc = 0, n_per = 0;
