@@ -335,66 +335,89 @@ __global__ void k_build_adjx(const int32_t* adj, const uint8_t* freemask, const 
   const int32_t ub = mask ? d2u[(int64_t)m * nf + first] : 0;
   adjx[k] = (mask << 29) | (uint32_t)(ub < 0 ? 0 : ub);
 }
-template <int NF>
+template <int NF, int NPW>
 __global__ void __launch_bounds__(256) k_spmv2(const double* __restrict__ nz, const double* __restrict__ x, double* __restrict__ y,
                                                const int32_t* __restrict__ adjptr, const uint32_t* __restrict__ adjx,
                                                const uint16_t* __restrict__ coloff, const int64_t* __restrict__ rowstart,
                                                const int32_t* __restrict__ d2u, int64_t nn) {
-  const int64_t n = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  // NPW nodes per warp, walked together: every level of the dependent chain (adjptr -> adjx / coloff -> x, values) is
+  // issued for all of them before the next one, which is what hides the DRAM latency
+  const int64_t n0 = ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5) * NPW;
   const int lane = threadIdx.x & 31;
-  if (n >= nn) return;
-  const int k0 = adjptr[n], k1 = adjptr[n + 1];
-  int64_t rs[NF];
-  double acc[NF];
-#pragma unroll
-  for (int d = 0; d < NF; ++d) { rs[d] = rowstart[n * NF + d]; acc[d] = 0.0; }
-  const int npairs = (k1 - k0) * NF;
+  if (n0 >= nn) return;
   constexpr int UN = 3;
-  uint32_t ax[UN];
-  int co[UN], dd[UN];
+  int k0[NPW], npairs[NPW];
+  int64_t rs[NPW][NF];
+  double acc[NPW][NF];
 #pragma unroll
-  for (int it = 0; it < UN; ++it) {
-    const int i = lane + 32 * it;
-    const bool valid = i < npairs;
-    const int k = k0 + (valid ? i / NF : 0);
-    dd[it] = i % NF;
-    ax[it] = valid ? adjx[k] : 0u;
-    co[it] = valid ? (int)coloff[k] : 0;
+  for (int u = 0; u < NPW; ++u) {
+    const bool on = n0 + u < nn;
+    const int64_t n = on ? n0 + u : n0;
+    k0[u] = adjptr[n];
+    npairs[u] = on ? (adjptr[n + 1] - k0[u]) * NF : 0;
+#pragma unroll
+    for (int d = 0; d < NF; ++d) { rs[u][d] = on ? rowstart[n * NF + d] : -1; acc[u][d] = 0.0; }
   }
-  double xv[UN];
-  int pos[UN];
+  uint32_t ax[NPW][UN];
+  int co[NPW][UN], dd[UN];
 #pragma unroll
-  for (int it = 0; it < UN; ++it) {
-    const unsigned mask = ax[it] >> 29;
-    const bool keep = (mask >> dd[it]) & 1u;
-    const int r = __popc(mask & ((1u << dd[it]) - 1u));
-    pos[it] = keep ? co[it] + r : -1;
-    xv[it] = keep ? x[(ax[it] & 0x1FFFFFFFu) + r] : 0.0;
-  }
+  for (int it = 0; it < UN; ++it) dd[it] = (lane + 32 * it) % NF;
 #pragma unroll
-  for (int it = 0; it < UN; ++it)
-    if (pos[it] >= 0) {
+  for (int u = 0; u < NPW; ++u)
+#pragma unroll
+    for (int it = 0; it < UN; ++it) {
+      const int i = lane + 32 * it;
+      const bool valid = i < npairs[u];
+      const int k = k0[u] + (valid ? i / NF : 0);
+      ax[u][it] = valid ? adjx[k] : 0u;
+      co[u][it] = valid ? (int)coloff[k] : 0;
+    }
+  double xv[NPW][UN];
+  int pos[NPW][UN];
+#pragma unroll
+  for (int u = 0; u < NPW; ++u)
+#pragma unroll
+    for (int it = 0; it < UN; ++it) {
+      const unsigned mask = ax[u][it] >> 29;
+      const bool keep = (mask >> dd[it]) & 1u;
+      const int r = __popc(mask & ((1u << dd[it]) - 1u));
+      pos[u][it] = keep ? co[u][it] + r : -1;
+      xv[u][it] = keep ? __ldg(x + (ax[u][it] & 0x1FFFFFFFu) + r) : 0.0;
+    }
+  // all value loads are issued before the first FMA (predicated, independent of each other)
+  double v[NPW][UN][NF];
+#pragma unroll
+  for (int u = 0; u < NPW; ++u)
+#pragma unroll
+    for (int it = 0; it < UN; ++it)
+#pragma unroll
+      for (int d = 0; d < NF; ++d) v[u][it][d] = (pos[u][it] >= 0 && rs[u][d] >= 0) ? __ldcs(nz + rs[u][d] + pos[u][it]) : 0.0;
+#pragma unroll
+  for (int u = 0; u < NPW; ++u)
+#pragma unroll
+    for (int it = 0; it < UN; ++it)
+#pragma unroll
+      for (int d = 0; d < NF; ++d) acc[u][d] = fma(v[u][it][d], xv[u][it], acc[u][d]);
+#pragma unroll
+  for (int u = 0; u < NPW; ++u) {
+    for (int i = lane + 32 * UN; i < npairs[u]; i += 32) {   // longer rows (unstructured meshes, higher valence)
+      const int k = k0[u] + i / NF, d2 = i % NF;
+      const uint32_t a = adjx[k];
+      const unsigned mask = a >> 29;
+      if (!((mask >> d2) & 1u)) continue;
+      const int r = __popc(mask & ((1u << d2) - 1u));
+      const int ps = coloff[k] + r;
+      const double xvv = x[(a & 0x1FFFFFFFu) + r];
 #pragma unroll
       for (int d = 0; d < NF; ++d)
-        if (rs[d] >= 0) acc[d] = fma(nz[rs[d] + pos[it]], xv[it], acc[d]);
+        if (rs[u][d] >= 0) acc[u][d] = fma(nz[rs[u][d] + ps], xvv, acc[u][d]);
     }
-  for (int i = lane + 32 * UN; i < npairs; i += 32) {   // longer rows (unstructured meshes, higher valence)
-    const int k = k0 + i / NF, d2 = i % NF;
-    const uint32_t a = adjx[k];
-    const unsigned mask = a >> 29;
-    if (!((mask >> d2) & 1u)) continue;
-    const int r = __popc(mask & ((1u << d2) - 1u));
-    const int ps = coloff[k] + r;
-    const double v = x[(a & 0x1FFFFFFFu) + r];
 #pragma unroll
-    for (int d = 0; d < NF; ++d)
-      if (rs[d] >= 0) acc[d] = fma(nz[rs[d] + ps], v, acc[d]);
-  }
-#pragma unroll
-  for (int d = 0; d < NF; ++d) {
-    double s = acc[d];
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0 && rs[d] >= 0) y[d2u[n * NF + d]] = s;
+    for (int d = 0; d < NF; ++d) {
+      double s = acc[u][d];
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0 && rs[u][d] >= 0) y[d2u[(n0 + u) * NF + d]] = s;
+    }
   }
 }
 
@@ -413,7 +436,9 @@ void spmv(fecb200_handle* h, const double* nz, const double* x, double* y) {
       h->adjx_ok = true;
       h->launches++;
     }
-#define SPMV2(NF_) k_spmv2<NF_><<<grid, 256, 0, h->stream>>>(nz, x, y, h->d_adjptr.p, h->d_adjx.p, h->d_coloff.p, h->d_rowstart.p, d2u, h->nn)
+    constexpr int NPW = 1;   // 2 nodes per warp measured slower (4.06 vs 3.36 ms at 192^3: registers, occupancy)
+    const int grid2 = grid_for((h->nn + NPW - 1) / NPW * 32);
+#define SPMV2(NF_) k_spmv2<NF_, NPW><<<grid2, 256, 0, h->stream>>>(nz, x, y, h->d_adjptr.p, h->d_adjx.p, h->d_coloff.p, h->d_rowstart.p, d2u, h->nn)
     switch (h->nf) {
       case 1: SPMV2(1); break;
       case 2: SPMV2(2); break;
