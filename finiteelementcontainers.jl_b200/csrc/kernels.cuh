@@ -100,9 +100,31 @@ FEC_DEV double invert(const double (&J)[ND][ND], double (&Ji)[ND][ND]) {
 //   J[i][j] = sum_a x[a][i] dN[a][j],  dN_X = dN J^-1,  JxW = det J * w.
 // dN_X is never formed: grad u = (sum_a u_a (x) dN_a) J^-1 and the scatter uses P J^-T, which is the
 // same arithmetic with 2*NNPE*ND*ND fewer FMAs per point.
-template <int ND, int NNPE, int NF, class Phys, int MODE, class Tab>
-FEC_DEV void vec_qp(const Tab& tab, const int q, const double (&x)[NNPE][ND], const double (&u)[NNPE][NF],
-                    const double (&v)[NNPE][NF], const double* props, const double fq, const double* so, double* sn,
+// where the element fields of the quadrature loop live: registers, or the thread's column of a shared-memory stash
+// (entry (a, c) at base[(a * C + c) * STRIDE], STRIDE = threads per CTA: conflict-free).  The stash is for elements whose
+// fields do not fit next to the constitutive temporaries (TET10 mechanics: 3 x 30 doubles): see vec_qstash below.
+template <int N, int C>
+struct FieldReg {
+  const double (&f)[N][C];
+  FEC_DEV double operator()(int a, int c) const { return f[a][c]; }
+};
+template <int C, int STRIDE>
+struct FieldStash {
+  const double* base;
+  FEC_DEV double operator()(int a, int c) const { return base[(a * C + c) * STRIDE]; }
+};
+#ifndef FEC_VEC_QSTASH
+#define FEC_VEC_QSTASH 1
+#endif
+#ifndef FEC_VEC_QSTASH_MINB
+#define FEC_VEC_QSTASH_MINB 1   // extra CTAs per SM of the stashed kernels (register cap 168 instead of 255)
+#endif
+template <int NNPE, int NF, bool WALSH>
+__host__ __device__ constexpr bool vec_qstash() { return FEC_VEC_QSTASH && !WALSH && NNPE >= 10 && NF == 3; }
+
+template <int ND, int NNPE, int NF, class Phys, int MODE, class Tab, class AX, class AU, class AV>
+FEC_DEV void vec_qp(const Tab& tab, const int q, const AX& x, const AU& u,
+                    const AV& v, const double* props, const double fq, const double* so, double* sn,
                     double (&r)[NNPE][NF]) {
   double J[ND][ND];
 #pragma unroll
@@ -111,7 +133,7 @@ FEC_DEV void vec_qp(const Tab& tab, const int q, const double (&x)[NNPE][ND], co
     for (int j = 0; j < ND; ++j) {
       double s = 0.0;
 #pragma unroll
-      for (int a = 0; a < NNPE; ++a) s = fma(x[a][i], tab.dN[q][a][j], s);
+      for (int a = 0; a < NNPE; ++a) s = fma(x(a, i), tab.dN[q][a][j], s);
       J[i][j] = s;
     }
   double Ji[ND][ND];
@@ -136,7 +158,7 @@ FEC_DEV void vec_qp(const Tab& tab, const int q, const double (&x)[NNPE][ND], co
     for (int d = 0; d < NF; ++d) {
       double s = 0.0;
 #pragma unroll
-      for (int a = 0; a < NNPE; ++a) s = fma(tab.N[q][a], v[a][d], s);
+      for (int a = 0; a < NNPE; ++a) s = fma(tab.N[q][a], v(a, d), s);
       s *= rho;
 #pragma unroll
       for (int a = 0; a < NNPE; ++a) r[a][d] = fma(tab.N[q][a], s, r[a][d]);
@@ -151,7 +173,7 @@ FEC_DEV void vec_qp(const Tab& tab, const int q, const double (&x)[NNPE][ND], co
       for (int j = 0; j < ND; ++j) {
         double s = 0.0;
 #pragma unroll
-        for (int a = 0; a < NNPE; ++a) s = fma(u[a][d], tab.dN[q][a][j], s);
+        for (int a = 0; a < NNPE; ++a) s = fma(u(a, d), tab.dN[q][a][j], s);
         gx[d][j] = s;
       }
 #pragma unroll
@@ -201,7 +223,7 @@ FEC_DEV void vec_qp(const Tab& tab, const int q, const double (&x)[NNPE][ND], co
         for (int j = 0; j < ND; ++j) {
           double s = 0.0;
 #pragma unroll
-          for (int a = 0; a < NNPE; ++a) s = fma(v[a][d], tab.dN[q][a][j], s);
+          for (int a = 0; a < NNPE; ++a) s = fma(v(a, d), tab.dN[q][a][j], s);
           gvx[d][j] = s;
         }
 #pragma unroll
@@ -528,7 +550,25 @@ __global__ void __launch_bounds__(TE, MINB) k_vec(const __grid_constant__ VecPar
     constexpr bool kStash = (NF == 3) && (MODE == MODE_ACTION_STIFFNESS || FEC_VEC_STASH_R);
     if (active) vec_element_walsh<NF, Phys, MODE, kStash, TE>(p, e, x, u, v, r, smem + tid);
   } else if (active) {
+    // TET10 mechanics: the element fields (3 x 30 doubles) wait in the thread's column of shared memory during the
+    // quadrature loop instead of in registers (the element-vector stage is idle until phase 4)
+    constexpr bool kQS = vec_qstash<NNPE, NF, WALSH>();
+    double* const st = smem + tid;
+    if constexpr (kQS) {
+#pragma unroll
+      for (int a = 0; a < NNPE; ++a) {
+#pragma unroll
+        for (int j = 0; j < ND; ++j) st[(a * ND + j) * TE] = x[a][j];
+#pragma unroll
+        for (int d = 0; d < NF; ++d) st[(NNPE * ND + a * NF + d) * TE] = u[a][d];
+        if constexpr (kNeedV) {
+#pragma unroll
+          for (int d = 0; d < NF; ++d) st[(NNPE * (ND + NF) + a * NF + d) * TE] = v[a][d];
+        }
+      }
+    }
     auto body = [&](const int q) {
+      if constexpr (kQS) asm volatile("" ::: "memory");   // keep the stash loads of later points from being hoisted
       double so[NS > 0 ? NS : 1], sn[NS > 0 ? NS : 1];
       if constexpr (NS > 0) {
 #pragma unroll
@@ -538,7 +578,12 @@ __global__ void __launch_bounds__(TE, MINB) k_vec(const __grid_constant__ VecPar
       if constexpr (Phys::kHasSource && MODE == MODE_RESIDUAL) {
         if (p.source) fq = p.source[(size_t)q * p.ne + e];
       }
-      vec_qp<ND, NNPE, NF, Phys, MODE>(p.tab, q, x, u, v, p.props, fq, so,
+      if constexpr (kQS)
+        vec_qp<ND, NNPE, NF, Phys, MODE>(p.tab, q, FieldStash<ND, TE>{st}, FieldStash<NF, TE>{st + NNPE * ND * TE},
+                                         FieldStash<NF, TE>{st + NNPE * (ND + NF) * TE}, p.props, fq, so,
+                                         (NS > 0 && MODE == MODE_RESIDUAL) ? sn : nullptr, r);
+      else
+      vec_qp<ND, NNPE, NF, Phys, MODE>(p.tab, q, FieldReg<NNPE, ND>{x}, FieldReg<NNPE, NF>{u}, FieldReg<NNPE, NF>{v}, p.props, fq, so,
                                        (NS > 0 && MODE == MODE_RESIDUAL) ? sn : nullptr, r);
       if constexpr (NS > 0 && MODE == MODE_RESIDUAL) {
 #pragma unroll
@@ -909,6 +954,7 @@ void run_vec_t(fecb200_handle* h, BlockPlan& b, const VecLaunch& a, const double
   size_t sm_stage = (size_t)NNPE * NF * TE * sizeof(double);
   size_t body = sm_nodes > sm_stage ? sm_nodes : sm_stage;
   if (WALSH && NF == 3) body = std::max(body, (size_t)(7 * 3 + 7 * NF) * TE * sizeof(double));   // the coefficient stash
+  if (vec_qstash<NNPE, NF, WALSH>()) body = std::max(body, (size_t)NNPE * (ND + nfields * NF) * TE * sizeof(double));   // the field stash
   p.body_doubles = (int32_t)(body / sizeof(double));
   p.max_nodes = b.max_tile_nodes;
   size_t smem = body + (size_t)(2 * b.max_tile_nodes + 1) * sizeof(int32_t) + (size_t)NNPE * TE * sizeof(uint16_t) + 8;
@@ -936,7 +982,10 @@ void run_vec(fecb200_handle* h, BlockPlan& b, const VecLaunch& a) {
       return;
     }
   }
-  run_vec_t<ND, NNPE, NF, NQT, Phys, MODE, TE, MINB, false>(h, b, a, 0.0);
+  // field stash (TET10 mechanics, J2 64^3 x 6): the residual fits 168 registers with 72 B of spills -> a third CTA per SM,
+  // 0.601 -> 0.495 ms; the action spills 336 B there (0.749 ms) and is better off at 2 CTAs per SM (0.757 -> 0.697 ms)
+  constexpr int QMINB = (vec_qstash<NNPE, NF, false>() && MODE == MODE_RESIDUAL) ? MINB + FEC_VEC_QSTASH_MINB : MINB;
+  run_vec_t<ND, NNPE, NF, NQT, Phys, MODE, TE, QMINB, false>(h, b, a, 0.0);
 }
 
 template <int ND, int NNPE, int NF, int NQT, class Phys>
