@@ -560,6 +560,9 @@ def run_gpu(args):
             t_res = op_ms(lambda: F.assemble_vector(asm, F.residual, dUu, p))
             t_tan = op_ms(lambda: F.assemble_stiffness(asm, F.stiffness, dUu, p))
             t_act = op_ms(lambda: F.assemble_matrix_free_action(asm, F.stiffness_action, dUu, Vu, p))
+            # the operator application of the device CG on the assembled CSR values (SpMV), next to the matrix-free one
+            Yu = torch.empty_like(Vu)
+            t_spmv = op_ms(lambda: F.matrix_multiply(asm, Vu, Yu))
             # dominant kernel alone: events recorded by the library around the element kernel launch
             check(lib.fecb200_enable_timing(h, 1))
             import ctypes as C
@@ -611,7 +614,8 @@ def run_gpu(args):
                    "tangent_elements_per_s": round(ne_local / (t_tan * 1e-3), 1),
                    "action_elements_per_s": round(ne_local / (t_act * 1e-3), 1),
                    "unfused_step_ms": round(t_unf, 4), "unfused_step_elements_per_s": round(ne_local / (t_unf * 1e-3), 1),
-                   "residual_ms": round(t_res, 4), "tangent_ms": round(t_tan, 4), "action_ms": round(t_act, 4)}
+                   "residual_ms": round(t_res, 4), "tangent_ms": round(t_tan, 4), "action_ms": round(t_act, 4),
+                   "csr_spmv_ms": round(t_spmv, 4)}
             if t_sb is not None:
                 ops["single_buffer_step_ms"] = round(t_sb, 4)   # same step with cudaMemset of the CSR values instead
         cpu = cpu_baseline(args.cpu_n) if (world == 1 and not args.no_cpu) else None
