@@ -272,3 +272,32 @@ def test_walsh_form_in_any_numbering(F, phys):
     F.assemble_stiffness(asm, F.stiffness, Uu, p)                          # tangent only
     assert rel_err(F.stiffness(asm).data, onz) < RTOL
     asm.close()
+
+
+@pytest.mark.parametrize("phys", ["poisson", "neo"])
+def test_spmv_versions_agree_with_scipy(F, phys, monkeypatch):
+    """y = K x of the device CG (fecb200_matrix_multiply): the packed-adjacency kernel (k_spmv2) and the first version
+    (FECB200_SPMV1) against the CSR values times x on the host, with Dirichlet-eliminated rows / columns present."""
+    rng = np.random.default_rng(3)
+    mesh = perturb(F.StructuredMesh("hex", (0, 0, 0), (1, 1, 1), (6, 5, 7)), 0.03)
+    nf = 1 if phys == "poisson" else 3
+    props = None if phys == "poisson" else np.array([1e3, 10e6, 1e6])
+    src = (lambda X: 1.0 + X[:, 0]) if phys == "poisson" else None
+    V = F.FunctionSpace(mesh, F.H1Field, F.Lagrange)
+    u = F.ScalarFunction(V, "u") if nf == 1 else F.VectorFunction(V, "displ")
+    asm = F.SparseMatrixAssembler(u, sparse_matrix_type="csr")
+    names = u.names()
+    dbcs = [F.DirichletBC(names[0], lambda X, t: np.zeros(X.shape[0]), nodeset_name="bottom")]   # one component only: partial masks
+    if nf == 3:
+        dbcs.append(F.DirichletBC(names[2], lambda X, t: np.zeros(X.shape[0]), nodeset_name="left"))
+    p = F.create_parameters(mesh, asm, product_physics(F, phys, 3, src), props, dirichlet_bcs=dbcs)
+    N = asm.sizes()[2]
+    Uu, x = 0.02 * rng.standard_normal(N), rng.standard_normal(N)
+    F.assemble_stiffness(asm, F.stiffness, Uu, p)
+    K = F.stiffness(asm)
+    ref = K @ x
+    y2 = np.asarray(F.matrix_multiply(asm, x))
+    monkeypatch.setenv("FECB200_SPMV1", "1")
+    y1 = np.asarray(F.matrix_multiply(asm, x))
+    assert rel_err(y2, ref) < 1e-13 and rel_err(y1, ref) < 1e-13
+    asm.close()
